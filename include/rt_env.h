@@ -1,0 +1,190 @@
+/*
+ * rt_env.h — C ABI of the B200-native batched radiotherapy environment step.
+ *
+ * The reference (rmaguado/ppo-radiotherapy) is pure Python and has no FFI layer
+ * (SURVEY.md §8b); this header is the boundary a maintainer binds with ctypes to
+ * replace the reference functions cited at each entry point.  Conventions:
+ *   - plain C symbols, plain pointers and sizes, no torch / Python types;
+ *   - every call returns 0 on success and a negative rt_status on failure, with a
+ *     thread-local message available from rt_last_error();
+ *   - pointers named *_dev are DEVICE pointers owned by the caller (e.g. PyTorch
+ *     allocations); calls taking a `stream` are asynchronous and stream-ordered and
+ *     never synchronise the host; `stream` is a cudaStream_t passed as void*;
+ *   - pointers named *_host are HOST pointers (pinned memory recommended); the
+ *     *_host calls copy host->device, run the same kernels, copy device->host and
+ *     return after the stream has drained;
+ *   - one handle drives one device and is not thread-safe.
+ *
+ * Array layouts are C-order.  G = grid = (67, 43, 70) for the bundled phantom,
+ * V = G0*G1*G2 voxels, linear voxel index = (i*G1 + j)*G2 + k (numpy C order of
+ * the reference's volumes, environment.py:29-30).
+ */
+#ifndef RT_ENV_H
+#define RT_ENV_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define RT_API __attribute__((visibility("default")))
+#else
+#define RT_API
+#endif
+
+#define RT_ABI_VERSION 1
+
+typedef enum {
+    RT_OK = 0,
+    RT_ERR_INVALID = -1,   /* bad argument */
+    RT_ERR_CUDA = -2,      /* CUDA runtime error (message has the detail) */
+    RT_ERR_NOMEM = -3,
+    RT_ERR_STATE = -4      /* call not valid in the handle's current state */
+} rt_status;
+
+/* Environment constants (environment.py:16-26). */
+#define RT_ACTION_SIZE 6
+#define RT_OBS_SIZE 9
+#define RT_MAX_TIME_STEPS 100
+#define RT_INFO_SIZE 16
+/* Upper bound on distinct voxels of one beam: 4 * (max(G) + 1) splat writes (draw_line.py:68-96). */
+#define RT_BEAM_CAP 288
+
+/* rt_create flags */
+#define RT_FLAG_DENSE 1u         /* full-volume dose update + from-scratch reductions every step
+                                    (the reference's own dataflow, environment.py:107-110,164-191) */
+#define RT_FLAG_RECORD_BEAMS 2u  /* keep the per-episode beam list (environment.py:110 self.beams) */
+
+/* Columns of the optional info block written by rt_step (float64 [N][RT_INFO_SIZE]);
+ * the reference's info dict, environment.py:222-241, plus episode statistics
+ * (gymnasium RecordEpisodeStatistics, train.py:36). */
+enum {
+    RT_INFO_REWARD_TOTAL = 0,   /* reward_components.total  */
+    RT_INFO_REWARD_TUMOUR = 1,  /* reward_components.tumour */
+    RT_INFO_REWARD_LUNG = 2,    /* reward_components.lung   */
+    RT_INFO_REWARD_DISTANCE = 3,/* reward_components.distance_to_tumour */
+    RT_INFO_DOSE_TUMOUR = 4,    /* doses.tumour */
+    RT_INFO_DOSE_LUNG = 5,      /* doses.lung   */
+    RT_INFO_OVERSHOOT_T0 = 6,   /* overshoot.translation[0..2] */
+    RT_INFO_OVERSHOOT_R = 9,    /* overshoot.rotation */
+    RT_INFO_EPISODE_RETURN = 10,/* episode.r (valid where terminated) */
+    RT_INFO_EPISODE_LENGTH = 11,/* episode.l */
+    RT_INFO_LUNG_COUNT = 12,    /* voxels of lungs\tumour with dose > 0.2 (environment.py:176-177) */
+    RT_INFO_STEPPED = 13,       /* 1 if this call advanced the env, 0 if it was the autoreset call */
+    RT_INFO_TUMOUR_ID = 14,
+    RT_INFO_T = 15
+};
+
+/* Phantom description, HOST pointers, copied to the device by rt_create.
+ * Built from the reference's data/lungs.npy and data/tumours/*.npy
+ * (environment.py:28-29,90-97) by tools/pack_phantom.py. */
+typedef struct {
+    int32_t grid[3];
+    const uint32_t *lungs_bits;    /* ceil(V/32) words, bit v = lungs.flat[v] */
+    int32_t n_tumours;
+    const int32_t *vox_offsets;    /* [n_tumours + 1] */
+    const int32_t *vox;            /* ascending linear voxel indices per tumour */
+    const double *centroid;        /* [n_tumours][3], environment.py:145-148 */
+    const float *tumour_sum;       /* [n_tumours], np.sum(tumours), environment.py:167 */
+    const float *lung_mask_sum;    /* [n_tumours], np.sum(lungs*(1-tumours)), environment.py:178 */
+} rt_phantom_desc;
+
+typedef struct rt_env rt_env;
+
+RT_API int rt_abi_version(void);
+RT_API const char *rt_last_error(void);
+
+/* ---- lifetime ----------------------------------------------------------------- */
+/* N resident episodes on CUDA device `device` (replaces constructing N
+ * RadiotherapyEnv objects inside SyncVectorEnv, train.py:93-95).  Episodes start
+ * un-reset: call rt_reset before rt_step. */
+RT_API int rt_create(rt_env **out, int device, int n_envs, uint32_t flags, const rt_phantom_desc *phantom);
+RT_API int rt_destroy(rt_env *env);
+RT_API int rt_num_envs(const rt_env *env);
+RT_API int64_t rt_device_bytes(const rt_env *env);
+
+/* ---- tumour choice (environment.py:90 np.random.choice) --------------------------- */
+/* Counter-based device RNG: episode e of env i uses tumour hash(seed, i, e) mod n_tumours. */
+RT_API int rt_seed(rt_env *env, uint64_t seed);
+/* Explicit schedule: episode e of env i uses ids_host[min(e, n_episodes-1)][i]; NULL returns to the RNG. */
+RT_API int rt_set_tumour_schedule(rt_env *env, const int32_t *ids_host, int n_episodes);
+
+/* ---- reset / step (environment.py:77-105, 193-243; SyncVectorEnv NEXT_STEP autoreset) ---- */
+/* Reset every env whose mask byte is non-zero (mask_dev NULL = all) and restart its
+ * episode counter at 0; obs_dev float32 [N][9] receives the observation of EVERY env. */
+RT_API int rt_reset(rt_env *env, const uint8_t *mask_dev, float *obs_dev, void *stream);
+
+/* One vector step.  actions_dev float32 [N][6].  Outputs (any may be NULL except obs_dev):
+ *   obs_dev float32 [N][9]      get_vector_observation, environment.py:259-268
+ *   reward_dev float64 [N]      environment.py:218     reward_f32_dev float32 [N] (same, rounded)
+ *   terminated_dev uint8 [N]    environment.py:220     truncated_dev uint8 [N] (always 0, :243)
+ *   info_dev float64 [N][RT_INFO_SIZE]
+ * An env that terminated on the previous call ignores its action, resets, and reports
+ * reward 0 / terminated 0 (gymnasium 1.0.0 AutoresetMode.NEXT_STEP, train.py:151). */
+RT_API int rt_step(rt_env *env, const float *actions_dev, float *obs_dev, double *reward_dev,
+                   float *reward_f32_dev, uint8_t *terminated_dev, uint8_t *truncated_dev,
+                   double *info_dev, void *stream);
+
+/* Host-buffer forms of the same calls (the reference's seam: train.py:151-158 passes
+ * numpy arrays).  Synchronous. */
+RT_API int rt_reset_host(rt_env *env, const uint8_t *mask_host, float *obs_host);
+RT_API int rt_step_host(rt_env *env, const float *actions_host, float *obs_host, double *reward_host,
+                        uint8_t *terminated_host, uint8_t *truncated_host, double *info_host);
+
+/* ---- state access ---------------------------------------------------------------- */
+/* pose_dev float64 [N][6] = (beam_position, beam_direction), environment.py:48-49. */
+RT_API int rt_get_pose(rt_env *env, double *pose_dev, void *stream);
+RT_API int rt_set_pose(rt_env *env, const double *pose_dev, void *stream);
+/* counters_dev int32 [N][6] = (t, tumour id, lung voxels above threshold, episode index,
+ * needs-reset flag, beams recorded) — environment.py:47 self.t and friends. */
+RT_API int rt_get_counters(rt_env *env, int32_t *counters_dev, void *stream);
+/* Dense float32 dose volume of one env, [V] (environment.py:42 self.dose). */
+RT_API int rt_get_dose(rt_env *env, int env_index, float *dose_dev, void *stream);
+/* Voxel observation, float32 [N][4][V] = clip(stack[lungs, tumours, dose, view], 0, 1)
+ * (get_volumes, environment.py:245-257); envs [first, first+count). */
+RT_API int rt_assemble_volumes(rt_env *env, int first, int count, float *obs_dev, void *stream);
+/* Recorded beams of one env (needs RT_FLAG_RECORD_BEAMS): float64 [100][6], returns count via n_dev. */
+RT_API int rt_get_beams(rt_env *env, int env_index, double *beams_dev, int32_t *n_dev, void *stream);
+
+/* ---- stateless geometry entry points (parity surface) ------------------------------- */
+/* draw_line.py:4 beam_voxels for m rays.  pos_dev/dir_dev float64 [m][3].  Per ray the
+ * distinct voxels hit and their summed float32 weights: idx_dev int32 [m][cap], w_dev
+ * float32 [m][cap], count_dev int32 [m]; count -1 flags the ValueError of draw_line.py:23-24
+ * ("Direction vector magnitude is too small.").  cap >= RT_BEAM_CAP. */
+RT_API int rt_beam_voxels(const int32_t grid[3], const double *pos_dev, const double *dir_dev, int m, int cap,
+                          int32_t *idx_dev, float *w_dev, int32_t *count_dev, void *stream);
+/* Same, written as the reference returns it: dense float32 [m][V] (zero-filled here). */
+RT_API int rt_beam_voxels_dense(const int32_t grid[3], const double *pos_dev, const double *dir_dev, int m,
+                                float *out_dev, int32_t *status_dev, void *stream);
+/* environment.py:112-143 + transforms.py:7-69 for m independent poses: actions float32 [m][6]
+ * -> new position / direction float64 [m][3], translation overshoot [m][3], rotation overshoot [m]. */
+RT_API int rt_pose_update(const int32_t grid[3], const double *pos_dev, const double *dir_dev,
+                          const float *actions_dev, int m, double *pos_out_dev, double *dir_out_dev,
+                          double *overshoot_t_dev, double *overshoot_r_dev, void *stream);
+
+/* transforms.py:7 apply_rotation(initial_direction, rotation_vector, min_angle) for m vectors:
+ * float64 [m][3] directions and rotation vectors -> new directions [m][3], overshoot [m]. */
+RT_API int rt_apply_rotation(const double *dir_dev, const double *rotvec_dev, int m, double min_angle,
+                             double *dir_out_dev, double *overshoot_dev, void *stream);
+/* transforms.py:62 apply_translation(position, translation_vector, bounds): clip(p + t, 0, bounds)
+ * and |p + t - clipped| for m positions; bounds is a HOST float64[3]. */
+RT_API int rt_apply_translation(const double *pos_dev, const double *translation_dev, int m,
+                                const double bounds[3], double *pos_out_dev, double *overshoot_dev,
+                                void *stream);
+
+/* ---- GAE (train.py:164-181) -------------------------------------------------------- */
+/* float32 [T][N] rewards/values/dones, [N] next_value/next_done -> advantages, returns [T][N]. */
+RT_API int rt_gae(const float *rewards_dev, const float *values_dev, const float *dones_dev,
+                  const float *next_value_dev, const float *next_done_dev, int T, int N,
+                  double gamma, double gae_lambda, float *advantages_dev, float *returns_dev, void *stream);
+
+/* ---- instrumentation ----------------------------------------------------------------- */
+/* Number of kernels this library has launched since load (for bench.py's gpu_launches). */
+RT_API int64_t rt_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RT_ENV_H */

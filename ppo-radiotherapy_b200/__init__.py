@@ -1,0 +1,30 @@
+"""B200-native batched environment step for rmaguado/ppo-radiotherapy.
+
+Public surface (mirrors the reference's module/function names for the hot path):
+
+    RadiotherapyEnv            environment.py:15    single episode, gymnasium reset/step API
+    RadiotherapyVectorEnv      train.py:93          SyncVectorEnv-compatible batch resident in HBM
+    BatchedEpisodes            —                    the device-resident engine under both
+    beam_voxels                draw_line.py:4
+    apply_rotation / apply_translation     transforms.py:7 / :62
+    compute_gae                train.py:164-181
+    Phantom                    environment.py:28-29,90-97 data, packed
+
+Everything computes in librtenv_b200.so (hand-written sm_100a CUDA behind the C ABI of
+include/rt_env.h).  There is no CPU fallback.
+"""
+from . import _native
+from ._native import RtError, build
+from .phantom import Phantom, default_phantom
+from .engine import BatchedEpisodes
+from .geometry import (apply_rotation, apply_rotation_batch, apply_translation, apply_translation_batch,
+                       beam_voxels, beam_voxels_batch, beam_voxels_dense_batch, compute_gae, pose_update_batch)
+from .vector_env import Box, RadiotherapyVectorEnv
+from .environment import RadiotherapyEnv
+
+__all__ = [
+    "RtError", "build", "Phantom", "default_phantom", "BatchedEpisodes", "RadiotherapyEnv",
+    "RadiotherapyVectorEnv", "Box", "beam_voxels", "beam_voxels_batch", "beam_voxels_dense_batch",
+    "apply_rotation", "apply_rotation_batch", "apply_translation", "apply_translation_batch",
+    "pose_update_batch", "compute_gae",
+]

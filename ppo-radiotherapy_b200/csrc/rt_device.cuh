@@ -1,0 +1,338 @@
+// rt_device.cuh — device-side building blocks of the environment step (sm_100a).
+//
+// Numerics contract (SURVEY.md §8a addendum): the float32 ray walk must reproduce
+// draw_line.py bit for bit, so every float32 operation below is an explicit
+// round-to-nearest intrinsic (__fmul_rn/__fadd_rn/__fsub_rn/__fdiv_rn/__fsqrt_rn):
+// ptxas never contracts those into FMA, whatever -fmad says.  The float64 pose
+// update follows transforms.py / scipy operation by operation with __dmul_rn/__dadd_rn.
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+namespace rt {
+
+constexpr int kWarp = 32;
+constexpr int kMaxChunks = 3;          // <= 96 slabs per beam; the bundled grid needs max(G)+1 = 71
+constexpr unsigned kFull = 0xffffffffu;
+
+struct Grid {
+    int g0, g1, g2;
+    int nvox;        // g0*g1*g2
+    int vstride;     // per-env dose stride in floats (nvox rounded up to 32 floats = 128 B)
+    int vwords;      // per-env words of the sector-valid bitmap (rounded up to 32 words)
+};
+
+// ---------------------------------------------------------------------------------
+// Pose update: environment.py:112-143 (map_translation / map_rotation) and
+// transforms.py:7-69 (apply_translation / apply_rotation); scipy Rotation restated
+// from scipy/spatial/transform/_rotation_xp.py:159-179,302-333,631-645.
+struct Pose {
+    double p[3];
+    double d[3];
+};
+
+__device__ __forceinline__ double dnorm3(double a, double b, double c)
+{
+    double s = __dmul_rn(a, a);
+    s = __dadd_rn(s, __dmul_rn(b, b));
+    s = __dadd_rn(s, __dmul_rn(c, c));
+    return sqrt(s);
+}
+
+__device__ __forceinline__ float clip1(float a) { return fminf(fmaxf(a, -1.0f), 1.0f); }
+
+// cos(pi/4) and sqrt(1 - cos(pi/4)^2) as glibc/NumPy evaluate them (transforms.py:36-37).
+constexpr double kCosMin = 0.70710678118654757;   // np.cos(np.pi/4)
+constexpr double kXYMag = 0.70710678118654746;    // np.sqrt(1 - np.cos(np.pi/4)**2)
+constexpr double kMinAngle = 0.78539816339744828; // np.pi/4
+constexpr double kPi = 3.1415926535897931;
+
+// transforms.py:62-69 apply_translation for one axis.
+__device__ __forceinline__ double translate_axis(double p, double t, double bound, double &overshoot)
+{
+    double tp = __dadd_rn(p, t);
+    double bp = fmin(fmax(tp, 0.0), bound);
+    overshoot = fabs(__dsub_rn(tp, bp));
+    return bp;
+}
+
+// transforms.py:7-59 apply_rotation.  cos_min = np.cos(min_angle), xy_mag = np.sqrt(1 - cos_min**2).
+__device__ __forceinline__ void apply_rotation(double (&d)[3], const double rv[3], double min_angle, double cos_min,
+                                               double xy_mag, double &os_r)
+{
+    double n = dnorm3(d[0], d[1], d[2]);                            // transforms.py:23
+    double d0 = __ddiv_rn(d[0], n), d1 = __ddiv_rn(d[1], n), d2 = __ddiv_rn(d[2], n);
+
+    double angle = dnorm3(rv[0], rv[1], rv[2]);                     // from_rotvec
+    double scale, qw;
+    if (angle <= 1e-3) {
+        double a2 = __dmul_rn(angle, angle);
+        scale = __dadd_rn(__dsub_rn(0.5, __ddiv_rn(a2, 48.0)), __ddiv_rn(__dmul_rn(a2, a2), 3840.0));
+        qw = cos(__ddiv_rn(angle, 2.0));
+    } else {
+        double sh, ch;
+        sincos(__ddiv_rn(angle, 2.0), &sh, &ch);
+        scale = __ddiv_rn(sh, angle);
+        qw = ch;
+    }
+    double x = __dmul_rn(scale, rv[0]), y = __dmul_rn(scale, rv[1]), z = __dmul_rn(scale, rv[2]), w = qw;
+    double x2 = __dmul_rn(x, x), y2 = __dmul_rn(y, y), z2 = __dmul_rn(z, z), w2 = __dmul_rn(w, w); // as_matrix
+    double xy = __dmul_rn(x, y), zw = __dmul_rn(z, w), xz = __dmul_rn(x, z);
+    double yw = __dmul_rn(y, w), yz = __dmul_rn(y, z), xw = __dmul_rn(x, w);
+    double m00 = __dadd_rn(__dsub_rn(__dsub_rn(x2, y2), z2), w2);
+    double m01 = __dmul_rn(2.0, __dsub_rn(xy, zw));
+    double m02 = __dmul_rn(2.0, __dadd_rn(xz, yw));
+    double m10 = __dmul_rn(2.0, __dadd_rn(xy, zw));
+    double m11 = __dadd_rn(__dsub_rn(__dadd_rn(-x2, y2), z2), w2);
+    double m12 = __dmul_rn(2.0, __dsub_rn(yz, xw));
+    double m20 = __dmul_rn(2.0, __dsub_rn(xz, yw));
+    double m21 = __dmul_rn(2.0, __dadd_rn(yz, xw));
+    double m22 = __dadd_rn(__dadd_rn(__dsub_rn(-x2, y2), z2), w2);
+    double r0 = __dadd_rn(__dadd_rn(__dmul_rn(m00, d0), __dmul_rn(m01, d1)), __dmul_rn(m02, d2)); // apply
+    double r1 = __dadd_rn(__dadd_rn(__dmul_rn(m10, d0), __dmul_rn(m11, d1)), __dmul_rn(m12, d2));
+    double r2 = __dadd_rn(__dadd_rn(__dmul_rn(m20, d0), __dmul_rn(m21, d1)), __dmul_rn(m22, d2));
+    n = dnorm3(r0, r1, r2);                                         // transforms.py:27
+    r0 = __ddiv_rn(r0, n); r1 = __ddiv_rn(r1, n); r2 = __ddiv_rn(r2, n);
+
+    double zc = fmin(fmax(r0, -1.0), 1.0);                          // :29
+    double sg = zc > 0.0 ? 1.0 : (zc < 0.0 ? -1.0 : 0.0);           // :30
+    double ang = acos(zc);                                          // :31
+    if (sg < 0.0) ang = __dsub_rn(kPi, ang);                        // :32-33
+    double n0, n1, n2;
+    if (fabs(ang) < min_angle) {                                    // :35-51
+        double px = r1, py = r2;
+        double pn = sqrt(__dadd_rn(__dmul_rn(px, px), __dmul_rn(py, py)));
+        if (pn < 1e-8) { px = 1.0; py = 0.0; }
+        else { px = __ddiv_rn(px, pn); py = __ddiv_rn(py, pn); }
+        n0 = __dmul_rn(sg, cos_min);
+        n1 = __dmul_rn(px, xy_mag);
+        n2 = __dmul_rn(py, xy_mag);
+    } else {
+        n0 = r0; n1 = r1; n2 = r2;
+    }
+    n = dnorm3(n0, n1, n2);                                         // :55
+    d[0] = __ddiv_rn(n0, n); d[1] = __ddiv_rn(n1, n); d[2] = __ddiv_rn(n2, n);
+    os_r = fmax(0.0, __dsub_rn(min_angle, ang));                    // :57
+}
+
+// environment.py:196-210: map the action, translate, rotate.
+__device__ __forceinline__ void pose_update(const Grid &G, const float a[6], Pose &s, double os_t[3], double &os_r)
+{
+    const double gs[3] = {(double)G.g0, (double)G.g1, (double)G.g2};
+    // map_translation: float32 clip * int64 shape -> float64, then * 0.2 (environment.py:122-125)
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        double t = __dmul_rn(__dmul_rn((double)clip1(a[i]), gs[i]), 0.2);
+        s.p[i] = translate_axis(s.p[i], t, gs[i], os_t[i]);
+    }
+    // map_rotation: float32 * float32(pi) * float32(0.5) (environment.py:139-141)
+    double rv[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+        rv[i] = (double)__fmul_rn(__fmul_rn(clip1(a[3 + i]), 3.14159274101257324f), 0.5f);
+    apply_rotation(s.d, rv, kMinAngle, kCosMin, kXYMag, os_r);
+}
+
+// ---------------------------------------------------------------------------------
+// draw_line.py:4-66: clip the infinite line to [0, G-1]^3 and set up the slab walk.
+struct Beam {
+    int nslab;       // slabs to visit; 0 = empty beam; -1 = ValueError (norm < eps)
+    int dom, o0, o1; // dominant axis and the two others in increasing order (:50-51)
+    int step;        // +-1 (:53)
+    int x0;          // first slab coordinate along dom (:55-57)
+    float y0, z0;    // intery/interz at entry (:62-63)
+    float sgy, sgz;  // gradient * step (:65-66, 98-99)
+};
+
+__device__ __forceinline__ Beam beam_setup(const Grid &G, const double pd[3], const double dd[3])
+{
+    const float eps = 9.99999997475242708e-07f;   // float32(1e-6)
+    Beam b;
+    b.nslab = 0; b.dom = 0; b.o0 = 1; b.o1 = 2; b.step = 1; b.x0 = 0;
+    b.y0 = b.z0 = b.sgy = b.sgz = 0.0f;
+    float p[3], v[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) { p[i] = __double2float_rn(pd[i]); v[i] = __double2float_rn(dd[i]); } // :19-20
+    // :22 np.linalg.norm -> OpenBLAS sdot: float32 products, float64 accumulation, float32 sqrt
+    double acc = (double)__fmul_rn(v[0], v[0]);
+    acc = __dadd_rn(acc, (double)__fmul_rn(v[1], v[1]));
+    acc = __dadd_rn(acc, (double)__fmul_rn(v[2], v[2]));
+    float norm = __fsqrt_rn(__double2float_rn(acc));
+    if (norm < eps) { b.nslab = -1; return b; }                        // :23-24
+#pragma unroll
+    for (int i = 0; i < 3; i++) v[i] = __fdiv_rn(v[i], norm);          // :25
+
+    const int gsz[3] = {G.g0, G.g1, G.g2};
+    float t_entry = -CUDART_INF_F, t_exit = CUDART_INF_F;
+    bool empty = false;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {                                      // :31-43
+        float gm1 = (float)(gsz[i] - 1);
+        float te, tx;
+        if (fabsf(v[i]) > eps) {
+            float t1 = __fdiv_rn(-p[i], v[i]);
+            float t2 = __fdiv_rn(__fsub_rn(gm1, p[i]), v[i]);
+            te = t1 < t2 ? t1 : t2;
+            tx = t1 < t2 ? t2 : t1;
+        } else {
+            if (p[i] < 0.0f || p[i] > gm1) empty = true;
+            te = -CUDART_INF_F;
+            tx = CUDART_INF_F;
+        }
+        if (te > t_entry) t_entry = te;                                // :44
+        if (tx < t_exit) t_exit = tx;                                  // :45
+    }
+    if (empty || t_entry > t_exit) return b;                           // :39, :46-47
+
+    float a0 = fabsf(v[0]), a1 = fabsf(v[1]), a2 = fabsf(v[2]);        // :49-50 first max wins
+    int dom = 0;
+    float best = a0;
+    if (a1 > best) { best = a1; dom = 1; }
+    if (a2 > best) { best = a2; dom = 2; }
+    int o0 = dom == 0 ? 1 : 0;                                         // :51
+    int o1 = dom == 2 ? 1 : 2;
+    float vd = dom == 0 ? v[0] : (dom == 1 ? v[1] : v[2]);
+    float pdm = dom == 0 ? p[0] : (dom == 1 ? p[1] : p[2]);
+    float v0 = o0 == 0 ? v[0] : v[1];
+    float p0 = o0 == 0 ? p[0] : p[1];
+    float v1 = o1 == 1 ? v[1] : v[2];
+    float p1 = o1 == 1 ? p[1] : p[2];
+    int step = vd > 0.0f ? 1 : -1;                                     // :53
+    int x0 = (int)floorf(__fadd_rn(pdm, __fmul_rn(t_entry, vd)));      // :55-57
+    int x1 = (int)floorf(__fadd_rn(pdm, __fmul_rn(t_exit, vd)));       // :58-60
+    b.y0 = __fadd_rn(p0, __fmul_rn(t_entry, v0));                      // :62
+    b.z0 = __fadd_rn(p1, __fmul_rn(t_entry, v1));                      // :63
+    float den = __fadd_rn(vd, eps);                                    // :65-66
+    float gy = __fdiv_rn(v0, den);
+    float gz = __fdiv_rn(v1, den);
+    b.sgy = step > 0 ? gy : -gy;                                       // gradient * step, exact
+    b.sgz = step > 0 ? gz : -gz;
+    b.dom = dom; b.o0 = o0; b.o1 = o1; b.step = step; b.x0 = x0;
+    int n = (x1 - x0) * step + 1;                                      // :69 while (x - end)*step <= 0
+    b.nslab = n < 0 ? 0 : n;
+    return b;
+}
+
+// ---------------------------------------------------------------------------------
+// draw_line.py:68-100, one warp per beam.  Lane l of chunk c owns slab k = 32c + l.
+// The walk  intery += gradient*step  (:98-99) is a chain of float32 adds that is not
+// re-associable, so the warp replays it once and each lane keeps the value at its k.
+// On return lin[c][j] is the linear voxel index of splat target j = 2*dy + dz of the
+// lane's slab (-1: out of bounds, no slab, or merged into the previous slab's lane)
+// and w[c][j] the float32 weight SUMMED over the (at most two) slabs that write that
+// voxel, added in the reference's order.  Every voxel appears exactly once per beam.
+__device__ __forceinline__ void beam_trace(const Grid &G, const Beam &b, int lane,
+                                           int (&lin)[kMaxChunks][4], float (&w)[kMaxChunks][4])
+{
+    float y = b.y0, z = b.z0;
+#pragma unroll
+    for (int c = 0; c < kMaxChunks; c++) {
+        float yc = 0.0f, zc = 0.0f;
+        int lim = b.nslab - c * kWarp;
+        lim = lim > kWarp ? kWarp : lim;
+        for (int i = 0; i < lim; i++) {
+            if (i == lane) { yc = y; zc = z; }
+            y = __fadd_rn(y, b.sgy);
+            z = __fadd_rn(z, b.sgz);
+        }
+        const bool have = lane < lim;
+        float yf = floorf(yc), zf = floorf(zc);                        // :76-82
+        float fy = __fsub_rn(yc, yf), fz = __fsub_rn(zc, zf);
+        float gy1 = __fsub_rn(1.0f, fy), gz1 = __fsub_rn(1.0f, fz);
+        int x = b.x0 + (c * kWarp + lane) * b.step;
+        int iy = (int)yf, iz = (int)zf;
+        int i0, i1, i2;                                                // idx[dom]=x, idx[o0]=iy, idx[o1]=iz
+        if (b.dom == 0) { i0 = x; i1 = iy; i2 = iz; }
+        else if (b.dom == 1) { i0 = iy; i1 = x; i2 = iz; }
+        else { i0 = iy; i1 = iz; i2 = x; }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {                                  // :84-96
+            const int dy = j >> 1, dz = j & 1;
+            float wy = dy ? fy : gy1;
+            float wz = dz ? fz : gz1;
+            int t1 = i1 + dy, t2 = i2 + dz;                            // :88-90 offsets on axes 1, 2
+            bool in = have && i0 >= 0 && i0 < G.g0 && t1 >= 0 && t1 < G.g1 && t2 >= 0 && t2 < G.g2;
+            lin[c][j] = in ? (i0 * G.g1 + t1) * G.g2 + t2 : -1;
+            w[c][j] = __fmul_rn(wy, wz);
+        }
+    }
+    // Merge: a voxel can be written by slab k and slab k+1 only (axis quirk).
+    // The earlier slab keeps the voxel and adds the later slab's weight; the later one drops it.
+    bool drop[kMaxChunks][4];
+    float add[kMaxChunks][4];
+#pragma unroll
+    for (int c = 0; c < kMaxChunks; c++) {
+        int nl[4], pl[4];
+        float nw[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            nl[j] = __shfl_down_sync(kFull, lin[c][j], 1);
+            nw[j] = __shfl_down_sync(kFull, w[c][j], 1);
+            pl[j] = __shfl_up_sync(kFull, lin[c][j], 1);
+            if (c + 1 < kMaxChunks) {
+                int tl = __shfl_sync(kFull, lin[c + 1 < kMaxChunks ? c + 1 : c][j], 0);
+                float tw = __shfl_sync(kFull, w[c + 1 < kMaxChunks ? c + 1 : c][j], 0);
+                if (lane == kWarp - 1) { nl[j] = tl; nw[j] = tw; }
+            } else if (lane == kWarp - 1) {
+                nl[j] = -1;
+            }
+            if (c > 0) {
+                int tl = __shfl_sync(kFull, lin[c > 0 ? c - 1 : c][j], kWarp - 1);
+                if (lane == 0) pl[j] = tl;
+            } else if (lane == 0) {
+                pl[j] = -1;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            drop[c][j] = false;
+            add[c][j] = 0.0f;
+            const int me = lin[c][j];
+            bool has_next = false;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                if (me >= 0 && nl[q] == me) { add[c][j] = nw[q]; has_next = true; }
+                if (me >= 0 && pl[q] == me) drop[c][j] = true;
+            }
+            if (has_next) w[c][j] = __fadd_rn(w[c][j], add[c][j]);     // (0 + w_k) + w_{k+1}
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < kMaxChunks; c++)
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (drop[c][j]) lin[c][j] = -1;
+}
+
+// ---------------------------------------------------------------------------------
+// Warp reductions.
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+__device__ __forceinline__ int warp_sum(int v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_min(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(kFull, v, o));
+    return v;
+}
+
+// splitmix64: counter-based choice of the next tumour (replaces np.random.choice, environment.py:90).
+__host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t x)
+{
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+
+}  // namespace rt

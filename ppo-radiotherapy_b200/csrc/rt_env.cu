@@ -1,0 +1,1115 @@
+// rt_env.cu — kernels and C ABI (include/rt_env.h) of the batched environment step.
+//
+// HBM layout per handle (N envs, V voxels):
+//   rec     [N]            128-byte env record: pose f64, accumulators, counters
+//   dose    [N][vstride]   float32 dose volumes, vstride = V rounded up to 32 floats
+//   valid   [N][vwords]    1 bit per 32-byte dose sector: "written this episode".
+//                          A sector whose bit is clear reads as zero, so reset never
+//                          touches the 807 KB volume: it clears 3.2 KB of bitmap
+//                          (L2-resident for thousands of envs) and the first write to a
+//                          sector needs no read from HBM.
+//   lungs_bits, tumour table, tumour bbox bitmasks, packed voxel lists: < 1 MB, replicated.
+//
+// One warp advances one env per step (rt_step_kernel): pose update (f64) -> beam
+// clip + slab walk (bit-exact f32) -> merge duplicate splat targets by shuffle ->
+// sparse dose read-modify-write -> incremental tumour/lung accumulators -> reward,
+// termination, observation, episode statistics; NEXT_STEP autoreset happens in the
+// same kernel.
+#include "../../include/rt_env.h"
+#include "rt_device.cuh"
+
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace rt;
+
+// ---------------------------------------------------------------------------------
+namespace {
+
+thread_local std::string g_err;
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const std::string &msg)
+{
+    g_err = msg;
+    return code;
+}
+
+#define RT_CUDA(expr)                                                                         \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess)                                                                \
+            return fail(RT_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));     \
+    } while (0)
+
+#define RT_LAUNCH_CHECK(name)                                                                 \
+    do {                                                                                      \
+        g_launches.fetch_add(1, std::memory_order_relaxed);                                   \
+        cudaError_t _e = cudaGetLastError();                                                  \
+        if (_e != cudaSuccess)                                                                \
+            return fail(RT_ERR_CUDA, std::string(name) + " launch: " + cudaGetErrorString(_e)); \
+    } while (0)
+
+struct __align__(128) EnvRec {
+    double pos[3];          // beam_position  (environment.py:101)
+    double dir[3];          // beam_direction (environment.py:102)
+    double tumour_dose;     // sum(dose * tumours), maintained incrementally
+    double lung_dose;       // sum(dose * lungs)
+    double ep_return;       // RecordEpisodeStatistics episode_returns
+    int32_t t;              // environment.py:47
+    int32_t tumour_id;
+    int32_t lung_count;     // #voxels of lungs\tumour with dose > 0.2
+    int32_t episode;        // episodes started since rt_reset (indexes the tumour schedule)
+    int32_t needs_reset;    // terminated on the previous call (NEXT_STEP autoreset)
+    int32_t n_beams;
+    int32_t pad[8];
+};
+static_assert(sizeof(EnvRec) == 128, "EnvRec must be one 128-byte line");
+
+struct __align__(16) Tumour {
+    int32_t lo[3];          // bbox origin
+    int32_t dim[3];         // bbox extent
+    int32_t n_vox;
+    int32_t vox_off;        // into vox_xyz
+    int32_t lin_lo, lin_hi; // smallest / largest linear voxel index of the tumour
+    float tumour_sum;       // np.sum(tumours)            (environment.py:167)
+    float lung_mask_sum;    // np.sum(lungs*(1-tumours))  (environment.py:178)
+    double centroid[3];     // tumour_position()          (environment.py:145-148)
+    double pad_;
+};
+static_assert(sizeof(Tumour) == 80, "Tumour table entry layout");
+
+struct Tables {
+    Grid G;
+    const uint32_t *lungs_bits;
+    const Tumour *tumours;
+    const uint32_t *tumour_bits;   // [n_tumours][bits_words] bbox-local occupancy
+    const uint32_t *vox_xyz;       // packed i | j<<8 | k<<16 per tumour voxel
+    int n_tumours;
+    int bits_words;
+};
+
+struct Schedule {
+    const int32_t *ids;     // [n_episodes][N] or nullptr
+    int n_episodes;
+    uint64_t seed;
+};
+
+struct StepOut {
+    float *obs;
+    double *reward;
+    float *reward_f32;
+    uint8_t *terminated;
+    uint8_t *truncated;
+    double *info;
+};
+
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ bool lung_bit(const Tables &T, int lin)
+{
+    return (__ldg(T.lungs_bits + (lin >> 5)) >> (lin & 31)) & 1u;
+}
+
+__device__ __forceinline__ bool tumour_bit(const Tables &T, const Tumour &tm, int tid, int lin)
+{
+    if (lin < tm.lin_lo || lin > tm.lin_hi) return false;     // cheap reject: almost every voxel of a beam
+    int k = lin % T.G.g2;
+    int r = lin / T.G.g2;
+    int j = r % T.G.g1;
+    int i = r / T.G.g1;
+    int li = i - tm.lo[0], lj = j - tm.lo[1], lk = k - tm.lo[2];
+    if ((unsigned)li >= (unsigned)tm.dim[0] || (unsigned)lj >= (unsigned)tm.dim[1] ||
+        (unsigned)lk >= (unsigned)tm.dim[2])
+        return false;
+    int b = (li * tm.dim[1] + lj) * tm.dim[2] + lk;
+    return (__ldg(T.tumour_bits + (size_t)tid * T.bits_words + (b >> 5)) >> (b & 31)) & 1u;
+}
+
+__device__ __forceinline__ int pick_tumour(const Tables &T, const Schedule &S, int env, int n_envs, int episode)
+{
+    if (S.ids) {
+        int e = episode < S.n_episodes ? episode : S.n_episodes - 1;
+        return S.ids[(size_t)e * n_envs + env];
+    }
+    uint64_t h = splitmix64(S.seed ^ splitmix64(((uint64_t)(uint32_t)env << 32) | (uint32_t)episode));
+    return (int)(h % (uint64_t)T.n_tumours);
+}
+
+// environment.py:259-268 get_vector_observation -> float32 (SyncVectorEnv copies into a float32 buffer).
+__device__ __forceinline__ void write_obs(const Tables &T, const Tumour &tm, const double p[3], const double d[3],
+                                          float *obs, int lane)
+{
+    if (lane < 9) {
+        const int a = lane % 3;
+        const double g = a == 0 ? (double)T.G.g0 : (a == 1 ? (double)T.G.g1 : (double)T.G.g2);
+        double v;
+        if (lane < 3) v = __dsub_rn(__dmul_rn(__ddiv_rn(a == 0 ? p[0] : (a == 1 ? p[1] : p[2]), g), 2.0), 1.0);
+        else if (lane < 6) v = a == 0 ? d[0] : (a == 1 ? d[1] : d[2]);
+        else v = __dsub_rn(__dmul_rn(__ddiv_rn(tm.centroid[a], g), 2.0), 1.0);
+        obs[lane] = (float)v;
+    }
+}
+
+// environment.py:77-105 for the warp's env: new tumour, centred pose, empty dose (= clear the
+// sector-valid bitmap), zero counters.
+__device__ __forceinline__ int reset_env(const Tables &T, const Schedule &S, EnvRec *rec, uint32_t *valid,
+                                         int env, int n_envs, int episode, int lane, float *obs)
+{
+    const int tid = pick_tumour(T, S, env, n_envs, episode);
+    uint4 *vw = reinterpret_cast<uint4 *>(valid + (size_t)env * T.G.vwords);
+    for (int i = lane; i < T.G.vwords / 4; i += kWarp) vw[i] = make_uint4(0u, 0u, 0u, 0u);
+    const double p[3] = {(double)T.G.g0 / 2.0, (double)T.G.g1 / 2.0, (double)T.G.g2 / 2.0};
+    const double d[3] = {0.0, 1.0, 0.0};
+    if (lane == 0) {
+        EnvRec r;
+        r.pos[0] = p[0]; r.pos[1] = p[1]; r.pos[2] = p[2];
+        r.dir[0] = d[0]; r.dir[1] = d[1]; r.dir[2] = d[2];
+        r.tumour_dose = 0.0; r.lung_dose = 0.0; r.ep_return = 0.0;
+        r.t = 0; r.tumour_id = tid; r.lung_count = 0; r.episode = episode; r.needs_reset = 0; r.n_beams = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) r.pad[i] = 0;
+        rec[env] = r;
+    }
+    const Tumour tm = T.tumours[tid];
+    if (obs) write_obs(T, tm, p, d, obs + (size_t)env * RT_OBS_SIZE, lane);
+    return tid;
+}
+
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) rt_reset_kernel(Tables T, Schedule S, EnvRec *rec, uint32_t *valid,
+                                                       int n_envs, const uint8_t *mask, float *obs)
+{
+    const int env = (blockIdx.x * blockDim.x + threadIdx.x) / kWarp;
+    const int lane = threadIdx.x & (kWarp - 1);
+    if (env >= n_envs) return;
+    if (mask == nullptr || mask[env]) {
+        reset_env(T, S, rec, valid, env, n_envs, 0, lane, obs);
+    } else if (obs) {
+        const EnvRec r = rec[env];
+        const Tumour tm = T.tumours[r.tumour_id];
+        write_obs(T, tm, r.pos, r.dir, obs + (size_t)env * RT_OBS_SIZE, lane);
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// The step.  One warp per env.
+__global__ void __launch_bounds__(256) rt_step_kernel(Tables T, Schedule S, EnvRec *rec, float *dose,
+                                                      uint32_t *valid, double *beams, int n_envs,
+                                                      const float *__restrict__ actions, StepOut out)
+{
+    const int env = (blockIdx.x * blockDim.x + threadIdx.x) / kWarp;
+    const int lane = threadIdx.x & (kWarp - 1);
+    if (env >= n_envs) return;
+    const Grid &G = T.G;
+    EnvRec *my = rec + env;
+
+    if (my->needs_reset) {
+        // gymnasium 1.0.0 NEXT_STEP: the call after a terminal step resets and reports reward 0.
+        const int episode = my->episode + 1;
+        __syncwarp();
+        const int new_tid = reset_env(T, S, rec, valid, env, n_envs, episode, lane, out.obs);
+        if (lane == 0) {
+            if (out.reward) out.reward[env] = 0.0;
+            if (out.reward_f32) out.reward_f32[env] = 0.0f;
+            if (out.terminated) out.terminated[env] = 0;
+            if (out.truncated) out.truncated[env] = 0;
+        }
+        if (out.info && lane < RT_INFO_SIZE) {
+            double v = 0.0;
+            if (lane == RT_INFO_TUMOUR_ID) v = (double)new_tid;
+            out.info[(size_t)env * RT_INFO_SIZE + lane] = v;
+        }
+        return;
+    }
+
+    // ---- state + action ------------------------------------------------------------
+    Pose s;
+#pragma unroll
+    for (int i = 0; i < 3; i++) { s.p[i] = my->pos[i]; s.d[i] = my->dir[i]; }
+    double tumour_dose = my->tumour_dose, lung_dose = my->lung_dose, ep_return = my->ep_return;
+    const int t = my->t + 1;                                                // environment.py:194
+    const int tid = my->tumour_id;
+    int lung_count = my->lung_count;
+    const int episode = my->episode;
+    const int n_beams = my->n_beams;
+    float a[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) a[i] = __ldg(actions + (size_t)env * RT_ACTION_SIZE + i);
+    const Tumour tm = T.tumours[tid];
+
+    // ---- pose (environment.py:196-210) -------------------------------------------------
+    double os_t[3], os_r;
+    pose_update(G, a, s, os_t, os_r);
+
+    // ---- beam (environment.py:212 -> draw_line.py) ------------------------------------
+    const Beam b = beam_setup(G, s.p, s.d);
+    int lin[kMaxChunks][4];
+    float w[kMaxChunks][4];
+    beam_trace(G, b, lane, lin, w);
+
+    // ---- distance_to_tumour_reward (environment.py:150-162), overlaps the dose traffic ----
+    double best = CUDART_INF;
+    for (int k = lane; k < tm.n_vox; k += kWarp) {
+        const uint32_t pk = __ldg(T.vox_xyz + tm.vox_off + k);
+        const double dx = __dsub_rn((double)(pk & 255u), s.p[0]);
+        const double dy = __dsub_rn((double)((pk >> 8) & 255u), s.p[1]);
+        const double dz = __dsub_rn((double)(pk >> 16), s.p[2]);
+        double d2 = __dmul_rn(dx, dx);
+        d2 = __dadd_rn(d2, __dmul_rn(dy, dy));
+        d2 = __dadd_rn(d2, __dmul_rn(dz, dz));
+        best = fmin(best, d2);
+    }
+
+    // ---- dose deposition (environment.py:107-110), sparse ---------------------------------
+    // dose' = clip(dose + beam*0.1, 0, 1) only changes the voxels the beam hits.
+    float *vol = dose + (size_t)env * G.vstride;
+    uint32_t *vbits = valid + (size_t)env * G.vwords;
+    bool fresh[kMaxChunks][4];
+#pragma unroll
+    for (int c = 0; c < kMaxChunks; c++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            fresh[c][j] = false;
+            if (lin[c][j] >= 0) {
+                const int sec = lin[c][j] >> 3;
+                fresh[c][j] = !((vbits[sec >> 5] >> (sec & 31)) & 1u);
+            }
+        }
+    __syncwarp();   // every lane has sampled the bitmap before any lane updates it
+    // first write to a sector this episode: materialise it as zeros and mark it valid
+#pragma unroll
+    for (int c = 0; c < kMaxChunks; c++)
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (fresh[c][j]) {
+                const int sec = lin[c][j] >> 3;
+                float4 *sp = reinterpret_cast<float4 *>(vol + (sec << 3));
+                sp[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+                sp[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                atomicOr(vbits + (sec >> 5), 1u << (sec & 31));
+            }
+    __syncwarp();
+    float old[kMaxChunks][4];
+#pragma unroll
+    for (int c = 0; c < kMaxChunks; c++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            old[c][j] = 0.0f;
+            if (lin[c][j] >= 0 && !fresh[c][j]) old[c][j] = vol[lin[c][j]];
+        }
+    double d_tum = 0.0, d_lung = 0.0;
+    int d_cnt = 0;
+#pragma unroll
+    for (int c = 0; c < kMaxChunks; c++)
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (lin[c][j] >= 0) {
+                const float o = old[c][j];
+                float nd = __fadd_rn(o, __fmul_rn(w[c][j], 0.100000001490116119f));   // beam * BEAM_DOSE, then +
+                nd = fminf(fmaxf(nd, 0.0f), 1.0f);                                     // np.clip(., 0, 1)
+                vol[lin[c][j]] = nd;
+                const bool in_t = tumour_bit(T, tm, tid, lin[c][j]);
+                const bool in_l = lung_bit(T, lin[c][j]);
+                const double delta = (double)nd - (double)o;
+                if (in_t) d_tum += delta;
+                if (in_l) d_lung += delta;
+                // lungs_mask = lungs*(1-tumours); dose is monotone, so the count only grows (environment.py:174-177)
+                if (in_l && !in_t && !(o > 0.200000002980232239f) && nd > 0.200000002980232239f) d_cnt++;
+            }
+    tumour_dose += warp_sum(d_tum);
+    lung_dose += warp_sum(d_lung);
+    lung_count += warp_sum(d_cnt);
+    best = warp_min(best);
+
+    // ---- rewards, termination (environment.py:158-191, 214-220) --------------------------
+    const float tsum_f32 = (float)tumour_dose;                                   // np.sum(dose*tumours) float32
+    const float ratio = __fdiv_rn(tsum_f32, tm.tumour_sum);
+    const float r_tumour = __fmul_rn(ratio, 10.0f);
+    const double r_lung = __dmul_rn(__ddiv_rn((double)lung_count, (double)tm.lung_mask_sum), -1.0);
+    const double gnorm = sqrt((double)(G.g0 * G.g0 + G.g1 * G.g1 + G.g2 * G.g2));
+    const double r_dist = __dmul_rn(__ddiv_rn(sqrt(best), gnorm), -1.0);
+    const double reward = __dadd_rn(__dadd_rn((double)r_tumour, r_lung), r_dist);
+    const bool done = (ratio >= 0.899999976158142090f) || (t >= RT_MAX_TIME_STEPS);
+    ep_return += reward;
+
+    // ---- write back --------------------------------------------------------------------
+    if (lane == 0) {
+        EnvRec r;
+        r.pos[0] = s.p[0]; r.pos[1] = s.p[1]; r.pos[2] = s.p[2];
+        r.dir[0] = s.d[0]; r.dir[1] = s.d[1]; r.dir[2] = s.d[2];
+        r.tumour_dose = tumour_dose; r.lung_dose = lung_dose; r.ep_return = ep_return;
+        r.t = t; r.tumour_id = tid; r.lung_count = lung_count; r.episode = episode;
+        r.needs_reset = done ? 1 : 0;
+        r.n_beams = n_beams + 1;
+#pragma unroll
+        for (int i = 0; i < 8; i++) r.pad[i] = 0;
+        *my = r;
+        if (out.reward) out.reward[env] = reward;
+        if (out.reward_f32) out.reward_f32[env] = (float)reward;
+        if (out.terminated) out.terminated[env] = done ? 1 : 0;
+        if (out.truncated) out.truncated[env] = 0;
+    }
+    if (beams && lane < 6 && n_beams < RT_MAX_TIME_STEPS)                       // environment.py:110
+        beams[((size_t)env * RT_MAX_TIME_STEPS + n_beams) * 6 + lane] = lane < 3 ? s.p[lane] : s.d[lane - 3];
+    write_obs(T, tm, s.p, s.d, out.obs + (size_t)env * RT_OBS_SIZE, lane);
+    if (out.info && lane < RT_INFO_SIZE) {
+        double v;
+        switch (lane) {
+        case RT_INFO_REWARD_TOTAL: v = reward; break;
+        case RT_INFO_REWARD_TUMOUR: v = (double)r_tumour; break;
+        case RT_INFO_REWARD_LUNG: v = r_lung; break;
+        case RT_INFO_REWARD_DISTANCE: v = r_dist; break;
+        case RT_INFO_DOSE_TUMOUR: v = (double)tsum_f32; break;
+        case RT_INFO_DOSE_LUNG: v = (double)(float)lung_dose; break;
+        case RT_INFO_OVERSHOOT_T0: v = os_t[0]; break;
+        case RT_INFO_OVERSHOOT_T0 + 1: v = os_t[1]; break;
+        case RT_INFO_OVERSHOOT_T0 + 2: v = os_t[2]; break;
+        case RT_INFO_OVERSHOOT_R: v = os_r; break;
+        case RT_INFO_EPISODE_RETURN: v = ep_return; break;
+        case RT_INFO_EPISODE_LENGTH: v = (double)t; break;
+        case RT_INFO_LUNG_COUNT: v = (double)lung_count; break;
+        case RT_INFO_STEPPED: v = 1.0; break;
+        case RT_INFO_TUMOUR_ID: v = (double)tid; break;
+        default: v = (double)t; break;
+        }
+        out.info[(size_t)env * RT_INFO_SIZE + lane] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// Stateless geometry kernels (parity surface): one warp per ray / one thread per pose.
+__global__ void __launch_bounds__(256) rt_beam_kernel(Grid G, const double *__restrict__ pos,
+                                                      const double *__restrict__ dir, int m, int cap,
+                                                      int32_t *idx, float *wout, int32_t *count)
+{
+    const int ray = (blockIdx.x * blockDim.x + threadIdx.x) / kWarp;
+    const int lane = threadIdx.x & (kWarp - 1);
+    if (ray >= m) return;
+    const double p[3] = {pos[3 * ray], pos[3 * ray + 1], pos[3 * ray + 2]};
+    const double d[3] = {dir[3 * ray], dir[3 * ray + 1], dir[3 * ray + 2]};
+    const Beam b = beam_setup(G, p, d);
+    if (b.nslab < 0) {
+        if (lane == 0) count[ray] = -1;
+        return;
+    }
+    int lin[kMaxChunks][4];
+    float w[kMaxChunks][4];
+    beam_trace(G, b, lane, lin, w);
+    int base = 0;
+#pragma unroll
+    for (int c = 0; c < kMaxChunks; c++) {
+        int mine = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) mine += lin[c][j] >= 0;
+        int incl = mine;                                   // warp inclusive scan
+#pragma unroll
+        for (int o = 1; o < kWarp; o <<= 1) {
+            int v = __shfl_up_sync(kFull, incl, o);
+            if (lane >= o) incl += v;
+        }
+        int at = base + incl - mine;
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (lin[c][j] >= 0) {
+                if (at < cap) {
+                    idx[(size_t)ray * cap + at] = lin[c][j];
+                    wout[(size_t)ray * cap + at] = w[c][j];
+                }
+                at++;
+            }
+        base += __shfl_sync(kFull, incl, kWarp - 1);
+    }
+    if (lane == 0) count[ray] = base < cap ? base : cap;
+}
+
+__global__ void __launch_bounds__(256) rt_beam_dense_kernel(Grid G, const double *__restrict__ pos,
+                                                            const double *__restrict__ dir, int m, float *out,
+                                                            int32_t *status)
+{
+    const int ray = (blockIdx.x * blockDim.x + threadIdx.x) / kWarp;
+    const int lane = threadIdx.x & (kWarp - 1);
+    if (ray >= m) return;
+    const double p[3] = {pos[3 * ray], pos[3 * ray + 1], pos[3 * ray + 2]};
+    const double d[3] = {dir[3 * ray], dir[3 * ray + 1], dir[3 * ray + 2]};
+    const Beam b = beam_setup(G, p, d);
+    if (lane == 0 && status) status[ray] = b.nslab < 0 ? -1 : 0;
+    if (b.nslab <= 0) return;
+    int lin[kMaxChunks][4];
+    float w[kMaxChunks][4];
+    beam_trace(G, b, lane, lin, w);
+    float *vol = out + (size_t)ray * G.nvox;
+#pragma unroll
+    for (int c = 0; c < kMaxChunks; c++)
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (lin[c][j] >= 0) vol[lin[c][j]] = w[c][j];
+}
+
+__global__ void __launch_bounds__(128) rt_pose_kernel(Grid G, const double *__restrict__ pos,
+                                                      const double *__restrict__ dir,
+                                                      const float *__restrict__ actions, int m, double *pos_out,
+                                                      double *dir_out, double *os_t_out, double *os_r_out)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= m) return;
+    Pose s;
+    float a[6];
+#pragma unroll
+    for (int i = 0; i < 3; i++) { s.p[i] = pos[3 * k + i]; s.d[i] = dir[3 * k + i]; }
+#pragma unroll
+    for (int i = 0; i < 6; i++) a[i] = actions[6 * k + i];
+    double os_t[3], os_r;
+    pose_update(G, a, s, os_t, os_r);
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        pos_out[3 * k + i] = s.p[i];
+        dir_out[3 * k + i] = s.d[i];
+        if (os_t_out) os_t_out[3 * k + i] = os_t[i];
+    }
+    if (os_r_out) os_r_out[k] = os_r;
+}
+
+__global__ void __launch_bounds__(128) rt_rotation_kernel(const double *__restrict__ dir,
+                                                          const double *__restrict__ rotvec, int m, double min_angle,
+                                                          double cos_min, double xy_mag, double *dir_out,
+                                                          double *os_out)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= m) return;
+    double d[3] = {dir[3 * k], dir[3 * k + 1], dir[3 * k + 2]};
+    const double rv[3] = {rotvec[3 * k], rotvec[3 * k + 1], rotvec[3 * k + 2]};
+    double os;
+    apply_rotation(d, rv, min_angle, cos_min, xy_mag, os);
+    dir_out[3 * k] = d[0]; dir_out[3 * k + 1] = d[1]; dir_out[3 * k + 2] = d[2];
+    if (os_out) os_out[k] = os;
+}
+
+__global__ void __launch_bounds__(128) rt_translation_kernel(const double *__restrict__ pos,
+                                                             const double *__restrict__ tr, int m, double b0,
+                                                             double b1, double b2, double *pos_out, double *os_out)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= 3 * m) return;
+    const int a = k % 3;
+    double os;
+    pos_out[k] = translate_axis(pos[k], tr[k], a == 0 ? b0 : (a == 1 ? b1 : b2), os);
+    if (os_out) os_out[k] = os;
+}
+
+// ---------------------------------------------------------------------------------
+// State access kernels.
+__global__ void rt_get_pose_kernel(const EnvRec *rec, int n, double *pose)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n * 6) return;
+    const int e = k / 6, c = k % 6;
+    pose[k] = c < 3 ? rec[e].pos[c] : rec[e].dir[c - 3];
+}
+
+__global__ void rt_set_pose_kernel(EnvRec *rec, int n, const double *pose)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n * 6) return;
+    const int e = k / 6, c = k % 6;
+    if (c < 3) rec[e].pos[c] = pose[k];
+    else rec[e].dir[c - 3] = pose[k];
+}
+
+__global__ void rt_get_counters_kernel(const EnvRec *rec, int n, int32_t *out)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const EnvRec r = rec[e];
+    int32_t *o = out + (size_t)e * 6;
+    o[0] = r.t; o[1] = r.tumour_id; o[2] = r.lung_count; o[3] = r.episode; o[4] = r.needs_reset; o[5] = r.n_beams;
+}
+
+// dense dose of one env: a sector that was never written this episode reads as zero
+__global__ void rt_get_dose_kernel(Grid G, const float *dose, const uint32_t *valid, int env, float *out)
+{
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= G.nvox) return;
+    const int sec = v >> 3;
+    const bool ok = (valid[(size_t)env * G.vwords + (sec >> 5)] >> (sec & 31)) & 1u;
+    out[v] = ok ? dose[(size_t)env * G.vstride + v] : 0.0f;
+}
+
+__global__ void rt_get_beams_kernel(const EnvRec *rec, const double *beams, int env, double *out, int32_t *n_out)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k == 0 && n_out) *n_out = rec[env].n_beams;
+    if (k < RT_MAX_TIME_STEPS * 6) out[k] = beams[(size_t)env * RT_MAX_TIME_STEPS * 6 + k];
+}
+
+// ---------------------------------------------------------------------------------
+// Voxel observation (environment.py:245-257): block per env.  The two view beams are
+// traced by warps 0 and 1 into a shared hit table; every thread then streams 4-voxel
+// groups: out[c][v] = clip({lungs, tumours, dose, view}[v], 0, 1).
+constexpr int kVolThreads = 512;
+constexpr int kViewCap = 2 * RT_BEAM_CAP;
+
+__global__ void __launch_bounds__(kVolThreads) rt_volumes_kernel(Tables T, const EnvRec *rec, const float *dose,
+                                                                 const uint32_t *valid, int first, float *out)
+{
+    extern __shared__ uint32_t smem[];
+    const Grid &G = T.G;
+    const int nwords = (G.nvox + 31) / 32;
+    uint32_t *hit_bits = smem;                                  // [nwords] voxel hit by a view beam
+    int *hit_idx = reinterpret_cast<int *>(smem + nwords);      // [kViewCap]
+    float *hit_w = reinterpret_cast<float *>(hit_idx + kViewCap);
+    __shared__ int hit_n;
+    const int env = first + blockIdx.x;
+    const int lane = threadIdx.x & (kWarp - 1);
+    const int warp = threadIdx.x / kWarp;
+    const EnvRec r = rec[env];
+    const Tumour tm = T.tumours[r.tumour_id];
+
+    for (int i = threadIdx.x; i < nwords; i += blockDim.x) hit_bits[i] = 0u;
+    if (threadIdx.x == 0) hit_n = 0;
+    __syncthreads();
+    if (warp < 2) {
+        // environment.py:246-249: beam along the current direction, and along (1,0,0)
+        const double horiz[3] = {1.0, 0.0, 0.0};
+        const Beam b = beam_setup(G, r.pos, warp == 0 ? r.dir : horiz);
+        if (b.nslab > 0) {
+            int lin[kMaxChunks][4];
+            float w[kMaxChunks][4];
+            beam_trace(G, b, lane, lin, w);
+#pragma unroll
+            for (int c = 0; c < kMaxChunks; c++)
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    if (lin[c][j] >= 0) {
+                        const int at = atomicAdd(&hit_n, 1);
+                        hit_idx[at] = lin[c][j];
+                        hit_w[at] = w[c][j];
+                        atomicOr(hit_bits + (lin[c][j] >> 5), 1u << (lin[c][j] & 31));
+                    }
+        }
+    }
+    __syncthreads();
+    const int nhit = hit_n;
+    const float *vol = dose + (size_t)env * G.vstride;
+    const uint32_t *vbits = valid + (size_t)env * G.vwords;
+    float *o = out + (size_t)blockIdx.x * 4 * G.nvox;
+    for (int v = threadIdx.x; v < G.nvox; v += blockDim.x) {
+        const int sec = v >> 3;
+        const bool ok = (vbits[sec >> 5] >> (sec & 31)) & 1u;
+        const float dv = ok ? vol[v] : 0.0f;
+        float view = 0.0f;
+        if ((hit_bits[v >> 5] >> (v & 31)) & 1u) {
+            // current_beam + horizontal_beam_center (:250): the direction beam's weight first
+            float wa = 0.0f, wb = 0.0f;
+            bool ha = false, hb = false;
+            for (int k = 0; k < nhit; k++)
+                if (hit_idx[k] == v) {
+                    if (!ha) { wa = hit_w[k]; ha = true; }
+                    else { wb = hit_w[k]; hb = true; }
+                }
+            view = hb ? __fadd_rn(wa, wb) : wa;
+        }
+        o[v] = lung_bit(T, v) ? 1.0f : 0.0f;
+        o[(size_t)G.nvox + v] = tumour_bit(T, tm, r.tumour_id, v) ? 1.0f : 0.0f;
+        o[(size_t)2 * G.nvox + v] = fminf(fmaxf(dv, 0.0f), 1.0f);
+        o[(size_t)3 * G.nvox + v] = fminf(fmaxf(view, 0.0f), 1.0f);
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// GAE (train.py:164-181): one thread per env walks t = T-1 .. 0.  float32, one rounding
+// per operation, in the order torch evaluates the reference expression.
+__global__ void __launch_bounds__(128) rt_gae_kernel(const float *__restrict__ rewards,
+                                                     const float *__restrict__ values,
+                                                     const float *__restrict__ dones,
+                                                     const float *__restrict__ next_value,
+                                                     const float *__restrict__ next_done, int T, int N, float g,
+                                                     float gl, float *__restrict__ adv, float *__restrict__ ret)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    float last = 0.0f;
+    float nnt = __fsub_rn(1.0f, next_done[i]);
+    float nv = next_value[i];
+#pragma unroll 8
+    for (int t = T - 1; t >= 0; t--) {
+        const size_t k = (size_t)t * N + i;
+        const float r = __ldg(rewards + k), v = __ldg(values + k), d = __ldg(dones + k);
+        float delta = __fsub_rn(__fadd_rn(r, __fmul_rn(__fmul_rn(g, nv), nnt)), v);
+        last = __fadd_rn(delta, __fmul_rn(__fmul_rn(gl, nnt), last));
+        adv[k] = last;
+        ret[k] = __fadd_rn(last, v);
+        nnt = __fsub_rn(1.0f, d);      // dones[t] gates step t-1
+        nv = v;
+    }
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------
+// Host side.
+struct rt_env {
+    int device = 0;
+    int n = 0;
+    uint32_t flags = 0;
+    Tables T{};
+    Schedule S{};
+    EnvRec *rec = nullptr;
+    float *dose = nullptr;
+    uint32_t *valid = nullptr;
+    double *beams = nullptr;
+    uint32_t *d_lungs = nullptr;
+    Tumour *d_tumours = nullptr;
+    uint32_t *d_tbits = nullptr;
+    uint32_t *d_vox = nullptr;
+    int32_t *d_sched = nullptr;
+    int64_t bytes = 0;
+    // staging for the *_host calls
+    cudaStream_t hstream = nullptr;
+    float *h_actions = nullptr, *h_obs = nullptr;
+    double *h_reward = nullptr, *h_info = nullptr;
+    uint8_t *h_term = nullptr, *h_trunc = nullptr, *h_mask = nullptr;
+};
+
+namespace {
+
+Grid make_grid(const int32_t g[3])
+{
+    Grid G;
+    G.g0 = g[0]; G.g1 = g[1]; G.g2 = g[2];
+    G.nvox = g[0] * g[1] * g[2];
+    G.vstride = (G.nvox + 31) / 32 * 32;
+    const int sectors = G.vstride / 8;
+    G.vwords = ((sectors + 31) / 32 + 31) / 32 * 32;
+    return G;
+}
+
+int check_grid(const int32_t g[3])
+{
+    if (!g) return fail(RT_ERR_INVALID, "grid is NULL");
+    for (int i = 0; i < 3; i++)
+        if (g[i] < 2 || g[i] > 255) return fail(RT_ERR_INVALID, "grid extents must be in [2, 255]");
+    int mx = g[0] > g[1] ? g[0] : g[1];
+    mx = mx > g[2] ? mx : g[2];
+    if (mx + 1 > kMaxChunks * kWarp) return fail(RT_ERR_INVALID, "grid extent too large for the slab walk");
+    return RT_OK;
+}
+
+template <typename T>
+int dev_alloc(T **p, size_t count, int64_t *bytes)
+{
+    cudaError_t e = cudaMalloc(reinterpret_cast<void **>(p), count * sizeof(T));
+    if (e != cudaSuccess) return fail(RT_ERR_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    *bytes += (int64_t)(count * sizeof(T));
+    return RT_OK;
+}
+
+inline int warps_grid(int n_warps, int threads) { return (int)(((int64_t)n_warps * kWarp + threads - 1) / threads); }
+
+}  // namespace
+
+extern "C" {
+
+int rt_abi_version(void) { return RT_ABI_VERSION; }
+const char *rt_last_error(void) { return g_err.c_str(); }
+int64_t rt_launch_count(void) { return g_launches.load(); }
+
+int rt_create(rt_env **out, int device, int n_envs, uint32_t flags, const rt_phantom_desc *ph)
+{
+    if (!out || !ph) return fail(RT_ERR_INVALID, "rt_create: NULL argument");
+    *out = nullptr;
+    if (n_envs < 1) return fail(RT_ERR_INVALID, "rt_create: n_envs must be >= 1");
+    if (int rc = check_grid(ph->grid)) return rc;
+    if (ph->n_tumours < 1 || !ph->lungs_bits || !ph->vox_offsets || !ph->vox || !ph->centroid ||
+        !ph->tumour_sum || !ph->lung_mask_sum)
+        return fail(RT_ERR_INVALID, "rt_create: incomplete phantom description");
+    RT_CUDA(cudaSetDevice(device));
+
+    rt_env *e = new rt_env();
+    e->device = device;
+    e->n = n_envs;
+    e->flags = flags;
+    const Grid G = make_grid(ph->grid);
+    e->T.G = G;
+    e->T.n_tumours = ph->n_tumours;
+
+    // tumour table: bbox, bbox-local bitmask, packed voxel coordinates
+    std::vector<Tumour> tum(ph->n_tumours);
+    const int total_vox = ph->vox_offsets[ph->n_tumours];
+    std::vector<uint32_t> vox_xyz((size_t)(total_vox > 0 ? total_vox : 1));
+    int max_bits = 1;
+    for (int t = 0; t < ph->n_tumours; t++) {
+        Tumour &tm = tum[t];
+        const int lo = ph->vox_offsets[t], hi = ph->vox_offsets[t + 1];
+        if (hi <= lo) { delete e; return fail(RT_ERR_INVALID, "rt_create: empty tumour"); }
+        int mn[3] = {1 << 30, 1 << 30, 1 << 30}, mx[3] = {-1, -1, -1};
+        for (int k = lo; k < hi; k++) {
+            const int v = ph->vox[k];
+            if (v < 0 || v >= G.nvox || (k > lo && v <= ph->vox[k - 1])) {
+                delete e;
+                return fail(RT_ERR_INVALID, "rt_create: tumour voxels must be ascending and inside the grid");
+            }
+            const int c[3] = {v / (G.g1 * G.g2), (v / G.g2) % G.g1, v % G.g2};
+            vox_xyz[k] = (uint32_t)c[0] | ((uint32_t)c[1] << 8) | ((uint32_t)c[2] << 16);
+            for (int a = 0; a < 3; a++) { mn[a] = c[a] < mn[a] ? c[a] : mn[a]; mx[a] = c[a] > mx[a] ? c[a] : mx[a]; }
+        }
+        for (int a = 0; a < 3; a++) { tm.lo[a] = mn[a]; tm.dim[a] = mx[a] - mn[a] + 1; }
+        tm.n_vox = hi - lo;
+        tm.vox_off = lo;
+        tm.lin_lo = ph->vox[lo];
+        tm.lin_hi = ph->vox[hi - 1];
+        tm.pad_ = 0.0;
+        tm.tumour_sum = ph->tumour_sum[t];
+        tm.lung_mask_sum = ph->lung_mask_sum[t];
+        for (int a = 0; a < 3; a++) tm.centroid[a] = ph->centroid[3 * t + a];
+        const int bits = tm.dim[0] * tm.dim[1] * tm.dim[2];
+        max_bits = bits > max_bits ? bits : max_bits;
+    }
+    e->T.bits_words = (max_bits + 31) / 32;
+    std::vector<uint32_t> tbits((size_t)ph->n_tumours * e->T.bits_words, 0u);
+    for (int t = 0; t < ph->n_tumours; t++) {
+        const Tumour &tm = tum[t];
+        for (int k = ph->vox_offsets[t]; k < ph->vox_offsets[t + 1]; k++) {
+            const uint32_t pk = vox_xyz[k];
+            const int li = (int)(pk & 255u) - tm.lo[0], lj = (int)((pk >> 8) & 255u) - tm.lo[1],
+                      lk = (int)(pk >> 16) - tm.lo[2];
+            const int b = (li * tm.dim[1] + lj) * tm.dim[2] + lk;
+            tbits[(size_t)t * e->T.bits_words + (b >> 5)] |= 1u << (b & 31);
+        }
+    }
+
+    int rc = RT_OK;
+    const size_t lung_words = (size_t)(G.nvox + 31) / 32;
+    if ((rc = dev_alloc(&e->d_lungs, lung_words, &e->bytes)) || (rc = dev_alloc(&e->d_tumours, tum.size(), &e->bytes)) ||
+        (rc = dev_alloc(&e->d_tbits, tbits.size(), &e->bytes)) || (rc = dev_alloc(&e->d_vox, vox_xyz.size(), &e->bytes)) ||
+        (rc = dev_alloc(&e->rec, (size_t)n_envs, &e->bytes)) ||
+        (rc = dev_alloc(&e->dose, (size_t)n_envs * G.vstride, &e->bytes)) ||
+        (rc = dev_alloc(&e->valid, (size_t)n_envs * G.vwords, &e->bytes))) {
+        rt_destroy(e);
+        return rc;
+    }
+    if (flags & RT_FLAG_RECORD_BEAMS)
+        if ((rc = dev_alloc(&e->beams, (size_t)n_envs * RT_MAX_TIME_STEPS * 6, &e->bytes))) { rt_destroy(e); return rc; }
+    cudaError_t ce = cudaSuccess;
+    auto chk = [&](cudaError_t x) { if (ce == cudaSuccess) ce = x; };
+    chk(cudaMemcpy(e->d_lungs, ph->lungs_bits, lung_words * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    chk(cudaMemcpy(e->d_tumours, tum.data(), tum.size() * sizeof(Tumour), cudaMemcpyHostToDevice));
+    chk(cudaMemcpy(e->d_tbits, tbits.data(), tbits.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    chk(cudaMemcpy(e->d_vox, vox_xyz.data(), vox_xyz.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    chk(cudaMemset(e->rec, 0, (size_t)n_envs * sizeof(EnvRec)));
+    chk(cudaMemset(e->valid, 0, (size_t)n_envs * G.vwords * sizeof(uint32_t)));
+    // dose is deliberately left uninitialised: a sector is only read once its valid bit is set
+    chk(cudaStreamCreateWithFlags(&e->hstream, cudaStreamNonBlocking));
+    chk(cudaMallocHost(&e->h_actions, (size_t)n_envs * RT_ACTION_SIZE * sizeof(float)));
+    chk(cudaMallocHost(&e->h_obs, (size_t)n_envs * RT_OBS_SIZE * sizeof(float)));
+    chk(cudaMallocHost(&e->h_reward, (size_t)n_envs * sizeof(double)));
+    chk(cudaMallocHost(&e->h_info, (size_t)n_envs * RT_INFO_SIZE * sizeof(double)));
+    chk(cudaMallocHost(&e->h_term, (size_t)n_envs));
+    chk(cudaMallocHost(&e->h_trunc, (size_t)n_envs));
+    chk(cudaMallocHost(&e->h_mask, (size_t)n_envs));
+    if (ce != cudaSuccess) {
+        rt_destroy(e);
+        return fail(RT_ERR_CUDA, std::string("rt_create: ") + cudaGetErrorString(ce));
+    }
+    e->T.lungs_bits = e->d_lungs;
+    e->T.tumours = e->d_tumours;
+    e->T.tumour_bits = e->d_tbits;
+    e->T.vox_xyz = e->d_vox;
+    e->S.ids = nullptr;
+    e->S.n_episodes = 0;
+    e->S.seed = 0;
+    *out = e;
+    return RT_OK;
+}
+
+int rt_destroy(rt_env *e)
+{
+    if (!e) return RT_OK;
+    cudaSetDevice(e->device);
+    cudaFree(e->d_lungs); cudaFree(e->d_tumours); cudaFree(e->d_tbits); cudaFree(e->d_vox);
+    cudaFree(e->rec); cudaFree(e->dose); cudaFree(e->valid); cudaFree(e->beams); cudaFree(e->d_sched);
+    // the *_host staging buffers are device-visible pinned allocations of the same sizes
+    cudaFreeHost(e->h_actions); cudaFreeHost(e->h_obs); cudaFreeHost(e->h_reward); cudaFreeHost(e->h_info);
+    cudaFreeHost(e->h_term); cudaFreeHost(e->h_trunc); cudaFreeHost(e->h_mask);
+    if (e->hstream) cudaStreamDestroy(e->hstream);
+    delete e;
+    return RT_OK;
+}
+
+int rt_num_envs(const rt_env *e) { return e ? e->n : 0; }
+int64_t rt_device_bytes(const rt_env *e) { return e ? e->bytes : 0; }
+
+int rt_seed(rt_env *e, uint64_t seed)
+{
+    if (!e) return fail(RT_ERR_INVALID, "rt_seed: NULL handle");
+    e->S.seed = seed;
+    return RT_OK;
+}
+
+int rt_set_tumour_schedule(rt_env *e, const int32_t *ids_host, int n_episodes)
+{
+    if (!e) return fail(RT_ERR_INVALID, "rt_set_tumour_schedule: NULL handle");
+    RT_CUDA(cudaSetDevice(e->device));
+    RT_CUDA(cudaDeviceSynchronize());
+    if (e->d_sched) { cudaFree(e->d_sched); e->d_sched = nullptr; }
+    e->S.ids = nullptr;
+    e->S.n_episodes = 0;
+    if (!ids_host) return RT_OK;
+    if (n_episodes < 1) return fail(RT_ERR_INVALID, "rt_set_tumour_schedule: n_episodes must be >= 1");
+    const size_t cnt = (size_t)n_episodes * e->n;
+    for (size_t k = 0; k < cnt; k++)
+        if (ids_host[k] < 0 || ids_host[k] >= e->T.n_tumours)
+            return fail(RT_ERR_INVALID, "rt_set_tumour_schedule: tumour id out of range");
+    RT_CUDA(cudaMalloc(reinterpret_cast<void **>(&e->d_sched), cnt * sizeof(int32_t)));
+    RT_CUDA(cudaMemcpy(e->d_sched, ids_host, cnt * sizeof(int32_t), cudaMemcpyHostToDevice));
+    e->S.ids = e->d_sched;
+    e->S.n_episodes = n_episodes;
+    return RT_OK;
+}
+
+int rt_reset(rt_env *e, const uint8_t *mask_dev, float *obs_dev, void *stream)
+{
+    if (!e) return fail(RT_ERR_INVALID, "rt_reset: NULL handle");
+    RT_CUDA(cudaSetDevice(e->device));
+    rt_reset_kernel<<<warps_grid(e->n, 256), 256, 0, (cudaStream_t)stream>>>(e->T, e->S, e->rec, e->valid, e->n,
+                                                                            mask_dev, obs_dev);
+    RT_LAUNCH_CHECK("rt_reset_kernel");
+    return RT_OK;
+}
+
+int rt_step(rt_env *e, const float *actions_dev, float *obs_dev, double *reward_dev, float *reward_f32_dev,
+            uint8_t *terminated_dev, uint8_t *truncated_dev, double *info_dev, void *stream)
+{
+    if (!e || !actions_dev || !obs_dev) return fail(RT_ERR_INVALID, "rt_step: NULL handle, actions or obs");
+    RT_CUDA(cudaSetDevice(e->device));
+    StepOut o{obs_dev, reward_dev, reward_f32_dev, terminated_dev, truncated_dev, info_dev};
+    rt_step_kernel<<<warps_grid(e->n, 256), 256, 0, (cudaStream_t)stream>>>(e->T, e->S, e->rec, e->dose, e->valid,
+                                                                           e->beams, e->n, actions_dev, o);
+    RT_LAUNCH_CHECK("rt_step_kernel");
+    return RT_OK;
+}
+
+int rt_reset_host(rt_env *e, const uint8_t *mask_host, float *obs_host)
+{
+    if (!e || !obs_host) return fail(RT_ERR_INVALID, "rt_reset_host: NULL argument");
+    RT_CUDA(cudaSetDevice(e->device));
+    uint8_t *dmask = nullptr;
+    uint8_t *d_mask_dev = nullptr;
+    if (mask_host) {
+        memcpy(e->h_mask, mask_host, (size_t)e->n);
+        RT_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void **>(&d_mask_dev), e->h_mask, 0));
+        dmask = d_mask_dev;
+    }
+    float *d_obs = nullptr;
+    RT_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void **>(&d_obs), e->h_obs, 0));
+    if (int rc = rt_reset(e, dmask, d_obs, e->hstream)) return rc;
+    RT_CUDA(cudaStreamSynchronize(e->hstream));
+    memcpy(obs_host, e->h_obs, (size_t)e->n * RT_OBS_SIZE * sizeof(float));
+    return RT_OK;
+}
+
+int rt_get_pose(rt_env *e, double *pose_dev, void *stream)
+{
+    if (!e || !pose_dev) return fail(RT_ERR_INVALID, "rt_get_pose: NULL argument");
+    RT_CUDA(cudaSetDevice(e->device));
+    rt_get_pose_kernel<<<(e->n * 6 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(e->rec, e->n, pose_dev);
+    RT_LAUNCH_CHECK("rt_get_pose_kernel");
+    return RT_OK;
+}
+
+int rt_set_pose(rt_env *e, const double *pose_dev, void *stream)
+{
+    if (!e || !pose_dev) return fail(RT_ERR_INVALID, "rt_set_pose: NULL argument");
+    RT_CUDA(cudaSetDevice(e->device));
+    rt_set_pose_kernel<<<(e->n * 6 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(e->rec, e->n, pose_dev);
+    RT_LAUNCH_CHECK("rt_set_pose_kernel");
+    return RT_OK;
+}
+
+int rt_get_counters(rt_env *e, int32_t *counters_dev, void *stream)
+{
+    if (!e || !counters_dev) return fail(RT_ERR_INVALID, "rt_get_counters: NULL argument");
+    RT_CUDA(cudaSetDevice(e->device));
+    rt_get_counters_kernel<<<(e->n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(e->rec, e->n, counters_dev);
+    RT_LAUNCH_CHECK("rt_get_counters_kernel");
+    return RT_OK;
+}
+
+int rt_get_dose(rt_env *e, int env_index, float *dose_dev, void *stream)
+{
+    if (!e || !dose_dev) return fail(RT_ERR_INVALID, "rt_get_dose: NULL argument");
+    if (env_index < 0 || env_index >= e->n) return fail(RT_ERR_INVALID, "rt_get_dose: env index out of range");
+    RT_CUDA(cudaSetDevice(e->device));
+    rt_get_dose_kernel<<<(e->T.G.nvox + 255) / 256, 256, 0, (cudaStream_t)stream>>>(e->T.G, e->dose, e->valid,
+                                                                                  env_index, dose_dev);
+    RT_LAUNCH_CHECK("rt_get_dose_kernel");
+    return RT_OK;
+}
+
+int rt_get_beams(rt_env *e, int env_index, double *beams_dev, int32_t *n_dev, void *stream)
+{
+    if (!e || !beams_dev) return fail(RT_ERR_INVALID, "rt_get_beams: NULL argument");
+    if (!e->beams) return fail(RT_ERR_STATE, "rt_get_beams: handle was created without RT_FLAG_RECORD_BEAMS");
+    if (env_index < 0 || env_index >= e->n) return fail(RT_ERR_INVALID, "rt_get_beams: env index out of range");
+    RT_CUDA(cudaSetDevice(e->device));
+    rt_get_beams_kernel<<<(RT_MAX_TIME_STEPS * 6 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+        e->rec, e->beams, env_index, beams_dev, n_dev);
+    RT_LAUNCH_CHECK("rt_get_beams_kernel");
+    return RT_OK;
+}
+
+int rt_assemble_volumes(rt_env *e, int first, int count, float *obs_dev, void *stream)
+{
+    if (!e || !obs_dev) return fail(RT_ERR_INVALID, "rt_assemble_volumes: NULL argument");
+    if (first < 0 || count < 1 || first + count > e->n)
+        return fail(RT_ERR_INVALID, "rt_assemble_volumes: env range out of bounds");
+    RT_CUDA(cudaSetDevice(e->device));
+    const size_t smem = ((size_t)(e->T.G.nvox + 31) / 32) * sizeof(uint32_t) + (size_t)kViewCap * (sizeof(int) + sizeof(float));
+    static bool attr_set = false;
+    if (!attr_set) {
+        RT_CUDA(cudaFuncSetAttribute(rt_volumes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    rt_volumes_kernel<<<count, kVolThreads, smem, (cudaStream_t)stream>>>(e->T, e->rec, e->dose, e->valid, first,
+                                                                         obs_dev);
+    RT_LAUNCH_CHECK("rt_volumes_kernel");
+    return RT_OK;
+}
+
+// Device alias of a host pointer if (and only if) it is page-locked, else NULL.
+static void *pinned_alias(const void *host)
+{
+    cudaPointerAttributes at;
+    if (!host || cudaPointerGetAttributes(&at, host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
+}
+
+int rt_step_host(rt_env *e, const float *actions_host, float *obs_host, double *reward_host,
+                 uint8_t *terminated_host, uint8_t *truncated_host, double *info_host)
+{
+    if (!e || !actions_host || !obs_host) return fail(RT_ERR_INVALID, "rt_step_host: NULL argument");
+    RT_CUDA(cudaSetDevice(e->device));
+    // Host buffers are reached zero-copy: the step kernel reads the actions and writes its
+    // results straight over PCIe into page-locked memory (one launch, no copy-engine round
+    // trips).  Caller buffers that are already pinned (e.g. torch pin_memory) are used in
+    // place; pageable ones are staged through the handle's own pinned buffers.
+    const size_t n = (size_t)e->n;
+    float *d_act = (float *)pinned_alias(actions_host);
+    float *d_obs = (float *)pinned_alias(obs_host);
+    double *d_rew = (double *)pinned_alias(reward_host);
+    uint8_t *d_term = (uint8_t *)pinned_alias(terminated_host);
+    uint8_t *d_trunc = (uint8_t *)pinned_alias(truncated_host);
+    double *d_info = (double *)pinned_alias(info_host);
+    const bool s_act = !d_act, s_obs = !d_obs, s_rew = reward_host && !d_rew, s_term = terminated_host && !d_term,
+               s_trunc = truncated_host && !d_trunc, s_info = info_host && !d_info;
+    if (s_act) { memcpy(e->h_actions, actions_host, n * RT_ACTION_SIZE * sizeof(float)); d_act = (float *)pinned_alias(e->h_actions); }
+    if (s_obs) d_obs = (float *)pinned_alias(e->h_obs);
+    if (s_rew) d_rew = (double *)pinned_alias(e->h_reward);
+    if (s_term) d_term = (uint8_t *)pinned_alias(e->h_term);
+    if (s_trunc) d_trunc = (uint8_t *)pinned_alias(e->h_trunc);
+    if (s_info) d_info = (double *)pinned_alias(e->h_info);
+    if (!d_act || !d_obs) return fail(RT_ERR_CUDA, "rt_step_host: pinned staging buffers are not device-mapped");
+    if (int rc = rt_step(e, d_act, d_obs, d_rew, nullptr, d_term, d_trunc, d_info, e->hstream)) return rc;
+    RT_CUDA(cudaStreamSynchronize(e->hstream));
+    if (s_obs) memcpy(obs_host, e->h_obs, n * RT_OBS_SIZE * sizeof(float));
+    if (s_rew) memcpy(reward_host, e->h_reward, n * sizeof(double));
+    if (s_term) memcpy(terminated_host, e->h_term, n);
+    if (s_trunc) memcpy(truncated_host, e->h_trunc, n);
+    if (s_info) memcpy(info_host, e->h_info, n * RT_INFO_SIZE * sizeof(double));
+    return RT_OK;
+}
+
+int rt_beam_voxels(const int32_t grid[3], const double *pos_dev, const double *dir_dev, int m, int cap,
+                   int32_t *idx_dev, float *w_dev, int32_t *count_dev, void *stream)
+{
+    if (int rc = check_grid(grid)) return rc;
+    if (!pos_dev || !dir_dev || !idx_dev || !w_dev || !count_dev) return fail(RT_ERR_INVALID, "rt_beam_voxels: NULL argument");
+    if (m < 0 || cap < RT_BEAM_CAP) return fail(RT_ERR_INVALID, "rt_beam_voxels: cap must be >= RT_BEAM_CAP");
+    if (m == 0) return RT_OK;
+    rt_beam_kernel<<<warps_grid(m, 256), 256, 0, (cudaStream_t)stream>>>(make_grid(grid), pos_dev, dir_dev, m, cap,
+                                                                        idx_dev, w_dev, count_dev);
+    RT_LAUNCH_CHECK("rt_beam_kernel");
+    return RT_OK;
+}
+
+int rt_beam_voxels_dense(const int32_t grid[3], const double *pos_dev, const double *dir_dev, int m, float *out_dev,
+                         int32_t *status_dev, void *stream)
+{
+    if (int rc = check_grid(grid)) return rc;
+    if (!pos_dev || !dir_dev || !out_dev) return fail(RT_ERR_INVALID, "rt_beam_voxels_dense: NULL argument");
+    if (m < 0) return fail(RT_ERR_INVALID, "rt_beam_voxels_dense: m < 0");
+    if (m == 0) return RT_OK;
+    const Grid G = make_grid(grid);
+    RT_CUDA(cudaMemsetAsync(out_dev, 0, (size_t)m * G.nvox * sizeof(float), (cudaStream_t)stream));
+    rt_beam_dense_kernel<<<warps_grid(m, 256), 256, 0, (cudaStream_t)stream>>>(G, pos_dev, dir_dev, m, out_dev,
+                                                                              status_dev);
+    RT_LAUNCH_CHECK("rt_beam_dense_kernel");
+    return RT_OK;
+}
+
+int rt_pose_update(const int32_t grid[3], const double *pos_dev, const double *dir_dev, const float *actions_dev,
+                   int m, double *pos_out_dev, double *dir_out_dev, double *overshoot_t_dev,
+                   double *overshoot_r_dev, void *stream)
+{
+    if (int rc = check_grid(grid)) return rc;
+    if (!pos_dev || !dir_dev || !actions_dev || !pos_out_dev || !dir_out_dev)
+        return fail(RT_ERR_INVALID, "rt_pose_update: NULL argument");
+    if (m < 0) return fail(RT_ERR_INVALID, "rt_pose_update: m < 0");
+    if (m == 0) return RT_OK;
+    rt_pose_kernel<<<(m + 127) / 128, 128, 0, (cudaStream_t)stream>>>(make_grid(grid), pos_dev, dir_dev, actions_dev, m,
+                                                                     pos_out_dev, dir_out_dev, overshoot_t_dev,
+                                                                     overshoot_r_dev);
+    RT_LAUNCH_CHECK("rt_pose_kernel");
+    return RT_OK;
+}
+
+int rt_apply_rotation(const double *dir_dev, const double *rotvec_dev, int m, double min_angle, double *dir_out_dev,
+                      double *overshoot_dev, void *stream)
+{
+    if (!dir_dev || !rotvec_dev || !dir_out_dev) return fail(RT_ERR_INVALID, "rt_apply_rotation: NULL argument");
+    if (m < 0) return fail(RT_ERR_INVALID, "rt_apply_rotation: m < 0");
+    if (m == 0) return RT_OK;
+    // transforms.py:36-37 evaluate np.cos(min_angle) and np.sqrt(1 - cos**2) on the host (glibc);
+    // so does this entry point, so the clamp target is the reference's to the last bit.
+    const double cos_min = cos(min_angle);
+    const double xy_mag = sqrt(1.0 - cos_min * cos_min);
+    rt_rotation_kernel<<<(m + 127) / 128, 128, 0, (cudaStream_t)stream>>>(dir_dev, rotvec_dev, m, min_angle, cos_min,
+                                                                         xy_mag, dir_out_dev, overshoot_dev);
+    RT_LAUNCH_CHECK("rt_rotation_kernel");
+    return RT_OK;
+}
+
+int rt_apply_translation(const double *pos_dev, const double *translation_dev, int m, const double bounds[3],
+                         double *pos_out_dev, double *overshoot_dev, void *stream)
+{
+    if (!pos_dev || !translation_dev || !bounds || !pos_out_dev)
+        return fail(RT_ERR_INVALID, "rt_apply_translation: NULL argument");
+    if (m < 0) return fail(RT_ERR_INVALID, "rt_apply_translation: m < 0");
+    if (m == 0) return RT_OK;
+    rt_translation_kernel<<<(3 * m + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+        pos_dev, translation_dev, m, bounds[0], bounds[1], bounds[2], pos_out_dev, overshoot_dev);
+    RT_LAUNCH_CHECK("rt_translation_kernel");
+    return RT_OK;
+}
+
+int rt_gae(const float *rewards_dev, const float *values_dev, const float *dones_dev, const float *next_value_dev,
+           const float *next_done_dev, int T, int N, double gamma, double gae_lambda, float *advantages_dev,
+           float *returns_dev, void *stream)
+{
+    if (!rewards_dev || !values_dev || !dones_dev || !next_value_dev || !next_done_dev || !advantages_dev || !returns_dev)
+        return fail(RT_ERR_INVALID, "rt_gae: NULL argument");
+    if (T < 0 || N < 0) return fail(RT_ERR_INVALID, "rt_gae: negative extent");
+    if (T == 0 || N == 0) return RT_OK;
+    rt_gae_kernel<<<(N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(rewards_dev, values_dev, dones_dev, next_value_dev,
+                                                                    next_done_dev, T, N, (float)gamma,
+                                                                    (float)(gamma * gae_lambda), advantages_dev,
+                                                                    returns_dev);
+    RT_LAUNCH_CHECK("rt_gae_kernel");
+    return RT_OK;
+}
+
+}  // extern "C"

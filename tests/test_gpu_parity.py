@@ -1,0 +1,439 @@
+"""Parity of the CUDA path (through the C ABI) against the golden vectors of the reference and
+against the CPU oracle on the same seeded inputs.  Needs a GPU: `pytest -m gpu`.
+
+Stated tolerances (north_star): voxel indices, per-beam weights, dose volumes, lung counts and
+done flags BIT-EXACT; float64 pose within 1e-12 absolute of the reference (CUDA sin/cos/acos differ
+from glibc by <= 2 ulp) and identical after rounding to float32 — which is all draw_line.py:19-20
+consumes; observations (float32) within 2e-7; rewards rtol 1e-6 / atol 1e-7; GAE bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+import ppo_radiotherapy_b200 as rt
+from ppo_radiotherapy_b200 import _native as nat
+from oracle import oracle as O
+from oracle.hashing import batch_hash, dense_hash
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+REW_RTOL, REW_ATOL = 1e-6, 1e-7
+OBS_ATOL = 2e-7
+POSE_ATOL = 1e-12
+GRID = np.array([67.0, 43.0, 70.0])
+
+
+def _cuda(a, dtype=None):
+    return torch.as_tensor(np.ascontiguousarray(a), device=DEV) if dtype is None else \
+        torch.as_tensor(np.ascontiguousarray(a), device=DEV).to(dtype)
+
+
+# ------------------------------------------------------------------------------------ beams
+def test_beams_golden_bit_exact(golden):
+    g = golden("beams")
+    idx, w, count = rt.beam_voxels_batch(_cuda(g["pos"]), _cuda(g["dir"]))
+    idx, w, count = idx.cpu().numpy(), w.cpu().numpy(), count.cpu().numpy()
+    assert (count >= 0).all()
+    nnz, h = batch_hash(idx, w, count)
+    assert np.array_equal(nnz, g["count"])
+    assert np.array_equal(h, g["hash"])
+    # no voxel appears twice in a trace
+    for k in range(0, idx.shape[0], 37):
+        assert len(set(idx[k, :count[k]].tolist())) == count[k]
+
+
+def test_beams_full_traces(golden):
+    g = golden("beams")
+    ids = g["full_ids"]
+    vols, status = rt.beam_voxels_dense_batch(_cuda(g["pos"][ids]), _cuda(g["dir"][ids]))
+    vols = vols.cpu().numpy().reshape(len(ids), -1)
+    assert (status.cpu().numpy() == 0).all()
+    for j in range(len(ids)):
+        nz = np.flatnonzero(vols[j])
+        lo, hi = g["full_off"][j], g["full_off"][j + 1]
+        assert np.array_equal(nz, g["full_idx"][lo:hi])
+        assert np.array_equal(vols[j][nz].view(np.uint32), g["full_w"][lo:hi].view(np.uint32))
+
+
+def test_beams_vs_oracle_random_100k():
+    rng = np.random.default_rng(99)
+    m = 100_000
+    pos = rng.uniform(-3, 73, (m, 3))
+    pos[: m // 2] = rng.uniform(0, 1, (m // 2, 3)) * GRID
+    d = rng.standard_normal((m, 3))
+    d[::7, rng.integers(3)] = 0.0
+    oi, ow, oc = O.beam_batch(pos, d)
+    idx, w, count = rt.beam_voxels_batch(_cuda(pos), _cuda(d))
+    n0, h0 = batch_hash(oi, ow, oc)
+    n1, h1 = batch_hash(idx.cpu().numpy(), w.cpu().numpy(), count.cpu().numpy())
+    assert np.array_equal(n0, n1)
+    assert np.array_equal(h0, h1)
+
+
+def test_beam_voxels_dropin_and_error():
+    base = np.zeros((67, 43, 70), dtype=np.float32)
+    pos, d = np.array([33.5, 21.5, 35.0]), np.array([0.3, 1.0, -0.2])
+    out = rt.beam_voxels(base, pos, d)
+    assert out.dtype == np.float32 and out.shape == base.shape
+    assert np.array_equal(out.view(np.uint32), O.beam_voxels(pos, d).view(np.uint32))
+    with pytest.raises(ValueError, match="too small"):
+        rt.beam_voxels(base, pos, np.array([0.0, 1e-9, 0.0]))
+    # empty cases: parallel to an axis and outside the slab; pointing away is still a line (not a ray)
+    assert not rt.beam_voxels(base, np.array([-5.0, 3.0, 3.0]), np.array([0.0, 1.0, 0.0])).any()
+    assert rt.beam_voxels(base, np.array([-5.0, 3.0, 3.0]), np.array([-1.0, 0.0, 0.0])).any()
+
+
+def test_beam_other_grid_shapes():
+    rng = np.random.default_rng(3)
+    for grid in [(8, 9, 10), (95, 4, 17), (2, 2, 2), (31, 64, 33)]:
+        g = np.array(grid)
+        pos = rng.uniform(-1, 1, (500, 3)) * g + g / 2
+        d = rng.standard_normal((500, 3))
+        oi, ow, oc = O.beam_batch(pos, d, grid=g, cap=4 * (max(grid) + 2))
+        idx, w, count = rt.beam_voxels_batch(_cuda(pos), _cuda(d), grid=grid)
+        n0, h0 = batch_hash(oi, ow, oc)
+        n1, h1 = batch_hash(idx.cpu().numpy(), w.cpu().numpy(), count.cpu().numpy())
+        assert np.array_equal(n0, n1) and np.array_equal(h0, h1), grid
+
+
+# ------------------------------------------------------------------------------------ pose
+def test_pose_golden(golden):
+    g = golden("poses")
+    acts = g["actions"]
+    C = acts.shape[0]
+    p_in = np.concatenate([np.broadcast_to(GRID / 2, (C, 1, 3)), g["pos"][:, :-1]], axis=1).reshape(-1, 3)
+    d_in = np.concatenate([np.broadcast_to(np.array([0.0, 1.0, 0.0]), (C, 1, 3)), g["dir"][:, :-1]], axis=1).reshape(-1, 3)
+    p, d, ot, orr = (x.cpu().numpy() for x in rt.pose_update_batch(_cuda(p_in), _cuda(d_in), _cuda(acts.reshape(-1, 6))))
+    assert np.array_equal(p, g["pos"].reshape(-1, 3))
+    assert np.array_equal(ot, g["overshoot_t"].reshape(-1, 3))
+    np.testing.assert_allclose(d, g["dir"].reshape(-1, 3), rtol=0, atol=POSE_ATOL)
+    np.testing.assert_allclose(orr, g["overshoot_r"].reshape(-1), rtol=0, atol=1e-11)
+    mism = (d.astype(np.float32) != g["dir"].reshape(-1, 3).astype(np.float32)).any(axis=1).sum()
+    assert mism == 0, f"{mism} of {d.shape[0]} directions differ after float32 rounding"
+
+
+def test_transform_dropins_vs_oracle():
+    rng = np.random.default_rng(5)
+    for _ in range(20):
+        d = rng.standard_normal(3)
+        rv = rng.uniform(-1.6, 1.6, 3) * rng.choice([1.0, 1e-4, 0.0])
+        ma = rng.choice([np.pi / 4, 0.3, 1.2])
+        got, ov = rt.apply_rotation(d, rv, ma)
+        want, ov_w = O.apply_rotation(d, rv, ma)
+        np.testing.assert_allclose(got, want, rtol=0, atol=POSE_ATOL)
+        assert abs(ov - ov_w) < 1e-11
+        p, t = rng.uniform(0, 70, 3), rng.uniform(-30, 30, 3)
+        gp, go = rt.apply_translation(p, t, GRID)
+        wp, wo = O.apply_translation(p, t, GRID)
+        assert np.array_equal(gp, wp) and np.array_equal(go, wo)
+
+
+# ------------------------------------------------------------------------------------ step
+def _compare_step(info, obs, reward, term, rec, done, mask=None):
+    m = slice(None) if mask is None else mask
+    np.testing.assert_allclose(obs[m], rec[m, 0:9].astype(np.float32), rtol=0, atol=OBS_ATOL)
+    np.testing.assert_allclose(reward[m], rec[m, 9], rtol=REW_RTOL, atol=REW_ATOL)
+    np.testing.assert_allclose(info[m, 0:4], rec[m, [9, 10, 11, 12]], rtol=REW_RTOL, atol=REW_ATOL)
+    np.testing.assert_allclose(info[m, 4:6], rec[m, 13:15], rtol=REW_RTOL, atol=REW_ATOL)
+    assert np.array_equal(info[m, nat.INFO_OVERSHOOT_T0:nat.INFO_OVERSHOOT_T0 + 3], rec[m, 15:18])
+    np.testing.assert_allclose(info[m, nat.INFO_OVERSHOOT_R], rec[m, 18], rtol=0, atol=1e-11)
+    assert np.array_equal(info[m, nat.INFO_LUNG_COUNT], rec[m, 19])
+    assert np.array_equal(term[m].astype(np.int8), done[m])
+
+
+def test_step_traces_golden(golden):
+    """30 reference episodes (uniform, normal and saves/20M.model actions) replayed as one batch."""
+    g = golden("steps")
+    tids = g["tumour_ids"]
+    E, T = g["actions"].shape[:2]
+    env = rt.RadiotherapyVectorEnv(E, visionless=True, device=DEV, tumour_ids=tids[None, :])
+    obs0, _ = env.reset()
+    np.testing.assert_allclose(obs0, g["reset_obs"].astype(np.float32), rtol=0, atol=OBS_ATOL)
+    f32_pose_mismatch = 0
+    for t in range(T):
+        obs, reward, term, trunc, _ = env.step(_cuda(g["actions"][:, t]))
+        info = env.engine.info.cpu().numpy()
+        _compare_step(info, obs.cpu().numpy(), reward.cpu().numpy(), term.cpu().numpy(), g["rec"][:, t], g["done"][:, t])
+        assert not trunc.any()
+        pose = env.engine.pose().cpu().numpy()
+        np.testing.assert_allclose(pose, g["pose"][:, t], rtol=0, atol=POSE_ATOL)
+        f32_pose_mismatch += int((pose.astype(np.float32) != g["pose"][:, t].astype(np.float32)).any(axis=1).sum())
+        if t % 9 == 0 or t == T - 1:
+            for e in range(0, E, 3):
+                assert dense_hash(env.engine.dose(e).cpu().numpy()) == g["dose_hash"][e, t], (e, t)
+    assert f32_pose_mismatch == 0
+    # final dose volumes, voxel by voxel
+    for e in range(E):
+        flat = env.engine.dose(e).cpu().numpy().reshape(-1)
+        nz = np.flatnonzero(flat)
+        lo, hi = g["final_off"][e], g["final_off"][e + 1]
+        assert np.array_equal(nz, g["final_idx"][lo:hi])
+        assert np.array_equal(flat[nz].view(np.uint32), g["final_val"][lo:hi].view(np.uint32))
+    env.close()
+
+
+def _tiny_phantom(g):
+    base = rt.default_phantom()
+    lungs = base.lungs_volume()
+    vols = []
+    for e in range(len(g["length"])):
+        v = np.zeros(lungs.size, dtype=np.float32)
+        v[g["vox"][g["vox_off"][e]:g["vox_off"][e + 1]]] = 1.0
+        vols.append(v.reshape(lungs.shape))
+    return rt.Phantom.from_volumes(lungs, vols, names=[str(x) for x in g["names"]])
+
+
+def test_tiny_tumours_early_termination_and_autoreset(golden):
+    """Few-voxel tumours reach dose ratio >= 0.9 after 9-18 beams (environment.py:184-191): the terminal
+    step, the NEXT_STEP autoreset call and the following episode all match the reference / oracle."""
+    g = golden("tiny")
+    ph = _tiny_phantom(g)
+    E = len(g["length"])
+    T = 40
+    acts = np.zeros((T, E, 6), dtype=np.float32)
+    for e in range(E):
+        L = int(g["length"][e])
+        acts[:min(L, T), e] = g["actions"][e, :min(L, T)]
+    rng = np.random.default_rng(8)
+    for e in range(E):
+        L = int(g["length"][e])
+        if L < T:
+            acts[L:, e] = rng.uniform(-1, 1, (T - L, 6))
+    sched = np.stack([np.arange(E), (np.arange(E) + 1) % E]).astype(np.int32)
+    env = rt.RadiotherapyVectorEnv(E, device=DEV, phantom=ph, tumour_ids=sched)
+    env.reset()
+    oph = O.Phantom()
+    oph.vox_offsets = np.ascontiguousarray(g["vox_off"].astype(np.int32))
+    oph.vox = np.ascontiguousarray(g["vox"].astype(np.int32))
+    ref_out, ref_done = O.rollout(oph, sched, acts)
+    saw_reset = 0
+    for t in range(T):
+        obs, reward, term, trunc, infos = env.step(_cuda(acts[t]))
+        info = env.engine.info.cpu().numpy()
+        stepped = info[:, nat.INFO_STEPPED] > 0
+        _compare_step(info, obs.cpu().numpy(), reward.cpu().numpy(), term.cpu().numpy(), ref_out[t], ref_done[t], stepped)
+        rs = ~stepped
+        if rs.any():
+            saw_reset += int(rs.sum())
+            assert (reward.cpu().numpy()[rs] == 0).all() and not term.cpu().numpy()[rs].any()
+            np.testing.assert_allclose(obs.cpu().numpy()[rs], ref_out[t, rs, 0:9].astype(np.float32), rtol=0, atol=OBS_ATOL)
+        for e in range(E):   # the reference's own numbers for the first episode
+            if t < g["length"][e]:
+                np.testing.assert_allclose(reward.cpu().numpy()[e], g["rec"][e, t, 9], rtol=REW_RTOL, atol=REW_ATOL)
+                assert bool(term.cpu().numpy()[e]) == bool(g["done"][e, t])
+                assert dense_hash(env.engine.dose(e).cpu().numpy()) == g["dose_hash"][e, t]
+        if "episode" in infos:
+            fin = infos["episode"]["_r"]
+            assert np.array_equal(fin, term.cpu().numpy() & stepped)
+            assert np.array_equal(infos["episode"]["l"][fin], info[fin, nat.INFO_T].astype(np.int64))
+    assert saw_reset >= 3
+    env.close()
+
+
+@pytest.mark.parametrize("kind", ["uniform", "normal"])
+def test_rollout_vs_oracle_256_envs(kind):
+    """SURVEY §8d C2 at reduced width: tumour id (i*7919) mod 1000, T = 101 calls (a full episode plus
+    the autoreset call) then 20 steps of the second episode."""
+    n, T = 256, 121
+    rng = np.random.default_rng(0 if kind == "uniform" else 1)
+    acts = (rng.uniform(-1, 1, (T, n, 6)) if kind == "uniform" else rng.standard_normal((T, n, 6))).astype(np.float32)
+    sched = np.stack([(np.arange(n) * 7919) % 1000, (np.arange(n) * 104729 + 17) % 1000]).astype(np.int32)
+    ref_out, ref_done = O.rollout(O.Phantom(), sched, acts, threads=8)
+    env = rt.RadiotherapyVectorEnv(n, device=DEV, tumour_ids=sched)
+    env.reset()
+    ep_ret = np.zeros(n)
+    for t in range(T):
+        obs, reward, term, trunc, infos = env.step(_cuda(acts[t]))
+        info = env.engine.info.cpu().numpy()
+        stepped = info[:, nat.INFO_STEPPED] > 0
+        assert stepped.all() == (t != 100)
+        _compare_step(info, obs.cpu().numpy(), reward.cpu().numpy(), term.cpu().numpy(), ref_out[t], ref_done[t], stepped)
+        np.testing.assert_allclose(obs.cpu().numpy(), ref_out[t, :, 0:9].astype(np.float32), rtol=0, atol=OBS_ATOL)
+        ep_ret += ref_out[t, :, 9]
+        if t == 99:
+            assert term.all()
+            np.testing.assert_allclose(infos["episode"]["r"], ep_ret, rtol=1e-9, atol=1e-9)
+            assert (infos["episode"]["l"] == 100).all()
+            ep_ret[:] = 0
+    env.close()
+
+
+def test_dose_volumes_bit_exact_vs_oracle():
+    n, T = 16, 100
+    rng = np.random.default_rng(4)
+    acts = rng.standard_normal((T, n, 6)).astype(np.float32) * 0.3     # slow motion: heavy re-irradiation, clipping at 1.0
+    tids = (np.arange(n) * 61 + 5).astype(np.int32) % 1000
+    env = rt.RadiotherapyVectorEnv(n, device=DEV, tumour_ids=tids[None, :])
+    env.reset()
+    for t in range(T):
+        env.step(_cuda(acts[t]))
+    ph = O.Phantom()
+    clipped = 0
+    for e in range(n):
+        o = O.OracleEnv(ph, int(tids[e]))
+        for t in range(T):
+            o.step(acts[t, e])
+        d = env.engine.dose(e).cpu().numpy()
+        assert np.array_equal(d.view(np.uint32), o.dose.view(np.uint32)), e
+        clipped += int((d == 1.0).sum())
+    assert clipped > 0        # the clip at 1.0 was exercised
+    env.close()
+
+
+# ------------------------------------------------------------------------------------ vision
+def test_vision_volumes(golden):
+    g = golden("steps")
+    sel = np.arange(0, len(g["tumour_ids"]), 5)
+    tids = g["tumour_ids"][sel]
+    env = rt.RadiotherapyVectorEnv(len(sel), visionless=False, device=DEV, tumour_ids=tids[None, :])
+    obs0, _ = env.reset()
+    assert obs0.shape == (len(sel), 4, 67, 43, 70) and obs0.dtype == np.float32
+    steps = g["vol_steps"]
+    ph = O.Phantom()
+    oenv = [O.OracleEnv(ph, int(t)) for t in tids]
+    for t in range(int(steps.max()) + 1):
+        obs, *_ = env.step(_cuda(g["actions"][sel, t]))
+        for j, e in enumerate(sel):
+            oenv[j].step(g["actions"][e, t])
+        for k, vs in enumerate(steps):
+            if t == vs:
+                vol = obs.cpu().numpy()
+                for j, e in enumerate(sel):
+                    assert dense_hash(vol[j]) == g["vol_hash"][e, k]
+                    assert np.array_equal(vol[j].view(np.uint32), oenv[j].volumes().view(np.uint32))
+    env.close()
+
+
+# ------------------------------------------------------------------------------------ GAE
+def test_gae_golden_bit_exact(golden):
+    g = golden("gae")
+    for tag in "abc":
+        adv, ret = rt.compute_gae(_cuda(g[f"{tag}_rewards"]), _cuda(g[f"{tag}_values"]), _cuda(g[f"{tag}_dones"]),
+                                  _cuda(g[f"{tag}_next_value"]), _cuda(g[f"{tag}_next_done"]),
+                                  float(g["gamma"]), float(g["gae_lambda"]))
+        assert np.array_equal(adv.cpu().numpy().view(np.uint32), g[f"{tag}_advantages"].view(np.uint32))
+        assert np.array_equal(ret.cpu().numpy().view(np.uint32), g[f"{tag}_returns"].view(np.uint32))
+
+
+def test_gae_vs_oracle_large():
+    rng = np.random.default_rng(2)
+    T, N = 128, 4096
+    r = rng.standard_normal((T, N)).astype(np.float32)
+    v = (rng.standard_normal((T, N)) * 5).astype(np.float32)
+    d = (rng.random((T, N)) < 0.02).astype(np.float32)
+    nv = rng.standard_normal(N).astype(np.float32)
+    nd = (rng.random(N) < 0.1).astype(np.float32)
+    a0, r0 = O.gae(r, v, d, nv, nd, 0.99, 0.95)
+    a1, r1 = rt.compute_gae(_cuda(r), _cuda(v), _cuda(d), _cuda(nv), _cuda(nd), 0.99, 0.95)
+    assert np.array_equal(a0.view(np.uint32), a1.cpu().numpy().view(np.uint32))
+    assert np.array_equal(r0.view(np.uint32), r1.cpu().numpy().view(np.uint32))
+
+
+# ------------------------------------------------------------------------------------ host path / API
+def test_host_path_equals_device_path():
+    n, T = 64, 30
+    rng = np.random.default_rng(12)
+    acts = rng.uniform(-1, 1, (T, n, 6)).astype(np.float32)
+    tids = (np.arange(n) * 7919 % 1000).astype(np.int32)[None, :]
+    a = rt.RadiotherapyVectorEnv(n, device=DEV, tumour_ids=tids)
+    b = rt.RadiotherapyVectorEnv(n, device=DEV, tumour_ids=tids)
+    oa, _ = a.reset()
+    ob, _ = b.reset()
+    assert np.array_equal(oa, ob)
+    for t in range(T):
+        o1, r1, d1, tr1, i1 = a.step(acts[t])                       # numpy in -> numpy out
+        o2, r2, d2, tr2, i2 = b.step(_cuda(acts[t]))                # tensor in -> tensor out
+        assert isinstance(o1, np.ndarray) and o1.dtype == np.float32 and r1.dtype == np.float64 and d1.dtype == bool
+        assert np.array_equal(o1, o2.cpu().numpy()) and np.array_equal(r1, r2.cpu().numpy())
+        assert np.array_equal(d1, d2.cpu().numpy())
+        for k in ("total", "tumour", "lung", "distance_to_tumour"):
+            assert np.array_equal(i1["reward_components"][k], i2["reward_components"][k])
+    a.close()
+    b.close()
+
+
+def test_single_env_facade():
+    env = rt.RadiotherapyEnv(visionless=True, device=DEV, tumour_id=7)
+    assert env.observation_space.shape == (9,) and env.action_space.shape == (6,)
+    obs, info = env.reset(options={"tumour_id": 7})
+    assert info == {} and obs.shape == (9,)
+    o = O.OracleEnv(O.Phantom(), 7)
+    rng = np.random.default_rng(0)
+    for _ in range(5):
+        a = rng.uniform(-1, 1, 6).astype(np.float32)
+        obs, reward, term, trunc, info = env.step(a)
+        want, dn = o.step(a)
+        np.testing.assert_allclose(obs, want[0:9].astype(np.float32), rtol=0, atol=OBS_ATOL)
+        np.testing.assert_allclose(reward, want[9], rtol=REW_RTOL, atol=REW_ATOL)
+        assert term == dn and trunc is False
+        assert set(info) == {"reward_components", "beam_position", "doses", "overshoot"}
+    assert len(env.beams) == 5 and env.t == 5
+    assert np.array_equal(env.dose.view(np.uint32), o.dose.view(np.uint32))
+    v = env.get_volumes()
+    assert np.array_equal(v.view(np.uint32), o.volumes().view(np.uint32))
+    env.close()
+    env2 = rt.RadiotherapyEnv(visionless=False, device=DEV)
+    assert env2.observation().shape == (4, 67, 43, 70)
+    ids = set()
+    for _ in range(6):
+        env2.reset()
+        ids.add(env2.tumour_id)
+    assert len(ids) > 1           # a fresh tumour per reset
+    env2.close()
+
+
+def test_rng_tumour_choice_is_seeded_and_spread():
+    a = rt.BatchedEpisodes(2048, device=DEV, seed=5)
+    b = rt.BatchedEpisodes(2048, device=DEV, seed=5)
+    c = rt.BatchedEpisodes(2048, device=DEV, seed=6)
+    for e in (a, b, c):
+        e.reset()
+    ia, ib, ic = (e.counters()[:, 1].cpu().numpy() for e in (a, b, c))
+    assert np.array_equal(ia, ib) and not np.array_equal(ia, ic)
+    assert ia.min() >= 0 and ia.max() < 1000 and len(np.unique(ia)) > 700
+    for e in (a, b, c):
+        e.close()
+
+
+# ------------------------------------------------------------------------------------ full size
+def test_full_size_properties_4096_envs():
+    """BASELINE.json configs[1] width.  Size-independent properties: dose is monotone non-decreasing
+    and <= 1; the lung count is monotone; rewards stay in their analytic ranges; every env terminates
+    at t = 100 exactly; the step after is a reset whose observation equals the initial one; a
+    checksum over all envs is reproducible run to run (determinism)."""
+    n, T = 4096, 102
+    g = torch.Generator(device=DEV).manual_seed(0)
+    acts = torch.rand((T, n, 6), device=DEV, generator=g) * 2 - 1
+    tids = ((np.arange(n) * 7919) % 1000).astype(np.int32)[None, :]
+
+    def run():
+        env = rt.RadiotherapyVectorEnv(n, device=DEV, tumour_ids=tids)
+        obs0, _ = env.reset(options={"backend": "torch"})
+        obs0 = obs0.clone()
+        prev_cnt = torch.zeros(n, dtype=torch.float64, device=DEV)
+        prev_dose = env.engine.dose(17).clone()
+        csum = torch.zeros((), dtype=torch.float64, device=DEV)
+        for t in range(T):
+            obs, reward, term, trunc, _ = env.step(acts[t])
+            info = env.engine.info
+            if t < 100:
+                assert bool((info[:, nat.INFO_LUNG_COUNT] >= prev_cnt).all())
+                prev_cnt = info[:, nat.INFO_LUNG_COUNT].clone()
+                assert bool((info[:, nat.INFO_REWARD_TUMOUR] >= 0).all() and (info[:, nat.INFO_REWARD_TUMOUR] <= 10).all())
+                assert bool((info[:, nat.INFO_REWARD_LUNG] <= 0).all() and (info[:, nat.INFO_REWARD_LUNG] >= -1).all())
+                assert bool((info[:, nat.INFO_REWARD_DISTANCE] <= 0).all() and (info[:, nat.INFO_REWARD_DISTANCE] >= -1).all())
+                assert bool(term.all()) == (t == 99)
+                if t % 10 == 0:
+                    d = env.engine.dose(17)
+                    assert bool((d >= prev_dose).all() and (d <= 1).all())
+                    prev_dose = d.clone()
+            elif t == 100:
+                assert bool((reward == 0).all()) and not bool(term.any())
+                assert torch.equal(obs, obs0)
+                assert float(env.engine.dose(17).abs().sum()) == 0.0
+            csum += reward.sum() + obs.double().sum()
+        out = float(csum)
+        env.close()
+        return out
+
+    assert run() == run()

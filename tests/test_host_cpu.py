@@ -1,0 +1,118 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/rt_env.h declares,
+the host logic (info merging, phantom packing) behaves, and the product refuses to run without
+its CUDA extension / device instead of falling back."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import ppo_radiotherapy_b200 as rt
+from ppo_radiotherapy_b200 import _native as nat
+from ppo_radiotherapy_b200.vector_env import build_infos
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    text = open(os.path.join(REPO, "include", "rt_env.h")).read()
+    return re.findall(r"RT_API\s+[\w\s\*]+?\b(rt_\w+)\s*\(", text)
+
+
+def test_library_exports_every_header_symbol():
+    syms = _header_symbols()
+    assert len(syms) >= 20 and len(set(syms)) == len(syms)
+    lib = ctypes.CDLL(nat.build())
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in rt_env.h but not exported"
+    # and the Python binding table covers exactly the header
+    assert set(nat.EXPORTS) == set(syms)
+    assert nat.lib().rt_abi_version() == nat.ABI_VERSION
+
+
+def test_header_constants_match_binding():
+    text = open(os.path.join(REPO, "include", "rt_env.h")).read()
+    defs = dict(re.findall(r"#define\s+(RT_\w+)\s+(\d+)u?\b", text))
+    assert int(defs["RT_ACTION_SIZE"]) == nat.ACTION_SIZE
+    assert int(defs["RT_OBS_SIZE"]) == nat.OBS_SIZE
+    assert int(defs["RT_INFO_SIZE"]) == nat.INFO_SIZE
+    assert int(defs["RT_BEAM_CAP"]) == nat.BEAM_CAP
+    assert int(defs["RT_MAX_TIME_STEPS"]) == nat.MAX_TIME_STEPS
+    assert int(defs["RT_ABI_VERSION"]) == nat.ABI_VERSION
+
+
+def test_invalid_arguments_are_reported_without_a_gpu():
+    L = nat.lib()
+    assert L.rt_create(None, 0, 4, 0, None) < 0
+    assert b"NULL" in L.rt_last_error()
+    grid = (ctypes.c_int32 * 3)(67, 43, 70)
+    assert L.rt_beam_voxels(grid, None, None, 1, 288, None, None, None, None) < 0
+    bad = (ctypes.c_int32 * 3)(67, 43, 700)
+    assert L.rt_beam_voxels(bad, None, None, 1, 288, None, None, None, None) < 0
+    assert b"grid" in L.rt_last_error()
+    assert L.rt_gae(None, None, None, None, None, 1, 1, 0.99, 0.95, None, None, None) < 0
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_no_cpu_fallback():
+    with pytest.raises(rt.RtError, match="no CPU fallback"):
+        rt.RadiotherapyVectorEnv(4)
+    with pytest.raises(rt.RtError):
+        rt.beam_voxels(np.zeros((4, 4, 4), np.float32), [1, 1, 1], [0, 1, 0])
+    with pytest.raises(rt.RtError):
+        rt.compute_gae(torch.zeros(2, 2), torch.zeros(2, 2), torch.zeros(2, 2), torch.zeros(2), torch.zeros(2), 0.99, 0.95)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(REPO, "ppo-radiotherapy_b200")
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(root, f)).read()
+                assert "oracle" not in src.lower() or f == "__none__", f"{f} mentions the oracle"
+
+
+def test_phantom_table():
+    ph = rt.default_phantom()
+    assert tuple(ph.grid) == (67, 43, 70) and ph.n_tumours == 1000
+    lungs = ph.lungs_volume()
+    assert lungs.sum() == 74029
+    sizes = np.diff(ph.vox_offsets)
+    assert sizes.min() == 16 and sizes.max() == 586
+    assert ph.names == sorted(ph.names)
+    # from_volumes reproduces the packed constants (the reference's own expressions)
+    ids = [0, 17, int(np.argmax(sizes))]
+    re_ph = rt.Phantom.from_volumes(lungs, [ph.tumour_volume(i) for i in ids])
+    for j, i in enumerate(ids):
+        assert np.array_equal(re_ph.tumour_voxels(j), ph.tumour_voxels(i))
+        assert np.array_equal(re_ph.centroid[j], ph.centroid[i])
+        assert re_ph.tumour_sum[j] == ph.tumour_sum[i] and re_ph.lung_mask_sum[j] == ph.lung_mask_sum[i]
+    assert np.array_equal(re_ph.lungs_bits, ph.lungs_bits)
+    with pytest.raises(ValueError):
+        rt.Phantom.from_volumes(lungs, [np.zeros_like(lungs)])
+
+
+def test_build_infos_merging():
+    n = 5
+    info = np.zeros((n, nat.INFO_SIZE))
+    info[:, nat.INFO_STEPPED] = [1, 1, 0, 1, 1]
+    info[:, nat.INFO_REWARD_TOTAL] = [1.0, 2.0, 9.0, 4.0, 5.0]
+    info[:, nat.INFO_EPISODE_RETURN] = [10, 20, 30, 40, 50]
+    info[:, nat.INFO_EPISODE_LENGTH] = [100, 7, 0, 100, 3]
+    term = np.array([1, 0, 0, 1, 0], dtype=np.uint8)
+    infos = build_infos(info, term, 1.5)
+    rc = infos["reward_components"]
+    assert np.array_equal(rc["_total"], [True, True, False, True, True])
+    assert rc["total"][2] == 0.0 and rc["total"][3] == 4.0
+    ep = infos["episode"]
+    assert np.array_equal(ep["_r"], [True, False, False, True, False])
+    assert np.array_equal(ep["r"], [10, 0, 0, 40, 0]) and np.array_equal(ep["l"], [100, 0, 0, 100, 0])
+    assert ep["l"].dtype == np.int64 and np.array_equal(infos["_episode"], ep["_r"])
+    # the reference's logger (train.py:42-66) works on it
+    assert np.mean(ep["r"][ep["_r"]]) == 25.0 and np.mean(rc["total"][ep["_r"]]) == 2.5
+    # no finished env -> no "episode" key (train.py:160); autoreset-only call -> empty dict
+    assert "episode" not in build_infos(info, np.zeros(n, np.uint8), 0.0)
+    info[:, nat.INFO_STEPPED] = 0
+    assert build_infos(info, term, 0.0) == {}
