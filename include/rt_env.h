@@ -49,7 +49,8 @@ typedef enum {
 #define RT_OBS_SIZE 9
 #define RT_MAX_TIME_STEPS 100
 #define RT_INFO_SIZE 16
-/* Upper bound on distinct voxels of one beam: 4 * (max(G) + 1) splat writes (draw_line.py:68-96). */
+/* Upper bound on distinct voxels of one beam for the bundled grid: 4 * (max(G) + 1) = 284 splat
+ * writes (draw_line.py:68-96), rounded up.  Other grids need cap >= 4 * (max(G) + 1). */
 #define RT_BEAM_CAP 288
 
 /* rt_create flags */
@@ -152,7 +153,7 @@ RT_API int rt_get_beams(rt_env *env, int env_index, double *beams_dev, int32_t *
 /* draw_line.py:4 beam_voxels for m rays.  pos_dev/dir_dev float64 [m][3].  Per ray the
  * distinct voxels hit and their summed float32 weights: idx_dev int32 [m][cap], w_dev
  * float32 [m][cap], count_dev int32 [m]; count -1 flags the ValueError of draw_line.py:23-24
- * ("Direction vector magnitude is too small.").  cap >= RT_BEAM_CAP. */
+ * ("Direction vector magnitude is too small.").  cap >= 4 * (max(grid) + 1). */
 RT_API int rt_beam_voxels(const int32_t grid[3], const double *pos_dev, const double *dir_dev, int m, int cap,
                           int32_t *idx_dev, float *w_dev, int32_t *count_dev, void *stream);
 /* Same, written as the reference returns it: dense float32 [m][V] (zero-filled here). */

@@ -13,7 +13,6 @@
 namespace rt {
 
 constexpr int kWarp = 32;
-constexpr int kMaxChunks = 3;          // <= 96 slabs per beam; the bundled grid needs max(G)+1 = 71
 constexpr unsigned kFull = 0xffffffffu;
 
 struct Grid {
@@ -215,94 +214,88 @@ __device__ __forceinline__ Beam beam_setup(const Grid &G, const double pd[3], co
 }
 
 // ---------------------------------------------------------------------------------
-// draw_line.py:68-100, one warp per beam.  Lane l of chunk c owns slab k = 32c + l.
-// The walk  intery += gradient*step  (:98-99) is a chain of float32 adds that is not
-// re-associable, so the warp replays it once and each lane keeps the value at its k.
-// On return lin[c][j] is the linear voxel index of splat target j = 2*dy + dz of the
-// lane's slab (-1: out of bounds, no slab, or merged into the previous slab's lane)
-// and w[c][j] the float32 weight SUMMED over the (at most two) slabs that write that
-// voxel, added in the reference's order.  Every voxel appears exactly once per beam.
-__device__ __forceinline__ void beam_trace(const Grid &G, const Beam &b, int lane,
-                                           int (&lin)[kMaxChunks][4], float (&w)[kMaxChunks][4])
+// draw_line.py:68-100.  The walk  intery += gradient*step  (:98-99) is a chain of float32
+// adds that is not re-associable, so ONE thread replays it and leaves intery/interz of
+// every slab in shared memory (ys[k], zs[k], k < nslab); the splat work is then spread
+// over a warp with lane = (slab, target).
+constexpr int kMaxSlabs = 96;          // grid extents <= 95 (check_grid): max(G) + 1 slabs
+constexpr int kSlabsPerRound = 8;      // 8 slabs x 4 splat targets = 32 lanes
+constexpr int kRounds = 6;             // rounds staged together: 48 slabs per pass
+
+__device__ __forceinline__ void beam_walk(const Beam &b, float *ys, float *zs)
 {
     float y = b.y0, z = b.z0;
-#pragma unroll
-    for (int c = 0; c < kMaxChunks; c++) {
-        float yc = 0.0f, zc = 0.0f;
-        int lim = b.nslab - c * kWarp;
-        lim = lim > kWarp ? kWarp : lim;
-        for (int i = 0; i < lim; i++) {
-            if (i == lane) { yc = y; zc = z; }
-            y = __fadd_rn(y, b.sgy);
-            z = __fadd_rn(z, b.sgz);
+    for (int k = 0; k < b.nslab; k++) {
+        ys[k] = y;
+        zs[k] = z;
+        y = __fadd_rn(y, b.sgy);
+        z = __fadd_rn(z, b.sgz);
+    }
+}
+
+struct SlabFrac {
+    int yf, zf;      // floor(intery), floor(interz)            (:76, :80)
+    float fy, fz;    // fractional parts                         (:77, :81)
+};
+
+__device__ __forceinline__ SlabFrac slab_frac(float y, float z)
+{
+    SlabFrac s;
+    float yfl = floorf(y), zfl = floorf(z);
+    s.yf = (int)yfl; s.zf = (int)zfl;
+    s.fy = __fsub_rn(y, yfl); s.fz = __fsub_rn(z, zfl);
+    return s;
+}
+
+__device__ __forceinline__ float splat_weight(const SlabFrac &s, int dy, int dz)   // :86-87
+{
+    float wy = dy ? s.fy : __fsub_rn(1.0f, s.fy);
+    float wz = dz ? s.fz : __fsub_rn(1.0f, s.fz);
+    return __fmul_rn(wy, wz);
+}
+
+// Splat target j = 2*dy + dz of slab k for the calling lane (lane = 4*(k - k_base) + j).
+// Returns the linear voxel index, or -1 when the target is out of bounds, the slab does not
+// exist, or the voxel is owned by the previous slab.  `w` is the float32 weight summed over
+// the (at most two) slabs that write the voxel, added in the reference's order.
+//
+// Why at most two: offsets dy, dz always go to array axes 1 and 2 (:88-90) even when one of
+// them is the dominant axis, so slab x writes planes x and x+1 of that axis and only slabs
+// x and x+-1 can meet.  For the neighbour slab at x' = x + delta the same voxel is its target
+//   dom == 1:  dy' = dy - delta,          dz' = zf + dz - zf'
+//   dom == 2:  dy' = zf + dy - zf',       dz' = dz - delta          (and yf' == yf in both)
+// when dy', dz' are both in {0, 1}.  The earlier slab owns the voxel: out = (0 + w_k) + w_{k+1}.
+__device__ __forceinline__ int splat_target(const Grid &G, const Beam &b, const float *ys, const float *zs, int k,
+                                            int j, float &w, int &packed)
+{
+    w = 0.0f;
+    packed = 0;
+    if (k >= b.nslab) return -1;
+    const int dy = j >> 1, dz = j & 1;
+    const SlabFrac s = slab_frac(ys[k], zs[k]);
+    w = splat_weight(s, dy, dz);
+    const int x = b.x0 + k * b.step;
+    int i0, i1, i2;                                  // idx[dom]=x, idx[o0]=yf, idx[o1]=zf, then +dy, +dz on axes 1, 2
+    if (b.dom == 0) { i0 = x; i1 = s.yf + dy; i2 = s.zf + dz; }
+    else if (b.dom == 1) { i0 = s.yf; i1 = x + dy; i2 = s.zf + dz; }
+    else { i0 = s.yf; i1 = s.zf + dy; i2 = x + dz; }
+    if ((unsigned)i0 >= (unsigned)G.g0 || (unsigned)i1 >= (unsigned)G.g1 || (unsigned)i2 >= (unsigned)G.g2) return -1;
+    if (b.dom != 0) {
+        if (k > 0) {                                 // does the previous slab write this voxel?  then it owns it
+            const SlabFrac p = slab_frac(ys[k - 1], zs[k - 1]);
+            const int pdy = b.dom == 1 ? dy + b.step : s.zf + dy - p.zf;
+            const int pdz = b.dom == 1 ? s.zf + dz - p.zf : dz + b.step;
+            if (p.yf == s.yf && (unsigned)pdy <= 1u && (unsigned)pdz <= 1u) return -1;
         }
-        const bool have = lane < lim;
-        float yf = floorf(yc), zf = floorf(zc);                        // :76-82
-        float fy = __fsub_rn(yc, yf), fz = __fsub_rn(zc, zf);
-        float gy1 = __fsub_rn(1.0f, fy), gz1 = __fsub_rn(1.0f, fz);
-        int x = b.x0 + (c * kWarp + lane) * b.step;
-        int iy = (int)yf, iz = (int)zf;
-        int i0, i1, i2;                                                // idx[dom]=x, idx[o0]=iy, idx[o1]=iz
-        if (b.dom == 0) { i0 = x; i1 = iy; i2 = iz; }
-        else if (b.dom == 1) { i0 = iy; i1 = x; i2 = iz; }
-        else { i0 = iy; i1 = iz; i2 = x; }
-#pragma unroll
-        for (int j = 0; j < 4; j++) {                                  // :84-96
-            const int dy = j >> 1, dz = j & 1;
-            float wy = dy ? fy : gy1;
-            float wz = dz ? fz : gz1;
-            int t1 = i1 + dy, t2 = i2 + dz;                            // :88-90 offsets on axes 1, 2
-            bool in = have && i0 >= 0 && i0 < G.g0 && t1 >= 0 && t1 < G.g1 && t2 >= 0 && t2 < G.g2;
-            lin[c][j] = in ? (i0 * G.g1 + t1) * G.g2 + t2 : -1;
-            w[c][j] = __fmul_rn(wy, wz);
+        if (k + 1 < b.nslab) {                       // does the next slab write it too?  add its weight
+            const SlabFrac n = slab_frac(ys[k + 1], zs[k + 1]);
+            const int ndy = b.dom == 1 ? dy - b.step : s.zf + dy - n.zf;
+            const int ndz = b.dom == 1 ? s.zf + dz - n.zf : dz - b.step;
+            if (n.yf == s.yf && (unsigned)ndy <= 1u && (unsigned)ndz <= 1u) w = __fadd_rn(w, splat_weight(n, ndy, ndz));
         }
     }
-    // Merge: a voxel can be written by slab k and slab k+1 only (axis quirk).
-    // The earlier slab keeps the voxel and adds the later slab's weight; the later one drops it.
-    bool drop[kMaxChunks][4];
-    float add[kMaxChunks][4];
-#pragma unroll
-    for (int c = 0; c < kMaxChunks; c++) {
-        int nl[4], pl[4];
-        float nw[4];
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            nl[j] = __shfl_down_sync(kFull, lin[c][j], 1);
-            nw[j] = __shfl_down_sync(kFull, w[c][j], 1);
-            pl[j] = __shfl_up_sync(kFull, lin[c][j], 1);
-            if (c + 1 < kMaxChunks) {
-                int tl = __shfl_sync(kFull, lin[c + 1 < kMaxChunks ? c + 1 : c][j], 0);
-                float tw = __shfl_sync(kFull, w[c + 1 < kMaxChunks ? c + 1 : c][j], 0);
-                if (lane == kWarp - 1) { nl[j] = tl; nw[j] = tw; }
-            } else if (lane == kWarp - 1) {
-                nl[j] = -1;
-            }
-            if (c > 0) {
-                int tl = __shfl_sync(kFull, lin[c > 0 ? c - 1 : c][j], kWarp - 1);
-                if (lane == 0) pl[j] = tl;
-            } else if (lane == 0) {
-                pl[j] = -1;
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            drop[c][j] = false;
-            add[c][j] = 0.0f;
-            const int me = lin[c][j];
-            bool has_next = false;
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-                if (me >= 0 && nl[q] == me) { add[c][j] = nw[q]; has_next = true; }
-                if (me >= 0 && pl[q] == me) drop[c][j] = true;
-            }
-            if (has_next) w[c][j] = __fadd_rn(w[c][j], add[c][j]);     // (0 + w_k) + w_{k+1}
-        }
-    }
-#pragma unroll
-    for (int c = 0; c < kMaxChunks; c++)
-#pragma unroll
-        for (int j = 0; j < 4; j++)
-            if (drop[c][j]) lin[c][j] = -1;
+    packed = i0 | (i1 << 8) | (i2 << 16);
+    return (i0 * G.g1 + i1) * G.g2 + i2;
 }
 
 // ---------------------------------------------------------------------------------

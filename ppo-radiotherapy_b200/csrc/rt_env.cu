@@ -115,13 +115,9 @@ __device__ __forceinline__ bool lung_bit(const Tables &T, int lin)
     return (__ldg(T.lungs_bits + (lin >> 5)) >> (lin & 31)) & 1u;
 }
 
-__device__ __forceinline__ bool tumour_bit(const Tables &T, const Tumour &tm, int tid, int lin)
+// membership of voxel (i, j, k) in the env's tumour: bbox test, then the bbox-local bitmask
+__device__ __forceinline__ bool tumour_bit(const Tables &T, const Tumour &tm, int tid, int i, int j, int k)
 {
-    if (lin < tm.lin_lo || lin > tm.lin_hi) return false;     // cheap reject: almost every voxel of a beam
-    int k = lin % T.G.g2;
-    int r = lin / T.G.g2;
-    int j = r % T.G.g1;
-    int i = r / T.G.g1;
     int li = i - tm.lo[0], lj = j - tm.lo[1], lk = k - tm.lo[2];
     if ((unsigned)li >= (unsigned)tm.dim[0] || (unsigned)lj >= (unsigned)tm.dim[1] ||
         (unsigned)lk >= (unsigned)tm.dim[2])
@@ -197,18 +193,67 @@ __global__ void __launch_bounds__(256) rt_reset_kernel(Tables T, Schedule S, Env
 }
 
 // ---------------------------------------------------------------------------------
-// The step.  One warp per env.
-__global__ void __launch_bounds__(256) rt_step_kernel(Tables T, Schedule S, EnvRec *rec, float *dose,
-                                                      uint32_t *valid, double *beams, int n_envs,
-                                                      const float *__restrict__ actions, StepOut out)
+// The step.  A block advances kEnvsPerBlock envs in two phases:
+//   A  one THREAD per env: float64 pose update, beam clip/setup, the serial float32 slab walk
+//      (left in shared memory).  Scalar, latency-bound work — done once, not once per lane.
+//   B  one WARP per env, lane = (slab, splat target): dose read-modify-write on the sparse set
+//      of voxels the beam hits, tumour/lung accumulators, warp-shuffle reductions, reward,
+//      termination, observation, episode statistics, NEXT_STEP autoreset.
+constexpr int kEnvsPerBlock = 8;
+constexpr int kStepThreads = kEnvsPerBlock * kWarp;
+
+struct EnvWork {
+    Beam beam;
+    int reset;               // this call is the env's autoreset call
+    int pad_;
+    double pos[3], dir[3];   // pose after the update
+    double os_t[3], os_r;    // overshoots (environment.py:237-240)
+    float ys[kMaxSlabs], zs[kMaxSlabs];
+};
+
+__global__ void __launch_bounds__(kStepThreads, 4) rt_step_kernel(Tables T, Schedule S, EnvRec *rec, float *dose,
+                                                                  uint32_t *valid, double *beams, int n_envs,
+                                                                  const float *__restrict__ actions, StepOut out)
 {
-    const int env = (blockIdx.x * blockDim.x + threadIdx.x) / kWarp;
-    const int lane = threadIdx.x & (kWarp - 1);
-    if (env >= n_envs) return;
+    __shared__ EnvWork work[kEnvsPerBlock];
     const Grid &G = T.G;
+    const int warp = threadIdx.x / kWarp;
+    const int lane = threadIdx.x & (kWarp - 1);
+    const int env0 = blockIdx.x * kEnvsPerBlock;
+
+    // ---- phase A ------------------------------------------------------------------------
+    if (threadIdx.x < kEnvsPerBlock && env0 + threadIdx.x < n_envs) {
+        const int e = env0 + threadIdx.x;
+        EnvWork &wk = work[threadIdx.x];
+        const EnvRec *my = rec + e;
+        wk.reset = my->needs_reset;
+        wk.beam.nslab = 0;
+        if (!wk.reset) {
+            Pose s;
+            float a[6];
+#pragma unroll
+            for (int i = 0; i < 3; i++) { s.p[i] = my->pos[i]; s.d[i] = my->dir[i]; }
+#pragma unroll
+            for (int i = 0; i < 6; i++) a[i] = __ldg(actions + (size_t)e * RT_ACTION_SIZE + i);
+            double os_t[3], os_r;
+            pose_update(G, a, s, os_t, os_r);                               // environment.py:196-210
+            const Beam b = beam_setup(G, s.p, s.d);                         // draw_line.py:19-66
+            beam_walk(b, wk.ys, wk.zs);                                     // draw_line.py:98-99
+            wk.beam = b;
+#pragma unroll
+            for (int i = 0; i < 3; i++) { wk.pos[i] = s.p[i]; wk.dir[i] = s.d[i]; wk.os_t[i] = os_t[i]; }
+            wk.os_r = os_r;
+        }
+    }
+    __syncthreads();
+
+    // ---- phase B ------------------------------------------------------------------------
+    const int env = env0 + warp;
+    if (env >= n_envs) return;
+    const EnvWork &wk = work[warp];
     EnvRec *my = rec + env;
 
-    if (my->needs_reset) {
+    if (wk.reset) {
         // gymnasium 1.0.0 NEXT_STEP: the call after a terminal step resets and reports reward 0.
         const int episode = my->episode + 1;
         __syncwarp();
@@ -219,114 +264,91 @@ __global__ void __launch_bounds__(256) rt_step_kernel(Tables T, Schedule S, EnvR
             if (out.terminated) out.terminated[env] = 0;
             if (out.truncated) out.truncated[env] = 0;
         }
-        if (out.info && lane < RT_INFO_SIZE) {
-            double v = 0.0;
-            if (lane == RT_INFO_TUMOUR_ID) v = (double)new_tid;
-            out.info[(size_t)env * RT_INFO_SIZE + lane] = v;
-        }
+        if (out.info && lane < RT_INFO_SIZE)
+            out.info[(size_t)env * RT_INFO_SIZE + lane] = lane == RT_INFO_TUMOUR_ID ? (double)new_tid : 0.0;
         return;
     }
 
-    // ---- state + action ------------------------------------------------------------
-    Pose s;
-#pragma unroll
-    for (int i = 0; i < 3; i++) { s.p[i] = my->pos[i]; s.d[i] = my->dir[i]; }
-    double tumour_dose = my->tumour_dose, lung_dose = my->lung_dose, ep_return = my->ep_return;
-    const int t = my->t + 1;                                                // environment.py:194
+    const Beam b = wk.beam;
     const int tid = my->tumour_id;
-    int lung_count = my->lung_count;
-    const int episode = my->episode;
-    const int n_beams = my->n_beams;
-    float a[6];
-#pragma unroll
-    for (int i = 0; i < 6; i++) a[i] = __ldg(actions + (size_t)env * RT_ACTION_SIZE + i);
     const Tumour tm = T.tumours[tid];
+    const double px = wk.pos[0], py = wk.pos[1], pz = wk.pos[2];
 
-    // ---- pose (environment.py:196-210) -------------------------------------------------
-    double os_t[3], os_r;
-    pose_update(G, a, s, os_t, os_r);
-
-    // ---- beam (environment.py:212 -> draw_line.py) ------------------------------------
-    const Beam b = beam_setup(G, s.p, s.d);
-    int lin[kMaxChunks][4];
-    float w[kMaxChunks][4];
-    beam_trace(G, b, lane, lin, w);
-
-    // ---- distance_to_tumour_reward (environment.py:150-162), overlaps the dose traffic ----
+    // distance_to_tumour_reward (environment.py:150-162): min over the tumour's voxel list
     double best = CUDART_INF;
     for (int k = lane; k < tm.n_vox; k += kWarp) {
         const uint32_t pk = __ldg(T.vox_xyz + tm.vox_off + k);
-        const double dx = __dsub_rn((double)(pk & 255u), s.p[0]);
-        const double dy = __dsub_rn((double)((pk >> 8) & 255u), s.p[1]);
-        const double dz = __dsub_rn((double)(pk >> 16), s.p[2]);
+        const double dx = __dsub_rn((double)(pk & 255u), px);
+        const double dy = __dsub_rn((double)((pk >> 8) & 255u), py);
+        const double dz = __dsub_rn((double)(pk >> 16), pz);
         double d2 = __dmul_rn(dx, dx);
         d2 = __dadd_rn(d2, __dmul_rn(dy, dy));
         d2 = __dadd_rn(d2, __dmul_rn(dz, dz));
         best = fmin(best, d2);
     }
 
-    // ---- dose deposition (environment.py:107-110), sparse ---------------------------------
-    // dose' = clip(dose + beam*0.1, 0, 1) only changes the voxels the beam hits.
+    // dose deposition (environment.py:107-110): dose' = clip(dose + beam*0.1, 0, 1) changes only
+    // the voxels the beam hits.
     float *vol = dose + (size_t)env * G.vstride;
     uint32_t *vbits = valid + (size_t)env * G.vwords;
-    bool fresh[kMaxChunks][4];
+    double d_tum = 0.0, d_lung = 0.0;
+    int d_cnt = 0;
+    for (int kbase = 0; kbase < b.nslab; kbase += kRounds * kSlabsPerRound) {
+        int lin[kRounds], pk[kRounds];
+        float w[kRounds], old[kRounds];
+        bool fresh[kRounds];
 #pragma unroll
-    for (int c = 0; c < kMaxChunks; c++)
+        for (int r = 0; r < kRounds; r++)
+            lin[r] = splat_target(G, b, wk.ys, wk.zs, kbase + r * kSlabsPerRound + (lane >> 2), lane & 3, w[r], pk[r]);
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            fresh[c][j] = false;
-            if (lin[c][j] >= 0) {
-                const int sec = lin[c][j] >> 3;
-                fresh[c][j] = !((vbits[sec >> 5] >> (sec & 31)) & 1u);
+        for (int r = 0; r < kRounds; r++) {
+            fresh[r] = false;
+            if (lin[r] >= 0) {
+                const int sec = lin[r] >> 3;
+                fresh[r] = !((vbits[sec >> 5] >> (sec & 31)) & 1u);
             }
         }
-    __syncwarp();   // every lane has sampled the bitmap before any lane updates it
-    // first write to a sector this episode: materialise it as zeros and mark it valid
+        __syncwarp();   // every lane has sampled the bitmap before any lane updates it
+        // first write to a sector this episode: materialise it as zeros and mark it valid
 #pragma unroll
-    for (int c = 0; c < kMaxChunks; c++)
-#pragma unroll
-        for (int j = 0; j < 4; j++)
-            if (fresh[c][j]) {
-                const int sec = lin[c][j] >> 3;
+        for (int r = 0; r < kRounds; r++)
+            if (fresh[r]) {
+                const int sec = lin[r] >> 3;
                 float4 *sp = reinterpret_cast<float4 *>(vol + (sec << 3));
                 sp[0] = make_float4(0.f, 0.f, 0.f, 0.f);
                 sp[1] = make_float4(0.f, 0.f, 0.f, 0.f);
                 atomicOr(vbits + (sec >> 5), 1u << (sec & 31));
             }
-    __syncwarp();
-    float old[kMaxChunks][4];
+        __syncwarp();
 #pragma unroll
-    for (int c = 0; c < kMaxChunks; c++)
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            old[c][j] = 0.0f;
-            if (lin[c][j] >= 0 && !fresh[c][j]) old[c][j] = vol[lin[c][j]];
+        for (int r = 0; r < kRounds; r++) {
+            old[r] = 0.0f;
+            if (lin[r] >= 0 && !fresh[r]) old[r] = vol[lin[r]];
         }
-    double d_tum = 0.0, d_lung = 0.0;
-    int d_cnt = 0;
 #pragma unroll
-    for (int c = 0; c < kMaxChunks; c++)
-#pragma unroll
-        for (int j = 0; j < 4; j++)
-            if (lin[c][j] >= 0) {
-                const float o = old[c][j];
-                float nd = __fadd_rn(o, __fmul_rn(w[c][j], 0.100000001490116119f));   // beam * BEAM_DOSE, then +
-                nd = fminf(fmaxf(nd, 0.0f), 1.0f);                                     // np.clip(., 0, 1)
-                vol[lin[c][j]] = nd;
-                const bool in_t = tumour_bit(T, tm, tid, lin[c][j]);
-                const bool in_l = lung_bit(T, lin[c][j]);
+        for (int r = 0; r < kRounds; r++)
+            if (lin[r] >= 0) {
+                const float o = old[r];
+                float nd = __fadd_rn(o, __fmul_rn(w[r], 0.100000001490116119f));   // beam * BEAM_DOSE, then +
+                nd = fminf(fmaxf(nd, 0.0f), 1.0f);                                  // np.clip(., 0, 1)
+                vol[lin[r]] = nd;
+                const bool in_t = tumour_bit(T, tm, tid, pk[r] & 255, (pk[r] >> 8) & 255, pk[r] >> 16);
+                const bool in_l = lung_bit(T, lin[r]);
                 const double delta = (double)nd - (double)o;
                 if (in_t) d_tum += delta;
                 if (in_l) d_lung += delta;
                 // lungs_mask = lungs*(1-tumours); dose is monotone, so the count only grows (environment.py:174-177)
                 if (in_l && !in_t && !(o > 0.200000002980232239f) && nd > 0.200000002980232239f) d_cnt++;
             }
-    tumour_dose += warp_sum(d_tum);
-    lung_dose += warp_sum(d_lung);
-    lung_count += warp_sum(d_cnt);
+        __syncwarp();
+    }
+    const double tumour_dose = my->tumour_dose + warp_sum(d_tum);
+    const double lung_dose = my->lung_dose + warp_sum(d_lung);
+    const int lung_count = my->lung_count + warp_sum(d_cnt);
     best = warp_min(best);
 
-    // ---- rewards, termination (environment.py:158-191, 214-220) --------------------------
+    // rewards, termination (environment.py:158-191, 214-220)
+    const int t = my->t + 1;                                                     // environment.py:194
     const float tsum_f32 = (float)tumour_dose;                                   // np.sum(dose*tumours) float32
     const float ratio = __fdiv_rn(tsum_f32, tm.tumour_sum);
     const float r_tumour = __fmul_rn(ratio, 10.0f);
@@ -335,28 +357,25 @@ __global__ void __launch_bounds__(256) rt_step_kernel(Tables T, Schedule S, EnvR
     const double r_dist = __dmul_rn(__ddiv_rn(sqrt(best), gnorm), -1.0);
     const double reward = __dadd_rn(__dadd_rn((double)r_tumour, r_lung), r_dist);
     const bool done = (ratio >= 0.899999976158142090f) || (t >= RT_MAX_TIME_STEPS);
-    ep_return += reward;
+    const double ep_return = my->ep_return + reward;
+    const int n_beams = my->n_beams;
+    __syncwarp();   // all lanes have read the record before lane 0 rewrites it
 
-    // ---- write back --------------------------------------------------------------------
     if (lane == 0) {
-        EnvRec r;
-        r.pos[0] = s.p[0]; r.pos[1] = s.p[1]; r.pos[2] = s.p[2];
-        r.dir[0] = s.d[0]; r.dir[1] = s.d[1]; r.dir[2] = s.d[2];
-        r.tumour_dose = tumour_dose; r.lung_dose = lung_dose; r.ep_return = ep_return;
-        r.t = t; r.tumour_id = tid; r.lung_count = lung_count; r.episode = episode;
-        r.needs_reset = done ? 1 : 0;
-        r.n_beams = n_beams + 1;
-#pragma unroll
-        for (int i = 0; i < 8; i++) r.pad[i] = 0;
-        *my = r;
+        my->pos[0] = px; my->pos[1] = py; my->pos[2] = pz;
+        my->dir[0] = wk.dir[0]; my->dir[1] = wk.dir[1]; my->dir[2] = wk.dir[2];
+        my->tumour_dose = tumour_dose; my->lung_dose = lung_dose; my->ep_return = ep_return;
+        my->t = t; my->lung_count = lung_count;
+        my->needs_reset = done ? 1 : 0;
+        my->n_beams = n_beams + 1;
         if (out.reward) out.reward[env] = reward;
         if (out.reward_f32) out.reward_f32[env] = (float)reward;
         if (out.terminated) out.terminated[env] = done ? 1 : 0;
         if (out.truncated) out.truncated[env] = 0;
     }
     if (beams && lane < 6 && n_beams < RT_MAX_TIME_STEPS)                       // environment.py:110
-        beams[((size_t)env * RT_MAX_TIME_STEPS + n_beams) * 6 + lane] = lane < 3 ? s.p[lane] : s.d[lane - 3];
-    write_obs(T, tm, s.p, s.d, out.obs + (size_t)env * RT_OBS_SIZE, lane);
+        beams[((size_t)env * RT_MAX_TIME_STEPS + n_beams) * 6 + lane] = lane < 3 ? wk.pos[lane] : wk.dir[lane - 3];
+    write_obs(T, tm, wk.pos, wk.dir, out.obs + (size_t)env * RT_OBS_SIZE, lane);
     if (out.info && lane < RT_INFO_SIZE) {
         double v;
         switch (lane) {
@@ -366,10 +385,10 @@ __global__ void __launch_bounds__(256) rt_step_kernel(Tables T, Schedule S, EnvR
         case RT_INFO_REWARD_DISTANCE: v = r_dist; break;
         case RT_INFO_DOSE_TUMOUR: v = (double)tsum_f32; break;
         case RT_INFO_DOSE_LUNG: v = (double)(float)lung_dose; break;
-        case RT_INFO_OVERSHOOT_T0: v = os_t[0]; break;
-        case RT_INFO_OVERSHOOT_T0 + 1: v = os_t[1]; break;
-        case RT_INFO_OVERSHOOT_T0 + 2: v = os_t[2]; break;
-        case RT_INFO_OVERSHOOT_R: v = os_r; break;
+        case RT_INFO_OVERSHOOT_T0: v = wk.os_t[0]; break;
+        case RT_INFO_OVERSHOOT_T0 + 1: v = wk.os_t[1]; break;
+        case RT_INFO_OVERSHOOT_T0 + 2: v = wk.os_t[2]; break;
+        case RT_INFO_OVERSHOOT_R: v = wk.os_r; break;
         case RT_INFO_EPISODE_RETURN: v = ep_return; break;
         case RT_INFO_EPISODE_LENGTH: v = (double)t; break;
         case RT_INFO_LUNG_COUNT: v = (double)lung_count; break;
@@ -383,46 +402,54 @@ __global__ void __launch_bounds__(256) rt_step_kernel(Tables T, Schedule S, EnvR
 
 // ---------------------------------------------------------------------------------
 // Stateless geometry kernels (parity surface): one warp per ray / one thread per pose.
+struct RayWork {
+    Beam beam;
+    float ys[kMaxSlabs], zs[kMaxSlabs];
+};
+
+// lane 0 of the warp clips the ray and replays the serial walk; returns the beam to every lane
+__device__ __forceinline__ Beam ray_prepare(const Grid &G, const double *pos3, const double *dir3, int lane,
+                                            RayWork &rw)
+{
+    if (lane == 0) {
+        const double p[3] = {pos3[0], pos3[1], pos3[2]};
+        const double d[3] = {dir3[0], dir3[1], dir3[2]};
+        const Beam b = beam_setup(G, p, d);
+        beam_walk(b, rw.ys, rw.zs);
+        rw.beam = b;
+    }
+    __syncwarp();
+    return rw.beam;
+}
+
 __global__ void __launch_bounds__(256) rt_beam_kernel(Grid G, const double *__restrict__ pos,
                                                       const double *__restrict__ dir, int m, int cap,
                                                       int32_t *idx, float *wout, int32_t *count)
 {
+    __shared__ RayWork work[8];
     const int ray = (blockIdx.x * blockDim.x + threadIdx.x) / kWarp;
     const int lane = threadIdx.x & (kWarp - 1);
     if (ray >= m) return;
-    const double p[3] = {pos[3 * ray], pos[3 * ray + 1], pos[3 * ray + 2]};
-    const double d[3] = {dir[3 * ray], dir[3 * ray + 1], dir[3 * ray + 2]};
-    const Beam b = beam_setup(G, p, d);
+    RayWork &rw = work[threadIdx.x / kWarp];
+    const Beam b = ray_prepare(G, pos + 3 * (size_t)ray, dir + 3 * (size_t)ray, lane, rw);
     if (b.nslab < 0) {
         if (lane == 0) count[ray] = -1;
         return;
     }
-    int lin[kMaxChunks][4];
-    float w[kMaxChunks][4];
-    beam_trace(G, b, lane, lin, w);
     int base = 0;
-#pragma unroll
-    for (int c = 0; c < kMaxChunks; c++) {
-        int mine = 0;
-#pragma unroll
-        for (int j = 0; j < 4; j++) mine += lin[c][j] >= 0;
-        int incl = mine;                                   // warp inclusive scan
-#pragma unroll
-        for (int o = 1; o < kWarp; o <<= 1) {
-            int v = __shfl_up_sync(kFull, incl, o);
-            if (lane >= o) incl += v;
-        }
-        int at = base + incl - mine;
-#pragma unroll
-        for (int j = 0; j < 4; j++)
-            if (lin[c][j] >= 0) {
-                if (at < cap) {
-                    idx[(size_t)ray * cap + at] = lin[c][j];
-                    wout[(size_t)ray * cap + at] = w[c][j];
-                }
-                at++;
+    for (int kbase = 0; kbase < b.nslab; kbase += kSlabsPerRound) {
+        float w;
+        int pk;
+        const int lin = splat_target(G, b, rw.ys, rw.zs, kbase + (lane >> 2), lane & 3, w, pk);
+        const unsigned hit = __ballot_sync(kFull, lin >= 0);
+        if (lin >= 0) {
+            const int at = base + __popc(hit & ((1u << lane) - 1u));
+            if (at < cap) {
+                idx[(size_t)ray * cap + at] = lin;
+                wout[(size_t)ray * cap + at] = w;
             }
-        base += __shfl_sync(kFull, incl, kWarp - 1);
+        }
+        base += __popc(hit);
     }
     if (lane == 0) count[ray] = base < cap ? base : cap;
 }
@@ -431,23 +458,20 @@ __global__ void __launch_bounds__(256) rt_beam_dense_kernel(Grid G, const double
                                                             const double *__restrict__ dir, int m, float *out,
                                                             int32_t *status)
 {
+    __shared__ RayWork work[8];
     const int ray = (blockIdx.x * blockDim.x + threadIdx.x) / kWarp;
     const int lane = threadIdx.x & (kWarp - 1);
     if (ray >= m) return;
-    const double p[3] = {pos[3 * ray], pos[3 * ray + 1], pos[3 * ray + 2]};
-    const double d[3] = {dir[3 * ray], dir[3 * ray + 1], dir[3 * ray + 2]};
-    const Beam b = beam_setup(G, p, d);
+    RayWork &rw = work[threadIdx.x / kWarp];
+    const Beam b = ray_prepare(G, pos + 3 * (size_t)ray, dir + 3 * (size_t)ray, lane, rw);
     if (lane == 0 && status) status[ray] = b.nslab < 0 ? -1 : 0;
-    if (b.nslab <= 0) return;
-    int lin[kMaxChunks][4];
-    float w[kMaxChunks][4];
-    beam_trace(G, b, lane, lin, w);
     float *vol = out + (size_t)ray * G.nvox;
-#pragma unroll
-    for (int c = 0; c < kMaxChunks; c++)
-#pragma unroll
-        for (int j = 0; j < 4; j++)
-            if (lin[c][j] >= 0) vol[lin[c][j]] = w[c][j];
+    for (int kbase = 0; kbase < b.nslab; kbase += kSlabsPerRound) {
+        float w;
+        int pk;
+        const int lin = splat_target(G, b, rw.ys, rw.zs, kbase + (lane >> 2), lane & 3, w, pk);
+        if (lin >= 0) vol[lin] = w;
+    }
 }
 
 __global__ void __launch_bounds__(128) rt_pose_kernel(Grid G, const double *__restrict__ pos,
@@ -557,6 +581,7 @@ __global__ void __launch_bounds__(kVolThreads) rt_volumes_kernel(Tables T, const
                                                                  const uint32_t *valid, int first, float *out)
 {
     extern __shared__ uint32_t smem[];
+    __shared__ RayWork view[2];
     const Grid &G = T.G;
     const int nwords = (G.nvox + 31) / 32;
     uint32_t *hit_bits = smem;                                  // [nwords] voxel hit by a view beam
@@ -575,21 +600,17 @@ __global__ void __launch_bounds__(kVolThreads) rt_volumes_kernel(Tables T, const
     if (warp < 2) {
         // environment.py:246-249: beam along the current direction, and along (1,0,0)
         const double horiz[3] = {1.0, 0.0, 0.0};
-        const Beam b = beam_setup(G, r.pos, warp == 0 ? r.dir : horiz);
-        if (b.nslab > 0) {
-            int lin[kMaxChunks][4];
-            float w[kMaxChunks][4];
-            beam_trace(G, b, lane, lin, w);
-#pragma unroll
-            for (int c = 0; c < kMaxChunks; c++)
-#pragma unroll
-                for (int j = 0; j < 4; j++)
-                    if (lin[c][j] >= 0) {
-                        const int at = atomicAdd(&hit_n, 1);
-                        hit_idx[at] = lin[c][j];
-                        hit_w[at] = w[c][j];
-                        atomicOr(hit_bits + (lin[c][j] >> 5), 1u << (lin[c][j] & 31));
-                    }
+        const Beam b = ray_prepare(G, r.pos, warp == 0 ? r.dir : horiz, lane, view[warp]);
+        for (int kbase = 0; kbase < b.nslab; kbase += kSlabsPerRound) {
+            float w;
+            int pk;
+            const int lin = splat_target(G, b, view[warp].ys, view[warp].zs, kbase + (lane >> 2), lane & 3, w, pk);
+            if (lin >= 0) {
+                const int at = atomicAdd(&hit_n, 1);
+                hit_idx[at] = lin;
+                hit_w[at] = w;
+                atomicOr(hit_bits + (lin >> 5), 1u << (lin & 31));
+            }
         }
     }
     __syncthreads();
@@ -614,7 +635,8 @@ __global__ void __launch_bounds__(kVolThreads) rt_volumes_kernel(Tables T, const
             view = hb ? __fadd_rn(wa, wb) : wa;
         }
         o[v] = lung_bit(T, v) ? 1.0f : 0.0f;
-        o[(size_t)G.nvox + v] = tumour_bit(T, tm, r.tumour_id, v) ? 1.0f : 0.0f;
+        const int vk = v % G.g2, vr = v / G.g2;
+        o[(size_t)G.nvox + v] = tumour_bit(T, tm, r.tumour_id, vr / G.g1, vr % G.g1, vk) ? 1.0f : 0.0f;
         o[(size_t)2 * G.nvox + v] = fminf(fmaxf(dv, 0.0f), 1.0f);
         o[(size_t)3 * G.nvox + v] = fminf(fmaxf(view, 0.0f), 1.0f);
     }
@@ -695,7 +717,7 @@ int check_grid(const int32_t g[3])
         if (g[i] < 2 || g[i] > 255) return fail(RT_ERR_INVALID, "grid extents must be in [2, 255]");
     int mx = g[0] > g[1] ? g[0] : g[1];
     mx = mx > g[2] ? mx : g[2];
-    if (mx + 1 > kMaxChunks * kWarp) return fail(RT_ERR_INVALID, "grid extent too large for the slab walk");
+    if (mx + 1 > kMaxSlabs) return fail(RT_ERR_INVALID, "grid extent too large for the slab walk");
     return RT_OK;
 }
 
@@ -887,7 +909,7 @@ int rt_step(rt_env *e, const float *actions_dev, float *obs_dev, double *reward_
     if (!e || !actions_dev || !obs_dev) return fail(RT_ERR_INVALID, "rt_step: NULL handle, actions or obs");
     RT_CUDA(cudaSetDevice(e->device));
     StepOut o{obs_dev, reward_dev, reward_f32_dev, terminated_dev, truncated_dev, info_dev};
-    rt_step_kernel<<<warps_grid(e->n, 256), 256, 0, (cudaStream_t)stream>>>(e->T, e->S, e->rec, e->dose, e->valid,
+    rt_step_kernel<<<(e->n + kEnvsPerBlock - 1) / kEnvsPerBlock, kStepThreads, 0, (cudaStream_t)stream>>>(e->T, e->S, e->rec, e->dose, e->valid,
                                                                            e->beams, e->n, actions_dev, o);
     RT_LAUNCH_CHECK("rt_step_kernel");
     return RT_OK;
@@ -1028,7 +1050,9 @@ int rt_beam_voxels(const int32_t grid[3], const double *pos_dev, const double *d
 {
     if (int rc = check_grid(grid)) return rc;
     if (!pos_dev || !dir_dev || !idx_dev || !w_dev || !count_dev) return fail(RT_ERR_INVALID, "rt_beam_voxels: NULL argument");
-    if (m < 0 || cap < RT_BEAM_CAP) return fail(RT_ERR_INVALID, "rt_beam_voxels: cap must be >= RT_BEAM_CAP");
+    int gmax = grid[0] > grid[1] ? grid[0] : grid[1];
+    gmax = gmax > grid[2] ? gmax : grid[2];
+    if (m < 0 || cap < 4 * (gmax + 1)) return fail(RT_ERR_INVALID, "rt_beam_voxels: cap must be >= 4 * (max(grid) + 1)");
     if (m == 0) return RT_OK;
     rt_beam_kernel<<<warps_grid(m, 256), 256, 0, (cudaStream_t)stream>>>(make_grid(grid), pos_dev, dir_dev, m, cap,
                                                                         idx_dev, w_dev, count_dev);

@@ -30,18 +30,19 @@ def _grid_arg(shape):
 def beam_voxels_batch(position: torch.Tensor, direction: torch.Tensor, grid=(67, 43, 70)):
     """Distinct voxels hit by m rays and their summed bilinear weights.
 
-    position, direction: float64 [m][3] CUDA tensors.  Returns (idx int32 [m][288],
-    weight float32 [m][288], count int32 [m]); count == -1 where the direction norm
+    position, direction: float64 [m][3] CUDA tensors.  Returns (idx int32 [m][cap],
+    weight float32 [m][cap], count int32 [m]) with cap = max(288, 4*(max(grid)+1)); count == -1 where the direction norm
     is below 1e-6 (the reference raises ValueError there)."""
     device = _require_cuda(position.device)
     pos = position.to(dtype=torch.float64).contiguous().reshape(-1, 3)
     dr = direction.to(device=device, dtype=torch.float64).contiguous().reshape(-1, 3)
     m = pos.shape[0]
-    idx = torch.zeros((m, nat.BEAM_CAP), dtype=torch.int32, device=device)
-    w = torch.zeros((m, nat.BEAM_CAP), dtype=torch.float32, device=device)
+    cap = max(nat.BEAM_CAP, 4 * (max(int(g) for g in grid) + 1))
+    idx = torch.zeros((m, cap), dtype=torch.int32, device=device)
+    w = torch.zeros((m, cap), dtype=torch.float32, device=device)
     count = torch.zeros(m, dtype=torch.int32, device=device)
     with torch.cuda.device(device):
-        nat.check(nat.lib().rt_beam_voxels(_grid_arg(grid), _ptr(pos), _ptr(dr), m, nat.BEAM_CAP, _ptr(idx),
+        nat.check(nat.lib().rt_beam_voxels(_grid_arg(grid), _ptr(pos), _ptr(dr), m, cap, _ptr(idx),
                                            _ptr(w), _ptr(count), _stream(device)), "rt_beam_voxels")
     return idx, w, count
 

@@ -130,15 +130,16 @@ def test_transform_dropins_vs_oracle():
 
 # ------------------------------------------------------------------------------------ step
 def _compare_step(info, obs, reward, term, rec, done, mask=None):
-    m = slice(None) if mask is None else mask
-    np.testing.assert_allclose(obs[m], rec[m, 0:9].astype(np.float32), rtol=0, atol=OBS_ATOL)
-    np.testing.assert_allclose(reward[m], rec[m, 9], rtol=REW_RTOL, atol=REW_ATOL)
-    np.testing.assert_allclose(info[m, 0:4], rec[m, [9, 10, 11, 12]], rtol=REW_RTOL, atol=REW_ATOL)
-    np.testing.assert_allclose(info[m, 4:6], rec[m, 13:15], rtol=REW_RTOL, atol=REW_ATOL)
-    assert np.array_equal(info[m, nat.INFO_OVERSHOOT_T0:nat.INFO_OVERSHOOT_T0 + 3], rec[m, 15:18])
-    np.testing.assert_allclose(info[m, nat.INFO_OVERSHOOT_R], rec[m, 18], rtol=0, atol=1e-11)
-    assert np.array_equal(info[m, nat.INFO_LUNG_COUNT], rec[m, 19])
-    assert np.array_equal(term[m].astype(np.int8), done[m])
+    if mask is not None:
+        info, obs, reward, term, rec, done = info[mask], obs[mask], reward[mask], term[mask], rec[mask], done[mask]
+    np.testing.assert_allclose(obs, rec[:, 0:9].astype(np.float32), rtol=0, atol=OBS_ATOL)
+    np.testing.assert_allclose(reward, rec[:, 9], rtol=REW_RTOL, atol=REW_ATOL)
+    np.testing.assert_allclose(info[:, 0:4], rec[:, 9:13], rtol=REW_RTOL, atol=REW_ATOL)
+    np.testing.assert_allclose(info[:, 4:6], rec[:, 13:15], rtol=REW_RTOL, atol=REW_ATOL)
+    assert np.array_equal(info[:, nat.INFO_OVERSHOOT_T0:nat.INFO_OVERSHOOT_T0 + 3], rec[:, 15:18])
+    np.testing.assert_allclose(info[:, nat.INFO_OVERSHOOT_R], rec[:, 18], rtol=0, atol=1e-11)
+    assert np.array_equal(info[:, nat.INFO_LUNG_COUNT], rec[:, 19])
+    assert np.array_equal(term.astype(np.int8), done)
 
 
 def test_step_traces_golden(golden):
@@ -252,7 +253,7 @@ def test_rollout_vs_oracle_256_envs(kind):
         ep_ret += ref_out[t, :, 9]
         if t == 99:
             assert term.all()
-            np.testing.assert_allclose(infos["episode"]["r"], ep_ret, rtol=1e-9, atol=1e-9)
+            np.testing.assert_allclose(infos["episode"]["r"], ep_ret, rtol=REW_RTOL, atol=1e-5)
             assert (infos["episode"]["l"] == 100).all()
             ep_ret[:] = 0
     env.close()
@@ -261,7 +262,8 @@ def test_rollout_vs_oracle_256_envs(kind):
 def test_dose_volumes_bit_exact_vs_oracle():
     n, T = 16, 100
     rng = np.random.default_rng(4)
-    acts = rng.standard_normal((T, n, 6)).astype(np.float32) * 0.3     # slow motion: heavy re-irradiation, clipping at 1.0
+    acts = rng.standard_normal((T, n, 6)).astype(np.float32) * 0.3     # slow motion: heavy re-irradiation
+    acts[:, : n // 2] *= 0.02                                          # nearly parked beams: the dose clips at 1.0
     tids = (np.arange(n) * 61 + 5).astype(np.int32) % 1000
     env = rt.RadiotherapyVectorEnv(n, device=DEV, tumour_ids=tids[None, :])
     env.reset()
