@@ -184,6 +184,12 @@ RT_API int rt_gae(const float *rewards_dev, const float *values_dev, const float
 /* ---- instrumentation ----------------------------------------------------------------- */
 /* Number of kernels this library has launched since load (for bench.py's gpu_launches). */
 RT_API int64_t rt_launch_count(void);
+/* Developer aid: when stamps_dev (int64 [N][12], device) is non-NULL the step kernel records clock64()
+ * at its stage boundaries per env (0 producer start, 1 producer done, 2 env warp ready, 3 past the
+ * barrier, 4 splat + bitmap loads issued, 5 dose loads / zero fill done, 6 stores issued, 7 end;
+ * 8 state loaded, 9 pose updated, 10 beam set up — producer sub-stages).
+ * NULL (the default) switches it off. */
+RT_API int rt_set_stage_clock(rt_env *env, long long *stamps_dev);
 
 #ifdef __cplusplus
 }

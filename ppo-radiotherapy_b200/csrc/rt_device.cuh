@@ -115,6 +115,74 @@ __device__ __forceinline__ void apply_rotation(double (&d)[3], const double rv[3
     os_r = fmax(0.0, __dsub_rn(min_angle, ang));                    // :57
 }
 
+// The reference decides the clamp with  abs(angle_with_z_axis) < pi/4  where the angle comes from
+// np.arccos (transforms.py:29-35).  For min_angle = pi/4 that test is equivalent, for every double z in
+// [-1, 1], to |z| >= kClampZ = nextafter(cos(pi/4), 1) (established against glibc's acos by scanning the
+// neighbourhood of +-cos(pi/4) ulp by ulp, oracle/gen_golden.py poses cover both branches).  The step
+// uses the comparison, so acos leaves the critical path: the overshoot (transforms.py:57, info only) is
+// evaluated after the beam has been published.
+constexpr double kClampZ = 0x1.6a09e667f3bcep-1;
+
+__device__ __forceinline__ double overshoot_from_z(double zc)                   // transforms.py:29-33, 57
+{
+    double ang = acos(zc);
+    if (zc < 0.0) ang = __dsub_rn(kPi, ang);
+    return fmax(0.0, __dsub_rn(kMinAngle, ang));
+}
+
+// transforms.py:7-55 for min_angle = pi/4; returns the clipped z component (:29) for overshoot_from_z.
+__device__ __forceinline__ double rotate_env(double (&d)[3], const double rv[3])
+{
+    double n = dnorm3(d[0], d[1], d[2]);                            // transforms.py:23
+    double d0 = __ddiv_rn(d[0], n), d1 = __ddiv_rn(d[1], n), d2 = __ddiv_rn(d[2], n);
+
+    double angle = dnorm3(rv[0], rv[1], rv[2]);                     // from_rotvec
+    double scale, qw;
+    if (angle <= 1e-3) {
+        double a2 = __dmul_rn(angle, angle);
+        scale = __dadd_rn(__dsub_rn(0.5, __ddiv_rn(a2, 48.0)), __ddiv_rn(__dmul_rn(a2, a2), 3840.0));
+        qw = cos(__ddiv_rn(angle, 2.0));
+    } else {
+        double sh, ch;
+        sincos(__ddiv_rn(angle, 2.0), &sh, &ch);
+        scale = __ddiv_rn(sh, angle);
+        qw = ch;
+    }
+    double x = __dmul_rn(scale, rv[0]), y = __dmul_rn(scale, rv[1]), z = __dmul_rn(scale, rv[2]), w = qw;
+    double x2 = __dmul_rn(x, x), y2 = __dmul_rn(y, y), z2 = __dmul_rn(z, z), w2 = __dmul_rn(w, w); // as_matrix
+    double xy = __dmul_rn(x, y), zw = __dmul_rn(z, w), xz = __dmul_rn(x, z);
+    double yw = __dmul_rn(y, w), yz = __dmul_rn(y, z), xw = __dmul_rn(x, w);
+    double m00 = __dadd_rn(__dsub_rn(__dsub_rn(x2, y2), z2), w2);
+    double m01 = __dmul_rn(2.0, __dsub_rn(xy, zw));
+    double m02 = __dmul_rn(2.0, __dadd_rn(xz, yw));
+    double m10 = __dmul_rn(2.0, __dadd_rn(xy, zw));
+    double m11 = __dadd_rn(__dsub_rn(__dadd_rn(-x2, y2), z2), w2);
+    double m12 = __dmul_rn(2.0, __dsub_rn(yz, xw));
+    double m20 = __dmul_rn(2.0, __dsub_rn(xz, yw));
+    double m21 = __dmul_rn(2.0, __dadd_rn(yz, xw));
+    double m22 = __dadd_rn(__dadd_rn(__dsub_rn(-x2, y2), z2), w2);
+    double r0 = __dadd_rn(__dadd_rn(__dmul_rn(m00, d0), __dmul_rn(m01, d1)), __dmul_rn(m02, d2)); // apply
+    double r1 = __dadd_rn(__dadd_rn(__dmul_rn(m10, d0), __dmul_rn(m11, d1)), __dmul_rn(m12, d2));
+    double r2 = __dadd_rn(__dadd_rn(__dmul_rn(m20, d0), __dmul_rn(m21, d1)), __dmul_rn(m22, d2));
+    n = dnorm3(r0, r1, r2);                                         // transforms.py:27
+    r0 = __ddiv_rn(r0, n); r1 = __ddiv_rn(r1, n); r2 = __ddiv_rn(r2, n);
+
+    const double zc = fmin(fmax(r0, -1.0), 1.0);                    // :29
+    double n0 = r0, n1 = r1, n2 = r2;
+    if (fabs(zc) >= kClampZ) {                                      // :35-51, see kClampZ
+        double px = r1, py = r2;
+        double pn = sqrt(__dadd_rn(__dmul_rn(px, px), __dmul_rn(py, py)));
+        if (pn < 1e-8) { px = 1.0; py = 0.0; }
+        else { px = __ddiv_rn(px, pn); py = __ddiv_rn(py, pn); }
+        n0 = zc > 0.0 ? kCosMin : -kCosMin;                         // sign(z) * cos(min_angle)
+        n1 = __dmul_rn(px, kXYMag);
+        n2 = __dmul_rn(py, kXYMag);
+    }
+    n = dnorm3(n0, n1, n2);                                         // :55
+    d[0] = __ddiv_rn(n0, n); d[1] = __ddiv_rn(n1, n); d[2] = __ddiv_rn(n2, n);
+    return zc;
+}
+
 // environment.py:196-210: map the action, translate, rotate.
 __device__ __forceinline__ void pose_update(const Grid &G, const float a[6], Pose &s, double os_t[3], double &os_r)
 {
@@ -130,7 +198,15 @@ __device__ __forceinline__ void pose_update(const Grid &G, const float a[6], Pos
 #pragma unroll
     for (int i = 0; i < 3; i++)
         rv[i] = (double)__fmul_rn(__fmul_rn(clip1(a[3 + i]), 3.14159274101257324f), 0.5f);
-    apply_rotation(s.d, rv, kMinAngle, kCosMin, kXYMag, os_r);
+    os_r = overshoot_from_z(rotate_env(s.d, rv));
+}
+
+// map_rotation (environment.py:139-141): float32 * float32(pi) * float32(0.5)
+__device__ __forceinline__ void map_rotation(const float a[6], double rv[3])
+{
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+        rv[i] = (double)__fmul_rn(__fmul_rn(clip1(a[3 + i]), 3.14159274101257324f), 0.5f);
 }
 
 // ---------------------------------------------------------------------------------
@@ -217,14 +293,12 @@ __device__ __forceinline__ Beam beam_setup(const Grid &G, const double pd[3], co
 // draw_line.py:68-100.  The walk  intery += gradient*step  (:98-99) is a chain of float32
 // adds that is not re-associable, so ONE thread replays it and leaves intery/interz of
 // every slab in shared memory (ys[k], zs[k], k < nslab); the splat work is then spread
-// over a warp with lane = (slab, target).
+// over a warp, one slab per lane.
 constexpr int kMaxSlabs = 96;          // grid extents <= 95 (check_grid): max(G) + 1 slabs
-constexpr int kSlabsPerRound = 8;      // 8 slabs x 4 splat targets = 32 lanes
-constexpr int kRounds = 6;             // rounds staged together: 48 slabs per pass
-
 __device__ __forceinline__ void beam_walk(const Beam &b, float *ys, float *zs)
 {
     float y = b.y0, z = b.z0;
+#pragma unroll 8
     for (int k = 0; k < b.nslab; k++) {
         ys[k] = y;
         zs[k] = z;
@@ -254,48 +328,79 @@ __device__ __forceinline__ float splat_weight(const SlabFrac &s, int dy, int dz)
     return __fmul_rn(wy, wz);
 }
 
-// Splat target j = 2*dy + dz of slab k for the calling lane (lane = 4*(k - k_base) + j).
-// Returns the linear voxel index, or -1 when the target is out of bounds, the slab does not
-// exist, or the voxel is owned by the previous slab.  `w` is the float32 weight summed over
-// the (at most two) slabs that write the voxel, added in the reference's order.
+// The four splat targets of slab k (draw_line.py:84-96), one slab per lane.
 //
-// Why at most two: offsets dy, dz always go to array axes 1 and 2 (:88-90) even when one of
-// them is the dominant axis, so slab x writes planes x and x+1 of that axis and only slabs
-// x and x+-1 can meet.  For the neighbour slab at x' = x + delta the same voxel is its target
-//   dom == 1:  dy' = dy - delta,          dz' = zf + dz - zf'
-//   dom == 2:  dy' = zf + dy - zf',       dz' = dz - delta          (and yf' == yf in both)
-// when dy', dz' are both in {0, 1}.  The earlier slab owns the voxel: out = (0 + w_k) + w_{k+1}.
-__device__ __forceinline__ int splat_target(const Grid &G, const Beam &b, const float *ys, const float *zs, int k,
-                                            int j, float &w, int &packed)
+// On return lin[j] (j = 2*dy + dz) is the linear voxel index of target (idx[0], idx[1]+dy, idx[2]+dz),
+// or -1 when it is out of bounds, the slab does not exist, or the voxel is owned by the previous slab;
+// w[j] is the float32 weight summed over the (at most two) slabs that write the voxel, added in the
+// reference's order; (c0, c1, c2) are the coordinates of target 0.
+//
+// Why at most two: the offsets dy, dz always go to array axes 1 and 2 (:88-90) even when one of them
+// is the dominant axis, so slab x writes planes x and x+1 of that axis and only slabs x and x+-1 can
+// meet.  Call q the offset along the dominant axis and o the other one (dom 1: q = dy, o = dz; dom 2:
+// q = dz, o = dy; dom 0: no overlap).  With qp = (step > 0 ? 0 : 1) and D = zf - zf' for a neighbour
+// slab that has the same yf:
+//   targets with q == qp   are also written by the PREVIOUS slab (as q' = 1-qp, o' = D + o) when o' is 0 or 1
+//   targets with q == 1-qp are also written by the NEXT slab     (as q' = qp,   o' = D + o) when o' is 0 or 1
+// The earlier slab owns the voxel: out = (0 + w_k) + w_{k+1}.
+__device__ __forceinline__ void slab_targets(const Grid &G, const Beam &b, const float *ys, const float *zs, int k,
+                                             int (&lin)[4], float (&w)[4], int &c0, int &c1, int &c2)
 {
-    w = 0.0f;
-    packed = 0;
-    if (k >= b.nslab) return -1;
-    const int dy = j >> 1, dz = j & 1;
-    const SlabFrac s = slab_frac(ys[k], zs[k]);
-    w = splat_weight(s, dy, dz);
+    const bool have = k < b.nslab;
+    const int kk = have ? k : 0;
+    const SlabFrac s = slab_frac(ys[kk], zs[kk]);
+    const float wy[2] = {__fsub_rn(1.0f, s.fy), s.fy};                       // :86
+    const float wz[2] = {__fsub_rn(1.0f, s.fz), s.fz};                       // :87
     const int x = b.x0 + k * b.step;
-    int i0, i1, i2;                                  // idx[dom]=x, idx[o0]=yf, idx[o1]=zf, then +dy, +dz on axes 1, 2
-    if (b.dom == 0) { i0 = x; i1 = s.yf + dy; i2 = s.zf + dz; }
-    else if (b.dom == 1) { i0 = s.yf; i1 = x + dy; i2 = s.zf + dz; }
-    else { i0 = s.yf; i1 = s.zf + dy; i2 = x + dz; }
-    if ((unsigned)i0 >= (unsigned)G.g0 || (unsigned)i1 >= (unsigned)G.g1 || (unsigned)i2 >= (unsigned)G.g2) return -1;
-    if (b.dom != 0) {
-        if (k > 0) {                                 // does the previous slab write this voxel?  then it owns it
-            const SlabFrac p = slab_frac(ys[k - 1], zs[k - 1]);
-            const int pdy = b.dom == 1 ? dy + b.step : s.zf + dy - p.zf;
-            const int pdz = b.dom == 1 ? s.zf + dz - p.zf : dz + b.step;
-            if (p.yf == s.yf && (unsigned)pdy <= 1u && (unsigned)pdz <= 1u) return -1;
-        }
-        if (k + 1 < b.nslab) {                       // does the next slab write it too?  add its weight
-            const SlabFrac n = slab_frac(ys[k + 1], zs[k + 1]);
-            const int ndy = b.dom == 1 ? dy - b.step : s.zf + dy - n.zf;
-            const int ndz = b.dom == 1 ? s.zf + dz - n.zf : dz - b.step;
-            if (n.yf == s.yf && (unsigned)ndy <= 1u && (unsigned)ndz <= 1u) w = __fadd_rn(w, splat_weight(n, ndy, ndz));
+    if (b.dom == 0) { c0 = x; c1 = s.yf; c2 = s.zf; }                        // idx[dom]=x, idx[o0]=yf, idx[o1]=zf
+    else if (b.dom == 1) { c0 = s.yf; c1 = x; c2 = s.zf; }
+    else { c0 = s.yf; c1 = s.zf; c2 = x; }
+    const bool ok0 = have && (unsigned)c0 < (unsigned)G.g0;
+    const bool ok1[2] = {(unsigned)c1 < (unsigned)G.g1, (unsigned)(c1 + 1) < (unsigned)G.g1};
+    const bool ok2[2] = {(unsigned)c2 < (unsigned)G.g2, (unsigned)(c2 + 1) < (unsigned)G.g2};
+    const int base = (c0 * G.g1 + c1) * G.g2 + c2;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int dy = j >> 1, dz = j & 1;
+        w[j] = __fmul_rn(wy[dy], wz[dz]);
+        lin[j] = (ok0 && ok1[dy] && ok2[dz]) ? base + dy * G.g2 + dz : -1;
+    }
+    if (b.dom == 0 || !have) return;
+    const int qp = b.step > 0 ? 0 : 1;
+    // previous slab: it owns the voxels both write
+    if (k > 0) {
+        const float py = ys[k - 1], pz = zs[k - 1];
+        const int D = s.zf - (int)floorf(pz);
+        if ((int)floorf(py) == s.yf) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int dy = j >> 1, dz = j & 1;
+                const int q = b.dom == 1 ? dy : dz, o = b.dom == 1 ? dz : dy;
+                if (q == qp && (unsigned)(D + o) <= 1u) lin[j] = -1;
+            }
         }
     }
-    packed = i0 | (i1 << 8) | (i2 << 16);
-    return (i0 * G.g1 + i1) * G.g2 + i2;
+    // next slab: add its weight for the voxels both write
+    if (k + 1 < b.nslab) {
+        const SlabFrac n = slab_frac(ys[k + 1], zs[k + 1]);
+        const int D = s.zf - n.zf;
+        if (n.yf == s.yf) {
+            const float ny[2] = {__fsub_rn(1.0f, n.fy), n.fy};
+            const float nz[2] = {__fsub_rn(1.0f, n.fz), n.fz};
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int dy = j >> 1, dz = j & 1;
+                const int q = b.dom == 1 ? dy : dz, o = b.dom == 1 ? dz : dy;
+                const int o2 = D + o;
+                if (q == 1 - qp && (unsigned)o2 <= 1u) {
+                    // the neighbour's target (q' = qp, o' = o2): dom 1 -> (dy', dz') = (qp, o2); dom 2 -> (o2, qp)
+                    const float pw = b.dom == 1 ? __fmul_rn(qp ? ny[1] : ny[0], o2 ? nz[1] : nz[0])
+                                                : __fmul_rn(o2 ? ny[1] : ny[0], qp ? nz[1] : nz[0]);
+                    w[j] = __fadd_rn(w[j], pw);
+                }
+            }
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------

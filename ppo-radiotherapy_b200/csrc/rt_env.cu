@@ -76,23 +76,31 @@ struct __align__(16) Tumour {
     int32_t dim[3];         // bbox extent
     int32_t n_vox;
     int32_t vox_off;        // into vox_xyz
-    int32_t lin_lo, lin_hi; // smallest / largest linear voxel index of the tumour
     float tumour_sum;       // np.sum(tumours)            (environment.py:167)
     float lung_mask_sum;    // np.sum(lungs*(1-tumours))  (environment.py:178)
-    double centroid[3];     // tumour_position()          (environment.py:145-148)
-    double pad_;
+    float obs_c[3];         // float32(tumour_position()/G*2-1), environment.py:145-148,261
+    int32_t pad_[3];
 };
-static_assert(sizeof(Tumour) == 80, "Tumour table entry layout");
+static_assert(sizeof(Tumour) == 64, "Tumour table entry layout");
+constexpr int kTumourWords = sizeof(Tumour) / 4;
+constexpr int kMaxTumourWords = 64;   // bbox occupancy words staged per env (bundled tumours need 38)
 
 struct Tables {
     Grid G;
+    double gnorm;                  // np.linalg.norm(LUNG_SHAPE), environment.py:161
     const uint32_t *lungs_bits;
     const Tumour *tumours;
     const uint32_t *tumour_bits;   // [n_tumours][bits_words] bbox-local occupancy
     const uint32_t *vox_xyz;       // packed i | j<<8 | k<<16 per tumour voxel
     int n_tumours;
     int bits_words;
+    long long *stage_clock;        // optional [N][8] clock64() stamps of the step kernel's stages (rt_set_stage_clock)
 };
+
+#define RT_STAMP(slot)                                                                   \
+    do {                                                                                 \
+        if (T.stage_clock && lane == 0) T.stage_clock[(size_t)stamp_env * 12 + (slot)] = clock64(); \
+    } while (0)
 
 struct Schedule {
     const int32_t *ids;     // [n_episodes][N] or nullptr
@@ -136,18 +144,23 @@ __device__ __forceinline__ int pick_tumour(const Tables &T, const Schedule &S, i
     return (int)(h % (uint64_t)T.n_tumours);
 }
 
-// environment.py:259-268 get_vector_observation -> float32 (SyncVectorEnv copies into a float32 buffer).
+// environment.py:259-268 get_vector_observation -> float32 (SyncVectorEnv copies into a float32 buffer):
+// lanes 0-2 position/G*2-1, lanes 3-5 direction, lanes 6-8 tumour centroid/G*2-1 (per-tumour constant).
 __device__ __forceinline__ void write_obs(const Tables &T, const Tumour &tm, const double p[3], const double d[3],
                                           float *obs, int lane)
 {
     if (lane < 9) {
         const int a = lane % 3;
-        const double g = a == 0 ? (double)T.G.g0 : (a == 1 ? (double)T.G.g1 : (double)T.G.g2);
-        double v;
-        if (lane < 3) v = __dsub_rn(__dmul_rn(__ddiv_rn(a == 0 ? p[0] : (a == 1 ? p[1] : p[2]), g), 2.0), 1.0);
-        else if (lane < 6) v = a == 0 ? d[0] : (a == 1 ? d[1] : d[2]);
-        else v = __dsub_rn(__dmul_rn(__ddiv_rn(tm.centroid[a], g), 2.0), 1.0);
-        obs[lane] = (float)v;
+        float v;
+        if (lane < 3) {
+            const double g = a == 0 ? (double)T.G.g0 : (a == 1 ? (double)T.G.g1 : (double)T.G.g2);
+            v = (float)__dsub_rn(__dmul_rn(__ddiv_rn(a == 0 ? p[0] : (a == 1 ? p[1] : p[2]), g), 2.0), 1.0);
+        } else if (lane < 6) {
+            v = (float)(a == 0 ? d[0] : (a == 1 ? d[1] : d[2]));
+        } else {
+            v = a == 0 ? tm.obs_c[0] : (a == 1 ? tm.obs_c[1] : tm.obs_c[2]);
+        }
+        obs[lane] = v;
     }
 }
 
@@ -193,21 +206,33 @@ __global__ void __launch_bounds__(256) rt_reset_kernel(Tables T, Schedule S, Env
 }
 
 // ---------------------------------------------------------------------------------
-// The step.  A block advances kEnvsPerBlock envs in two phases:
-//   A  one THREAD per env: float64 pose update, beam clip/setup, the serial float32 slab walk
-//      (left in shared memory).  Scalar, latency-bound work — done once, not once per lane.
-//   B  one WARP per env, lane = (slab, splat target): dose read-modify-write on the sparse set
-//      of voxels the beam hits, tumour/lung accumulators, warp-shuffle reductions, reward,
-//      termination, observation, episode statistics, NEXT_STEP autoreset.
-constexpr int kEnvsPerBlock = 8;
-constexpr int kStepThreads = kEnvsPerBlock * kWarp;
+// The step.  A block of 8 warps advances kEnvsPerBlock = 7 envs:
+//   producer warp, one THREAD per env: the float64 rotation (sincos/acos/div/sqrt chain), beam
+//      clip/setup and the serial float32 slab walk, left in shared memory.  Scalar latency-bound
+//      work is issued once per env instead of once per lane.
+//   7 env warps, one WARP per env: while the producer runs they load the env record and tumour
+//      entry, apply the translation and reduce the distance-to-tumour term; after the barrier,
+//      lane = (slab, splat target): sparse dose read-modify-write, tumour/lung accumulators,
+//      warp-shuffle reductions, reward, termination, observation, episode statistics and the
+//      NEXT_STEP autoreset.
+// 4 blocks x 256 threads x 64 registers fill an SM; 586 blocks cover 4096 envs in one wave of 592 slots.
+constexpr int kEnvsPerBlock = 7;
+constexpr int kStepThreads = (kEnvsPerBlock + 1) * kWarp;
+
+struct EnvScalars {           // env-warp values parked in shared memory while the dose loop runs
+    double px, py, pz;
+    double os_t[3];
+    double tumour_dose, lung_dose, ep_return, best;
+    float obs_p[3];
+    int t, lung_count, n_beams;
+};
 
 struct EnvWork {
     Beam beam;
-    int reset;               // this call is the env's autoreset call
+    double dir[3];           // direction after the rotation
+    double os_r;             // rotation overshoot (environment.py:239), published after the barrier
+    int os_ready;            // set by the producer once os_r is valid
     int pad_;
-    double pos[3], dir[3];   // pose after the update
-    double os_t[3], os_r;    // overshoots (environment.py:237-240)
     float ys[kMaxSlabs], zs[kMaxSlabs];
 };
 
@@ -216,44 +241,126 @@ __global__ void __launch_bounds__(kStepThreads, 4) rt_step_kernel(Tables T, Sche
                                                                   const float *__restrict__ actions, StepOut out)
 {
     __shared__ EnvWork work[kEnvsPerBlock];
+    __shared__ Tumour tum[kEnvsPerBlock];
+    __shared__ EnvScalars park[kEnvsPerBlock];
+    __shared__ uint32_t tbits[kEnvsPerBlock][kMaxTumourWords];
     const Grid &G = T.G;
     const int warp = threadIdx.x / kWarp;
     const int lane = threadIdx.x & (kWarp - 1);
     const int env0 = blockIdx.x * kEnvsPerBlock;
 
-    // ---- phase A ------------------------------------------------------------------------
-    if (threadIdx.x < kEnvsPerBlock && env0 + threadIdx.x < n_envs) {
-        const int e = env0 + threadIdx.x;
-        EnvWork &wk = work[threadIdx.x];
-        const EnvRec *my = rec + e;
-        wk.reset = my->needs_reset;
-        wk.beam.nslab = 0;
-        if (!wk.reset) {
+    // ---- producer warp ---------------------------------------------------------------------
+    if (warp == kEnvsPerBlock) {
+        const int e = env0 + lane;
+        if (T.stage_clock && lane < kEnvsPerBlock && e < n_envs) T.stage_clock[(size_t)e * 12 + 0] = clock64();
+        const bool mine = lane < kEnvsPerBlock && e < n_envs;
+        double zc = 0.0;
+        bool stepped = false;
+        if (mine) {
+            EnvWork &wk = work[lane];
+            const EnvRec *my = rec + e;
+            // every load is issued before the first use: one round trip to L2
+            const int needs_reset = my->needs_reset;
             Pose s;
             float a[6];
 #pragma unroll
             for (int i = 0; i < 3; i++) { s.p[i] = my->pos[i]; s.d[i] = my->dir[i]; }
 #pragma unroll
             for (int i = 0; i < 6; i++) a[i] = __ldg(actions + (size_t)e * RT_ACTION_SIZE + i);
-            double os_t[3], os_r;
-            pose_update(G, a, s, os_t, os_r);                               // environment.py:196-210
-            const Beam b = beam_setup(G, s.p, s.d);                         // draw_line.py:19-66
-            beam_walk(b, wk.ys, wk.zs);                                     // draw_line.py:98-99
-            wk.beam = b;
+            wk.beam.nslab = 0;
+            wk.os_ready = 0;
+            if (!needs_reset) {
+                stepped = true;
+                if (T.stage_clock) T.stage_clock[(size_t)e * 12 + 8] = clock64() + (long long)(s.d[0] * 0.0);
+                const double gs[3] = {(double)G.g0, (double)G.g1, (double)G.g2};
+                double os_t[3], rv[3];
 #pragma unroll
-            for (int i = 0; i < 3; i++) { wk.pos[i] = s.p[i]; wk.dir[i] = s.d[i]; wk.os_t[i] = os_t[i]; }
-            wk.os_r = os_r;
+                for (int i = 0; i < 3; i++)                                 // environment.py:122-125, transforms.py:65-67
+                    s.p[i] = translate_axis(s.p[i], __dmul_rn(__dmul_rn((double)clip1(a[i]), gs[i]), 0.2), gs[i], os_t[i]);
+                map_rotation(a, rv);
+                zc = rotate_env(s.d, rv);                                   // transforms.py:7-55
+                if (T.stage_clock) T.stage_clock[(size_t)e * 12 + 9] = clock64() + (long long)(s.d[0] * 0.0);
+                const Beam b = beam_setup(G, s.p, s.d);                     // draw_line.py:19-66
+                if (T.stage_clock) T.stage_clock[(size_t)e * 12 + 10] = clock64() + (b.nslab < -5);
+                beam_walk(b, wk.ys, wk.zs);                                 // draw_line.py:98-99
+                wk.beam = b;
+#pragma unroll
+                for (int i = 0; i < 3; i++) wk.dir[i] = s.d[i];
+            }
+            if (T.stage_clock) T.stage_clock[(size_t)e * 12 + 1] = clock64();
+        }
+        __syncthreads();
+        if (stepped) {                                                      // off the env warps' critical path
+            volatile EnvWork &wk = work[lane];
+            wk.os_r = overshoot_from_z(zc);                                 // transforms.py:29-33, 57
+            __threadfence_block();
+            wk.os_ready = 1;
+        }
+        return;
+    }
+
+    // ---- env warps, before the barrier (overlaps the producer) ------------------------------
+    const int env = env0 + warp;
+    const bool active = env < n_envs;
+    EnvRec *my = rec + (active ? env : 0);
+    Tumour &tm = tum[warp];
+    EnvScalars &sc = park[warp];
+    bool needs_reset = false;
+    int tid = 0;
+    if (active) {
+        needs_reset = my->needs_reset != 0;
+        if (!needs_reset) {
+            tid = my->tumour_id;
+            if (lane < kTumourWords)
+                reinterpret_cast<uint32_t *>(&tm)[lane] = __ldg(reinterpret_cast<const uint32_t *>(T.tumours + tid) + lane);
+            for (int i = lane; i < T.bits_words; i += kWarp)                    // bits_words <= kMaxTumourWords (rt_create)
+                tbits[warp][i] = __ldg(T.tumour_bits + (size_t)tid * T.bits_words + i);
+            // translation (environment.py:122-125, transforms.py:65-67): same operations as the producer
+            const double gs[3] = {(double)G.g0, (double)G.g1, (double)G.g2};
+            double p[3], os_t[3];
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                const float ai = __ldg(actions + (size_t)env * RT_ACTION_SIZE + i);
+                const double tr = __dmul_rn(__dmul_rn((double)clip1(ai), gs[i]), 0.2);
+                p[i] = translate_axis(my->pos[i], tr, gs[i], os_t[i]);
+            }
+            if (lane < 3) {                                                     // environment.py:260
+                const double pl = lane == 0 ? p[0] : (lane == 1 ? p[1] : p[2]);
+                const double gl = lane == 0 ? gs[0] : (lane == 1 ? gs[1] : gs[2]);
+                sc.obs_p[lane] = (float)__dsub_rn(__dmul_rn(__ddiv_rn(pl, gl), 2.0), 1.0);
+                sc.os_t[lane] = lane == 0 ? os_t[0] : (lane == 1 ? os_t[1] : os_t[2]);
+            }
+            if (lane == 0) {
+                sc.px = p[0]; sc.py = p[1]; sc.pz = p[2];
+                sc.tumour_dose = my->tumour_dose; sc.lung_dose = my->lung_dose; sc.ep_return = my->ep_return;
+                sc.t = my->t + 1;                                               // environment.py:194
+                sc.lung_count = my->lung_count; sc.n_beams = my->n_beams;
+            }
+            __syncwarp();
+            // distance_to_tumour_reward (environment.py:150-162): min over the tumour's voxel list
+            double best = CUDART_INF;
+            const int nv = tm.n_vox, off = tm.vox_off;
+            for (int k = lane; k < nv; k += kWarp) {
+                const uint32_t pk = __ldg(T.vox_xyz + off + k);
+                const double dx = __dsub_rn((double)(pk & 255u), p[0]);
+                const double dy = __dsub_rn((double)((pk >> 8) & 255u), p[1]);
+                const double dz = __dsub_rn((double)(pk >> 16), p[2]);
+                double d2 = __dmul_rn(dx, dx);
+                d2 = __dadd_rn(d2, __dmul_rn(dy, dy));
+                d2 = __dadd_rn(d2, __dmul_rn(dz, dz));
+                best = fmin(best, d2);
+            }
+            best = warp_min(best);
+            if (lane == 0) sc.best = best;
         }
     }
+    const int stamp_env = active ? env : 0;
+    if (active) RT_STAMP(2);
     __syncthreads();
+    if (!active) return;
+    RT_STAMP(3);
 
-    // ---- phase B ------------------------------------------------------------------------
-    const int env = env0 + warp;
-    if (env >= n_envs) return;
-    const EnvWork &wk = work[warp];
-    EnvRec *my = rec + env;
-
-    if (wk.reset) {
+    if (needs_reset) {
         // gymnasium 1.0.0 NEXT_STEP: the call after a terminal step resets and reports reward 0.
         const int episode = my->episode + 1;
         __syncwarp();
@@ -269,100 +376,121 @@ __global__ void __launch_bounds__(kStepThreads, 4) rt_step_kernel(Tables T, Sche
         return;
     }
 
+    // ---- env warps, after the barrier: dose deposition (environment.py:107-110) --------------
+    // dose' = clip(dose + beam*0.1, 0, 1) changes only the voxels the beam hits.
+    const EnvWork &wk = work[warp];
     const Beam b = wk.beam;
-    const int tid = my->tumour_id;
-    const Tumour tm = T.tumours[tid];
-    const double px = wk.pos[0], py = wk.pos[1], pz = wk.pos[2];
-
-    // distance_to_tumour_reward (environment.py:150-162): min over the tumour's voxel list
-    double best = CUDART_INF;
-    for (int k = lane; k < tm.n_vox; k += kWarp) {
-        const uint32_t pk = __ldg(T.vox_xyz + tm.vox_off + k);
-        const double dx = __dsub_rn((double)(pk & 255u), px);
-        const double dy = __dsub_rn((double)((pk >> 8) & 255u), py);
-        const double dz = __dsub_rn((double)(pk >> 16), pz);
-        double d2 = __dmul_rn(dx, dx);
-        d2 = __dadd_rn(d2, __dmul_rn(dy, dy));
-        d2 = __dadd_rn(d2, __dmul_rn(dz, dz));
-        best = fmin(best, d2);
-    }
-
-    // dose deposition (environment.py:107-110): dose' = clip(dose + beam*0.1, 0, 1) changes only
-    // the voxels the beam hits.
     float *vol = dose + (size_t)env * G.vstride;
     uint32_t *vbits = valid + (size_t)env * G.vwords;
     double d_tum = 0.0, d_lung = 0.0;
     int d_cnt = 0;
-    for (int kbase = 0; kbase < b.nslab; kbase += kRounds * kSlabsPerRound) {
-        int lin[kRounds], pk[kRounds];
-        float w[kRounds], old[kRounds];
-        bool fresh[kRounds];
+    const int li0 = tm.lo[0], li1 = tm.lo[1], li2 = tm.lo[2];
+    const int td0 = tm.dim[0], td1 = tm.dim[1], td2 = tm.dim[2];
+    // One slab per lane; kPass chunks of 32 slabs are staged together so that their bitmap loads, then
+    // their dose loads, are all in flight at once (a beam has 37 slabs on average, 71 at most).
+    constexpr int kPass = 1;
+    for (int kbase = 0; kbase < b.nslab; kbase += kPass * kWarp) {
+        int lin[kPass][4], c0[kPass], c1[kPass], c2[kPass];
+        float w[kPass][4], old[kPass][4];
+        uint32_t vw[kPass][4], lw[kPass][4];
+        bool use[kPass];
 #pragma unroll
-        for (int r = 0; r < kRounds; r++)
-            lin[r] = splat_target(G, b, wk.ys, wk.zs, kbase + r * kSlabsPerRound + (lane >> 2), lane & 3, w[r], pk[r]);
+        for (int c = 0; c < kPass; c++) {
+            use[c] = kbase + c * kWarp < b.nslab;                       // warp-uniform
 #pragma unroll
-        for (int r = 0; r < kRounds; r++) {
-            fresh[r] = false;
-            if (lin[r] >= 0) {
-                const int sec = lin[r] >> 3;
-                fresh[r] = !((vbits[sec >> 5] >> (sec & 31)) & 1u);
-            }
+            for (int j = 0; j < 4; j++) { lin[c][j] = -1; w[c][j] = 0.0f; }
+            c0[c] = c1[c] = c2[c] = 0;
+            if (use[c]) slab_targets(G, b, wk.ys, wk.zs, kbase + c * kWarp + lane, lin[c], w[c], c0[c], c1[c], c2[c]);
         }
+#pragma unroll
+        for (int c = 0; c < kPass; c++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) {               // all bitmap loads in flight together
+                vw[c][j] = 0xffffffffu;
+                lw[c][j] = 0u;
+                old[c][j] = 0.0f;
+                if (lin[c][j] >= 0) {
+                    vw[c][j] = vbits[lin[c][j] >> 8];   // sector = lin >> 3, word = sector >> 5
+                    lw[c][j] = __ldg(T.lungs_bits + (lin[c][j] >> 5));
+                    // issued before the valid bit is known (one memory round trip instead of two); the value
+                    // is discarded below when the sector has not been written this episode
+                    old[c][j] = vol[lin[c][j]];
+                }
+            }
+        if (kbase == 0) RT_STAMP(4);
+        bool fresh[kPass][4];
+#pragma unroll
+        for (int c = 0; c < kPass; c++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                fresh[c][j] = lin[c][j] >= 0 && !((vw[c][j] >> ((lin[c][j] >> 3) & 31)) & 1u);
+                if (fresh[c][j]) old[c][j] = 0.0f;      // never written this episode: the sector reads as zero
+            }
         __syncwarp();   // every lane has sampled the bitmap before any lane updates it
         // first write to a sector this episode: materialise it as zeros and mark it valid
 #pragma unroll
-        for (int r = 0; r < kRounds; r++)
-            if (fresh[r]) {
-                const int sec = lin[r] >> 3;
-                float4 *sp = reinterpret_cast<float4 *>(vol + (sec << 3));
-                sp[0] = make_float4(0.f, 0.f, 0.f, 0.f);
-                sp[1] = make_float4(0.f, 0.f, 0.f, 0.f);
-                atomicOr(vbits + (sec >> 5), 1u << (sec & 31));
-            }
-        __syncwarp();
+        for (int c = 0; c < kPass; c++)
 #pragma unroll
-        for (int r = 0; r < kRounds; r++) {
-            old[r] = 0.0f;
-            if (lin[r] >= 0 && !fresh[r]) old[r] = vol[lin[r]];
+            for (int j = 0; j < 4; j++)
+                if (fresh[c][j]) {
+                    const int sec = lin[c][j] >> 3;
+                    float4 *sp = reinterpret_cast<float4 *>(vol + (sec << 3));
+                    sp[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    sp[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    atomicOr(vbits + (sec >> 5), 1u << (sec & 31));
+                }
+        __syncwarp();   // zero fill (any lane) is ordered before the voxel stores below
+        if (kbase == 0) RT_STAMP(5);
+#pragma unroll
+        for (int c = 0; c < kPass; c++) {
+            if (!use[c]) continue;
+            // tumour membership of the slab's 2x2 block: bbox test on the shared coordinates, then the bitmask
+            const int ti = c0[c] - li0, tj = c1[c] - li1, tk = c2[c] - li2;
+            const bool near_t = (unsigned)ti < (unsigned)td0 && tj >= -1 && tj < td1 && tk >= -1 && tk < td2;
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (lin[c][j] >= 0) {
+                    const int dy = j >> 1, dz = j & 1;
+                    const float o = old[c][j];
+                    float nd = __fadd_rn(o, __fmul_rn(w[c][j], 0.100000001490116119f));   // beam * BEAM_DOSE, then +
+                    nd = fminf(fmaxf(nd, 0.0f), 1.0f);                                     // np.clip(., 0, 1)
+                    vol[lin[c][j]] = nd;
+                    bool in_t = false;
+                    if (near_t && (unsigned)(tj + dy) < (unsigned)td1 && (unsigned)(tk + dz) < (unsigned)td2) {
+                        const int bit = (ti * td1 + tj + dy) * td2 + tk + dz;
+                        in_t = (tbits[warp][bit >> 5] >> (bit & 31)) & 1u;
+                    }
+                    const bool in_l = (lw[c][j] >> (lin[c][j] & 31)) & 1u;
+                    if (in_t || in_l) {
+                        const double delta = (double)nd - (double)o;
+                        if (in_t) d_tum += delta;
+                        if (in_l) d_lung += delta;
+                        // lungs_mask = lungs*(1-tumours); dose is monotone, so the count only grows (environment.py:174-177)
+                        if (!in_t && !(o > 0.200000002980232239f) && nd > 0.200000002980232239f) d_cnt++;
+                    }
+                }
         }
-#pragma unroll
-        for (int r = 0; r < kRounds; r++)
-            if (lin[r] >= 0) {
-                const float o = old[r];
-                float nd = __fadd_rn(o, __fmul_rn(w[r], 0.100000001490116119f));   // beam * BEAM_DOSE, then +
-                nd = fminf(fmaxf(nd, 0.0f), 1.0f);                                  // np.clip(., 0, 1)
-                vol[lin[r]] = nd;
-                const bool in_t = tumour_bit(T, tm, tid, pk[r] & 255, (pk[r] >> 8) & 255, pk[r] >> 16);
-                const bool in_l = lung_bit(T, lin[r]);
-                const double delta = (double)nd - (double)o;
-                if (in_t) d_tum += delta;
-                if (in_l) d_lung += delta;
-                // lungs_mask = lungs*(1-tumours); dose is monotone, so the count only grows (environment.py:174-177)
-                if (in_l && !in_t && !(o > 0.200000002980232239f) && nd > 0.200000002980232239f) d_cnt++;
-            }
         __syncwarp();
     }
-    const double tumour_dose = my->tumour_dose + warp_sum(d_tum);
-    const double lung_dose = my->lung_dose + warp_sum(d_lung);
-    const int lung_count = my->lung_count + warp_sum(d_cnt);
-    best = warp_min(best);
+    RT_STAMP(6);
+    __syncwarp();
+    const double tumour_dose = sc.tumour_dose + warp_sum(d_tum);
+    const double lung_dose = sc.lung_dose + warp_sum(d_lung);
+    const int lung_count = sc.lung_count + __reduce_add_sync(kFull, d_cnt);
+    const int t = sc.t, n_beams = sc.n_beams;
 
     // rewards, termination (environment.py:158-191, 214-220)
-    const int t = my->t + 1;                                                     // environment.py:194
     const float tsum_f32 = (float)tumour_dose;                                   // np.sum(dose*tumours) float32
     const float ratio = __fdiv_rn(tsum_f32, tm.tumour_sum);
     const float r_tumour = __fmul_rn(ratio, 10.0f);
     const double r_lung = __dmul_rn(__ddiv_rn((double)lung_count, (double)tm.lung_mask_sum), -1.0);
-    const double gnorm = sqrt((double)(G.g0 * G.g0 + G.g1 * G.g1 + G.g2 * G.g2));
-    const double r_dist = __dmul_rn(__ddiv_rn(sqrt(best), gnorm), -1.0);
+    const double r_dist = __dmul_rn(__ddiv_rn(sqrt(sc.best), T.gnorm), -1.0);
     const double reward = __dadd_rn(__dadd_rn((double)r_tumour, r_lung), r_dist);
     const bool done = (ratio >= 0.899999976158142090f) || (t >= RT_MAX_TIME_STEPS);
-    const double ep_return = my->ep_return + reward;
-    const int n_beams = my->n_beams;
-    __syncwarp();   // all lanes have read the record before lane 0 rewrites it
+    const double ep_return = sc.ep_return + reward;
 
     if (lane == 0) {
-        my->pos[0] = px; my->pos[1] = py; my->pos[2] = pz;
+        my->pos[0] = sc.px; my->pos[1] = sc.py; my->pos[2] = sc.pz;
         my->dir[0] = wk.dir[0]; my->dir[1] = wk.dir[1]; my->dir[2] = wk.dir[2];
         my->tumour_dose = tumour_dose; my->lung_dose = lung_dose; my->ep_return = ep_return;
         my->t = t; my->lung_count = lung_count;
@@ -373,9 +501,17 @@ __global__ void __launch_bounds__(kStepThreads, 4) rt_step_kernel(Tables T, Sche
         if (out.terminated) out.terminated[env] = done ? 1 : 0;
         if (out.truncated) out.truncated[env] = 0;
     }
-    if (beams && lane < 6 && n_beams < RT_MAX_TIME_STEPS)                       // environment.py:110
-        beams[((size_t)env * RT_MAX_TIME_STEPS + n_beams) * 6 + lane] = lane < 3 ? wk.pos[lane] : wk.dir[lane - 3];
-    write_obs(T, tm, wk.pos, wk.dir, out.obs + (size_t)env * RT_OBS_SIZE, lane);
+    if (lane < 9) {                                                              // environment.py:259-268
+        float v;
+        if (lane >= 6) v = tm.obs_c[lane - 6];
+        else if (lane >= 3) v = (float)wk.dir[lane - 3];
+        else v = sc.obs_p[lane];
+        out.obs[(size_t)env * RT_OBS_SIZE + lane] = v;
+    }
+    if (beams && lane < 6 && n_beams < RT_MAX_TIME_STEPS) {                      // environment.py:110
+        const double pv = lane == 0 ? sc.px : (lane == 1 ? sc.py : sc.pz);
+        beams[((size_t)env * RT_MAX_TIME_STEPS + n_beams) * 6 + lane] = lane < 3 ? pv : wk.dir[lane - 3];
+    }
     if (out.info && lane < RT_INFO_SIZE) {
         double v;
         switch (lane) {
@@ -385,10 +521,14 @@ __global__ void __launch_bounds__(kStepThreads, 4) rt_step_kernel(Tables T, Sche
         case RT_INFO_REWARD_DISTANCE: v = r_dist; break;
         case RT_INFO_DOSE_TUMOUR: v = (double)tsum_f32; break;
         case RT_INFO_DOSE_LUNG: v = (double)(float)lung_dose; break;
-        case RT_INFO_OVERSHOOT_T0: v = wk.os_t[0]; break;
-        case RT_INFO_OVERSHOOT_T0 + 1: v = wk.os_t[1]; break;
-        case RT_INFO_OVERSHOOT_T0 + 2: v = wk.os_t[2]; break;
-        case RT_INFO_OVERSHOOT_R: v = wk.os_r; break;
+        case RT_INFO_OVERSHOOT_T0: v = sc.os_t[0]; break;
+        case RT_INFO_OVERSHOOT_T0 + 1: v = sc.os_t[1]; break;
+        case RT_INFO_OVERSHOOT_T0 + 2: v = sc.os_t[2]; break;
+        case RT_INFO_OVERSHOOT_R:
+            while (reinterpret_cast<const volatile EnvWork &>(wk).os_ready == 0) {}   // long since published
+            __threadfence_block();
+            v = reinterpret_cast<const volatile EnvWork &>(wk).os_r;
+            break;
         case RT_INFO_EPISODE_RETURN: v = ep_return; break;
         case RT_INFO_EPISODE_LENGTH: v = (double)t; break;
         case RT_INFO_LUNG_COUNT: v = (double)lung_count; break;
@@ -398,6 +538,7 @@ __global__ void __launch_bounds__(kStepThreads, 4) rt_step_kernel(Tables T, Sche
         }
         out.info[(size_t)env * RT_INFO_SIZE + lane] = v;
     }
+    RT_STAMP(7);
 }
 
 // ---------------------------------------------------------------------------------
@@ -437,19 +578,30 @@ __global__ void __launch_bounds__(256) rt_beam_kernel(Grid G, const double *__re
         return;
     }
     int base = 0;
-    for (int kbase = 0; kbase < b.nslab; kbase += kSlabsPerRound) {
-        float w;
-        int pk;
-        const int lin = splat_target(G, b, rw.ys, rw.zs, kbase + (lane >> 2), lane & 3, w, pk);
-        const unsigned hit = __ballot_sync(kFull, lin >= 0);
-        if (lin >= 0) {
-            const int at = base + __popc(hit & ((1u << lane) - 1u));
-            if (at < cap) {
-                idx[(size_t)ray * cap + at] = lin;
-                wout[(size_t)ray * cap + at] = w;
-            }
+    for (int kbase = 0; kbase < b.nslab; kbase += kWarp) {
+        int lin[4], c0, c1, c2;
+        float w[4];
+        slab_targets(G, b, rw.ys, rw.zs, kbase + lane, lin, w, c0, c1, c2);
+        int mine = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) mine += lin[j] >= 0;
+        int incl = mine;                                   // warp inclusive scan
+#pragma unroll
+        for (int o = 1; o < kWarp; o <<= 1) {
+            const int v = __shfl_up_sync(kFull, incl, o);
+            if (lane >= o) incl += v;
         }
-        base += __popc(hit);
+        int at = base + incl - mine;
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (lin[j] >= 0) {
+                if (at < cap) {
+                    idx[(size_t)ray * cap + at] = lin[j];
+                    wout[(size_t)ray * cap + at] = w[j];
+                }
+                at++;
+            }
+        base += __shfl_sync(kFull, incl, kWarp - 1);
     }
     if (lane == 0) count[ray] = base < cap ? base : cap;
 }
@@ -466,11 +618,13 @@ __global__ void __launch_bounds__(256) rt_beam_dense_kernel(Grid G, const double
     const Beam b = ray_prepare(G, pos + 3 * (size_t)ray, dir + 3 * (size_t)ray, lane, rw);
     if (lane == 0 && status) status[ray] = b.nslab < 0 ? -1 : 0;
     float *vol = out + (size_t)ray * G.nvox;
-    for (int kbase = 0; kbase < b.nslab; kbase += kSlabsPerRound) {
-        float w;
-        int pk;
-        const int lin = splat_target(G, b, rw.ys, rw.zs, kbase + (lane >> 2), lane & 3, w, pk);
-        if (lin >= 0) vol[lin] = w;
+    for (int kbase = 0; kbase < b.nslab; kbase += kWarp) {
+        int lin[4], c0, c1, c2;
+        float w[4];
+        slab_targets(G, b, rw.ys, rw.zs, kbase + lane, lin, w, c0, c1, c2);
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (lin[j] >= 0) vol[lin[j]] = w[j];
     }
 }
 
@@ -601,16 +755,18 @@ __global__ void __launch_bounds__(kVolThreads) rt_volumes_kernel(Tables T, const
         // environment.py:246-249: beam along the current direction, and along (1,0,0)
         const double horiz[3] = {1.0, 0.0, 0.0};
         const Beam b = ray_prepare(G, r.pos, warp == 0 ? r.dir : horiz, lane, view[warp]);
-        for (int kbase = 0; kbase < b.nslab; kbase += kSlabsPerRound) {
-            float w;
-            int pk;
-            const int lin = splat_target(G, b, view[warp].ys, view[warp].zs, kbase + (lane >> 2), lane & 3, w, pk);
-            if (lin >= 0) {
-                const int at = atomicAdd(&hit_n, 1);
-                hit_idx[at] = lin;
-                hit_w[at] = w;
-                atomicOr(hit_bits + (lin >> 5), 1u << (lin & 31));
-            }
+        for (int kbase = 0; kbase < b.nslab; kbase += kWarp) {
+            int lin[4], c0, c1, c2;
+            float w[4];
+            slab_targets(G, b, view[warp].ys, view[warp].zs, kbase + lane, lin, w, c0, c1, c2);
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (lin[j] >= 0) {
+                    const int at = atomicAdd(&hit_n, 1);
+                    hit_idx[at] = lin[j];
+                    hit_w[at] = w[j];
+                    atomicOr(hit_bits + (lin[j] >> 5), 1u << (lin[j] & 31));
+                }
         }
     }
     __syncthreads();
@@ -757,7 +913,9 @@ int rt_create(rt_env **out, int device, int n_envs, uint32_t flags, const rt_pha
     e->flags = flags;
     const Grid G = make_grid(ph->grid);
     e->T.G = G;
+    e->T.gnorm = sqrt((double)(G.g0 * G.g0 + G.g1 * G.g1 + G.g2 * G.g2));
     e->T.n_tumours = ph->n_tumours;
+    e->T.stage_clock = nullptr;
 
     // tumour table: bbox, bbox-local bitmask, packed voxel coordinates
     std::vector<Tumour> tum(ph->n_tumours);
@@ -782,16 +940,24 @@ int rt_create(rt_env **out, int device, int n_envs, uint32_t flags, const rt_pha
         for (int a = 0; a < 3; a++) { tm.lo[a] = mn[a]; tm.dim[a] = mx[a] - mn[a] + 1; }
         tm.n_vox = hi - lo;
         tm.vox_off = lo;
-        tm.lin_lo = ph->vox[lo];
-        tm.lin_hi = ph->vox[hi - 1];
-        tm.pad_ = 0.0;
         tm.tumour_sum = ph->tumour_sum[t];
         tm.lung_mask_sum = ph->lung_mask_sum[t];
-        for (int a = 0; a < 3; a++) tm.centroid[a] = ph->centroid[3 * t + a];
+        for (int a = 0; a < 3; a++) {
+            // environment.py:261: tumour_position() / LUNG_SHAPE * 2 - 1, one rounding per operation, then float32
+            volatile double q = ph->centroid[3 * t + a] / (double)ph->grid[a];
+            volatile double m2 = q * 2.0;
+            volatile double v = m2 - 1.0;
+            tm.obs_c[a] = (float)v;
+            tm.pad_[a] = 0;
+        }
         const int bits = tm.dim[0] * tm.dim[1] * tm.dim[2];
         max_bits = bits > max_bits ? bits : max_bits;
     }
     e->T.bits_words = (max_bits + 31) / 32;
+    if (e->T.bits_words > kMaxTumourWords) {
+        delete e;
+        return fail(RT_ERR_INVALID, "rt_create: a tumour's bounding box exceeds 2048 voxels");
+    }
     std::vector<uint32_t> tbits((size_t)ph->n_tumours * e->T.bits_words, 0u);
     for (int t = 0; t < ph->n_tumours; t++) {
         const Tumour &tm = tum[t];
@@ -931,6 +1097,13 @@ int rt_reset_host(rt_env *e, const uint8_t *mask_host, float *obs_host)
     if (int rc = rt_reset(e, dmask, d_obs, e->hstream)) return rc;
     RT_CUDA(cudaStreamSynchronize(e->hstream));
     memcpy(obs_host, e->h_obs, (size_t)e->n * RT_OBS_SIZE * sizeof(float));
+    return RT_OK;
+}
+
+int rt_set_stage_clock(rt_env *e, long long *stamps_dev)
+{
+    if (!e) return fail(RT_ERR_INVALID, "rt_set_stage_clock: NULL handle");
+    e->T.stage_clock = stamps_dev;
     return RT_OK;
 }
 

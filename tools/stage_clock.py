@@ -1,0 +1,33 @@
+#!/usr/bin/env python
+"""Per-stage clock64() profile of the step kernel (rt_set_stage_clock)."""
+import sys, os, ctypes as C
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import ppo_radiotherapy_b200 as rt
+from ppo_radiotherapy_b200 import _native as nat
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+dev = torch.device("cuda:0")
+eng = rt.BatchedEpisodes(n, device=dev); eng.reset()
+g = torch.Generator(device=dev).manual_seed(0)
+acts = torch.rand((40, n, 6), device=dev, generator=g) * 2 - 1
+for i in range(20): eng.step(acts[i], want_info=False)
+stamps = torch.zeros((n, 12), dtype=torch.int64, device=dev)
+nat.check(nat.lib().rt_set_stage_clock(eng._h, C.c_void_p(stamps.data_ptr())))
+res = []
+for i in range(20, 40):
+    eng.step(acts[i], want_info=False); torch.cuda.synchronize()
+    s = stamps.cpu().numpy().astype(np.float64)
+    res.append(s)
+s = np.stack(res)            # [iters, n, 12]
+ok = (s[:, :, :11] > 0).all(axis=2)          # envs that walked a beam this step (all stamps written)
+rel = s - s[:, :, 0:1]                        # clock64 is per SM: only differences within an env's block are meaningful
+order = [0, 8, 9, 10, 1, 2, 3, 4, 5, 6, 7]
+names = {0: "producer start", 8: "producer: state loaded", 9: "producer: pose updated", 10: "producer: beam set up",
+         1: "producer done (walk)", 2: "env warp ready", 3: "past barrier", 4: "splat + bitmap loads issued",
+         5: "dose loads / zero fill done", 6: "stores issued (all passes)", 7: "end"}
+print(f"n={n}: cycles since the block's producer start (mean / p50 / p99 over {int(ok.sum())} env-steps)")
+for k in order:
+    v = rel[:, :, k][ok]
+    print(f"  {k:2d} {names[k]:30s} {v.mean():9.0f} {np.percentile(v,50):9.0f} {np.percentile(v,99):9.0f}")
+eng.close()
