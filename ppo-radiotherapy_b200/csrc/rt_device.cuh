@@ -118,7 +118,7 @@ __device__ __forceinline__ void apply_rotation(double (&d)[3], const double rv[3
 // The reference decides the clamp with  abs(angle_with_z_axis) < pi/4  where the angle comes from
 // np.arccos (transforms.py:29-35).  For min_angle = pi/4 that test is equivalent, for every double z in
 // [-1, 1], to |z| >= kClampZ = nextafter(cos(pi/4), 1) (established against glibc's acos by scanning the
-// neighbourhood of +-cos(pi/4) ulp by ulp, oracle/gen_golden.py poses cover both branches).  The step
+// neighbourhood of +-cos(pi/4) ulp by ulp; the golden pose chains in tests/golden cover both branches).  The step
 // uses the comparison, so acos leaves the critical path: the overshoot (transforms.py:57, info only) is
 // evaluated after the beam has been published.
 constexpr double kClampZ = 0x1.6a09e667f3bcep-1;
