@@ -8,6 +8,8 @@ Public surface (mirrors the reference's module/function names for the hot path):
     beam_voxels                draw_line.py:4
     apply_rotation / apply_translation     transforms.py:7 / :62
     compute_gae                train.py:164-181
+    PPO, PPO_3DCNN             networks.py:54,107   (PyTorch; checkpoint-compatible)
+    train.train / train.main   train.py:91,285      device-resident CleanRL loop, NCCL grad all-reduce
     Phantom                    environment.py:28-29,90-97 data, packed
 
 Everything computes in librtenv_b200.so (hand-written sm_100a CUDA behind the C ABI of
@@ -21,10 +23,12 @@ from .geometry import (apply_rotation, apply_rotation_batch, apply_translation, 
                        beam_voxels, beam_voxels_batch, beam_voxels_dense_batch, compute_gae, pose_update_batch)
 from .vector_env import Box, RadiotherapyVectorEnv
 from .environment import RadiotherapyEnv
+from .networks import PPO, PPO_3DCNN, FeaturesExtractor3D
+from . import train as train          # noqa: F401  (ppo_radiotherapy_b200.train.train / main)
 
 __all__ = [
     "RtError", "build", "Phantom", "default_phantom", "BatchedEpisodes", "RadiotherapyEnv",
     "RadiotherapyVectorEnv", "Box", "beam_voxels", "beam_voxels_batch", "beam_voxels_dense_batch",
     "apply_rotation", "apply_rotation_batch", "apply_translation", "apply_translation_batch",
-    "pose_update_batch", "compute_gae",
+    "pose_update_batch", "compute_gae", "PPO", "PPO_3DCNN", "FeaturesExtractor3D", "train",
 ]

@@ -117,6 +117,18 @@ struct StepOut {
     double *info;
 };
 
+// Dense mode (RT_FLAG_DENSE): hand-over from the step kernel to rt_dense_kernel, one per env in HBM.
+struct __align__(16) DenseWork {
+    int mode;                 // 0 accumulate this beam, 1 zero the volume (reset), 2 nothing to do
+    int n_hits;
+    int tid, t, n_beams, pad_;
+    double best;              // min squared distance to the tumour
+    double os_t[3], os_r;
+    double ep_return;
+    int lin[RT_BEAM_CAP];     // distinct voxels of the beam and their summed weights
+    float w[RT_BEAM_CAP];
+};
+
 // ---------------------------------------------------------------------------------
 __device__ __forceinline__ bool lung_bit(const Tables &T, int lin)
 {
@@ -167,11 +179,13 @@ __device__ __forceinline__ void write_obs(const Tables &T, const Tumour &tm, con
 // environment.py:77-105 for the warp's env: new tumour, centred pose, empty dose (= clear the
 // sector-valid bitmap), zero counters.
 __device__ __forceinline__ int reset_env(const Tables &T, const Schedule &S, EnvRec *rec, uint32_t *valid,
-                                         int env, int n_envs, int episode, int lane, float *obs)
+                                         int env, int n_envs, int episode, int lane, float *obs, bool dense = false)
 {
     const int tid = pick_tumour(T, S, env, n_envs, episode);
     uint4 *vw = reinterpret_cast<uint4 *>(valid + (size_t)env * T.G.vwords);
-    for (int i = lane; i < T.G.vwords / 4; i += kWarp) vw[i] = make_uint4(0u, 0u, 0u, 0u);
+    // sparse mode: no sector is valid (reads as zero); dense mode: the volume itself is zeroed, all valid
+    const uint32_t fill = dense ? 0xffffffffu : 0u;
+    for (int i = lane; i < T.G.vwords / 4; i += kWarp) vw[i] = make_uint4(fill, fill, fill, fill);
     const double p[3] = {(double)T.G.g0 / 2.0, (double)T.G.g1 / 2.0, (double)T.G.g2 / 2.0};
     const double d[3] = {0.0, 1.0, 0.0};
     if (lane == 0) {
@@ -191,13 +205,16 @@ __device__ __forceinline__ int reset_env(const Tables &T, const Schedule &S, Env
 
 // ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) rt_reset_kernel(Tables T, Schedule S, EnvRec *rec, uint32_t *valid,
-                                                       int n_envs, const uint8_t *mask, float *obs)
+                                                       int n_envs, const uint8_t *mask, float *obs,
+                                                       DenseWork *dense)
 {
     const int env = (blockIdx.x * blockDim.x + threadIdx.x) / kWarp;
     const int lane = threadIdx.x & (kWarp - 1);
     if (env >= n_envs) return;
-    if (mask == nullptr || mask[env]) {
-        reset_env(T, S, rec, valid, env, n_envs, 0, lane, obs);
+    const bool mine = mask == nullptr || mask[env];
+    if (dense && lane == 0) dense[env].mode = mine ? 1 : 2;
+    if (mine) {
+        reset_env(T, S, rec, valid, env, n_envs, 0, lane, obs, dense != nullptr);
     } else if (obs) {
         const EnvRec r = rec[env];
         const Tumour tm = T.tumours[r.tumour_id];
@@ -236,9 +253,11 @@ struct EnvWork {
     float ys[kMaxSlabs], zs[kMaxSlabs];
 };
 
+template <bool kDense>
 __global__ void __launch_bounds__(kStepThreads, 4) rt_step_kernel(Tables T, Schedule S, EnvRec *rec, float *dose,
                                                                   uint32_t *valid, double *beams, int n_envs,
-                                                                  const float *__restrict__ actions, StepOut out)
+                                                                  const float *__restrict__ actions, StepOut out,
+                                                                  DenseWork *dense)
 {
     __shared__ EnvWork work[kEnvsPerBlock];
     __shared__ Tumour tum[kEnvsPerBlock];
@@ -364,7 +383,8 @@ __global__ void __launch_bounds__(kStepThreads, 4) rt_step_kernel(Tables T, Sche
         // gymnasium 1.0.0 NEXT_STEP: the call after a terminal step resets and reports reward 0.
         const int episode = my->episode + 1;
         __syncwarp();
-        const int new_tid = reset_env(T, S, rec, valid, env, n_envs, episode, lane, out.obs);
+        const int new_tid = reset_env(T, S, rec, valid, env, n_envs, episode, lane, out.obs, kDense);
+        if (kDense && lane == 0) dense[env].mode = 1;
         if (lane == 0) {
             if (out.reward) out.reward[env] = 0.0;
             if (out.reward_f32) out.reward_f32[env] = 0.0f;
@@ -380,6 +400,62 @@ __global__ void __launch_bounds__(kStepThreads, 4) rt_step_kernel(Tables T, Sche
     // dose' = clip(dose + beam*0.1, 0, 1) changes only the voxels the beam hits.
     const EnvWork &wk = work[warp];
     const Beam b = wk.beam;
+    if (kDense) {
+        // Dense mode: publish the beam (distinct voxels + weights) and the pose; rt_dense_kernel streams the
+        // whole volume, recomputes the reductions from scratch and finishes the step.
+        DenseWork &dw = dense[env];
+        int base = 0;
+        for (int kbase = 0; kbase < b.nslab; kbase += kWarp) {
+            int lin[4], c0, c1, c2;
+            float w[4];
+            slab_targets(G, b, wk.ys, wk.zs, kbase + lane, lin, w, c0, c1, c2);
+            int mine = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) mine += lin[j] >= 0;
+            int incl = mine;
+#pragma unroll
+            for (int o = 1; o < kWarp; o <<= 1) {
+                const int v = __shfl_up_sync(kFull, incl, o);
+                if (lane >= o) incl += v;
+            }
+            int at = base + incl - mine;
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (lin[j] >= 0 && at < RT_BEAM_CAP) {
+                    dw.lin[at] = lin[j];
+                    dw.w[at] = w[j];
+                    at++;
+                }
+            base += __shfl_sync(kFull, incl, kWarp - 1);
+        }
+        if (lane == 0) {
+            dw.mode = 0;
+            dw.n_hits = base < RT_BEAM_CAP ? base : RT_BEAM_CAP;
+            dw.tid = tid; dw.t = sc.t; dw.n_beams = sc.n_beams;
+            dw.best = sc.best;
+            dw.os_t[0] = sc.os_t[0]; dw.os_t[1] = sc.os_t[1]; dw.os_t[2] = sc.os_t[2];
+            while (reinterpret_cast<const volatile EnvWork &>(wk).os_ready == 0) {}
+            __threadfence_block();
+            dw.os_r = reinterpret_cast<const volatile EnvWork &>(wk).os_r;
+            dw.ep_return = sc.ep_return;
+            my->pos[0] = sc.px; my->pos[1] = sc.py; my->pos[2] = sc.pz;
+            my->dir[0] = wk.dir[0]; my->dir[1] = wk.dir[1]; my->dir[2] = wk.dir[2];
+            my->t = sc.t;
+            my->n_beams = sc.n_beams + 1;
+        }
+        if (lane < 9) {                                                          // environment.py:259-268
+            float v;
+            if (lane >= 6) v = tm.obs_c[lane - 6];
+            else if (lane >= 3) v = (float)wk.dir[lane - 3];
+            else v = sc.obs_p[lane];
+            out.obs[(size_t)env * RT_OBS_SIZE + lane] = v;
+        }
+        if (beams && lane < 6 && sc.n_beams < RT_MAX_TIME_STEPS) {
+            const double pv = lane == 0 ? sc.px : (lane == 1 ? sc.py : sc.pz);
+            beams[((size_t)env * RT_MAX_TIME_STEPS + sc.n_beams) * 6 + lane] = lane < 3 ? pv : wk.dir[lane - 3];
+        }
+        return;
+    }
     float *vol = dose + (size_t)env * G.vstride;
     uint32_t *vbits = valid + (size_t)env * G.vwords;
     double d_tum = 0.0, d_lung = 0.0;
@@ -539,6 +615,141 @@ __global__ void __launch_bounds__(kStepThreads, 4) rt_step_kernel(Tables T, Sche
         out.info[(size_t)env * RT_INFO_SIZE + lane] = v;
     }
     RT_STAMP(7);
+}
+
+// ---------------------------------------------------------------------------------
+// Dense mode, second kernel (BASELINE configs[4], the reference's own dataflow): one block per env streams
+// the whole float32 volume  dose = clip(dose + beam*0.1, 0, 1)  (environment.py:107-110) and recomputes
+// sum(dose*tumours), sum(dose*lungs) and count(dose*mask > 0.2) from scratch (environment.py:164-191,
+// 234-235), then finishes the step.  1.61 MB of HBM traffic per env-step, everything else on chip.
+constexpr int kDenseThreads = 512;
+
+__global__ void __launch_bounds__(kDenseThreads) rt_dense_kernel(Tables T, EnvRec *rec, float *dose, DenseWork *dense,
+                                                                 StepOut out)
+{
+    extern __shared__ uint32_t smem[];
+    const Grid &G = T.G;
+    const int env = blockIdx.x;
+    DenseWork &dw = dense[env];
+    const int mode = dw.mode;
+    if (mode == 2) return;
+    float4 *vol4 = reinterpret_cast<float4 *>(dose + (size_t)env * G.vstride);
+    const int ngroups = G.vstride / 4;
+    if (mode == 1) {                                    // reset: environment.py:104-105
+        for (int q = threadIdx.x; q < ngroups; q += blockDim.x) __stcs(vol4 + q, make_float4(0.f, 0.f, 0.f, 0.f));
+        return;
+    }
+    const int nwords = G.vstride / 32;
+    uint32_t *tum_bits = smem;                          // [nwords] voxel belongs to the tumour
+    uint32_t *hit_bits = smem + nwords;                 // [nwords] voxel is hit by this step's beam
+    int *hit_lin = reinterpret_cast<int *>(smem + 2 * nwords);
+    float *hit_w = reinterpret_cast<float *>(hit_lin + RT_BEAM_CAP);
+    __shared__ double red_t[kDenseThreads / kWarp], red_l[kDenseThreads / kWarp];
+    __shared__ int red_c[kDenseThreads / kWarp];
+    const int tid = dw.tid;
+    const Tumour tm = T.tumours[tid];
+    const int nhit = dw.n_hits;
+    for (int i = threadIdx.x; i < 2 * nwords; i += blockDim.x) smem[i] = 0u;
+    __syncthreads();
+    for (int k = threadIdx.x; k < tm.n_vox; k += blockDim.x) {
+        const uint32_t pk = __ldg(T.vox_xyz + tm.vox_off + k);
+        const int lin = ((int)(pk & 255u) * G.g1 + (int)((pk >> 8) & 255u)) * G.g2 + (int)(pk >> 16);
+        atomicOr(tum_bits + (lin >> 5), 1u << (lin & 31));
+    }
+    for (int k = threadIdx.x; k < nhit; k += blockDim.x) {
+        const int lin = dw.lin[k];
+        hit_lin[k] = lin;
+        hit_w[k] = dw.w[k];
+        atomicOr(hit_bits + (lin >> 5), 1u << (lin & 31));
+    }
+    __syncthreads();
+
+    double s_t = 0.0, s_l = 0.0;
+    int cnt = 0;
+    for (int q = threadIdx.x; q < ngroups; q += blockDim.x) {
+        float4 v = __ldcs(vol4 + q);
+        const int v0 = q * 4, sh = v0 & 31;
+        const uint32_t hb = (hit_bits[v0 >> 5] >> sh) & 15u;
+        const uint32_t tb = (tum_bits[v0 >> 5] >> sh) & 15u;
+        const uint32_t lb = (__ldg(T.lungs_bits + (v0 >> 5)) >> sh) & 15u;
+        float e[4] = {v.x, v.y, v.z, v.w};
+        if (hb) {
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                if ((hb >> i) & 1u) {
+                    float wsum = 0.0f;
+                    for (int k = 0; k < nhit; k++)
+                        if (hit_lin[k] == v0 + i) wsum = hit_w[k];
+                    const float nd = __fadd_rn(e[i], __fmul_rn(wsum, 0.100000001490116119f));
+                    e[i] = fminf(fmaxf(nd, 0.0f), 1.0f);
+                }
+        }
+        // voxels the beam misses: dose + 0*0.1 == dose and the clip is the identity on [0, 1] — written back anyway
+        __stcs(vol4 + q, make_float4(e[0], e[1], e[2], e[3]));
+        if (tb | lb) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const bool in_t = (tb >> i) & 1u, in_l = (lb >> i) & 1u;
+                if (in_t) s_t += (double)e[i];
+                if (in_l) s_l += (double)e[i];
+                if (in_l && !in_t && e[i] > 0.200000002980232239f) cnt++;
+            }
+        }
+    }
+    s_t = warp_sum(s_t);
+    s_l = warp_sum(s_l);
+    cnt = __reduce_add_sync(kFull, cnt);
+    const int warp = threadIdx.x / kWarp, lane = threadIdx.x & (kWarp - 1);
+    if (lane == 0) { red_t[warp] = s_t; red_l[warp] = s_l; red_c[warp] = cnt; }
+    __syncthreads();
+    if (warp != 0) return;
+    s_t = lane < kDenseThreads / kWarp ? red_t[lane] : 0.0;
+    s_l = lane < kDenseThreads / kWarp ? red_l[lane] : 0.0;
+    cnt = lane < kDenseThreads / kWarp ? red_c[lane] : 0;
+    const double tumour_dose = warp_sum(s_t), lung_dose = warp_sum(s_l);
+    const int lung_count = __reduce_add_sync(kFull, cnt);
+
+    EnvRec *my = rec + env;
+    const int t = dw.t;
+    const float tsum_f32 = (float)tumour_dose;
+    const float ratio = __fdiv_rn(tsum_f32, tm.tumour_sum);
+    const float r_tumour = __fmul_rn(ratio, 10.0f);
+    const double r_lung = __dmul_rn(__ddiv_rn((double)lung_count, (double)tm.lung_mask_sum), -1.0);
+    const double r_dist = __dmul_rn(__ddiv_rn(sqrt(dw.best), T.gnorm), -1.0);
+    const double reward = __dadd_rn(__dadd_rn((double)r_tumour, r_lung), r_dist);
+    const bool done = (ratio >= 0.899999976158142090f) || (t >= RT_MAX_TIME_STEPS);
+    const double ep_return = dw.ep_return + reward;
+    if (lane == 0) {
+        my->tumour_dose = tumour_dose; my->lung_dose = lung_dose; my->ep_return = ep_return;
+        my->lung_count = lung_count;
+        my->needs_reset = done ? 1 : 0;
+        if (out.reward) out.reward[env] = reward;
+        if (out.reward_f32) out.reward_f32[env] = (float)reward;
+        if (out.terminated) out.terminated[env] = done ? 1 : 0;
+        if (out.truncated) out.truncated[env] = 0;
+    }
+    if (out.info && lane < RT_INFO_SIZE) {
+        double v;
+        switch (lane) {
+        case RT_INFO_REWARD_TOTAL: v = reward; break;
+        case RT_INFO_REWARD_TUMOUR: v = (double)r_tumour; break;
+        case RT_INFO_REWARD_LUNG: v = r_lung; break;
+        case RT_INFO_REWARD_DISTANCE: v = r_dist; break;
+        case RT_INFO_DOSE_TUMOUR: v = (double)tsum_f32; break;
+        case RT_INFO_DOSE_LUNG: v = (double)(float)lung_dose; break;
+        case RT_INFO_OVERSHOOT_T0: v = dw.os_t[0]; break;
+        case RT_INFO_OVERSHOOT_T0 + 1: v = dw.os_t[1]; break;
+        case RT_INFO_OVERSHOOT_T0 + 2: v = dw.os_t[2]; break;
+        case RT_INFO_OVERSHOOT_R: v = dw.os_r; break;
+        case RT_INFO_EPISODE_RETURN: v = ep_return; break;
+        case RT_INFO_EPISODE_LENGTH: v = (double)t; break;
+        case RT_INFO_LUNG_COUNT: v = (double)lung_count; break;
+        case RT_INFO_STEPPED: v = 1.0; break;
+        case RT_INFO_TUMOUR_ID: v = (double)tid; break;
+        default: v = (double)t; break;
+        }
+        out.info[(size_t)env * RT_INFO_SIZE + lane] = v;
+    }
 }
 
 // ---------------------------------------------------------------------------------
@@ -840,6 +1051,8 @@ struct rt_env {
     float *dose = nullptr;
     uint32_t *valid = nullptr;
     double *beams = nullptr;
+    DenseWork *dense = nullptr;
+    size_t dense_smem = 0;
     uint32_t *d_lungs = nullptr;
     Tumour *d_tumours = nullptr;
     uint32_t *d_tbits = nullptr;
@@ -982,6 +1195,15 @@ int rt_create(rt_env **out, int device, int n_envs, uint32_t flags, const rt_pha
     }
     if (flags & RT_FLAG_RECORD_BEAMS)
         if ((rc = dev_alloc(&e->beams, (size_t)n_envs * RT_MAX_TIME_STEPS * 6, &e->bytes))) { rt_destroy(e); return rc; }
+    if (flags & RT_FLAG_DENSE) {
+        int gmax = G.g0 > G.g1 ? G.g0 : G.g1;
+        gmax = gmax > G.g2 ? gmax : G.g2;
+        if (4 * (gmax + 1) > RT_BEAM_CAP) { rt_destroy(e); return fail(RT_ERR_INVALID, "rt_create: dense mode needs 4*(max(grid)+1) <= RT_BEAM_CAP"); }
+        if ((rc = dev_alloc(&e->dense, (size_t)n_envs, &e->bytes))) { rt_destroy(e); return rc; }
+        e->dense_smem = (size_t)(2 * (G.vstride / 32)) * sizeof(uint32_t) + (size_t)RT_BEAM_CAP * (sizeof(int) + sizeof(float));
+        cudaError_t ae = cudaFuncSetAttribute(rt_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->dense_smem);
+        if (ae != cudaSuccess) { rt_destroy(e); return fail(RT_ERR_CUDA, std::string("rt_dense_kernel smem: ") + cudaGetErrorString(ae)); }
+    }
     cudaError_t ce = cudaSuccess;
     auto chk = [&](cudaError_t x) { if (ce == cudaSuccess) ce = x; };
     chk(cudaMemcpy(e->d_lungs, ph->lungs_bits, lung_words * sizeof(uint32_t), cudaMemcpyHostToDevice));
@@ -1019,7 +1241,7 @@ int rt_destroy(rt_env *e)
     if (!e) return RT_OK;
     cudaSetDevice(e->device);
     cudaFree(e->d_lungs); cudaFree(e->d_tumours); cudaFree(e->d_tbits); cudaFree(e->d_vox);
-    cudaFree(e->rec); cudaFree(e->dose); cudaFree(e->valid); cudaFree(e->beams); cudaFree(e->d_sched);
+    cudaFree(e->rec); cudaFree(e->dose); cudaFree(e->valid); cudaFree(e->beams); cudaFree(e->dense); cudaFree(e->d_sched);
     // the *_host staging buffers are device-visible pinned allocations of the same sizes
     cudaFreeHost(e->h_actions); cudaFreeHost(e->h_obs); cudaFreeHost(e->h_reward); cudaFreeHost(e->h_info);
     cudaFreeHost(e->h_term); cudaFreeHost(e->h_trunc); cudaFreeHost(e->h_mask);
@@ -1064,8 +1286,13 @@ int rt_reset(rt_env *e, const uint8_t *mask_dev, float *obs_dev, void *stream)
     if (!e) return fail(RT_ERR_INVALID, "rt_reset: NULL handle");
     RT_CUDA(cudaSetDevice(e->device));
     rt_reset_kernel<<<warps_grid(e->n, 256), 256, 0, (cudaStream_t)stream>>>(e->T, e->S, e->rec, e->valid, e->n,
-                                                                            mask_dev, obs_dev);
+                                                                            mask_dev, obs_dev, e->dense);
     RT_LAUNCH_CHECK("rt_reset_kernel");
+    if (e->dense) {
+        StepOut none{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+        rt_dense_kernel<<<e->n, kDenseThreads, e->dense_smem, (cudaStream_t)stream>>>(e->T, e->rec, e->dose, e->dense, none);
+        RT_LAUNCH_CHECK("rt_dense_kernel");
+    }
     return RT_OK;
 }
 
@@ -1075,9 +1302,18 @@ int rt_step(rt_env *e, const float *actions_dev, float *obs_dev, double *reward_
     if (!e || !actions_dev || !obs_dev) return fail(RT_ERR_INVALID, "rt_step: NULL handle, actions or obs");
     RT_CUDA(cudaSetDevice(e->device));
     StepOut o{obs_dev, reward_dev, reward_f32_dev, terminated_dev, truncated_dev, info_dev};
-    rt_step_kernel<<<(e->n + kEnvsPerBlock - 1) / kEnvsPerBlock, kStepThreads, 0, (cudaStream_t)stream>>>(e->T, e->S, e->rec, e->dose, e->valid,
-                                                                           e->beams, e->n, actions_dev, o);
-    RT_LAUNCH_CHECK("rt_step_kernel");
+    const int grid = (e->n + kEnvsPerBlock - 1) / kEnvsPerBlock;
+    if (e->dense) {
+        rt_step_kernel<true><<<grid, kStepThreads, 0, (cudaStream_t)stream>>>(e->T, e->S, e->rec, e->dose, e->valid,
+                                                                             e->beams, e->n, actions_dev, o, e->dense);
+        RT_LAUNCH_CHECK("rt_step_kernel<dense>");
+        rt_dense_kernel<<<e->n, kDenseThreads, e->dense_smem, (cudaStream_t)stream>>>(e->T, e->rec, e->dose, e->dense, o);
+        RT_LAUNCH_CHECK("rt_dense_kernel");
+    } else {
+        rt_step_kernel<false><<<grid, kStepThreads, 0, (cudaStream_t)stream>>>(e->T, e->S, e->rec, e->dose, e->valid,
+                                                                              e->beams, e->n, actions_dev, o, nullptr);
+        RT_LAUNCH_CHECK("rt_step_kernel");
+    }
     return RT_OK;
 }
 

@@ -38,7 +38,7 @@ class BatchedEpisodes:
     """N independent RadiotherapyEnv episodes (environment.py:15) stepped by one kernel launch."""
 
     def __init__(self, num_envs: int, device="cuda", phantom: Optional[Phantom] = None,
-                 record_beams: bool = False, seed: int = 0):
+                 record_beams: bool = False, seed: int = 0, dense: bool = False):
         self.device = _require_cuda(device)
         self.num_envs = int(num_envs)
         self.phantom = phantom if phantom is not None else default_phantom()
@@ -46,7 +46,10 @@ class BatchedEpisodes:
         self.nvox = self.phantom.nvox
         self._lib = nat.lib()
         self._h = C.c_void_p()
-        flags = nat.FLAG_RECORD_BEAMS if record_beams else 0
+        # dense=True: full-volume dose update and from-scratch reductions every step (the reference's own
+        # dataflow; BASELINE configs[4] "dose-grid stress") instead of the sparse incremental step
+        self.dense = bool(dense)
+        flags = (nat.FLAG_RECORD_BEAMS if record_beams else 0) | (nat.FLAG_DENSE if dense else 0)
         desc = self.phantom.desc()
         with torch.cuda.device(self.device):
             nat.check(self._lib.rt_create(C.byref(self._h), self.device.index, self.num_envs, flags, C.byref(desc)),

@@ -1,0 +1,105 @@
+"""Policy / value networks with the reference's interface and checkpoint layout (networks.py:8-147).
+
+PyTorch modules (the north star keeps the networks in PyTorch).  Module names and Sequential
+indices match the reference so `saves/*.model` state dicts load unchanged:
+    PPO:        critic.{0,2,4}, actor_mean.{0,2,4}, actor_logstd
+    PPO_3DCNN:  features_extractor.cnn.{0,3,6}, features_extractor.mlp.0, critic.*, actor_mean.*, actor_logstd
+"""
+import math
+from typing import Sequence
+
+import torch
+import torch.nn as nn
+from torch.distributions.normal import Normal
+
+
+def layer_init(layer: nn.Module, std: float = math.sqrt(2.0), bias_const: float = 0.0) -> nn.Module:
+    """Orthogonal weights, constant bias (networks.py:48-51)."""
+    nn.init.orthogonal_(layer.weight, std)
+    nn.init.constant_(layer.bias, bias_const)
+    return layer
+
+
+def _head(n_in: int, hidden: int, n_out: int, out_std: float) -> nn.Sequential:
+    """Linear-Tanh-Linear-Tanh-Linear, the shape of both the actor and the critic (networks.py:62-78,113-130)."""
+    return nn.Sequential(layer_init(nn.Linear(n_in, hidden)), nn.Tanh(),
+                         layer_init(nn.Linear(hidden, hidden)), nn.Tanh(),
+                         layer_init(nn.Linear(hidden, n_out), std=out_std))
+
+
+def _prod(shape: Sequence[int]) -> int:
+    return int(math.prod(int(s) for s in shape))
+
+
+class _GaussianActorCritic(nn.Module):
+    """State-independent log-std diagonal Gaussian policy + value head (networks.py:80-97,132-147)."""
+
+    def features(self, x: torch.Tensor) -> torch.Tensor:
+        return x
+
+    def get_value(self, x: torch.Tensor) -> torch.Tensor:
+        return self.critic(self.features(x))
+
+    def get_action_and_value(self, x: torch.Tensor, action: torch.Tensor = None):
+        f = self.features(x)
+        mean = self.actor_mean(f)
+        dist = Normal(mean, torch.exp(self.actor_logstd.expand_as(mean)))
+        if action is None:
+            action = dist.sample()
+        return action, dist.log_prob(action).sum(1), dist.entropy().sum(1), self.critic(f)
+
+
+class PPO(_GaussianActorCritic):
+    def __init__(self, observation_shape, action_space, feature_dim: int = 64):
+        super().__init__()
+        self.feature_dim, self.observation_shape, self.action_space = feature_dim, observation_shape, action_space
+        n_obs, n_act = _prod(observation_shape), _prod(action_space)
+        self.critic = _head(n_obs, feature_dim, 1, 1.0)
+        self.actor_mean = _head(n_obs, feature_dim, n_act, 0.01)
+        self.actor_logstd = nn.Parameter(torch.zeros(1, n_act))
+
+
+class FeaturesExtractor3D(nn.Module):
+    """C3D-style trunk (networks.py:8-45): Conv3d(C,16,3) ReLU MaxPool(2,2,pad) Conv3d(16,16,3,g=2) ReLU
+    MaxPool(2) Conv3d(16,16,3,g=4) ReLU MaxPool(2) Flatten Linear ReLU.  `compute_dtype=torch.bfloat16`
+    runs the convolutions on the tensor cores (channels-last-3d, cuDNN)."""
+
+    def __init__(self, observation_shape, features_dim: int, compute_dtype: torch.dtype = None):
+        super().__init__()
+        self.observation_shape = observation_shape
+        self.compute_dtype = compute_dtype
+        pad = tuple((int(observation_shape[i + 1]) - 2) % 2 for i in range(3))
+        self.cnn = nn.Sequential(
+            nn.Conv3d(int(observation_shape[0]), 16, 3), nn.ReLU(), nn.MaxPool3d(2, 2, padding=pad),
+            nn.Conv3d(16, 16, 3, groups=2), nn.ReLU(), nn.MaxPool3d(2, 2),
+            nn.Conv3d(16, 16, 3, groups=4), nn.ReLU(), nn.MaxPool3d(2, 2),
+            nn.Flatten())
+        with torch.no_grad():
+            n_flat = self.cnn(torch.zeros((1,) + tuple(int(s) for s in observation_shape))).shape[1]
+        self.mlp = nn.Sequential(nn.Linear(n_flat, features_dim), nn.ReLU())
+
+    def forward(self, observations: torch.Tensor) -> torch.Tensor:
+        if self.compute_dtype is not None and observations.is_cuda:
+            with torch.autocast("cuda", dtype=self.compute_dtype):
+                x = self.cnn(observations.contiguous(memory_format=torch.channels_last_3d))
+            return self.mlp(x.float())
+        return self.mlp(self.cnn(observations))
+
+
+class PPO_3DCNN(_GaussianActorCritic):
+    def __init__(self, observation_shape, action_space, feature_dim: int = 64, compute_dtype: torch.dtype = None):
+        super().__init__()
+        self.feature_dim, self.observation_shape, self.action_space = feature_dim, observation_shape, action_space
+        n_act = _prod(action_space)
+        self.features_extractor = FeaturesExtractor3D(observation_shape, feature_dim, compute_dtype)
+        self.critic = _head(feature_dim, feature_dim, 1, 1.0)
+        self.actor_mean = _head(feature_dim, feature_dim, n_act, 0.01)
+        self.actor_logstd = nn.Parameter(torch.zeros(1, n_act))
+
+    def features(self, x: torch.Tensor) -> torch.Tensor:
+        return self.features_extractor(x)
+
+    def summary(self):
+        n = sum(p.numel() for p in self.parameters())
+        print(f"Observation shape: {self.observation_shape}\nAction space: {self.action_space}\n"
+              f"Feature dim: {self.feature_dim}\nParameters: {n}")

@@ -1,0 +1,317 @@
+"""CleanRL-style PPO on the device-resident vector env — the reference's train.py:91-282 with the
+host round trips removed.
+
+    python -m torch.distributed.run --nproc-per-node 8 -m ppo_radiotherapy_b200.train --config-file cfg.yaml --output-dir out
+    python ppo_radiotherapy_b200_train.py ...   (single GPU)
+
+What stays as in the reference: config field names (configs/default.yaml.template), the agent classes and
+their checkpoint layout, the loss (clipped surrogate, clipped value loss, per-minibatch advantage
+normalisation, Adam eps 1e-5, grad-norm clip 0.5), the TensorBoard tags, `agent.state_dict()` checkpoints.
+What changes: observations, actions, rewards and dones never leave the GPU (train.py:151-158 did two
+copies per step); GAE is one kernel (rt_gae) instead of 2048 tiny launches (train.py:164-181); episode
+statistics are reduced on the device and read once per iteration; under torchrun every rank owns
+num_envs / world_size envs and gradients are averaged with ONE NCCL all-reduce of the flattened
+gradient per optimiser step (between backward and clip_grad_norm_, i.e. train.py:246-247).
+Advantage normalisation is per rank and per minibatch (train.py:215-218 semantics on the local shard).
+"""
+import argparse
+import os
+import random
+import time
+from types import SimpleNamespace
+from typing import Optional
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+import torch.optim as optim
+
+from . import _native as nat
+from .geometry import compute_gae
+from .networks import PPO, PPO_3DCNN
+from .vector_env import RadiotherapyVectorEnv
+
+DEFAULTS = dict(
+    exp_name="default", seed=1, torch_deterministic=True, cuda=True, save_model=True, use_tqdm=False,
+    total_timesteps=10_000_000, num_saves=5, learning_rate=3e-4, num_envs=16, num_steps=2048, anneal_lr=False,
+    num_minibatches=32, update_epochs=10, gamma=0.99, gae_lambda=0.95, norm_adv=True, clip_coef=0.1,
+    clip_vloss=True, ent_coef=0.0, vf_coef=0.5, max_grad_norm=0.5, feature_dim=64, visionless=True,
+)
+
+
+def load_config(path: Optional[str] = None, **overrides) -> SimpleNamespace:
+    """YAML -> namespace with the derived sizes of train.py:292-297."""
+    cfg = dict(DEFAULTS)
+    if path:
+        import yaml
+        with open(path) as f:
+            cfg.update(yaml.safe_load(f) or {})
+    cfg.update(overrides)
+    cfg = SimpleNamespace(**cfg)
+    finalize_config(cfg)
+    return cfg
+
+
+def finalize_config(cfg: SimpleNamespace, world_size: int = 1) -> SimpleNamespace:
+    cfg.batch_size = int(cfg.num_envs * cfg.num_steps)
+    cfg.minibatch_size = int(cfg.batch_size // cfg.num_minibatches)
+    cfg.num_iterations = int(cfg.total_timesteps // cfg.batch_size)
+    cfg.save_frequency_iterations = cfg.num_iterations // cfg.num_saves if cfg.num_saves > 0 else 0
+    if cfg.num_envs % world_size:
+        raise ValueError(f"num_envs={cfg.num_envs} is not divisible by world_size={world_size}")
+    return cfg
+
+
+# --------------------------------------------------------------------------------------------
+# multi-GPU plumbing (exercised on CPU with gloo in tests/test_distributed_cpu.py)
+def shard_range(total: int, world_size: int, rank: int):
+    """Contiguous env shard of a rank: env i lives on rank i // (total / world_size)."""
+    if total % world_size:
+        raise ValueError("total must be divisible by world_size")
+    per = total // world_size
+    return rank * per, (rank + 1) * per
+
+
+class FlatGradAllReduce:
+    """One all-reduce of the flattened gradient per optimiser step, averaged over ranks."""
+
+    def __init__(self, params, group=None):
+        self.params = [p for p in params if p.requires_grad]
+        self.group = group
+        n = sum(p.numel() for p in self.params)
+        ref = self.params[0]
+        self.flat = torch.zeros(n, dtype=ref.dtype, device=ref.device)
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+
+    def __call__(self):
+        if self.world == 1:
+            return
+        off = 0
+        for p in self.params:
+            n = p.numel()
+            if p.grad is None:
+                self.flat[off:off + n].zero_()
+            else:
+                self.flat[off:off + n].copy_(p.grad.reshape(-1))
+            off += n
+        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+        self.flat.div_(self.world)
+        off = 0
+        for p in self.params:
+            n = p.numel()
+            if p.grad is None:
+                p.grad = self.flat[off:off + n].reshape(p.shape).clone()
+            else:
+                p.grad.copy_(self.flat[off:off + n].reshape(p.shape))
+            off += n
+
+
+def broadcast_parameters(module: nn.Module, src: int = 0):
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        for t in list(module.parameters()) + list(module.buffers()):
+            dist.broadcast(t.data, src)
+
+
+# --------------------------------------------------------------------------------------------
+def ppo_update(agent, optimizer, cfg, b_obs, b_actions, b_logprobs, b_advantages, b_returns, b_values,
+               sync_grads=None, generator: Optional[torch.Generator] = None):
+    """train.py:191-248 on device tensors.  Returns the last minibatch's statistics like the reference."""
+    n = b_obs.shape[0]
+    mb = max(1, n // cfg.num_minibatches)
+    clipfracs = []
+    stats = {}
+    for _ in range(cfg.update_epochs):
+        perm = torch.randperm(n, device=b_obs.device, generator=generator)
+        for start in range(0, n - mb + 1, mb):
+            idx = perm[start:start + mb]
+            _, newlogprob, entropy, newvalue = agent.get_action_and_value(b_obs[idx], b_actions[idx])
+            logratio = newlogprob - b_logprobs[idx]
+            ratio = logratio.exp()
+            with torch.no_grad():
+                old_approx_kl = (-logratio).mean()
+                approx_kl = ((ratio - 1) - logratio).mean()
+                clipfracs.append(((ratio - 1.0).abs() > cfg.clip_coef).float().mean())
+            adv = b_advantages[idx]
+            if cfg.norm_adv:
+                adv = (adv - adv.mean()) / (adv.std() + 1e-8)
+            pg_loss = torch.max(-adv * ratio, -adv * torch.clamp(ratio, 1 - cfg.clip_coef, 1 + cfg.clip_coef)).mean()
+            newvalue = newvalue.view(-1)
+            if cfg.clip_vloss:
+                v_unclipped = (newvalue - b_returns[idx]) ** 2
+                v_clipped = b_values[idx] + torch.clamp(newvalue - b_values[idx], -cfg.clip_coef, cfg.clip_coef)
+                v_loss = 0.5 * torch.max(v_unclipped, (v_clipped - b_returns[idx]) ** 2).mean()
+            else:
+                v_loss = 0.5 * ((newvalue - b_returns[idx]) ** 2).mean()
+            entropy_loss = entropy.mean()
+            loss = pg_loss - cfg.ent_coef * entropy_loss + v_loss * cfg.vf_coef
+            optimizer.zero_grad()
+            loss.backward()
+            if sync_grads is not None:
+                sync_grads()
+            nn.utils.clip_grad_norm_(agent.parameters(), cfg.max_grad_norm)
+            optimizer.step()
+            stats = dict(pg_loss=pg_loss.detach(), v_loss=v_loss.detach(), entropy=entropy_loss.detach(),
+                         old_approx_kl=old_approx_kl, approx_kl=approx_kl)
+    stats["clipfrac"] = torch.stack(clipfracs).mean() if clipfracs else torch.zeros((), device=b_obs.device)
+    return stats
+
+
+def train(cfg, writer=None, device="cuda", output_dir: Optional[str] = None, run_name: str = "run", log=print):
+    """The reference's train(cfg, writer, device) (train.py:91) on one rank's env shard."""
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    finalize_config(cfg, world)
+    device = torch.device(device)
+    lo, hi = shard_range(cfg.num_envs, world, rank)
+    n_local = hi - lo
+
+    envs = RadiotherapyVectorEnv(n_local, visionless=cfg.visionless, device=device, seed=cfg.seed * 1_000_003 + rank)
+    obs_shape = envs.single_observation_space.shape
+    act_shape = envs.single_action_space.shape
+    if cfg.visionless:
+        agent = PPO(obs_shape, act_shape, cfg.feature_dim).to(device)
+    else:
+        agent = PPO_3DCNN(obs_shape, act_shape, cfg.feature_dim, compute_dtype=torch.bfloat16).to(device)
+    broadcast_parameters(agent)
+    optimizer = optim.Adam(agent.parameters(), lr=cfg.learning_rate, eps=1e-5)
+    sync_grads = FlatGradAllReduce(agent.parameters()) if world > 1 else None
+
+    T = cfg.num_steps
+    obs = torch.zeros((T, n_local) + obs_shape, device=device)
+    actions = torch.zeros((T, n_local) + act_shape, device=device)
+    logprobs = torch.zeros((T, n_local), device=device)
+    rewards = torch.zeros((T, n_local), device=device)
+    dones = torch.zeros((T, n_local), device=device)
+    values = torch.zeros((T, n_local), device=device)
+
+    eng = envs.engine
+    next_obs, _ = envs.reset(seed=None, options={"backend": "torch"})
+    next_obs = next_obs.clone()
+    next_done = torch.zeros(n_local, device=device)
+    global_step = 0
+    start = time.time()
+    history = []
+
+    for iteration in range(1, cfg.num_iterations + 1):
+        if cfg.anneal_lr:
+            optimizer.param_groups[0]["lr"] = (1.0 - (iteration - 1.0) / cfg.num_iterations) * cfg.learning_rate
+        # per-iteration episode statistics, reduced on the device: [finished, sum return, sum length,
+        # sum of last-step reward components (tumour, lung, distance, total)] (train.py:42-66)
+        ep = torch.zeros(7, dtype=torch.float64, device=device)
+        for step in range(T):
+            global_step += cfg.num_envs
+            obs[step] = next_obs
+            dones[step] = next_done
+            with torch.no_grad():
+                action, logprob, _, value = agent.get_action_and_value(next_obs)
+            values[step] = value.flatten()
+            actions[step] = action
+            logprobs[step] = logprob
+            o, _, term, trunc, info = eng.step(action, want_info=True)          # train.py:151, on the device
+            if not cfg.visionless:
+                o = envs._volumes()
+            next_obs = o.clone() if cfg.visionless else o
+            rewards[step] = eng.reward_f32
+            next_done = (term | trunc).float()
+            fin = term.bool()
+            f64 = fin.double()
+            ep[0] += f64.sum()
+            ep[1] += (info[:, nat.INFO_EPISODE_RETURN] * f64).sum()
+            ep[2] += (info[:, nat.INFO_EPISODE_LENGTH] * f64).sum()
+            ep[3] += (info[:, nat.INFO_REWARD_TUMOUR] * f64).sum()
+            ep[4] += (info[:, nat.INFO_REWARD_LUNG] * f64).sum()
+            ep[5] += (info[:, nat.INFO_REWARD_DISTANCE] * f64).sum()
+            ep[6] += (info[:, nat.INFO_REWARD_TOTAL] * f64).sum()
+
+        with torch.no_grad():
+            next_value = agent.get_value(next_obs).reshape(-1)
+            advantages, returns = compute_gae(rewards, values, dones, next_value, next_done, cfg.gamma, cfg.gae_lambda)
+
+        stats = ppo_update(agent, optimizer, cfg,
+                           obs.reshape((-1,) + obs_shape), actions.reshape((-1,) + act_shape), logprobs.reshape(-1),
+                           advantages.reshape(-1), returns.reshape(-1), values.reshape(-1), sync_grads)
+
+        if world > 1:
+            dist.all_reduce(ep, op=dist.ReduceOp.SUM)
+        epc = ep.cpu().numpy()
+        y_pred, y_true = values.reshape(-1), returns.reshape(-1)
+        var_y = torch.var(y_true)
+        explained = float("nan") if float(var_y) == 0 else float(1 - torch.var(y_true - y_pred) / var_y)
+        rec = dict(iteration=iteration, global_step=global_step, sps=global_step / max(time.time() - start, 1e-9),
+                   episodes=int(epc[0]), explained_variance=explained,
+                   **{k: float(v) for k, v in stats.items()})
+        if epc[0] > 0:
+            rec.update(episodic_return=epc[1] / epc[0], episodic_length=epc[2] / epc[0],
+                       episodic_tumour_reward=epc[3] / epc[0], episodic_lung_reward=epc[4] / epc[0],
+                       episodic_distance_reward=epc[5] / epc[0], episodic_total_reward=epc[6] / epc[0])
+        history.append(rec)
+        if rank == 0:
+            if writer is not None:
+                for k in ("episodic_return", "episodic_length", "episodic_tumour_reward", "episodic_lung_reward",
+                          "episodic_distance_reward", "episodic_total_reward"):
+                    if k in rec:
+                        writer.add_scalar(f"charts/{k}", rec[k], global_step)
+                writer.add_scalar("charts/learning_rate", optimizer.param_groups[0]["lr"], global_step)
+                for tag, k in (("value_loss", "v_loss"), ("policy_loss", "pg_loss"), ("entropy", "entropy"),
+                               ("old_approx_kl", "old_approx_kl"), ("approx_kl", "approx_kl"), ("clipfrac", "clipfrac")):
+                    writer.add_scalar(f"losses/{tag}", rec[k], global_step)
+                writer.add_scalar("losses/explained_variance", explained, global_step)
+            if log is not None:
+                log(f"iter {iteration}/{cfg.num_iterations} step {global_step} sps {rec['sps']:.0f} "
+                    f"return {rec.get('episodic_return', float('nan')):.2f} v_loss {rec['v_loss']:.4f}")
+            if cfg.save_model and output_dir and (
+                    (cfg.save_frequency_iterations and iteration % cfg.save_frequency_iterations == 0)
+                    or iteration == cfg.num_iterations):
+                d = os.path.join(output_dir, "models", run_name)
+                os.makedirs(d, exist_ok=True)
+                path = os.path.join(d, f"{cfg.exp_name}_{iteration}.model")
+                torch.save(agent.state_dict(), path)                           # train.py:270-279
+                if log is not None:
+                    log(f"model saved to {path}")
+    envs.close()
+    agent.history = history
+    return agent
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser(description="PPO on the B200 radiotherapy vector env")
+    ap.add_argument("--config-file", type=str, default=None, help="YAML with the reference's field names")
+    ap.add_argument("--output-dir", type=str, default="runs_b200")
+    ap.add_argument("--set", nargs="*", default=[], help="overrides key=value")
+    args = ap.parse_args(argv)
+    over = {}
+    for kv in args.set:
+        k, v = kv.split("=", 1)
+        over[k] = type(DEFAULTS[k])(v) if k in DEFAULTS and not isinstance(DEFAULTS[k], bool) else (v.lower() == "true")
+    cfg = load_config(args.config_file, **over)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("training needs a CUDA device (the environment step has no CPU fallback)")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    random.seed(cfg.seed + rank)
+    np.random.seed(cfg.seed + rank)
+    torch.manual_seed(cfg.seed + rank)
+    torch.backends.cudnn.deterministic = cfg.torch_deterministic
+    run_name = f"{cfg.exp_name}_{int(time.time())}"
+    writer = None
+    if rank == 0:
+        try:
+            from torch.utils.tensorboard import SummaryWriter
+            writer = SummaryWriter(os.path.join(args.output_dir, "tensorboard", run_name))
+        except Exception:
+            writer = None
+    train(cfg, writer, device, args.output_dir, run_name)
+    if writer is not None:
+        writer.close()
+    if dist.is_initialized():
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -172,11 +172,11 @@ class RadiotherapyVectorEnv:
     metadata = {"render_modes": ["human"], "render_fps": 30, "autoreset_mode": "next_step"}
 
     def __init__(self, num_envs: int, visionless: bool = True, device="cuda", phantom: Optional[Phantom] = None,
-                 seed: int = 0, tumour_ids=None, record_beams: bool = False):
+                 seed: int = 0, tumour_ids=None, record_beams: bool = False, dense: bool = False):
         self.num_envs = int(num_envs)
         self.visionless = bool(visionless)
         self.engine = BatchedEpisodes(self.num_envs, device=device, phantom=phantom, record_beams=record_beams,
-                                      seed=seed)
+                                      seed=seed, dense=dense)
         self.device = self.engine.device
         grid = self.engine.grid
         obs_shape = (nat.OBS_SIZE,) if self.visionless else (4,) + grid

@@ -282,6 +282,39 @@ def test_dose_volumes_bit_exact_vs_oracle():
     env.close()
 
 
+def test_dense_mode_equals_sparse_mode_and_oracle():
+    """RT_FLAG_DENSE (BASELINE configs[4]): full-volume update + from-scratch reductions give the same
+    episode as the sparse incremental step — dose volumes bit-identical, rewards within tolerance —
+    through a termination and the autoreset call."""
+    n, T = 24, 104
+    rng = np.random.default_rng(21)
+    acts = rng.uniform(-1, 1, (T, n, 6)).astype(np.float32)
+    acts[:, :4] *= 0.02
+    sched = np.stack([(np.arange(n) * 7919) % 1000, (np.arange(n) * 31 + 3) % 1000]).astype(np.int32)
+    a = rt.RadiotherapyVectorEnv(n, device=DEV, tumour_ids=sched)
+    b = rt.RadiotherapyVectorEnv(n, device=DEV, tumour_ids=sched, dense=True)
+    ref_out, ref_done = O.rollout(O.Phantom(), sched, acts, threads=8)
+    oa, _ = a.reset()
+    ob, _ = b.reset()
+    assert np.array_equal(oa, ob)
+    for t in range(T):
+        o1, r1, d1, _, _ = a.step(_cuda(acts[t]))
+        o2, r2, d2, _, _ = b.step(_cuda(acts[t]))
+        i1, i2 = a.engine.info.cpu().numpy(), b.engine.info.cpu().numpy()
+        assert torch.equal(o1, o2) and torch.equal(d1, d2)
+        np.testing.assert_allclose(r2.cpu().numpy(), r1.cpu().numpy(), rtol=REW_RTOL, atol=REW_ATOL)
+        assert np.array_equal(i1[:, nat.INFO_LUNG_COUNT], i2[:, nat.INFO_LUNG_COUNT])
+        np.testing.assert_allclose(i2[:, :12], i1[:, :12], rtol=REW_RTOL, atol=REW_ATOL)
+        stepped = i2[:, nat.INFO_STEPPED] > 0
+        _compare_step(i2, o2.cpu().numpy(), r2.cpu().numpy(), d2.cpu().numpy(), ref_out[t], ref_done[t], stepped)
+        if t in (0, 50, 99, 100, 103):
+            for e in (0, 5, 23):
+                assert torch.equal(a.engine.dose(e), b.engine.dose(e))
+    assert torch.equal(a.engine.counters(), b.engine.counters())
+    a.close()
+    b.close()
+
+
 # ------------------------------------------------------------------------------------ vision
 def test_vision_volumes(golden):
     g = golden("steps")
