@@ -130,22 +130,6 @@ struct __align__(16) DenseWork {
 };
 
 // ---------------------------------------------------------------------------------
-__device__ __forceinline__ bool lung_bit(const Tables &T, int lin)
-{
-    return (__ldg(T.lungs_bits + (lin >> 5)) >> (lin & 31)) & 1u;
-}
-
-// membership of voxel (i, j, k) in the env's tumour: bbox test, then the bbox-local bitmask
-__device__ __forceinline__ bool tumour_bit(const Tables &T, const Tumour &tm, int tid, int i, int j, int k)
-{
-    int li = i - tm.lo[0], lj = j - tm.lo[1], lk = k - tm.lo[2];
-    if ((unsigned)li >= (unsigned)tm.dim[0] || (unsigned)lj >= (unsigned)tm.dim[1] ||
-        (unsigned)lk >= (unsigned)tm.dim[2])
-        return false;
-    int b = (li * tm.dim[1] + lj) * tm.dim[2] + lk;
-    return (__ldg(T.tumour_bits + (size_t)tid * T.bits_words + (b >> 5)) >> (b & 31)) & 1u;
-}
-
 __device__ __forceinline__ int pick_tumour(const Tables &T, const Schedule &S, int env, int n_envs, int episode)
 {
     if (S.ids) {
@@ -618,6 +602,33 @@ __global__ void __launch_bounds__(kStepThreads, 4) rt_step_kernel(Tables T, Sche
 }
 
 // ---------------------------------------------------------------------------------
+// Shared-memory hash table voxel -> summed beam weight for the streaming kernels (a beam hits <= 284
+// voxels of 201,670, so a per-voxel lookup must be O(1)).  1024 slots, linear probing.
+constexpr int kHashSlots = 1024;
+
+__device__ __forceinline__ int hash_slot(int lin) { return (int)(((uint32_t)lin * 2654435761u) >> 22); }
+
+__device__ __forceinline__ void hash_add(int *keys, float *vals, int lin, float w)
+{
+    int slot = hash_slot(lin);
+    while (true) {
+        const int prev = atomicCAS(keys + slot, -1, lin);
+        if (prev == -1 || prev == lin) {
+            atomicAdd(vals + slot, w);      // at most two addends per voxel: (0 + a) + b is order-independent
+            return;
+        }
+        slot = (slot + 1) & (kHashSlots - 1);
+    }
+}
+
+__device__ __forceinline__ float hash_get(const int *keys, const float *vals, int lin)
+{
+    int slot = hash_slot(lin);
+    while (keys[slot] != lin) slot = (slot + 1) & (kHashSlots - 1);
+    return vals[slot];
+}
+
+// ---------------------------------------------------------------------------------
 // Dense mode, second kernel (BASELINE configs[4], the reference's own dataflow): one block per env streams
 // the whole float32 volume  dose = clip(dose + beam*0.1, 0, 1)  (environment.py:107-110) and recomputes
 // sum(dose*tumours), sum(dose*lungs) and count(dose*mask > 0.2) from scratch (environment.py:164-191,
@@ -642,14 +653,15 @@ __global__ void __launch_bounds__(kDenseThreads) rt_dense_kernel(Tables T, EnvRe
     const int nwords = G.vstride / 32;
     uint32_t *tum_bits = smem;                          // [nwords] voxel belongs to the tumour
     uint32_t *hit_bits = smem + nwords;                 // [nwords] voxel is hit by this step's beam
-    int *hit_lin = reinterpret_cast<int *>(smem + 2 * nwords);
-    float *hit_w = reinterpret_cast<float *>(hit_lin + RT_BEAM_CAP);
+    int *hkeys = reinterpret_cast<int *>(smem + 2 * nwords);
+    float *hvals = reinterpret_cast<float *>(hkeys + kHashSlots);
     __shared__ double red_t[kDenseThreads / kWarp], red_l[kDenseThreads / kWarp];
     __shared__ int red_c[kDenseThreads / kWarp];
     const int tid = dw.tid;
     const Tumour tm = T.tumours[tid];
     const int nhit = dw.n_hits;
     for (int i = threadIdx.x; i < 2 * nwords; i += blockDim.x) smem[i] = 0u;
+    for (int i = threadIdx.x; i < kHashSlots; i += blockDim.x) { hkeys[i] = -1; hvals[i] = 0.0f; }
     __syncthreads();
     for (int k = threadIdx.x; k < tm.n_vox; k += blockDim.x) {
         const uint32_t pk = __ldg(T.vox_xyz + tm.vox_off + k);
@@ -658,41 +670,49 @@ __global__ void __launch_bounds__(kDenseThreads) rt_dense_kernel(Tables T, EnvRe
     }
     for (int k = threadIdx.x; k < nhit; k += blockDim.x) {
         const int lin = dw.lin[k];
-        hit_lin[k] = lin;
-        hit_w[k] = dw.w[k];
+        hash_add(hkeys, hvals, lin, dw.w[k]);
         atomicOr(hit_bits + (lin >> 5), 1u << (lin & 31));
     }
     __syncthreads();
 
     double s_t = 0.0, s_l = 0.0;
     int cnt = 0;
-    for (int q = threadIdx.x; q < ngroups; q += blockDim.x) {
-        float4 v = __ldcs(vol4 + q);
-        const int v0 = q * 4, sh = v0 & 31;
-        const uint32_t hb = (hit_bits[v0 >> 5] >> sh) & 15u;
-        const uint32_t tb = (tum_bits[v0 >> 5] >> sh) & 15u;
-        const uint32_t lb = (__ldg(T.lungs_bits + (v0 >> 5)) >> sh) & 15u;
-        float e[4] = {v.x, v.y, v.z, v.w};
-        if (hb) {
+    constexpr int kUnroll = 4;                          // independent 16-byte loads in flight per thread
+    for (int q0 = threadIdx.x; q0 < ngroups; q0 += kUnroll * kDenseThreads) {
+        float4 v[kUnroll];
 #pragma unroll
-            for (int i = 0; i < 4; i++)
-                if ((hb >> i) & 1u) {
-                    float wsum = 0.0f;
-                    for (int k = 0; k < nhit; k++)
-                        if (hit_lin[k] == v0 + i) wsum = hit_w[k];
-                    const float nd = __fadd_rn(e[i], __fmul_rn(wsum, 0.100000001490116119f));
-                    e[i] = fminf(fmaxf(nd, 0.0f), 1.0f);
-                }
+        for (int u = 0; u < kUnroll; u++) {
+            const int q = q0 + u * kDenseThreads;
+            v[u] = q < ngroups ? __ldcs(vol4 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        // voxels the beam misses: dose + 0*0.1 == dose and the clip is the identity on [0, 1] — written back anyway
-        __stcs(vol4 + q, make_float4(e[0], e[1], e[2], e[3]));
-        if (tb | lb) {
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const bool in_t = (tb >> i) & 1u, in_l = (lb >> i) & 1u;
-                if (in_t) s_t += (double)e[i];
-                if (in_l) s_l += (double)e[i];
-                if (in_l && !in_t && e[i] > 0.200000002980232239f) cnt++;
+        for (int u = 0; u < kUnroll; u++) {
+            const int q = q0 + u * kDenseThreads;
+            if (q >= ngroups) break;
+            const int v0 = q * 4, sh = v0 & 31;
+            const uint32_t hb = (hit_bits[v0 >> 5] >> sh) & 15u;
+            const uint32_t tb = (tum_bits[v0 >> 5] >> sh) & 15u;
+            const uint32_t lb = (__ldg(T.lungs_bits + (v0 >> 5)) >> sh) & 15u;
+            float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+            if (hb) {
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+                    if ((hb >> i) & 1u) {
+                        const float wsum = hash_get(hkeys, hvals, v0 + i);
+                        const float nd = __fadd_rn(e[i], __fmul_rn(wsum, 0.100000001490116119f));
+                        e[i] = fminf(fmaxf(nd, 0.0f), 1.0f);
+                    }
+            }
+            // voxels the beam misses: dose + 0*0.1 == dose and the clip is the identity on [0, 1] — written back anyway
+            __stcs(vol4 + q, make_float4(e[0], e[1], e[2], e[3]));
+            if (tb | lb) {
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const bool in_t = (tb >> i) & 1u, in_l = (lb >> i) & 1u;
+                    if (in_t) s_t += (double)e[i];
+                    if (in_l) s_l += (double)e[i];
+                    if (in_l && !in_t && e[i] > 0.200000002980232239f) cnt++;
+                }
             }
         }
     }
@@ -936,11 +956,11 @@ __global__ void rt_get_beams_kernel(const EnvRec *rec, const double *beams, int 
 }
 
 // ---------------------------------------------------------------------------------
-// Voxel observation (environment.py:245-257): block per env.  The two view beams are
-// traced by warps 0 and 1 into a shared hit table; every thread then streams 4-voxel
-// groups: out[c][v] = clip({lungs, tumours, dose, view}[v], 0, 1).
+// Voxel observation (environment.py:245-257): block per env.  The two view beams are traced by warps 0
+// and 1 into a shared hit table, the tumour is expanded into a shared bitset, then every thread streams
+// voxel pairs: out[c][v] = clip({lungs, tumours, dose, view}[v], 0, 1) with 8-byte loads and stores
+// (V is even, so every channel plane stays 8-byte aligned).  4.03 MB of HBM traffic per env.
 constexpr int kVolThreads = 512;
-constexpr int kViewCap = 2 * RT_BEAM_CAP;
 
 __global__ void __launch_bounds__(kVolThreads) rt_volumes_kernel(Tables T, const EnvRec *rec, const float *dose,
                                                                  const uint32_t *valid, int first, float *out)
@@ -948,19 +968,19 @@ __global__ void __launch_bounds__(kVolThreads) rt_volumes_kernel(Tables T, const
     extern __shared__ uint32_t smem[];
     __shared__ RayWork view[2];
     const Grid &G = T.G;
-    const int nwords = (G.nvox + 31) / 32;
+    const int nwords = G.vstride / 32;
     uint32_t *hit_bits = smem;                                  // [nwords] voxel hit by a view beam
-    int *hit_idx = reinterpret_cast<int *>(smem + nwords);      // [kViewCap]
-    float *hit_w = reinterpret_cast<float *>(hit_idx + kViewCap);
-    __shared__ int hit_n;
+    uint32_t *tum_bits = smem + nwords;                         // [nwords] voxel belongs to the tumour
+    int *hkeys = reinterpret_cast<int *>(smem + 2 * nwords);    // voxel -> current_beam + horizontal_beam_center
+    float *hvals = reinterpret_cast<float *>(hkeys + kHashSlots);
     const int env = first + blockIdx.x;
     const int lane = threadIdx.x & (kWarp - 1);
     const int warp = threadIdx.x / kWarp;
     const EnvRec r = rec[env];
     const Tumour tm = T.tumours[r.tumour_id];
 
-    for (int i = threadIdx.x; i < nwords; i += blockDim.x) hit_bits[i] = 0u;
-    if (threadIdx.x == 0) hit_n = 0;
+    for (int i = threadIdx.x; i < 2 * nwords; i += blockDim.x) smem[i] = 0u;
+    for (int i = threadIdx.x; i < kHashSlots; i += blockDim.x) { hkeys[i] = -1; hvals[i] = 0.0f; }
     __syncthreads();
     if (warp < 2) {
         // environment.py:246-249: beam along the current direction, and along (1,0,0)
@@ -973,39 +993,58 @@ __global__ void __launch_bounds__(kVolThreads) rt_volumes_kernel(Tables T, const
 #pragma unroll
             for (int j = 0; j < 4; j++)
                 if (lin[j] >= 0) {
-                    const int at = atomicAdd(&hit_n, 1);
-                    hit_idx[at] = lin[j];
-                    hit_w[at] = w[j];
+                    hash_add(hkeys, hvals, lin[j], w[j]);          // :250 current_beam + horizontal_beam_center
                     atomicOr(hit_bits + (lin[j] >> 5), 1u << (lin[j] & 31));
                 }
         }
+    } else {
+        for (int k = threadIdx.x - 2 * kWarp; k < tm.n_vox; k += blockDim.x - 2 * kWarp) {
+            const uint32_t pk = __ldg(T.vox_xyz + tm.vox_off + k);
+            const int lin = ((int)(pk & 255u) * G.g1 + (int)((pk >> 8) & 255u)) * G.g2 + (int)(pk >> 16);
+            atomicOr(tum_bits + (lin >> 5), 1u << (lin & 31));
+        }
     }
     __syncthreads();
-    const int nhit = hit_n;
-    const float *vol = dose + (size_t)env * G.vstride;
+    const float2 *vol2 = reinterpret_cast<const float2 *>(dose + (size_t)env * G.vstride);
     const uint32_t *vbits = valid + (size_t)env * G.vwords;
     float *o = out + (size_t)blockIdx.x * 4 * G.nvox;
-    for (int v = threadIdx.x; v < G.nvox; v += blockDim.x) {
-        const int sec = v >> 3;
-        const bool ok = (vbits[sec >> 5] >> (sec & 31)) & 1u;
-        const float dv = ok ? vol[v] : 0.0f;
-        float view = 0.0f;
-        if ((hit_bits[v >> 5] >> (v & 31)) & 1u) {
-            // current_beam + horizontal_beam_center (:250): the direction beam's weight first
-            float wa = 0.0f, wb = 0.0f;
-            bool ha = false, hb = false;
-            for (int k = 0; k < nhit; k++)
-                if (hit_idx[k] == v) {
-                    if (!ha) { wa = hit_w[k]; ha = true; }
-                    else { wb = hit_w[k]; hb = true; }
-                }
-            view = hb ? __fadd_rn(wa, wb) : wa;
+    float2 *o0 = reinterpret_cast<float2 *>(o), *o1 = reinterpret_cast<float2 *>(o + (size_t)G.nvox);
+    float2 *o2 = reinterpret_cast<float2 *>(o + (size_t)2 * G.nvox), *o3 = reinterpret_cast<float2 *>(o + (size_t)3 * G.nvox);
+    const int npairs = G.nvox / 2;                               // rt_assemble_volumes requires an even V
+    constexpr int kUnroll = 4;
+    for (int q0 = threadIdx.x; q0 < npairs; q0 += kUnroll * kVolThreads) {
+        float2 d[kUnroll];
+        bool ok[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; u++) {
+            const int q = q0 + u * kVolThreads;
+            ok[u] = false;
+            d[u] = make_float2(0.f, 0.f);
+            if (q < npairs) {
+                const int sec = q >> 2;                          // 2 voxels per pair, 8 per sector
+                ok[u] = (vbits[sec >> 5] >> (sec & 31)) & 1u;
+                if (ok[u]) d[u] = vol2[q];              // a sector never written this episode reads as zero
+            }
         }
-        o[v] = lung_bit(T, v) ? 1.0f : 0.0f;
-        const int vk = v % G.g2, vr = v / G.g2;
-        o[(size_t)G.nvox + v] = tumour_bit(T, tm, r.tumour_id, vr / G.g1, vr % G.g1, vk) ? 1.0f : 0.0f;
-        o[(size_t)2 * G.nvox + v] = fminf(fmaxf(dv, 0.0f), 1.0f);
-        o[(size_t)3 * G.nvox + v] = fminf(fmaxf(view, 0.0f), 1.0f);
+#pragma unroll
+        for (int u = 0; u < kUnroll; u++) {
+            const int q = q0 + u * kVolThreads;
+            if (q >= npairs) break;
+            const int v = 2 * q, sh = v & 31;
+            const uint32_t hb = (hit_bits[v >> 5] >> sh) & 3u;
+            const uint32_t tb = (tum_bits[v >> 5] >> sh) & 3u;
+            const uint32_t lb = (__ldg(T.lungs_bits + (v >> 5)) >> sh) & 3u;
+            float view2[2] = {0.0f, 0.0f};
+            if (hb) {
+#pragma unroll
+                for (int i = 0; i < 2; i++)
+                    if ((hb >> i) & 1u) view2[i] = hash_get(hkeys, hvals, v + i);
+            }
+            o0[q] = (make_float2((lb & 1u) ? 1.0f : 0.0f, (lb & 2u) ? 1.0f : 0.0f));
+            o1[q] = (make_float2((tb & 1u) ? 1.0f : 0.0f, (tb & 2u) ? 1.0f : 0.0f));
+            o2[q] = (make_float2(fminf(fmaxf(d[u].x, 0.0f), 1.0f), fminf(fmaxf(d[u].y, 0.0f), 1.0f)));
+            o3[q] = (make_float2(fminf(fmaxf(view2[0], 0.0f), 1.0f), fminf(fmaxf(view2[1], 0.0f), 1.0f)));
+        }
     }
 }
 
@@ -1200,7 +1239,7 @@ int rt_create(rt_env **out, int device, int n_envs, uint32_t flags, const rt_pha
         gmax = gmax > G.g2 ? gmax : G.g2;
         if (4 * (gmax + 1) > RT_BEAM_CAP) { rt_destroy(e); return fail(RT_ERR_INVALID, "rt_create: dense mode needs 4*(max(grid)+1) <= RT_BEAM_CAP"); }
         if ((rc = dev_alloc(&e->dense, (size_t)n_envs, &e->bytes))) { rt_destroy(e); return rc; }
-        e->dense_smem = (size_t)(2 * (G.vstride / 32)) * sizeof(uint32_t) + (size_t)RT_BEAM_CAP * (sizeof(int) + sizeof(float));
+        e->dense_smem = (size_t)(2 * (G.vstride / 32)) * sizeof(uint32_t) + (size_t)kHashSlots * (sizeof(int) + sizeof(float));
         cudaError_t ae = cudaFuncSetAttribute(rt_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->dense_smem);
         if (ae != cudaSuccess) { rt_destroy(e); return fail(RT_ERR_CUDA, std::string("rt_dense_kernel smem: ") + cudaGetErrorString(ae)); }
     }
@@ -1399,7 +1438,8 @@ int rt_assemble_volumes(rt_env *e, int first, int count, float *obs_dev, void *s
     if (first < 0 || count < 1 || first + count > e->n)
         return fail(RT_ERR_INVALID, "rt_assemble_volumes: env range out of bounds");
     RT_CUDA(cudaSetDevice(e->device));
-    const size_t smem = ((size_t)(e->T.G.nvox + 31) / 32) * sizeof(uint32_t) + (size_t)kViewCap * (sizeof(int) + sizeof(float));
+    if (e->T.G.nvox % 2) return fail(RT_ERR_INVALID, "rt_assemble_volumes: the voxel count must be even");
+    const size_t smem = (size_t)(2 * (e->T.G.vstride / 32)) * sizeof(uint32_t) + (size_t)kHashSlots * (sizeof(int) + sizeof(float));
     static bool attr_set = false;
     if (!attr_set) {
         RT_CUDA(cudaFuncSetAttribute(rt_volumes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

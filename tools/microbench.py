@@ -33,5 +33,21 @@ for m in (4096, 32768):
     print("  step             %8.2f us" % timeit(lambda: eng.step(a, want_info=False)))
     print("  step+info        %8.2f us" % timeit(lambda: eng.step(a, want_info=True)))
     r = torch.randn((128, m), device=dev); 
-    print("  gae T=128        %8.2f us" % timeit(lambda: rt.compute_gae(r, r, torch.zeros_like(r), r[0], r[1], 0.99, 0.95), reps=20))
+    zz = torch.zeros_like(r); oa = torch.empty_like(r); ob = torch.empty_like(r)
+    us = timeit(lambda: rt.compute_gae(r, r, zz, r[0], r[1], 0.99, 0.95, out=(oa, ob)), reps=20)
+    print("  gae T=128        %8.2f us  -> %.0f GB/s (20 B per element)" % (us, 128 * m * 20 / us / 1e3))
     eng.close()
+    if m <= 4096:
+        nd = 1024
+        de = rt.BatchedEpisodes(nd, device=dev, dense=True); de.reset()
+        ad = a[:nd].contiguous()
+        us = timeit(lambda: de.step(ad, want_info=False), reps=20)
+        byt = nd * 2 * de.phantom.nvox * 4
+        print("  dense step n=%d  %8.2f us  -> %.0f GB/s (R+W of the dose volumes)" % (nd, us, byt / us / 1e3))
+        de.close()
+        ve = rt.BatchedEpisodes(256, device=dev); ve.reset()
+        for i in range(10): ve.step(a[:256].contiguous(), want_info=False)
+        out = torch.empty((256, 4) + ve.grid, dtype=torch.float32, device=dev)
+        us = timeit(lambda: ve.volumes(0, 256, out=out), reps=20)
+        print("  volumes n=256     %8.2f us  -> %.0f GB/s (5 x V x 4 B per env)" % (us, 256 * 5 * ve.nvox * 4 / us / 1e3))
+        ve.close()
