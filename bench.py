@@ -35,8 +35,8 @@ import numpy as np  # noqa: E402
 # SURVEY.md §8(d), sparse visionless step under a uniform-random policy (re-measured by
 # tools/measure_traffic.py): payload P = 202 + 8*U + 4*W bytes, sector-granular
 # S = 256 + 64*Sec + 32*Sec_ep/100 bytes per env-step.
-ALGO_BYTES_PAYLOAD = 1716.0
-ALGO_BYTES_SECTOR = 5640.0
+ALGO_BYTES_PAYLOAD = 1690.0     # P = 202 + 8*116.6 + 4*138.7
+ALGO_BYTES_SECTOR = 5637.0      # S = 256 + 64*59.1 + 32*4994/100
 GRAPH_CHUNK = 50
 
 
@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-buffer leg (default min(steps, 500))")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-kernels", action="store_true", help="skip the dense / voxel-obs / GAE side measurements")
     ap.add_argument("--no-graph", action="store_true", help="launch every step from Python instead of CUDA graphs")
     return ap.parse_args()
 
@@ -162,6 +163,68 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------------------------
+def other_kernels(rt, dev, peak):
+    """The streaming kernels of the path, each timed alone with CUDA events on working sets > L2."""
+    import torch
+
+    def timed(fn, reps):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) * 1e-3 / reps
+
+    out = []
+    g = torch.Generator(device=dev).manual_seed(7)
+    # dense-mode step (BASELINE configs[4]): read + write every dose volume, 1,613,360 B per env-step
+    n = 1024
+    de = rt.BatchedEpisodes(n, device=dev, dense=True, seed=3)
+    de.reset()
+    a = torch.rand((n, 6), device=dev, generator=g) * 2 - 1
+    s = timed(lambda: de.step(a, want_info=False), 10)
+    b = n * 2 * de.nvox * 4
+    out.append({"kernel": "rt_step_kernel<dense> + rt_dense_kernel", "workload": f"{n} envs, full-volume dose update",
+                "bytes": b, "us": s * 1e6, "achieved": b / s / 1e9, "unit": "GB/s", "frac": b / s / 1e9 / peak,
+                "env_steps_per_s": n / s})
+    de.close()
+    # voxel observation (BASELINE configs[3]): 4 planes written + dose read, 4,033,400 B per env
+    n = 256
+    ve = rt.BatchedEpisodes(n, device=dev, seed=4)
+    ve.reset()
+    a = torch.rand((n, 6), device=dev, generator=g) * 2 - 1
+    for _ in range(20):
+        ve.step(a, want_info=False)
+    vol = torch.empty((n, 4) + ve.grid, dtype=torch.float32, device=dev)
+    s = timed(lambda: ve.volumes(0, n, out=vol), 10)
+    b = n * 5 * ve.nvox * 4
+    out.append({"kernel": "rt_volumes_kernel", "workload": f"{n} envs, (4,67,43,70) float32 observations",
+                "bytes": b, "us": s * 1e6, "achieved": b / s / 1e9, "unit": "GB/s", "frac": b / s / 1e9 / peak,
+                "env_steps_per_s": n / s})
+    ve.close()
+    del vol
+    # GAE (train.py:164-181): T=128, N=65536 (BASELINE configs[2] size), 20 B per element, two rotating sets > L2
+    T, N = 128, 65536
+    sets = [[torch.randn((T, N), device=dev, generator=g) for _ in range(3)] + [torch.empty((T, N), device=dev) for _ in range(2)]
+            for _ in range(2)]
+    nv, nd = torch.randn(N, device=dev, generator=g), torch.zeros(N, device=dev)
+    k = [0]
+
+    def gae():
+        r, v, d, oa, ob = sets[k[0] % 2]
+        k[0] += 1
+        rt.compute_gae(r, v, d, nv, nd, 0.99, 0.95, out=(oa, ob))
+    s = timed(gae, 10)
+    b = T * N * 20
+    out.append({"kernel": "rt_gae_kernel", "workload": f"T={T}, N={N}", "bytes": b, "us": s * 1e6,
+                "achieved": b / s / 1e9, "unit": "GB/s", "frac": b / s / 1e9 / peak})
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -255,15 +318,15 @@ def run_ours(args):
         h_rew = torch.empty(E, dtype=torch.float64, pin_memory=True)
         h_term = torch.empty(E, dtype=torch.uint8, pin_memory=True)
         h_trunc = torch.empty(E, dtype=torch.uint8, pin_memory=True)
-        hn = [h_act[i].numpy() for i in range(n_act)]
         ho, hr, ht, hu = h_obs.numpy(), h_rew.numpy(), h_term.numpy(), h_trunc.numpy()
+        calls = [eng.bind_step_host(h_act[i].numpy(), ho, hr, ht, hu) for i in range(n_act)]
         for i in range(5):
-            eng.step_host(hn[i], ho, hr, ht, hu)
+            calls[i]()
         barrier()
         t0 = time.perf_counter()
         acc = 0.0
         for i in range(Ke):
-            eng.step_host(hn[i % n_act], ho, hr, ht, hu)
+            calls[i % n_act]()                      # host actions in, host obs/reward/flags out, synchronous
             acc += float(hr[0])                     # the host reads the step's result
         torch.cuda.synchronize(dev)
         e2e_s = time.perf_counter() - t0
@@ -308,8 +371,11 @@ def run_ours(args):
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline()
-        print(json.dumps(line))
     eng.close()
+    if rank == 0:
+        if world == 1 and not args.no_other_kernels:
+            line["other_kernels"] = other_kernels(rt, dev, peak)
+        print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 

@@ -127,6 +127,25 @@ class BatchedEpisodes:
                                              C.c_void_p(truncated.ctypes.data),
                                              None if info is None else C.c_void_p(info.ctypes.data)), "rt_step_host")
 
+    def bind_step_host(self, actions: np.ndarray, obs: np.ndarray, reward: np.ndarray, terminated: np.ndarray,
+                       truncated: np.ndarray, info: Optional[np.ndarray] = None):
+        """Pre-bound host-buffer step for fixed buffers: returns a zero-argument callable (the per-call Python
+        cost is one ctypes call; `ndarray.ctypes` alone costs more than the kernel launch)."""
+        fn, h = self._lib.rt_step_host, self._h
+        args = (h, C.c_void_p(actions.ctypes.data), C.c_void_p(obs.ctypes.data), C.c_void_p(reward.ctypes.data),
+                C.c_void_p(terminated.ctypes.data), C.c_void_p(truncated.ctypes.data),
+                None if info is None else C.c_void_p(info.ctypes.data))
+        keep = (actions, obs, reward, terminated, truncated, info)
+        dev_index = self.device.index
+
+        def call(_keep=keep):
+            if torch.cuda.current_device() != dev_index:
+                torch.cuda.set_device(dev_index)
+            rc = fn(*args)
+            if rc != 0:
+                nat.check(rc, "rt_step_host")
+        return call
+
     def reset_host(self, obs: np.ndarray, mask: Optional[np.ndarray] = None):
         with torch.cuda.device(self.device):
             nat.check(self._lib.rt_reset_host(self._h, None if mask is None else C.c_void_p(mask.ctypes.data),

@@ -202,6 +202,9 @@ class RadiotherapyVectorEnv:
         self._h_info = torch.zeros((n, nat.INFO_SIZE), dtype=torch.float64, pin_memory=pin)
         self._vol = None
         self._last_on_host = False
+        self._host_step = self.engine.bind_step_host(self._h_actions.numpy(), self._h_obs.numpy(),
+                                                     self._h_reward.numpy(), self._h_term.numpy(),
+                                                     self._h_trunc.numpy(), self._h_info.numpy())
 
     # -- helpers ----------------------------------------------------------------------
     def last_info(self) -> np.ndarray:
@@ -250,8 +253,7 @@ class RadiotherapyVectorEnv:
         if actions.shape != (n, nat.ACTION_SIZE):
             raise ValueError(f"actions must have shape {(n, nat.ACTION_SIZE)}, got {actions.shape}")
         self._h_actions.numpy()[...] = actions            # cast to float32 = the declared action dtype
-        self.engine.step_host(self._h_actions.numpy(), self._h_obs.numpy(), self._h_reward.numpy(),
-                              self._h_term.numpy(), self._h_trunc.numpy(), self._h_info.numpy())
+        self._host_step()
         self._last_on_host = True
         term = self._h_term.numpy().astype(bool)
         infos = build_infos(self._h_info.numpy(), term, time.perf_counter() - self._t0)
