@@ -223,7 +223,7 @@ constexpr int kStepThreads = (kEnvsPerBlock + 1) * kWarp;
 struct EnvScalars {           // env-warp values parked in shared memory while the dose loop runs
     double px, py, pz;
     double os_t[3];
-    double tumour_dose, lung_dose, ep_return, best;
+    double tumour_dose, lung_dose, ep_return, best, r_dist;
     float obs_p[3];
     int t, lung_count, n_beams;
 };
@@ -247,10 +247,19 @@ __global__ void __launch_bounds__(kStepThreads, 4) rt_step_kernel(Tables T, Sche
     __shared__ Tumour tum[kEnvsPerBlock];
     __shared__ EnvScalars park[kEnvsPerBlock];
     __shared__ uint32_t tbits[kEnvsPerBlock][kMaxTumourWords];
+    // the env's sector-valid bitmap (3.2 KB), staged while the producer runs: the first-touch test after the
+    // barrier is a shared-memory lookup and dose values are only loaded for sectors that hold data
+    extern __shared__ uint32_t vsm_all[];
     const Grid &G = T.G;
     const int warp = threadIdx.x / kWarp;
     const int lane = threadIdx.x & (kWarp - 1);
     const int env0 = blockIdx.x * kEnvsPerBlock;
+
+    // Programmatic dependent launch: when this launch follows another step in the stream its blocks may be
+    // scheduled while that step drains; nothing of the previous step's state is read before this point.
+    // The trigger lets the NEXT launch do the same with respect to this one.
+    cudaGridDependencySynchronize();
+    cudaTriggerProgrammaticLaunchCompletion();
 
     // ---- producer warp ---------------------------------------------------------------------
     if (warp == kEnvsPerBlock) {
@@ -308,12 +317,18 @@ __global__ void __launch_bounds__(kStepThreads, 4) rt_step_kernel(Tables T, Sche
     EnvRec *my = rec + (active ? env : 0);
     Tumour &tm = tum[warp];
     EnvScalars &sc = park[warp];
+    uint32_t *vsm = vsm_all + (size_t)warp * G.vwords;
     bool needs_reset = false;
     int tid = 0;
     if (active) {
         needs_reset = my->needs_reset != 0;
         if (!needs_reset) {
             tid = my->tumour_id;
+            if (!kDense) {
+                const uint4 *src = reinterpret_cast<const uint4 *>(valid + (size_t)env * G.vwords);
+                uint4 *dst = reinterpret_cast<uint4 *>(vsm);
+                for (int i = lane; i < G.vwords / 4; i += kWarp) dst[i] = src[i];
+            }
             if (lane < kTumourWords)
                 reinterpret_cast<uint32_t *>(&tm)[lane] = __ldg(reinterpret_cast<const uint32_t *>(T.tumours + tid) + lane);
             for (int i = lane; i < T.bits_words; i += kWarp)                    // bits_words <= kMaxTumourWords (rt_create)
@@ -354,7 +369,10 @@ __global__ void __launch_bounds__(kStepThreads, 4) rt_step_kernel(Tables T, Sche
                 best = fmin(best, d2);
             }
             best = warp_min(best);
-            if (lane == 0) sc.best = best;
+            if (lane == 0) {
+                sc.best = best;
+                sc.r_dist = __dmul_rn(__ddiv_rn(sqrt(best), T.gnorm), -1.0);     // environment.py:158-162
+            }
         }
     }
     const int stamp_env = active ? env : 0;
@@ -452,7 +470,7 @@ __global__ void __launch_bounds__(kStepThreads, 4) rt_step_kernel(Tables T, Sche
     for (int kbase = 0; kbase < b.nslab; kbase += kPass * kWarp) {
         int lin[kPass][4], c0[kPass], c1[kPass], c2[kPass];
         float w[kPass][4], old[kPass][4];
-        uint32_t vw[kPass][4], lw[kPass][4];
+        uint32_t lw[kPass][4];
         bool use[kPass];
 #pragma unroll
         for (int c = 0; c < kPass; c++) {
@@ -462,41 +480,37 @@ __global__ void __launch_bounds__(kStepThreads, 4) rt_step_kernel(Tables T, Sche
             c0[c] = c1[c] = c2[c] = 0;
             if (use[c]) slab_targets(G, b, wk.ys, wk.zs, kbase + c * kWarp + lane, lin[c], w[c], c0[c], c1[c], c2[c]);
         }
-#pragma unroll
-        for (int c = 0; c < kPass; c++)
-#pragma unroll
-            for (int j = 0; j < 4; j++) {               // all bitmap loads in flight together
-                vw[c][j] = 0xffffffffu;
-                lw[c][j] = 0u;
-                old[c][j] = 0.0f;
-                if (lin[c][j] >= 0) {
-                    vw[c][j] = vbits[lin[c][j] >> 8];   // sector = lin >> 3, word = sector >> 5
-                    lw[c][j] = __ldg(T.lungs_bits + (lin[c][j] >> 5));
-                    // issued before the valid bit is known (one memory round trip instead of two); the value
-                    // is discarded below when the sector has not been written this episode
-                    old[c][j] = vol[lin[c][j]];
-                }
-            }
-        if (kbase == 0) RT_STAMP(4);
         bool fresh[kPass][4];
 #pragma unroll
         for (int c = 0; c < kPass; c++)
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                fresh[c][j] = lin[c][j] >= 0 && !((vw[c][j] >> ((lin[c][j] >> 3) & 31)) & 1u);
-                if (fresh[c][j]) old[c][j] = 0.0f;      // never written this episode: the sector reads as zero
+                lw[c][j] = 0u;
+                old[c][j] = 0.0f;
+                fresh[c][j] = false;
+                if (lin[c][j] >= 0) {
+                    const int sec = lin[c][j] >> 3;
+                    fresh[c][j] = !((vsm[sec >> 5] >> (sec & 31)) & 1u);        // never written this episode: reads as zero
+                    lw[c][j] = __ldg(T.lungs_bits + (lin[c][j] >> 5));
+                    if (!fresh[c][j]) old[c][j] = vol[lin[c][j]];               // re-touched sector: read from HBM/L2
+                }
             }
+        if (kbase == 0) RT_STAMP(4);
         __syncwarp();   // every lane has sampled the bitmap before any lane updates it
-        // first write to a sector this episode: materialise it as zeros and mark it valid
+        // first write to a sector this episode: materialise it as zeros and mark it valid (shared copy for the
+        // next pass of this warp, global copy for the next step).  Targets 2q and 2q+1 of a slab are neighbours
+        // in memory, so the second one usually shares the first one's sector and skips the fill.
 #pragma unroll
         for (int c = 0; c < kPass; c++)
 #pragma unroll
             for (int j = 0; j < 4; j++)
                 if (fresh[c][j]) {
                     const int sec = lin[c][j] >> 3;
+                    if ((j & 1) && fresh[c][j - 1] && (lin[c][j - 1] >> 3) == sec) continue;
                     float4 *sp = reinterpret_cast<float4 *>(vol + (sec << 3));
                     sp[0] = make_float4(0.f, 0.f, 0.f, 0.f);
                     sp[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    atomicOr(vsm + (sec >> 5), 1u << (sec & 31));
                     atomicOr(vbits + (sec >> 5), 1u << (sec & 31));
                 }
         __syncwarp();   // zero fill (any lane) is ordered before the voxel stores below
@@ -544,7 +558,7 @@ __global__ void __launch_bounds__(kStepThreads, 4) rt_step_kernel(Tables T, Sche
     const float ratio = __fdiv_rn(tsum_f32, tm.tumour_sum);
     const float r_tumour = __fmul_rn(ratio, 10.0f);
     const double r_lung = __dmul_rn(__ddiv_rn((double)lung_count, (double)tm.lung_mask_sum), -1.0);
-    const double r_dist = __dmul_rn(__ddiv_rn(sqrt(sc.best), T.gnorm), -1.0);
+    const double r_dist = sc.r_dist;
     const double reward = __dadd_rn(__dadd_rn((double)r_tumour, r_lung), r_dist);
     const bool done = (ratio >= 0.899999976158142090f) || (t >= RT_MAX_TIME_STEPS);
     const double ep_return = sc.ep_return + reward;
@@ -1092,6 +1106,8 @@ struct rt_env {
     double *beams = nullptr;
     DenseWork *dense = nullptr;
     size_t dense_smem = 0;
+    size_t step_smem = 0;
+    bool use_pdl = true;      // RT_PDL=0 in the environment switches programmatic dependent launch off
     uint32_t *d_lungs = nullptr;
     Tumour *d_tumours = nullptr;
     uint32_t *d_tbits = nullptr;
@@ -1234,6 +1250,12 @@ int rt_create(rt_env **out, int device, int n_envs, uint32_t flags, const rt_pha
     }
     if (flags & RT_FLAG_RECORD_BEAMS)
         if ((rc = dev_alloc(&e->beams, (size_t)n_envs * RT_MAX_TIME_STEPS * 6, &e->bytes))) { rt_destroy(e); return rc; }
+    if (const char *v = getenv("RT_PDL")) e->use_pdl = atoi(v) != 0;
+    e->step_smem = (size_t)kEnvsPerBlock * G.vwords * sizeof(uint32_t);
+    {
+        cudaError_t ae = cudaFuncSetAttribute(rt_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->step_smem);
+        if (ae != cudaSuccess) { rt_destroy(e); return fail(RT_ERR_CUDA, std::string("rt_step_kernel smem: ") + cudaGetErrorString(ae)); }
+    }
     if (flags & RT_FLAG_DENSE) {
         int gmax = G.g0 > G.g1 ? G.g0 : G.g1;
         gmax = gmax > G.g2 ? gmax : G.g2;
@@ -1349,8 +1371,19 @@ int rt_step(rt_env *e, const float *actions_dev, float *obs_dev, double *reward_
         rt_dense_kernel<<<e->n, kDenseThreads, e->dense_smem, (cudaStream_t)stream>>>(e->T, e->rec, e->dose, e->dense, o);
         RT_LAUNCH_CHECK("rt_dense_kernel");
     } else {
-        rt_step_kernel<false><<<grid, kStepThreads, 0, (cudaStream_t)stream>>>(e->T, e->S, e->rec, e->dose, e->valid,
-                                                                              e->beams, e->n, actions_dev, o, nullptr);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(kStepThreads);
+        cfg.dynamicSmemBytes = e->step_smem;
+        cfg.stream = (cudaStream_t)stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = e->use_pdl ? 1 : 0;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        DenseWork *no_dense = nullptr;
+        RT_CUDA(cudaLaunchKernelEx(&cfg, rt_step_kernel<false>, e->T, e->S, e->rec, e->dose, e->valid, e->beams, e->n,
+                                   actions_dev, o, no_dense));
         RT_LAUNCH_CHECK("rt_step_kernel");
     }
     return RT_OK;
