@@ -43,9 +43,13 @@ class _GaussianActorCritic(nn.Module):
     def get_action_and_value(self, x: torch.Tensor, action: torch.Tensor = None):
         f = self.features(x)
         mean = self.actor_mean(f)
-        dist = Normal(mean, torch.exp(self.actor_logstd.expand_as(mean)))
+        # validate_args=False: the argument check synchronises with the host, which a CUDA-graph capture forbids
+        dist = Normal(mean, torch.exp(self.actor_logstd.expand_as(mean)), validate_args=False)
         if action is None:
-            action = dist.sample()
+            # dist.sample() == randn * std + mean; written out because torch.normal(mean, std) validates std
+            # with a host synchronisation, which a CUDA-graph capture forbids
+            with torch.no_grad():
+                action = torch.randn_like(mean) * dist.scale + mean
         return action, dist.log_prob(action).sum(1), dist.entropy().sum(1), self.critic(f)
 
 

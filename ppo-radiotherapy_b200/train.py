@@ -37,6 +37,7 @@ DEFAULTS = dict(
     total_timesteps=10_000_000, num_saves=5, learning_rate=3e-4, num_envs=16, num_steps=2048, anneal_lr=False,
     num_minibatches=32, update_epochs=10, gamma=0.99, gae_lambda=0.95, norm_adv=True, clip_coef=0.1,
     clip_vloss=True, ent_coef=0.0, vf_coef=0.5, max_grad_norm=0.5, feature_dim=64, visionless=True,
+    cuda_graph=True,     # replay one captured rollout step (policy + env + buffer writes) instead of ~50 launches
 )
 
 
@@ -189,6 +190,52 @@ def train(cfg, writer=None, device="cuda", output_dir: Optional[str] = None, run
     next_obs, _ = envs.reset(seed=None, options={"backend": "torch"})
     next_obs = next_obs.clone()
     next_done = torch.zeros(n_local, device=device)
+    step_idx = torch.zeros(1, dtype=torch.long, device=device)
+    # per-iteration episode statistics, reduced on the device: [finished, sum return, sum length,
+    # sum of last-step reward components (tumour, lung, distance, total)] (train.py:42-66)
+    ep = torch.zeros(7, dtype=torch.float64, device=device)
+    ep_cols = torch.tensor([nat.INFO_EPISODE_RETURN, nat.INFO_EPISODE_LENGTH, nat.INFO_REWARD_TUMOUR,
+                            nat.INFO_REWARD_LUNG, nat.INFO_REWARD_DISTANCE, nat.INFO_REWARD_TOTAL], device=device)
+
+    def rollout_step():
+        """train.py:139-158 for the step selected by the device-side counter `step_idx` (so that one captured
+        CUDA graph serves every step of the rollout)."""
+        obs.index_copy_(0, step_idx, next_obs.unsqueeze(0))
+        dones.index_copy_(0, step_idx, next_done.unsqueeze(0))
+        with torch.no_grad():
+            action, logprob, _, value = agent.get_action_and_value(next_obs)
+        values.index_copy_(0, step_idx, value.reshape(1, -1))
+        actions.index_copy_(0, step_idx, action.unsqueeze(0))
+        logprobs.index_copy_(0, step_idx, logprob.unsqueeze(0))
+        o, _, term, trunc, info = eng.step(action, want_info=True)              # train.py:151, on the device
+        if not cfg.visionless:
+            o = envs._volumes()
+        next_obs.copy_(o)
+        rewards.index_copy_(0, step_idx, eng.reward_f32.unsqueeze(0))
+        next_done.copy_((term | trunc).float())
+        f64 = term.double()
+        ep[0:1] += f64.sum()
+        ep[1:7] += (info.index_select(1, ep_cols) * f64.unsqueeze(1)).sum(0)
+        step_idx.add_(1)
+
+    graph = None
+    if getattr(cfg, "cuda_graph", True) and cfg.visionless:
+        side = torch.cuda.Stream(device)
+        side.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(side):
+            for _ in range(min(3, T)):              # warm-up on the side stream (allocator, cuBLAS handles)
+                rollout_step()
+            side.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=side):
+                rollout_step()
+        torch.cuda.current_stream(device).wait_stream(side)
+        # the warm-up steps advanced the envs; start the run from a clean reset
+        envs.engine.reset()
+        next_obs.copy_(eng.obs)
+        next_done.zero_()
+        ep.zero_()
+
     global_step = 0
     start = time.time()
     history = []
@@ -196,33 +243,14 @@ def train(cfg, writer=None, device="cuda", output_dir: Optional[str] = None, run
     for iteration in range(1, cfg.num_iterations + 1):
         if cfg.anneal_lr:
             optimizer.param_groups[0]["lr"] = (1.0 - (iteration - 1.0) / cfg.num_iterations) * cfg.learning_rate
-        # per-iteration episode statistics, reduced on the device: [finished, sum return, sum length,
-        # sum of last-step reward components (tumour, lung, distance, total)] (train.py:42-66)
-        ep = torch.zeros(7, dtype=torch.float64, device=device)
+        ep.zero_()
+        step_idx.zero_()
         for step in range(T):
             global_step += cfg.num_envs
-            obs[step] = next_obs
-            dones[step] = next_done
-            with torch.no_grad():
-                action, logprob, _, value = agent.get_action_and_value(next_obs)
-            values[step] = value.flatten()
-            actions[step] = action
-            logprobs[step] = logprob
-            o, _, term, trunc, info = eng.step(action, want_info=True)          # train.py:151, on the device
-            if not cfg.visionless:
-                o = envs._volumes()
-            next_obs = o.clone() if cfg.visionless else o
-            rewards[step] = eng.reward_f32
-            next_done = (term | trunc).float()
-            fin = term.bool()
-            f64 = fin.double()
-            ep[0] += f64.sum()
-            ep[1] += (info[:, nat.INFO_EPISODE_RETURN] * f64).sum()
-            ep[2] += (info[:, nat.INFO_EPISODE_LENGTH] * f64).sum()
-            ep[3] += (info[:, nat.INFO_REWARD_TUMOUR] * f64).sum()
-            ep[4] += (info[:, nat.INFO_REWARD_LUNG] * f64).sum()
-            ep[5] += (info[:, nat.INFO_REWARD_DISTANCE] * f64).sum()
-            ep[6] += (info[:, nat.INFO_REWARD_TOTAL] * f64).sum()
+            if graph is not None:
+                graph.replay()
+            else:
+                rollout_step()
 
         with torch.no_grad():
             next_value = agent.get_value(next_obs).reshape(-1)
