@@ -1063,8 +1063,11 @@ __global__ void __launch_bounds__(kVolThreads) rt_volumes_kernel(Tables T, const
 }
 
 // ---------------------------------------------------------------------------------
-// GAE (train.py:164-181): one thread per env walks t = T-1 .. 0.  float32, one rounding
-// per operation, in the order torch evaluates the reference expression.
+// GAE (train.py:164-181): one thread per env walks t = T-1 .. 0.  float32, one rounding per operation, in
+// the order torch evaluates the reference expression.  The recurrence is serial in t, the loads are not: each
+// thread keeps kGaeDepth timesteps (3 loads each) in flight, which is what bounds the achieved bandwidth.
+constexpr int kGaeDepth = 16;
+
 __global__ void __launch_bounds__(128) rt_gae_kernel(const float *__restrict__ rewards,
                                                      const float *__restrict__ values,
                                                      const float *__restrict__ dones,
@@ -1077,16 +1080,30 @@ __global__ void __launch_bounds__(128) rt_gae_kernel(const float *__restrict__ r
     float last = 0.0f;
     float nnt = __fsub_rn(1.0f, next_done[i]);
     float nv = next_value[i];
-#pragma unroll 8
-    for (int t = T - 1; t >= 0; t--) {
-        const size_t k = (size_t)t * N + i;
-        const float r = __ldg(rewards + k), v = __ldg(values + k), d = __ldg(dones + k);
-        float delta = __fsub_rn(__fadd_rn(r, __fmul_rn(__fmul_rn(g, nv), nnt)), v);
-        last = __fadd_rn(delta, __fmul_rn(__fmul_rn(gl, nnt), last));
-        adv[k] = last;
-        ret[k] = __fadd_rn(last, v);
-        nnt = __fsub_rn(1.0f, d);      // dones[t] gates step t-1
-        nv = v;
+    for (int t0 = T - 1; t0 >= 0; t0 -= kGaeDepth) {
+        float r[kGaeDepth], v[kGaeDepth], d[kGaeDepth];
+#pragma unroll
+        for (int u = 0; u < kGaeDepth; u++) {
+            const int t = t0 - u;
+            if (t >= 0) {
+                const size_t k = (size_t)t * N + i;
+                r[u] = __ldcs(rewards + k);
+                v[u] = __ldcs(values + k);
+                d[u] = __ldcs(dones + k);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kGaeDepth; u++) {
+            const int t = t0 - u;
+            if (t < 0) break;
+            const size_t k = (size_t)t * N + i;
+            const float delta = __fsub_rn(__fadd_rn(r[u], __fmul_rn(__fmul_rn(g, nv), nnt)), v[u]);
+            last = __fadd_rn(delta, __fmul_rn(__fmul_rn(gl, nnt), last));
+            __stcs(adv + k, last);
+            __stcs(ret + k, __fadd_rn(last, v[u]));
+            nnt = __fsub_rn(1.0f, d[u]);      // dones[t] gates step t-1
+            nv = v[u];
+        }
     }
 }
 
@@ -1541,6 +1558,7 @@ int rt_beam_voxels(const int32_t grid[3], const double *pos_dev, const double *d
                    int32_t *idx_dev, float *w_dev, int32_t *count_dev, void *stream)
 {
     if (int rc = check_grid(grid)) return rc;
+    if (m == 0) return RT_OK;
     if (!pos_dev || !dir_dev || !idx_dev || !w_dev || !count_dev) return fail(RT_ERR_INVALID, "rt_beam_voxels: NULL argument");
     int gmax = grid[0] > grid[1] ? grid[0] : grid[1];
     gmax = gmax > grid[2] ? gmax : grid[2];
@@ -1556,6 +1574,7 @@ int rt_beam_voxels_dense(const int32_t grid[3], const double *pos_dev, const dou
                          int32_t *status_dev, void *stream)
 {
     if (int rc = check_grid(grid)) return rc;
+    if (m == 0) return RT_OK;
     if (!pos_dev || !dir_dev || !out_dev) return fail(RT_ERR_INVALID, "rt_beam_voxels_dense: NULL argument");
     if (m < 0) return fail(RT_ERR_INVALID, "rt_beam_voxels_dense: m < 0");
     if (m == 0) return RT_OK;
@@ -1572,6 +1591,7 @@ int rt_pose_update(const int32_t grid[3], const double *pos_dev, const double *d
                    double *overshoot_r_dev, void *stream)
 {
     if (int rc = check_grid(grid)) return rc;
+    if (m == 0) return RT_OK;
     if (!pos_dev || !dir_dev || !actions_dev || !pos_out_dev || !dir_out_dev)
         return fail(RT_ERR_INVALID, "rt_pose_update: NULL argument");
     if (m < 0) return fail(RT_ERR_INVALID, "rt_pose_update: m < 0");
@@ -1586,6 +1606,7 @@ int rt_pose_update(const int32_t grid[3], const double *pos_dev, const double *d
 int rt_apply_rotation(const double *dir_dev, const double *rotvec_dev, int m, double min_angle, double *dir_out_dev,
                       double *overshoot_dev, void *stream)
 {
+    if (m == 0) return RT_OK;
     if (!dir_dev || !rotvec_dev || !dir_out_dev) return fail(RT_ERR_INVALID, "rt_apply_rotation: NULL argument");
     if (m < 0) return fail(RT_ERR_INVALID, "rt_apply_rotation: m < 0");
     if (m == 0) return RT_OK;
@@ -1602,6 +1623,7 @@ int rt_apply_rotation(const double *dir_dev, const double *rotvec_dev, int m, do
 int rt_apply_translation(const double *pos_dev, const double *translation_dev, int m, const double bounds[3],
                          double *pos_out_dev, double *overshoot_dev, void *stream)
 {
+    if (m == 0) return RT_OK;
     if (!pos_dev || !translation_dev || !bounds || !pos_out_dev)
         return fail(RT_ERR_INVALID, "rt_apply_translation: NULL argument");
     if (m < 0) return fail(RT_ERR_INVALID, "rt_apply_translation: m < 0");
@@ -1616,10 +1638,10 @@ int rt_gae(const float *rewards_dev, const float *values_dev, const float *dones
            const float *next_done_dev, int T, int N, double gamma, double gae_lambda, float *advantages_dev,
            float *returns_dev, void *stream)
 {
-    if (!rewards_dev || !values_dev || !dones_dev || !next_value_dev || !next_done_dev || !advantages_dev || !returns_dev)
-        return fail(RT_ERR_INVALID, "rt_gae: NULL argument");
     if (T < 0 || N < 0) return fail(RT_ERR_INVALID, "rt_gae: negative extent");
     if (T == 0 || N == 0) return RT_OK;
+    if (!rewards_dev || !values_dev || !dones_dev || !next_value_dev || !next_done_dev || !advantages_dev || !returns_dev)
+        return fail(RT_ERR_INVALID, "rt_gae: NULL argument");
     rt_gae_kernel<<<(N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(rewards_dev, values_dev, dones_dev, next_value_dev,
                                                                     next_done_dev, T, N, (float)gamma,
                                                                     (float)(gamma * gae_lambda), advantages_dev,

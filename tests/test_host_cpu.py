@@ -53,6 +53,9 @@ def test_invalid_arguments_are_reported_without_a_gpu():
     assert L.rt_beam_voxels(bad, None, None, 1, 288, None, None, None, None) < 0
     assert b"grid" in L.rt_last_error()
     assert L.rt_gae(None, None, None, None, None, 1, 1, 0.99, 0.95, None, None, None) < 0
+    # empty batches are valid and need no buffers
+    assert L.rt_gae(None, None, None, None, None, 0, 4, 0.99, 0.95, None, None, None) == 0
+    assert L.rt_beam_voxels(grid, None, None, 0, 288, None, None, None, None) == 0
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
