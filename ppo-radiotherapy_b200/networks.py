@@ -66,7 +66,8 @@ class PPO(_GaussianActorCritic):
 class FeaturesExtractor3D(nn.Module):
     """C3D-style trunk (networks.py:8-45): Conv3d(C,16,3) ReLU MaxPool(2,2,pad) Conv3d(16,16,3,g=2) ReLU
     MaxPool(2) Conv3d(16,16,3,g=4) ReLU MaxPool(2) Flatten Linear ReLU.  `compute_dtype=torch.bfloat16`
-    runs the convolutions on the tensor cores (channels-last-3d, cuDNN)."""
+    runs the convolutions under bf16 autocast (cuDNN, NCDHW: measured faster than channels-last-3d for this
+    4->16-channel trunk, whose last pooling layer is pathological in channels-last; tools/c3d_layers.py)."""
 
     def __init__(self, observation_shape, features_dim: int, compute_dtype: torch.dtype = None):
         super().__init__()
@@ -85,7 +86,7 @@ class FeaturesExtractor3D(nn.Module):
     def forward(self, observations: torch.Tensor) -> torch.Tensor:
         if self.compute_dtype is not None and observations.is_cuda:
             with torch.autocast("cuda", dtype=self.compute_dtype):
-                x = self.cnn(observations.contiguous(memory_format=torch.channels_last_3d))
+                x = self.cnn(observations)
             return self.mlp(x.float())
         return self.mlp(self.cnn(observations))
 
