@@ -73,6 +73,7 @@ class FeaturesExtractor3D(nn.Module):
         super().__init__()
         self.observation_shape = observation_shape
         self.compute_dtype = compute_dtype
+        self.fused_first_block = True       # rollout (no_grad) path: rt_conv1_relu_pool instead of cuDNN + 4 more kernels
         pad = tuple((int(observation_shape[i + 1]) - 2) % 2 for i in range(3))
         self.cnn = nn.Sequential(
             nn.Conv3d(int(observation_shape[0]), 16, 3), nn.ReLU(), nn.MaxPool3d(2, 2, padding=pad),
@@ -83,7 +84,43 @@ class FeaturesExtractor3D(nn.Module):
             n_flat = self.cnn(torch.zeros((1,) + tuple(int(s) for s in observation_shape))).shape[1]
         self.mlp = nn.Sequential(nn.Linear(n_flat, features_dim), nn.ReLU())
 
+    def _fused_first_block(self, observations: torch.Tensor):
+        """Conv3d + ReLU + MaxPool3d (cnn[0:3]) as one tensor-core kernel of librtenv_b200.so (inference only:
+        no autograd graph).  Returns None for shapes / dtypes the kernel does not cover."""
+        import ctypes as C
+        from . import _native as nat
+        conv = self.cnn[0]
+        x = observations
+        if (x.dtype != torch.float32 or x.dim() != 5 or x.shape[1] != 4 or conv.out_channels != 16
+                or tuple(conv.kernel_size) != (3, 3, 3) or x.shape[4] % 2 or not x.is_contiguous()):
+            return None
+        n, _, D, H, W = x.shape
+        Do, Ho, Wo = D - 2, H - 2, W - 2
+        pd, ph = Do % 2, Ho % 2
+        shape = (n, 16, (Do + 2 * pd - 2) // 2 + 1, (Ho + 2 * ph - 2) // 2 + 1, (Wo - 2) // 2 + 1)
+        out = torch.empty(shape, dtype=torch.bfloat16, device=x.device)
+        if getattr(self, "_conv_scratch", None) is None or self._conv_scratch.device != x.device:
+            self._conv_scratch = torch.empty(2304, dtype=torch.int32, device=x.device)
+        w = conv.weight.detach().float().contiguous()
+        b = conv.bias.detach().float().contiguous()
+        with torch.cuda.device(x.device):
+            rc = nat.lib().rt_conv1_relu_pool(C.c_void_p(x.data_ptr()), C.c_void_p(w.data_ptr()), C.c_void_p(b.data_ptr()),
+                                              n, D, H, W, C.c_void_p(out.data_ptr()),
+                                              C.c_void_p(self._conv_scratch.data_ptr()),
+                                              C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream))
+        if rc == -1:                                    # RT_ERR_INVALID: shape not covered
+            return None
+        nat.check(rc, "rt_conv1_relu_pool")
+        return out
+
     def forward(self, observations: torch.Tensor) -> torch.Tensor:
+        if (self.compute_dtype == torch.bfloat16 and observations.is_cuda and not torch.is_grad_enabled()
+                and self.fused_first_block):
+            h = self._fused_first_block(observations)
+            if h is not None:
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    h = self.cnn[3:](h)
+                return self.mlp(h.float())
         if self.compute_dtype is not None and observations.is_cuda:
             with torch.autocast("cuda", dtype=self.compute_dtype):
                 x = self.cnn(observations)

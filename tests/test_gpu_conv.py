@@ -1,0 +1,86 @@
+"""Fused Conv3d(4->16,k3)+bias+ReLU+MaxPool3d tensor-core kernel (rt_conv1_relu_pool) against PyTorch.
+
+Tolerance: the kernel multiplies bf16-rounded inputs and weights exactly and accumulates in float32, so against
+a float32 torch convolution of the same bf16-rounded operands only the summation order and the final bf16
+rounding of the output differ: |diff| <= 2^-8 relative + 1e-3 absolute."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import ppo_radiotherapy_b200 as rt
+from ppo_radiotherapy_b200 import _native as nat
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _fused(x, w, b):
+    n, _, D, H, W = x.shape
+    Do, Ho, Wo = D - 2, H - 2, W - 2
+    pd, ph = Do % 2, Ho % 2
+    out = torch.empty((n, 16, (Do + 2 * pd - 2) // 2 + 1, (Ho + 2 * ph - 2) // 2 + 1, (Wo - 2) // 2 + 1),
+                      dtype=torch.bfloat16, device=x.device)
+    scratch = torch.empty(2304, dtype=torch.int32, device=x.device)
+    rc = nat.lib().rt_conv1_relu_pool(C.c_void_p(x.data_ptr()), C.c_void_p(w.data_ptr()), C.c_void_p(b.data_ptr()), n, D, H, W,
+                                      C.c_void_p(out.data_ptr()), C.c_void_p(scratch.data_ptr()),
+                                      C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    return rc, out
+
+
+def _reference(x, w, b):
+    xb, wb = x.bfloat16().float(), w.bfloat16().float()
+    y = F.relu(F.conv3d(xb, wb, b))
+    pad = tuple((y.shape[i + 2]) % 2 for i in range(3))
+    return F.max_pool3d(y, 2, 2, padding=pad)
+
+
+@pytest.mark.parametrize("shape", [(2, 67, 43, 70), (3, 9, 12, 10), (1, 8, 11, 14), (2, 5, 5, 6), (5, 16, 3, 4)])
+def test_conv1_block_matches_torch(shape):
+    n, D, H, W = shape
+    g = torch.Generator(device=DEV).manual_seed(D * 1000 + H)
+    x = torch.rand((n, 4, D, H, W), device=DEV, generator=g)
+    x[:, :2] = (x[:, :2] > 0.5).float()                       # lungs / tumour planes are {0, 1}
+    w = torch.randn((16, 4, 3, 3, 3), device=DEV, generator=g) * 0.2
+    b = torch.randn(16, device=DEV, generator=g) * 0.1
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    rc, out = _fused(x, w, b)
+    assert rc == 0
+    want = _reference(x, w, b)
+    assert out.shape == want.shape
+    got = out.float()
+    err = (got - want).abs()
+    tol = want.abs() * 2.0 ** -7 + 2e-3
+    assert bool((err <= tol).all()), f"max err {float(err.max())} at {int(err.argmax())}"
+    assert float(got.max()) > 0.1                             # not trivially zero
+
+
+def test_conv1_rejects_uncovered_shapes():
+    x = torch.rand((1, 4, 8, 8, 9), device=DEV)               # odd width: pool padding 1 on the last axis
+    w = torch.randn((16, 4, 3, 3, 3), device=DEV)
+    rc, _ = _fused(x.contiguous(), w, torch.zeros(16, device=DEV))
+    assert rc == -1
+
+
+def test_features_extractor_fused_path_matches_unfused():
+    torch.manual_seed(0)
+    fe = rt.FeaturesExtractor3D((4, 67, 43, 70), 64, compute_dtype=torch.bfloat16).to(DEV)
+    envs = rt.RadiotherapyVectorEnv(6, visionless=False, device=DEV, seed=5)
+    obs, _ = envs.reset(options={"backend": "torch"})
+    a = torch.rand((6, 6), device=DEV) * 2 - 1
+    for _ in range(5):
+        obs, *_ = envs.step(a)
+    with torch.no_grad():
+        fe.fused_first_block = True
+        y1 = fe(obs)
+        fe.fused_first_block = False
+        y2 = fe(obs)
+    assert y1.shape == (6, 64)
+    assert float((y1 - y2).abs().max()) <= 0.05 * float(y2.abs().max()) + 1e-2
+    # with autograd enabled the module takes the differentiable cuDNN path
+    y3 = fe(obs)
+    assert y3.requires_grad
+    envs.close()
