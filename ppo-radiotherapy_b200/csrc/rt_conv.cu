@@ -43,7 +43,11 @@ struct ConvShape {
     int Pd, Ph, Pw;       // pooled output
     int plane_vox;        // voxels per shared-memory plane buffer (H*W rounded up + halo reach)
     int tiles;            // 32-position warp tiles per plane
+    uint32_t mW, mPw, mPhPw;   // ceil(2^32 / divisor), 0 for divisor 1 (2^32 does not fit)
 };
+
+// n / divisor for the small dividends used here (n < 2^16, divisor < 2^12: n * (magic * d - 2^32) < 2^32)
+__device__ __forceinline__ int fastdiv(int n, uint32_t magic) { return magic ? (int)__umulhi((uint32_t)n, magic) : n; }
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b)
 {
@@ -186,7 +190,7 @@ __global__ void __launch_bounds__(kThreads, 1) rt_conv1_kernel(ConvShape S, int 
 #pragma unroll
                 for (int half = 0; half < 2; half++) {
                     const int f = f0 + mi * 16 + half * 8 + lane / 4;
-                    const int h = f / S.W, w = f - h * S.W;
+                    const int h = fastdiv(f, S.mW), w = f - h * S.W;
                     float v[2][2];
 #pragma unroll
                     for (int nt = 0; nt < 2; nt++)
@@ -219,8 +223,8 @@ __global__ void __launch_bounds__(kThreads, 1) rt_conv1_kernel(ConvShape S, int 
         for (int i = 0; i < kMaxStash; i++) {
             const int e = tid + i * kThreads;
             if (e < pooled_elems) {
-                const int ch = e / (S.Ph * S.Pw), rem = e - ch * (S.Ph * S.Pw);
-                const int py = rem / S.Pw, px = rem - py * S.Pw;
+                const int ch = fastdiv(e, S.mPhPw), rem = e - ch * (S.Ph * S.Pw);
+                const int py = fastdiv(rem, S.mPw), px = rem - py * S.Pw;
                 const int h0 = 2 * py - S.ph;
                 float m = 0.0f;                        // every candidate is >= 0 after ReLU
                 if (h0 >= 0 && h0 < S.Ho) m = __bfloat162float(R[((size_t)h0 * S.Pw + px) * kCout + ch]);
@@ -263,6 +267,11 @@ int rt_conv1_relu_pool(const float *x_dev, const float *weight_dev, const float 
     S.tiles = (H * W + 31) / 32;
     S.plane_vox = S.tiles * 32 + 2 * W + 8;                         // rows read up to f + 2W + 3 (+1 for the voxel pair)
     if (S.Ph * S.Pw * kCout > kMaxStash * kThreads) return RT_ERR_INVALID;
+    auto magic = [](int d) { return d == 1 ? 0u : (uint32_t)(((1ull << 32) + (uint64_t)d - 1) / (uint64_t)d); };
+    S.mW = magic(W);
+    S.mPw = magic(S.Pw);
+    S.mPhPw = magic(S.Ph * S.Pw);
+    if (S.tiles * 32 + 64 >= 65536 || S.Ph * S.Pw * kCout >= 65536) return RT_ERR_INVALID;
     const size_t smem = (size_t)3 * S.plane_vox * 16 + (size_t)S.Ho * S.Pw * kCout * sizeof(__nv_bfloat16);
     int dev = 0, max_smem = 0, sms = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return RT_ERR_CUDA;
