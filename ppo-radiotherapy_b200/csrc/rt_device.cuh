@@ -130,21 +130,38 @@ __device__ __forceinline__ double overshoot_from_z(double zc)                   
     return fmax(0.0, __dsub_rn(kMinAngle, ang));
 }
 
+// x / n with a shared reciprocal r = __drcp_rn(n): one multiply and one Markstein correction step
+// (q = RN(x*r); q' = RN(q + r*(x - q*n)), the residual is exact in an FMA).  With r correctly rounded q' is
+// the correctly rounded quotient, i.e. the value __ddiv_rn / NumPy produce, at 3 instructions instead of the
+// ~25 of a full division; the three components of a normalisation share r.
+__device__ __forceinline__ double div_shared(double x, double n, double r)
+{
+    const double q = __dmul_rn(x, r);
+    return __fma_rn(__fma_rn(-q, n, x), r, q);
+}
+
+__device__ __forceinline__ void normalize3(double &a, double &b, double &c)     // v / np.linalg.norm(v)
+{
+    const double n = dnorm3(a, b, c);
+    const double r = __drcp_rn(n);
+    a = div_shared(a, n, r); b = div_shared(b, n, r); c = div_shared(c, n, r);
+}
+
 // transforms.py:7-55 for min_angle = pi/4; returns the clipped z component (:29) for overshoot_from_z.
 __device__ __forceinline__ double rotate_env(double (&d)[3], const double rv[3])
 {
-    double n = dnorm3(d[0], d[1], d[2]);                            // transforms.py:23
-    double d0 = __ddiv_rn(d[0], n), d1 = __ddiv_rn(d[1], n), d2 = __ddiv_rn(d[2], n);
+    double d0 = d[0], d1 = d[1], d2 = d[2];
+    normalize3(d0, d1, d2);                                         // transforms.py:23
 
     double angle = dnorm3(rv[0], rv[1], rv[2]);                     // from_rotvec
     double scale, qw;
     if (angle <= 1e-3) {
         double a2 = __dmul_rn(angle, angle);
         scale = __dadd_rn(__dsub_rn(0.5, __ddiv_rn(a2, 48.0)), __ddiv_rn(__dmul_rn(a2, a2), 3840.0));
-        qw = cos(__ddiv_rn(angle, 2.0));
+        qw = cos(__dmul_rn(angle, 0.5));
     } else {
         double sh, ch;
-        sincos(__ddiv_rn(angle, 2.0), &sh, &ch);
+        sincos(__dmul_rn(angle, 0.5), &sh, &ch);                    // angle / 2 is exact either way
         scale = __ddiv_rn(sh, angle);
         qw = ch;
     }
@@ -164,22 +181,21 @@ __device__ __forceinline__ double rotate_env(double (&d)[3], const double rv[3])
     double r0 = __dadd_rn(__dadd_rn(__dmul_rn(m00, d0), __dmul_rn(m01, d1)), __dmul_rn(m02, d2)); // apply
     double r1 = __dadd_rn(__dadd_rn(__dmul_rn(m10, d0), __dmul_rn(m11, d1)), __dmul_rn(m12, d2));
     double r2 = __dadd_rn(__dadd_rn(__dmul_rn(m20, d0), __dmul_rn(m21, d1)), __dmul_rn(m22, d2));
-    n = dnorm3(r0, r1, r2);                                         // transforms.py:27
-    r0 = __ddiv_rn(r0, n); r1 = __ddiv_rn(r1, n); r2 = __ddiv_rn(r2, n);
+    normalize3(r0, r1, r2);                                         // transforms.py:27
 
     const double zc = fmin(fmax(r0, -1.0), 1.0);                    // :29
     double n0 = r0, n1 = r1, n2 = r2;
     if (fabs(zc) >= kClampZ) {                                      // :35-51, see kClampZ
         double px = r1, py = r2;
-        double pn = sqrt(__dadd_rn(__dmul_rn(px, px), __dmul_rn(py, py)));
+        const double pn = sqrt(__dadd_rn(__dmul_rn(px, px), __dmul_rn(py, py)));
         if (pn < 1e-8) { px = 1.0; py = 0.0; }
-        else { px = __ddiv_rn(px, pn); py = __ddiv_rn(py, pn); }
+        else { const double pr = __drcp_rn(pn); px = div_shared(px, pn, pr); py = div_shared(py, pn, pr); }
         n0 = zc > 0.0 ? kCosMin : -kCosMin;                         // sign(z) * cos(min_angle)
         n1 = __dmul_rn(px, kXYMag);
         n2 = __dmul_rn(py, kXYMag);
     }
-    n = dnorm3(n0, n1, n2);                                         // :55
-    d[0] = __ddiv_rn(n0, n); d[1] = __ddiv_rn(n1, n); d[2] = __ddiv_rn(n2, n);
+    normalize3(n0, n1, n2);                                         // :55
+    d[0] = n0; d[1] = n1; d[2] = n2;
     return zc;
 }
 
@@ -307,6 +323,18 @@ __device__ __forceinline__ void beam_walk(const Beam &b, float *ys, float *zs)
     }
 }
 
+// Same walk, (intery, interz) interleaved so that one 64-bit shared-memory store publishes a slab.
+__device__ __forceinline__ void beam_walk2(const Beam &b, float2 *yz)
+{
+    float y = b.y0, z = b.z0;
+#pragma unroll 8
+    for (int k = 0; k < b.nslab; k++) {
+        yz[k] = make_float2(y, z);
+        y = __fadd_rn(y, b.sgy);
+        z = __fadd_rn(z, b.sgz);
+    }
+}
+
 struct SlabFrac {
     int yf, zf;      // floor(intery), floor(interz)            (:76, :80)
     float fy, fz;    // fractional parts                         (:77, :81)
@@ -343,12 +371,12 @@ __device__ __forceinline__ float splat_weight(const SlabFrac &s, int dy, int dz)
 //   targets with q == qp   are also written by the PREVIOUS slab (as q' = 1-qp, o' = D + o) when o' is 0 or 1
 //   targets with q == 1-qp are also written by the NEXT slab     (as q' = qp,   o' = D + o) when o' is 0 or 1
 // The earlier slab owns the voxel: out = (0 + w_k) + w_{k+1}.
-__device__ __forceinline__ void slab_targets(const Grid &G, const Beam &b, const float *ys, const float *zs, int k,
-                                             int (&lin)[4], float (&w)[4], int &c0, int &c1, int &c2)
+__device__ __forceinline__ void slab_targets_yz(const Grid &G, const Beam &b, int k, float2 cur, float2 prev, float2 next,
+                                                int (&lin)[4], float (&w)[4], int &c0, int &c1, int &c2)
 {
+    // cur = (intery, interz) of slab k; prev / next = those of slabs k-1 / k+1 (only used when they exist)
     const bool have = k < b.nslab;
-    const int kk = have ? k : 0;
-    const SlabFrac s = slab_frac(ys[kk], zs[kk]);
+    const SlabFrac s = slab_frac(cur.x, cur.y);
     const float wy[2] = {__fsub_rn(1.0f, s.fy), s.fy};                       // :86
     const float wz[2] = {__fsub_rn(1.0f, s.fz), s.fz};                       // :87
     const int x = b.x0 + k * b.step;
@@ -369,9 +397,8 @@ __device__ __forceinline__ void slab_targets(const Grid &G, const Beam &b, const
     const int qp = b.step > 0 ? 0 : 1;
     // previous slab: it owns the voxels both write
     if (k > 0) {
-        const float py = ys[k - 1], pz = zs[k - 1];
-        const int D = s.zf - (int)floorf(pz);
-        if ((int)floorf(py) == s.yf) {
+        const int D = s.zf - (int)floorf(prev.y);
+        if ((int)floorf(prev.x) == s.yf) {
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 const int dy = j >> 1, dz = j & 1;
@@ -382,7 +409,7 @@ __device__ __forceinline__ void slab_targets(const Grid &G, const Beam &b, const
     }
     // next slab: add its weight for the voxels both write
     if (k + 1 < b.nslab) {
-        const SlabFrac n = slab_frac(ys[k + 1], zs[k + 1]);
+        const SlabFrac n = slab_frac(next.x, next.y);
         const int D = s.zf - n.zf;
         if (n.yf == s.yf) {
             const float ny[2] = {__fsub_rn(1.0f, n.fy), n.fy};
@@ -401,6 +428,15 @@ __device__ __forceinline__ void slab_targets(const Grid &G, const Beam &b, const
             }
         }
     }
+}
+
+__device__ __forceinline__ void slab_targets(const Grid &G, const Beam &b, const float *ys, const float *zs, int k,
+                                             int (&lin)[4], float (&w)[4], int &c0, int &c1, int &c2)
+{
+    const int kk = k < b.nslab ? k : 0;
+    const int kp = kk > 0 ? kk - 1 : 0, kn = kk + 1 < b.nslab ? kk + 1 : kk;
+    slab_targets_yz(G, b, k, make_float2(ys[kk], zs[kk]), make_float2(ys[kp], zs[kp]), make_float2(ys[kn], zs[kn]),
+                    lin, w, c0, c1, c2);
 }
 
 // ---------------------------------------------------------------------------------

@@ -84,6 +84,7 @@ struct __align__(16) Tumour {
 static_assert(sizeof(Tumour) == 64, "Tumour table entry layout");
 constexpr int kTumourWords = sizeof(Tumour) / 4;
 constexpr int kMaxTumourWords = 64;   // bbox occupancy words staged per env (bundled tumours need 38)
+constexpr int kMaxPTumourWords = 96;  // same for the bitmask padded by one voxel on axes 1 and 2 (+1 word of slack)
 
 struct Tables {
     Grid G;
@@ -92,8 +93,11 @@ struct Tables {
     const Tumour *tumours;
     const uint32_t *tumour_bits;   // [n_tumours][bits_words] bbox-local occupancy
     const uint32_t *vox_xyz;       // packed i | j<<8 | k<<16 per tumour voxel
+    const uint32_t *tumour_pbits;  // [n_tumours][pbits_words] occupancy of the bbox grown by one voxel on axes 1 and 2
     int n_tumours;
     int bits_words;
+    int pbits_words;
+    int lung_words16;              // words of lungs_bits rounded up to a multiple of 4 (16-byte bulk copies)
     long long *stage_clock;        // optional [N][8] clock64() stamps of the step kernel's stages (rt_set_stage_clock)
 };
 
@@ -615,6 +619,10 @@ __global__ void __launch_bounds__(kStepThreads, 4) rt_step_kernel(Tables T, Sche
     RT_STAMP(7);
 }
 
+}  // namespace
+#include "rt_step.cuh"
+namespace {
+
 // ---------------------------------------------------------------------------------
 // Shared-memory hash table voxel -> summed beam weight for the streaming kernels (a beam hits <= 284
 // voxels of 201,670, so a per-voxel lookup must be O(1)).  1024 slots, linear probing.
@@ -1124,10 +1132,12 @@ struct rt_env {
     DenseWork *dense = nullptr;
     size_t dense_smem = 0;
     size_t step_smem = 0;
+    int step_kb = 0;          // envs per block of rt_step3_kernel (7, 14 or 28); 0 = the two-role kernel of rt_step_kernel
     bool use_pdl = true;      // RT_PDL=0 in the environment switches programmatic dependent launch off
     uint32_t *d_lungs = nullptr;
     Tumour *d_tumours = nullptr;
     uint32_t *d_tbits = nullptr;
+    uint32_t *d_ptbits = nullptr;
     uint32_t *d_vox = nullptr;
     int32_t *d_sched = nullptr;
     int64_t bytes = 0;
@@ -1255,10 +1265,35 @@ int rt_create(rt_env **out, int device, int n_envs, uint32_t flags, const rt_pha
         }
     }
 
+    // padded variant for rt_step3_kernel: bit ((li*(d1+2)) + lj+1)*(d2+2) + lk+1, one spare zero word at the end
+    int max_pbits = 1;
+    for (int t = 0; t < ph->n_tumours; t++) {
+        const Tumour &tm = tum[t];
+        const int pb = tm.dim[0] * (tm.dim[1] + 2) * (tm.dim[2] + 2);
+        max_pbits = pb > max_pbits ? pb : max_pbits;
+    }
+    e->T.pbits_words = (max_pbits + 31) / 32 + 1;
+    if (e->T.pbits_words > kMaxPTumourWords) {
+        delete e;
+        return fail(RT_ERR_INVALID, "rt_create: a tumour's padded bounding box exceeds 3040 voxels");
+    }
+    std::vector<uint32_t> ptbits((size_t)ph->n_tumours * e->T.pbits_words, 0u);
+    for (int t = 0; t < ph->n_tumours; t++) {
+        const Tumour &tm = tum[t];
+        for (int k = ph->vox_offsets[t]; k < ph->vox_offsets[t + 1]; k++) {
+            const uint32_t pk = vox_xyz[k];
+            const int li = (int)(pk & 255u) - tm.lo[0], lj = (int)((pk >> 8) & 255u) - tm.lo[1],
+                      lk = (int)(pk >> 16) - tm.lo[2];
+            const int b = (li * (tm.dim[1] + 2) + lj + 1) * (tm.dim[2] + 2) + lk + 1;
+            ptbits[(size_t)t * e->T.pbits_words + (b >> 5)] |= 1u << (b & 31);
+        }
+    }
+
     int rc = RT_OK;
     const size_t lung_words = (size_t)(G.nvox + 31) / 32;
-    if ((rc = dev_alloc(&e->d_lungs, lung_words, &e->bytes)) || (rc = dev_alloc(&e->d_tumours, tum.size(), &e->bytes)) ||
-        (rc = dev_alloc(&e->d_tbits, tbits.size(), &e->bytes)) || (rc = dev_alloc(&e->d_vox, vox_xyz.size(), &e->bytes)) ||
+    e->T.lung_words16 = (int)((lung_words + 3) / 4 * 4);
+    if ((rc = dev_alloc(&e->d_lungs, (size_t)e->T.lung_words16, &e->bytes)) || (rc = dev_alloc(&e->d_tumours, tum.size(), &e->bytes)) ||
+        (rc = dev_alloc(&e->d_tbits, tbits.size(), &e->bytes)) || (rc = dev_alloc(&e->d_ptbits, ptbits.size(), &e->bytes)) || (rc = dev_alloc(&e->d_vox, vox_xyz.size(), &e->bytes)) ||
         (rc = dev_alloc(&e->rec, (size_t)n_envs, &e->bytes)) ||
         (rc = dev_alloc(&e->dose, (size_t)n_envs * G.vstride, &e->bytes)) ||
         (rc = dev_alloc(&e->valid, (size_t)n_envs * G.vwords, &e->bytes))) {
@@ -1268,9 +1303,32 @@ int rt_create(rt_env **out, int device, int n_envs, uint32_t flags, const rt_pha
     if (flags & RT_FLAG_RECORD_BEAMS)
         if ((rc = dev_alloc(&e->beams, (size_t)n_envs * RT_MAX_TIME_STEPS * 6, &e->bytes))) { rt_destroy(e); return rc; }
     if (const char *v = getenv("RT_PDL")) e->use_pdl = atoi(v) != 0;
-    e->step_smem = (size_t)kEnvsPerBlock * G.vwords * sizeof(uint32_t);
     {
-        cudaError_t ae = cudaFuncSetAttribute(rt_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->step_smem);
+        // Envs per block of the step kernel: 7 while that covers the envs with one block per SM, else 14 (two
+        // blocks per SM; measured a little faster than one block of 28 both at 4096 envs and at 65536).
+        // RT_STEP_KB overrides: 7, 14, 28 (the stage-clock instrumentation exists for 28 only), 0 = the previous
+        // two-role kernel rt_step_kernel<false>.
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+        const int per_sm = (n_envs + sms - 1) / sms;
+        e->step_kb = per_sm <= 7 ? 7 : 14;
+        if (const char *v = getenv("RT_STEP_KB")) {
+            const int kb = atoi(v);
+            if (kb == 0 || kb == 7 || kb == 14 || kb == 28) e->step_kb = kb;
+        }
+        const int kb = e->step_kb ? e->step_kb : kEnvsPerBlock;
+        e->step_smem = (size_t)kb * G.vwords * sizeof(uint32_t) + (e->step_kb ? (size_t)e->T.lung_words16 * sizeof(uint32_t) : 0);
+        cudaError_t ae = cudaSuccess;
+        switch (e->step_kb) {
+        case 0: ae = cudaFuncSetAttribute(rt_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->step_smem); break;
+        case 7: ae = cudaFuncSetAttribute(rt_step3_kernel<7, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->step_smem); break;
+        case 14: ae = cudaFuncSetAttribute(rt_step3_kernel<14, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->step_smem); break;
+        default:
+            ae = cudaFuncSetAttribute(rt_step3_kernel<28, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->step_smem);
+            if (ae == cudaSuccess)
+                ae = cudaFuncSetAttribute(rt_step3_kernel<28, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->step_smem);
+            break;
+        }
         if (ae != cudaSuccess) { rt_destroy(e); return fail(RT_ERR_CUDA, std::string("rt_step_kernel smem: ") + cudaGetErrorString(ae)); }
     }
     if (flags & RT_FLAG_DENSE) {
@@ -1284,9 +1342,11 @@ int rt_create(rt_env **out, int device, int n_envs, uint32_t flags, const rt_pha
     }
     cudaError_t ce = cudaSuccess;
     auto chk = [&](cudaError_t x) { if (ce == cudaSuccess) ce = x; };
+    chk(cudaMemset(e->d_lungs, 0, (size_t)e->T.lung_words16 * sizeof(uint32_t)));
     chk(cudaMemcpy(e->d_lungs, ph->lungs_bits, lung_words * sizeof(uint32_t), cudaMemcpyHostToDevice));
     chk(cudaMemcpy(e->d_tumours, tum.data(), tum.size() * sizeof(Tumour), cudaMemcpyHostToDevice));
     chk(cudaMemcpy(e->d_tbits, tbits.data(), tbits.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    chk(cudaMemcpy(e->d_ptbits, ptbits.data(), ptbits.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     chk(cudaMemcpy(e->d_vox, vox_xyz.data(), vox_xyz.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     chk(cudaMemset(e->rec, 0, (size_t)n_envs * sizeof(EnvRec)));
     chk(cudaMemset(e->valid, 0, (size_t)n_envs * G.vwords * sizeof(uint32_t)));
@@ -1306,6 +1366,7 @@ int rt_create(rt_env **out, int device, int n_envs, uint32_t flags, const rt_pha
     e->T.lungs_bits = e->d_lungs;
     e->T.tumours = e->d_tumours;
     e->T.tumour_bits = e->d_tbits;
+    e->T.tumour_pbits = e->d_ptbits;
     e->T.vox_xyz = e->d_vox;
     e->S.ids = nullptr;
     e->S.n_episodes = 0;
@@ -1318,7 +1379,7 @@ int rt_destroy(rt_env *e)
 {
     if (!e) return RT_OK;
     cudaSetDevice(e->device);
-    cudaFree(e->d_lungs); cudaFree(e->d_tumours); cudaFree(e->d_tbits); cudaFree(e->d_vox);
+    cudaFree(e->d_lungs); cudaFree(e->d_tumours); cudaFree(e->d_tbits); cudaFree(e->d_ptbits); cudaFree(e->d_vox);
     cudaFree(e->rec); cudaFree(e->dose); cudaFree(e->valid); cudaFree(e->beams); cudaFree(e->dense); cudaFree(e->d_sched);
     // the *_host staging buffers are device-visible pinned allocations of the same sizes
     cudaFreeHost(e->h_actions); cudaFreeHost(e->h_obs); cudaFreeHost(e->h_reward); cudaFreeHost(e->h_info);
@@ -1388,9 +1449,10 @@ int rt_step(rt_env *e, const float *actions_dev, float *obs_dev, double *reward_
         rt_dense_kernel<<<e->n, kDenseThreads, e->dense_smem, (cudaStream_t)stream>>>(e->T, e->rec, e->dose, e->dense, o);
         RT_LAUNCH_CHECK("rt_dense_kernel");
     } else {
+        const int kb = e->step_kb ? e->step_kb : kEnvsPerBlock;
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(grid);
-        cfg.blockDim = dim3(kStepThreads);
+        cfg.gridDim = dim3((e->n + kb - 1) / kb);
+        cfg.blockDim = dim3((kb + 1) * kWarp);
         cfg.dynamicSmemBytes = e->step_smem;
         cfg.stream = (cudaStream_t)stream;
         cudaLaunchAttribute attr[1];
@@ -1399,8 +1461,24 @@ int rt_step(rt_env *e, const float *actions_dev, float *obs_dev, double *reward_
         cfg.attrs = attr;
         cfg.numAttrs = 1;
         DenseWork *no_dense = nullptr;
-        RT_CUDA(cudaLaunchKernelEx(&cfg, rt_step_kernel<false>, e->T, e->S, e->rec, e->dose, e->valid, e->beams, e->n,
-                                   actions_dev, o, no_dense));
+        switch (e->step_kb) {
+        case 0:
+            RT_CUDA(cudaLaunchKernelEx(&cfg, rt_step_kernel<false>, e->T, e->S, e->rec, e->dose, e->valid, e->beams, e->n,
+                                       actions_dev, o, no_dense));
+            break;
+        case 7:
+            RT_CUDA(cudaLaunchKernelEx(&cfg, rt_step3_kernel<7, false>, e->T, e->S, e->rec, e->dose, e->valid, e->beams, e->n, actions_dev, o));
+            break;
+        case 14:
+            RT_CUDA(cudaLaunchKernelEx(&cfg, rt_step3_kernel<14, false>, e->T, e->S, e->rec, e->dose, e->valid, e->beams, e->n, actions_dev, o));
+            break;
+        default:
+            if (e->T.stage_clock)
+                RT_CUDA(cudaLaunchKernelEx(&cfg, rt_step3_kernel<28, true>, e->T, e->S, e->rec, e->dose, e->valid, e->beams, e->n, actions_dev, o));
+            else
+                RT_CUDA(cudaLaunchKernelEx(&cfg, rt_step3_kernel<28, false>, e->T, e->S, e->rec, e->dose, e->valid, e->beams, e->n, actions_dev, o));
+            break;
+        }
         RT_LAUNCH_CHECK("rt_step_kernel");
     }
     return RT_OK;
@@ -1428,6 +1506,8 @@ int rt_reset_host(rt_env *e, const uint8_t *mask_host, float *obs_host)
 int rt_set_stage_clock(rt_env *e, long long *stamps_dev)
 {
     if (!e) return fail(RT_ERR_INVALID, "rt_set_stage_clock: NULL handle");
+    if (stamps_dev && e->step_kb != 0 && e->step_kb != 28)
+        return fail(RT_ERR_STATE, "rt_set_stage_clock: the instrumented step kernel exists for 28 envs per block only (RT_STEP_KB=28)");
     e->T.stage_clock = stamps_dev;
     return RT_OK;
 }

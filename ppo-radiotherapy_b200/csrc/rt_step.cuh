@@ -1,0 +1,530 @@
+// rt_step.cuh — the sparse environment step (RadiotherapyEnv.step, environment.py:193-243), included by
+// rt_env.cu after the record / table definitions.
+//
+// A block advances kB envs with kB + 1 warps and two kinds of work:
+//
+//   scalar warp (warp 0), one THREAD per env: everything that is one value per env — record and action
+//      load, float64 translation and rotation (transforms.py:7-69), beam clip/set-up and the serial float32
+//      slab walk (draw_line.py:19-66, 98-99), rewards, termination, observation, episode statistics, the
+//      record update and the NEXT_STEP autoreset.  One warp instruction serves up to 28 envs.
+//   env warps (1..kB), one WARP per env: the only part that is wide — one slab per lane, its 2x2 splat
+//      targets, the sparse dose read-modify-write, tumour / lung deltas (environment.py:107-110,164-182) —
+//      plus the distance-to-tumour minimum (environment.py:150-162) while the scalar warp is busy.
+//
+// Timeline of a block:
+//      scalar: load, translate | rotate, beam set-up, walk        | obs, distance reward, pose | reward, outputs
+//      env:    TMA bitmap      | tumour entry, min distance       | dose deposition            |
+//                          barrier A                          barrier 1                    barrier 2
+//
+// The env's sector-valid bitmap (3.2 KB) is brought to shared memory by one cp.async.bulk per env, issued
+// before anything else and waited for on an mbarrier right before the deposition, so the first-touch test is
+// a shared-memory lookup and dose values are only loaded for sectors that hold data.
+#pragma once
+
+namespace {
+
+struct __align__(16) EnvShared {
+    Beam beam;               // scalar warp -> env warp (barrier 1)
+    int needs_reset;         // scalar warp -> env warp (barrier A)
+    double p[3];             // translated beam position (barrier A)
+    double best;             // env warp -> scalar warp: min squared distance to the tumour (barrier 1)
+    double d_tum, d_lung;    // env warp -> scalar warp: dose deltas of this beam (barrier 2)
+    int tid;
+    int d_cnt;
+    double os_t[3];          // translation overshoot (info only), parked by the scalar warp for itself
+};
+
+constexpr int kYZStride = kMaxSlabs + 1;   // odd float2 stride: the scalar warp's lanes store to distinct banks
+constexpr int kMaxPass = (kMaxSlabs + kWarp - 1) / kWarp;   // 32-slab passes of one beam (3)
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+// global -> shared bulk copy (TMA, no tensor map); bytes and both addresses are multiples of 16
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t mbar)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity)
+{
+    asm volatile("{\n"
+                 ".reg .pred p;\n"
+                 "RT_MBAR_WAIT:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                 "@p bra RT_MBAR_DONE;\n"
+                 "bra RT_MBAR_WAIT;\n"
+                 "RT_MBAR_DONE:\n"
+                 "}" ::"r"(mbar), "r"(parity) : "memory");
+}
+
+__device__ __forceinline__ void red_or(uint32_t *p, uint32_t v)
+{
+    asm volatile("red.global.or.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+#define RT_STAMP3(env_, slot)                                                                    \
+    do {                                                                                         \
+        if (kClock) T.stage_clock[(size_t)(env_) * 12 + (slot)] = clock64();                     \
+    } while (0)
+
+// The four splat targets of slab k (draw_line.py:84-96) in two steps, so that the dose loads can be issued
+// between them.  slab_coords: floor / fraction of the slab's (intery, interz), voxel coordinates, bounds;
+// target j = 2*dy + dz is voxel  base + dy*g2 + dz,  bit j of `inb` says it is inside the grid.
+struct SlabCoord {
+    int yf, zf;
+    float fy, fz;
+};
+
+template <int DOM>
+__device__ __forceinline__ SlabCoord slab_coords(const Grid &G, const Beam &b, int k, float2 cur, int &base, uint32_t &inb,
+                                                 int &c0, int &c1, int &c2)
+{
+    SlabCoord s;
+    const bool have = k < b.nslab;
+    const float yfl = floorf(cur.x), zfl = floorf(cur.y);                    // :76, :80
+    s.yf = (int)yfl; s.zf = (int)zfl;
+    s.fy = __fsub_rn(cur.x, yfl); s.fz = __fsub_rn(cur.y, zfl);              // :77, :81
+    const int x = b.x0 + k * b.step;
+    if (DOM == 0) { c0 = x; c1 = s.yf; c2 = s.zf; }                          // idx[dom]=x, idx[o0]=yf, idx[o1]=zf
+    else if (DOM == 1) { c0 = s.yf; c1 = x; c2 = s.zf; }
+    else { c0 = s.yf; c1 = s.zf; c2 = x; }
+    const bool a0 = have && (unsigned)c0 < (unsigned)G.g0;
+    const bool a10 = a0 && (unsigned)c1 < (unsigned)G.g1, a11 = a0 && (unsigned)(c1 + 1) < (unsigned)G.g1;
+    const bool a20 = (unsigned)c2 < (unsigned)G.g2, a21 = (unsigned)(c2 + 1) < (unsigned)G.g2;
+    base = (c0 * G.g1 + c1) * G.g2 + c2;
+    inb = (a10 && a20 ? 1u : 0u) | (a10 && a21 ? 2u : 0u) | (a11 && a20 ? 4u : 0u) | (a11 && a21 ? 8u : 0u);
+    return s;
+}
+
+// slab_weights: the splat weights, specialised on the warp-uniform dominant axis DOM and on QP = (step > 0 ? 0 : 1).
+// Same rule as slab_targets_yz (rt_device.cuh): a voxel that two neighbouring slabs write is owned by the earlier
+// slab with weight  (0 + w_k) + w_{k+1};  `drop` gets the bits of the targets the previous slab owns.
+template <int DOM, int QP>
+__device__ __forceinline__ void slab_weights(const Beam &b, int k, const SlabCoord &s, float2 prev, float2 next,
+                                             uint32_t &drop, float (&w)[4])
+{
+    const float gy = __fsub_rn(1.0f, s.fy), gz = __fsub_rn(1.0f, s.fz);     // :86-87
+    w[0] = __fmul_rn(gy, gz); w[1] = __fmul_rn(gy, s.fz); w[2] = __fmul_rn(s.fy, gz); w[3] = __fmul_rn(s.fy, s.fz);
+    drop = 0u;
+    if (DOM == 0) return;
+    // q = offset along the dominant axis, o = the other one: DOM 1 -> j = 2q + o, DOM 2 -> j = 2o + q
+    if (k > 0 && (int)floorf(prev.x) == s.yf) {                              // the previous slab owns what both write
+        const int D = s.zf - (int)floorf(prev.y);
+        constexpr uint32_t m0 = DOM == 1 ? 1u << (2 * QP) : 1u << QP;                // (q, o) = (QP, 0)
+        constexpr uint32_t m1 = DOM == 1 ? 1u << (2 * QP + 1) : 1u << (2 + QP);      // (q, o) = (QP, 1)
+        if ((unsigned)D <= 1u) drop |= m0;
+        if ((unsigned)(D + 1) <= 1u) drop |= m1;
+    }
+    if (k + 1 < b.nslab) {                                                   // add the next slab's weight for shared voxels
+        const float nyfl = floorf(next.x), nzfl = floorf(next.y);
+        if ((int)nyfl == s.yf) {
+            const int D = s.zf - (int)nzfl;
+            const float nfy = __fsub_rn(next.x, nyfl), nfz = __fsub_rn(next.y, nzfl);
+            const float ngy = __fsub_rn(1.0f, nfy), ngz = __fsub_rn(1.0f, nfz);
+            // my target (q, o) = (1-QP, o) is the neighbour's (QP, o2 = D + o) when o2 is 0 or 1
+#pragma unroll
+            for (int o = 0; o < 2; o++) {
+                const int o2 = D + o;
+                if ((unsigned)o2 <= 1u) {
+                    const float pw = DOM == 1 ? __fmul_rn(QP ? nfy : ngy, o2 ? nfz : ngz)
+                                              : __fmul_rn(o2 ? nfy : ngy, QP ? nfz : ngz);
+                    constexpr int jq = DOM == 1 ? 2 * (1 - QP) : (1 - QP);
+                    const int j = DOM == 1 ? jq + o : jq + 2 * o;
+                    if (j == 0) w[0] = __fadd_rn(w[0], pw);
+                    else if (j == 1) w[1] = __fadd_rn(w[1], pw);
+                    else if (j == 2) w[2] = __fadd_rn(w[2], pw);
+                    else w[3] = __fadd_rn(w[3], pw);
+                }
+            }
+        }
+    }
+}
+
+// One 32-slab pass of a beam, as held by a lane between the load and the store phase of the deposition:
+// the lane's slab writes up to four voxels  base + dy*g2 + dz.
+struct PassState {
+    int base;          // linear index of target (dy, dz) = (0, 0)
+    uint32_t flags;    // bit j: target j is written by this lane; 4+j: this lane zero-fills its (fresh) sector;
+                       // 8+j: voxel belongs to the tumour
+    float w[4];        // summed splat weights
+    float old[4];      // dose before the beam (0 for fresh sectors)
+};
+
+template <int kB, bool kClock>
+__global__ void __launch_bounds__((kB + 1) * kWarp, 28 / kB)
+rt_step3_kernel(Tables T, Schedule S, EnvRec *rec, float *dose, uint32_t *valid, double *beams, int n_envs,
+                const float *__restrict__ actions, StepOut out)
+{
+    __shared__ EnvShared sh[kB];
+    __shared__ Tumour tum[kB];
+    __shared__ uint32_t tbits[kB][kMaxPTumourWords];
+    __shared__ float2 yz[kB][kYZStride];
+    __shared__ __align__(8) unsigned long long mbars[kB + 1];
+    // outputs are staged here by the scalar warp's lanes and copied out row-contiguously (full-line stores:
+    // the host-buffer entry points map these arrays over PCIe)
+    __shared__ float s_obs[kB * RT_OBS_SIZE];
+    __shared__ double s_rew[kB];
+    __shared__ uint8_t s_term[kB];
+    __shared__ double s_info[kB * RT_INFO_SIZE];
+    extern __shared__ __align__(128) uint32_t dyn_smem[];         // [lung_words16] lungs bitmask, [kB][vwords] sector-valid bitmaps
+    const Grid &G = T.G;
+    const int warp = threadIdx.x / kWarp;
+    const int lane = threadIdx.x & (kWarp - 1);
+    const int env0 = blockIdx.x * kB;
+    uint32_t *slungs = dyn_smem;
+    uint32_t *vsm_all = dyn_smem + T.lung_words16;
+
+    if (lane == 0) mbar_init(smem_u32(&mbars[warp]), 1);          // mbars[0]: lungs bitmask, mbars[1 + le]: env le's bitmap
+    // Programmatic dependent launch: nothing the previous step wrote is read before this point; the trigger
+    // lets the next launch's blocks be scheduled as soon as ours retire.
+    cudaGridDependencySynchronize();
+    cudaTriggerProgrammaticLaunchCompletion();
+
+    // =====================================================================================================
+    if (warp == 0) {
+        const int e = env0 + lane;
+        const bool mine = lane < kB && e < n_envs;
+        if (lane == 0) bulk_load(smem_u32(slungs), T.lungs_bits, (uint32_t)(T.lung_words16 * sizeof(uint32_t)), smem_u32(&mbars[0]));
+        if (mine) RT_STAMP3(e, 0);
+        EnvRec *my = rec + (mine ? e : 0);
+        EnvShared &se = sh[lane < kB ? lane : 0];
+        const double gs[3] = {(double)G.g0, (double)G.g1, (double)G.g2};
+        bool stepping = false;
+        Pose s;
+        float ar[3] = {0.f, 0.f, 0.f};                                     // rotation part of the action
+        int tid = 0;
+        if (mine) {
+            // every load is issued before the first use: one round trip to L2
+            const int needs_reset = my->needs_reset;
+            tid = my->tumour_id;
+            double p0[3];
+#pragma unroll
+            for (int i = 0; i < 3; i++) { p0[i] = my->pos[i]; s.d[i] = my->dir[i]; }
+            const float2 *ap = reinterpret_cast<const float2 *>(actions + (size_t)e * RT_ACTION_SIZE);
+            const float2 a01 = __ldg(ap), a23 = __ldg(ap + 1), a45 = __ldg(ap + 2);
+            const float at[3] = {a01.x, a01.y, a23.x};
+            ar[0] = a23.y; ar[1] = a45.x; ar[2] = a45.y;
+            stepping = needs_reset == 0;
+            se.needs_reset = needs_reset;
+            se.tid = tid;
+            se.beam.nslab = 0;
+            if (stepping) {
+#pragma unroll
+                for (int i = 0; i < 3; i++) {                              // environment.py:122-125, transforms.py:65-67
+                    double os;
+                    s.p[i] = translate_axis(p0[i], __dmul_rn(__dmul_rn((double)clip1(at[i]), gs[i]), 0.2), gs[i], os);
+                    se.p[i] = s.p[i];
+                    if (out.info) se.os_t[i] = os;
+                }
+                if (kClock) T.stage_clock[(size_t)e * 12 + 8] = clock64() + (long long)(s.p[0] * 0.0);
+            }
+        }
+        __syncthreads();                                                   // ---- barrier A
+        double zc = 0.0;
+        if (stepping) {
+            double rv[3];
+#pragma unroll
+            for (int i = 0; i < 3; i++)                                    // environment.py:139-141
+                rv[i] = (double)__fmul_rn(__fmul_rn(clip1(ar[i]), 3.14159274101257324f), 0.5f);
+            zc = rotate_env(s.d, rv);                                      // transforms.py:7-55
+            if (kClock) T.stage_clock[(size_t)e * 12 + 9] = clock64() + (long long)(s.d[0] * 0.0);
+            const Beam b = beam_setup(G, s.p, s.d);                        // draw_line.py:19-66
+            if (kClock) T.stage_clock[(size_t)e * 12 + 10] = clock64() + (b.nslab < -5);
+            beam_walk2(b, yz[lane]);                                       // draw_line.py:98-99
+            se.beam = b;
+            RT_STAMP3(e, 1);
+        }
+        __syncthreads();                                                   // ---- barrier 1
+
+        // While the env warps deposit the dose: everything that does not depend on it.
+        const Tumour &tm = tum[lane < kB ? lane : 0];
+        int t = 0, n_beams = 0, lung_count = 0;
+        double r_dist = 0.0, os_r = 0.0, rcp_mask = 0.0, mask_sum = 1.0;
+        double tumour_dose = 0.0, lung_dose = 0.0, ep_return = 0.0;
+        if (stepping) {
+            tumour_dose = my->tumour_dose; lung_dose = my->lung_dose; ep_return = my->ep_return;   // consumed after barrier 2
+            t = my->t + 1;                                                 // environment.py:194
+            lung_count = my->lung_count;
+            n_beams = my->n_beams;
+            float *obs = s_obs + lane * RT_OBS_SIZE;                       // environment.py:259-268
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                obs[i] = (float)__dsub_rn(__dmul_rn(__ddiv_rn(s.p[i], gs[i]), 2.0), 1.0);
+                obs[3 + i] = (float)s.d[i];
+                obs[6 + i] = tm.obs_c[i];
+                my->pos[i] = s.p[i];
+                my->dir[i] = s.d[i];
+            }
+            r_dist = __dmul_rn(__ddiv_rn(sqrt(se.best), T.gnorm), -1.0);   // environment.py:158-162
+            mask_sum = (double)tm.lung_mask_sum;
+            rcp_mask = __drcp_rn(mask_sum);
+            if (out.info) os_r = overshoot_from_z(zc);                     // transforms.py:29-33, 57 (info only)
+            if (beams && n_beams < RT_MAX_TIME_STEPS) {                    // environment.py:110
+                double *bp = beams + ((size_t)e * RT_MAX_TIME_STEPS + n_beams) * 6;
+#pragma unroll
+                for (int i = 0; i < 3; i++) { bp[i] = s.p[i]; bp[3 + i] = s.d[i]; }
+            }
+        } else if (mine) {
+            // gymnasium 1.0.0 NEXT_STEP: the call after a terminal step resets and reports reward 0
+            // (environment.py:77-105; the env warp clears the sector-valid bitmap).
+            const int episode = my->episode + 1;
+            tid = pick_tumour(T, S, e, n_envs, episode);
+            const Tumour *tg = T.tumours + tid;
+            float *obs = s_obs + lane * RT_OBS_SIZE;
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                const double p = gs[i] / 2.0, d = i == 1 ? 1.0 : 0.0;
+                my->pos[i] = p;
+                my->dir[i] = d;
+                obs[i] = (float)__dsub_rn(__dmul_rn(__ddiv_rn(p, gs[i]), 2.0), 1.0);
+                obs[3 + i] = (float)d;
+                obs[6 + i] = __ldg(&tg->obs_c[i]);
+            }
+            my->tumour_dose = 0.0; my->lung_dose = 0.0; my->ep_return = 0.0;
+            my->t = 0; my->tumour_id = tid; my->lung_count = 0; my->episode = episode; my->needs_reset = 0; my->n_beams = 0;
+            s_rew[lane] = 0.0;
+            s_term[lane] = 0;
+            if (out.info) {
+                double *ip = s_info + lane * RT_INFO_SIZE;
+#pragma unroll
+                for (int i = 0; i < RT_INFO_SIZE; i++) ip[i] = i == RT_INFO_TUMOUR_ID ? (double)tid : 0.0;
+            }
+        }
+        const int nb = min(kB, n_envs - env0);                             // envs of this block
+        __syncwarp();
+        for (int i = lane; i < nb * RT_OBS_SIZE; i += kWarp) out.obs[(size_t)env0 * RT_OBS_SIZE + i] = s_obs[i];
+        mbar_wait(smem_u32(&mbars[0]), 0);                                 // the lungs copy must land before the block retires
+        __syncthreads();                                                   // ---- barrier 2
+        if (stepping) {
+            RT_STAMP3(e, 11);
+            tumour_dose += (double)se.d_tum;
+            lung_dose += (double)se.d_lung;
+            lung_count += se.d_cnt;
+            // rewards, termination (environment.py:158-191, 214-220)
+            const float tsum_f32 = (float)tumour_dose;                      // np.sum(dose*tumours) float32
+            const float ratio = __fdiv_rn(tsum_f32, tm.tumour_sum);
+            const float r_tumour = __fmul_rn(ratio, 10.0f);
+            const double r_lung = __dmul_rn(div_shared((double)lung_count, mask_sum, rcp_mask), -1.0);
+            const double reward = __dadd_rn(__dadd_rn((double)r_tumour, r_lung), r_dist);
+            const bool done = (ratio >= 0.899999976158142090f) || (t >= RT_MAX_TIME_STEPS);
+            ep_return += reward;
+            my->tumour_dose = tumour_dose; my->lung_dose = lung_dose; my->ep_return = ep_return;
+            my->t = t; my->lung_count = lung_count; my->needs_reset = done ? 1 : 0; my->n_beams = n_beams + 1;
+            s_rew[lane] = reward;
+            s_term[lane] = done ? 1 : 0;
+            if (out.info) {
+                double *ip = s_info + lane * RT_INFO_SIZE;
+                ip[RT_INFO_REWARD_TOTAL] = reward;
+                ip[RT_INFO_REWARD_TUMOUR] = (double)r_tumour;
+                ip[RT_INFO_REWARD_LUNG] = r_lung;
+                ip[RT_INFO_REWARD_DISTANCE] = r_dist;
+                ip[RT_INFO_DOSE_TUMOUR] = (double)tsum_f32;
+                ip[RT_INFO_DOSE_LUNG] = (double)(float)lung_dose;
+                ip[RT_INFO_OVERSHOOT_T0] = se.os_t[0];
+                ip[RT_INFO_OVERSHOOT_T0 + 1] = se.os_t[1];
+                ip[RT_INFO_OVERSHOOT_T0 + 2] = se.os_t[2];
+                ip[RT_INFO_OVERSHOOT_R] = os_r;
+                ip[RT_INFO_EPISODE_RETURN] = ep_return;
+                ip[RT_INFO_EPISODE_LENGTH] = (double)t;
+                ip[RT_INFO_LUNG_COUNT] = (double)lung_count;
+                ip[RT_INFO_STEPPED] = 1.0;
+                ip[RT_INFO_TUMOUR_ID] = (double)tid;
+                ip[RT_INFO_T] = (double)t;
+            }
+            RT_STAMP3(e, 7);
+        }
+        __syncwarp();
+        if (lane < nb) {
+            if (out.reward) out.reward[env0 + lane] = s_rew[lane];
+            if (out.reward_f32) out.reward_f32[env0 + lane] = (float)s_rew[lane];
+            if (out.terminated) out.terminated[env0 + lane] = s_term[lane];
+            if (out.truncated) out.truncated[env0 + lane] = 0;
+        }
+        if (out.info)
+            for (int i = lane; i < nb * RT_INFO_SIZE; i += kWarp) out.info[(size_t)env0 * RT_INFO_SIZE + i] = s_info[i];
+        return;
+    }
+
+    // =====================================================================================================
+    // env warps
+    const int le = warp - 1;
+    const int env = env0 + le;
+    const bool active = env < n_envs;
+    uint32_t *vsm = vsm_all + (size_t)le * G.vwords;
+    const uint32_t mbar = smem_u32(&mbars[warp]);
+    if (active && lane == 0)
+        bulk_load(smem_u32(vsm), valid + (size_t)env * G.vwords, (uint32_t)(G.vwords * sizeof(uint32_t)), mbar);
+    __syncthreads();                                                       // ---- barrier A
+    EnvShared &se = sh[le];
+    Tumour &tm = tum[le];
+    uint32_t *tb = tbits[le];
+    const bool stepping = active && se.needs_reset == 0;
+    if (stepping) {
+        const int tid = se.tid;
+        if (lane < kTumourWords)
+            reinterpret_cast<uint32_t *>(&tm)[lane] = __ldg(reinterpret_cast<const uint32_t *>(T.tumours + tid) + lane);
+        for (int i = lane; i < T.pbits_words; i += kWarp)                  // pbits_words <= kMaxPTumourWords (rt_create)
+            tb[i] = __ldg(T.tumour_pbits + (size_t)tid * T.pbits_words + i);
+        __syncwarp();
+        // distance_to_tumour_reward (environment.py:150-162): min over the tumour's voxel list
+        const double p0 = se.p[0], p1 = se.p[1], p2 = se.p[2];
+        double best = CUDART_INF;
+        const int nv = tm.n_vox;
+        const uint32_t *vx = T.vox_xyz + tm.vox_off;
+        for (int k = lane; k < nv; k += kWarp) {
+            const uint32_t pk = __ldg(vx + k);
+            const double dx = (double)(pk & 255u) - p0;
+            const double dy = (double)((pk >> 8) & 255u) - p1;
+            const double dz = (double)(pk >> 16) - p2;
+            const double d2 = __fma_rn(dz, dz, __fma_rn(dy, dy, dx * dx));
+            best = d2 < best ? d2 : best;
+        }
+        // min of non-negative doubles = min of their bit patterns: two integer warp reductions
+        const uint32_t hi = (uint32_t)__double2hiint(best);
+        const uint32_t mhi = __reduce_min_sync(kFull, hi);
+        const uint32_t mlo = __reduce_min_sync(kFull, hi == mhi ? (uint32_t)__double2loint(best) : 0xffffffffu);
+        if (lane == 0) se.best = __hiloint2double((int)mhi, (int)mlo);
+    } else if (active) {
+        // autoreset (environment.py:104-105): no sector of the new episode's dose volume is valid
+        uint4 *vw = reinterpret_cast<uint4 *>(valid + (size_t)env * G.vwords);
+        for (int i = lane; i < G.vwords / 4; i += kWarp) vw[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    if (active && lane == 0) RT_STAMP3(env, 2);
+    __syncthreads();                                                       // ---- barrier 1
+    if (active) mbar_wait(mbar, 0);                                        // the staged bitmap has landed
+    if (stepping) {
+        mbar_wait(smem_u32(&mbars[0]), 0);                                 // and so has the lungs bitmask
+        if (lane == 0) RT_STAMP3(env, 3);
+        // ---- dose deposition (environment.py:107-110): dose' = clip(dose + beam*0.1, 0, 1) on the voxels hit.
+        // All (up to three) 32-slab passes of the beam go through each phase together, so the beam costs one
+        // round trip to HBM however long it is:  targets + loads | zero fill | stores + accumulation.
+        const Beam b = se.beam;
+        const float2 *myz = yz[le];
+        float *vol = dose + (size_t)env * G.vstride;
+        uint32_t *vbits = valid + (size_t)env * G.vwords;
+        const int g2 = G.g2;
+        const int li0 = tm.lo[0], li1 = tm.lo[1] - 1, li2 = tm.lo[2] - 1;  // origin of the padded bbox
+        const int td0 = tm.dim[0], td1 = tm.dim[1], td2 = tm.dim[2];
+        const int pd1 = td1 + 2, pd2 = td2 + 2;
+        const int variant = b.dom == 0 ? 0 : (b.dom * 2 - 1 + (b.step > 0 ? 0 : 1));   // warp-uniform
+        PassState ps[kMaxPass];
+#pragma unroll
+        for (int c = 0; c < kMaxPass; c++) {
+            if (c * kWarp >= b.nslab) break;                               // warp-uniform
+            PassState &q = ps[c];
+            const int k = c * kWarp + lane;
+            const int kk = k < b.nslab ? k : 0;
+            const float2 cur = myz[kk], prv = myz[kk > 0 ? kk - 1 : 0], nxt = myz[kk + 1 < b.nslab ? kk + 1 : kk];
+            int c0, c1, c2;
+            uint32_t inb;
+            const SlabCoord sc = b.dom == 0 ? slab_coords<0>(G, b, k, cur, q.base, inb, c0, c1, c2)
+                               : b.dom == 1 ? slab_coords<1>(G, b, k, cur, q.base, inb, c0, c1, c2)
+                                            : slab_coords<2>(G, b, k, cur, q.base, inb, c0, c1, c2);
+            // the dose loads go out first (a voxel the previous slab owns is loaded for nothing: harmless)
+            uint32_t freshm = 0u;
+            int sec[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const bool inj = (inb >> j) & 1u;
+                const int l = inj ? q.base + (j >> 1) * g2 + (j & 1) : 0;
+                sec[j] = l >> 3;
+                const bool fresh = inj && !((vsm[sec[j] >> 5] >> (sec[j] & 31)) & 1u);   // never written this episode: reads as zero
+                q.old[j] = 0.0f;
+                if (inj && !fresh) q.old[j] = vol[l];                      // re-touched sector: read from HBM / L2
+                freshm |= fresh ? 1u << j : 0u;
+            }
+            uint32_t drop;
+            switch (variant) {
+            case 0: slab_weights<0, 0>(b, k, sc, prv, nxt, drop, q.w); break;
+            case 1: slab_weights<1, 0>(b, k, sc, prv, nxt, drop, q.w); break;
+            case 2: slab_weights<1, 1>(b, k, sc, prv, nxt, drop, q.w); break;
+            case 3: slab_weights<2, 0>(b, k, sc, prv, nxt, drop, q.w); break;
+            default: slab_weights<2, 1>(b, k, sc, prv, nxt, drop, q.w); break;
+            }
+            const uint32_t ok = inb & ~drop;
+            freshm &= ok;
+            // tumour membership of the 2x2 block: one range test against the bounding box grown by one voxel on
+            // axes 1 and 2 (the padded bitmask has empty border cells, so the four bits are always addressable)
+            uint32_t tmask = 0u;
+            const int ti = c0 - li0, tj = c1 - li1, tk = c2 - li2;
+            if ((unsigned)ti < (unsigned)td0 && (unsigned)tj <= (unsigned)td1 && (unsigned)tk <= (unsigned)td2) {
+                const int b0 = (ti * pd1 + tj) * pd2 + tk, b1 = b0 + pd2;
+                const uint32_t r0 = __funnelshift_r(tb[b0 >> 5], tb[(b0 >> 5) + 1], b0 & 31) & 3u;
+                const uint32_t r1 = __funnelshift_r(tb[b1 >> 5], tb[(b1 >> 5) + 1], b1 & 31) & 3u;
+                tmask = r0 | (r1 << 2);
+            }
+            // targets 2q and 2q+1 are neighbours in memory: the second one usually shares the first one's sector
+            uint32_t fill = freshm;
+            if ((freshm & 3u) == 3u && sec[0] == sec[1]) fill &= ~2u;
+            if ((freshm & 12u) == 12u && sec[2] == sec[3]) fill &= ~8u;
+            q.flags = ok | (fill << 4) | ((tmask & ok) << 8);
+        }
+        if (lane == 0) RT_STAMP3(env, 4);
+        // First write to a sector this episode: materialise it as zeros and mark it valid for the next step.
+        // Freshness of every pass was decided on the bitmap as it was before the beam, so no pass can wipe what
+        // another one stored: all fills come before all stores.
+#pragma unroll
+        for (int c = 0; c < kMaxPass; c++) {
+            if (c * kWarp >= b.nslab) break;
+            const PassState &q = ps[c];
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (q.flags & (16u << j)) {
+                    const int sec = (q.base + (j >> 1) * g2 + (j & 1)) >> 3;
+                    float4 *sp = reinterpret_cast<float4 *>(vol + (sec << 3));
+                    sp[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    sp[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    red_or(vbits + (sec >> 5), 1u << (sec & 31));
+                }
+        }
+        __syncwarp();   // zero fill (any lane) is ordered before the voxel stores below
+        if (lane == 0) RT_STAMP3(env, 5);
+        // per-lane partial sums of at most 12 float32 deltas; the running totals are float64 (scalar warp)
+        float d_tum = 0.0f, d_lung = 0.0f;
+        int d_cnt = 0;
+#pragma unroll
+        for (int c = 0; c < kMaxPass; c++) {
+            if (c * kWarp >= b.nslab) break;
+            const PassState &q = ps[c];
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (q.flags & (1u << j)) {
+                    const int l = q.base + (j >> 1) * g2 + (j & 1);
+                    const float o = q.old[j];
+                    const float nd = fminf(__fadd_rn(o, __fmul_rn(q.w[j], 0.100000001490116119f)), 1.0f);   // clip(dose + beam*0.1, 0, 1), dose >= 0
+                    vol[l] = nd;
+                    const bool in_t = q.flags & (256u << j);
+                    const bool in_l = (slungs[l >> 5] >> (l & 31)) & 1u;
+                    const float delta = nd - o;
+                    d_tum += in_t ? delta : 0.0f;
+                    d_lung += in_l ? delta : 0.0f;
+                    // lungs_mask = lungs*(1-tumours); dose is monotone, so the count only grows (environment.py:174-177)
+                    d_cnt += (in_l && !in_t && !(o > 0.200000002980232239f) && nd > 0.200000002980232239f) ? 1 : 0;
+                }
+        }
+        if (lane == 0) RT_STAMP3(env, 6);
+        // both sums in one butterfly: after the first exchange the lower half-warp carries the tumour sum, the
+        // upper one the lung sum
+        {
+            const bool upper = lane >= 16;
+            const float keep = upper ? d_lung : d_tum, give = upper ? d_tum : d_lung;
+            double v = (double)keep + (double)__shfl_xor_sync(kFull, give, 16);
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+            d_cnt = __reduce_add_sync(kFull, d_cnt);
+            if (lane == 0) { se.d_tum = v; se.d_cnt = d_cnt; }
+            if (lane == 16) se.d_lung = v;
+        }
+    }
+    __syncthreads();                                                       // ---- barrier 2
+}
+
+}  // namespace

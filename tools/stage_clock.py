@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Per-stage clock64() profile of the step kernel (rt_set_stage_clock)."""
 import sys, os, ctypes as C
+os.environ["RT_STEP_KB"] = "28"          # the instrumented kernel is the 28-envs-per-block variant
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import ppo_radiotherapy_b200 as rt
@@ -20,12 +21,13 @@ for i in range(20, 40):
     s = stamps.cpu().numpy().astype(np.float64)
     res.append(s)
 s = np.stack(res)            # [iters, n, 12]
-ok = (s[:, :, :11] > 0).all(axis=2)          # envs that walked a beam this step (all stamps written)
+ok = (s[:, :, :12] > 0).all(axis=2)          # envs that walked a beam this step (all stamps written)
 rel = s - s[:, :, 0:1]                        # clock64 is per SM: only differences within an env's block are meaningful
-order = [0, 8, 9, 10, 1, 2, 3, 4, 5, 6, 7]
-names = {0: "producer start", 8: "producer: state loaded", 9: "producer: pose updated", 10: "producer: beam set up",
-         1: "producer done (walk)", 2: "env warp ready", 3: "past barrier", 4: "splat + bitmap loads issued",
-         5: "dose loads / zero fill done", 6: "stores issued (all passes)", 7: "end"}
+order = [0, 8, 9, 10, 1, 2, 3, 4, 5, 6, 11, 7]
+names = {0: "scalar warp start", 8: "scalar: state loaded, translated", 9: "scalar: pose updated", 10: "scalar: beam set up",
+         1: "scalar: walk done", 2: "env warp: tumour + distance done", 3: "env warp: past barrier 1, bitmap landed",
+         4: "env warp: splat + loads issued", 5: "env warp: zero fill done (pass 1)", 6: "env warp: all passes done",
+         11: "scalar: past barrier 2", 7: "end"}
 print(f"n={n}: cycles since the block's producer start (mean / p50 / p99 over {int(ok.sum())} env-steps)")
 for k in order:
     v = rel[:, :, k][ok]
