@@ -27,6 +27,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -44,6 +45,7 @@ struct ConvShape {
     int plane_vox;        // voxels per shared-memory plane buffer (H*W rounded up + halo reach)
     int tiles;            // 32-position warp tiles per plane
     uint32_t mW, mPw, mPhPw;   // ceil(2^32 / divisor), 0 for divisor 1 (2^32 does not fit)
+    int r_elems;          // bf16 elements of the R buffer (Ho * Pw * 16, rounded up to 64)
 };
 
 // n / divisor for the small dividends used here (n < 2^16, divisor < 2^12: n * (magic * d - 2^32) < 2^32)
@@ -243,6 +245,249 @@ __global__ void __launch_bounds__(kThreads, 1) rt_conv1_kernel(ConvShape S, int 
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// The same block on the 5th-generation tensor cores (tcgen05): accumulators in tensor memory, operands read
+// from shared memory through matrix descriptors, one thread issues the MMAs.
+//
+// A operand = the Toeplitz view of the channels-last planes, expressed directly in the shared-memory
+// descriptor: K-major, no swizzle, where a core matrix is 8 rows x 16 bytes with rows 16 bytes apart.  Row r of
+// a 128-position tile is voxel f0 + r (16 bytes = 8 bf16 channel slots), so consecutive rows are consecutive
+// voxels: the stride between 8-row groups (SBO) is 128 bytes and the second 8-wide K chunk of the row is the NEXT
+// voxel, i.e. the leading-dimension offset (LBO) is 16 bytes.  The core matrices overlap in memory; nothing is
+// gathered or copied.  One tcgen05.mma (M = 128, N = 16, K = 16) per (kd, kh, kw pair): 18 per tile, all into
+// the same 16 tensor-memory columns.  B operand (weights, 16 x 16 per MMA) sits in shared memory once per block.
+//
+// A plane of H*W positions is ceil(H*W/128) tiles; each tile owns 16 TMEM columns (32 tiles fit the 512 columns),
+// signals an mbarrier through tcgen05.commit when its 18 MMAs are done, and is drained by the warp that may
+// touch its lane quarter (warp % 4): tcgen05.ld 32x32b.x16 gives every thread one position x 16 channels, then
+// bias, ReLU, max over the w pair (neighbouring lane) and the bf16 row goes to R as before.
+namespace tc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity)
+{
+    asm volatile("{\n"
+                 ".reg .pred p;\n"
+                 "RT_TC_WAIT:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                 "@p bra RT_TC_DONE;\n"
+                 "bra RT_TC_WAIT;\n"
+                 "RT_TC_DONE:\n"
+                 "}" ::"r"(mbar), "r"(parity) : "memory");
+}
+
+// K-major, SWIZZLE_NONE shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address, leading
+// and stride byte offsets in 16-byte units, descriptor version 1 (Blackwell) at bit 46.
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes)
+{
+    return (uint64_t)((addr >> 4) & 0x3FFFu) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
+           (1ull << 46);
+}
+
+// kind::f16 instruction descriptor: D = f32 (bits 4-5 = 1), A = B = bf16 (bits 7-9, 10-12 = 1), both K-major,
+// N >> 3 at bit 17, M >> 4 at bit 24.
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((16u >> 3) << 17) | ((128u >> 4) << 24);
+
+__device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate)
+{
+    asm volatile("{\n"
+                 ".reg .pred p;\n"
+                 "setp.ne.b32 p, %4, 0;\n"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+                 "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(kIdesc), "r"(accumulate) : "memory");
+}
+
+__device__ __forceinline__ void commit(uint32_t mbar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+}  // namespace tc
+
+constexpr int kTcTileRows = 128;
+constexpr int kTcMaxTiles = 32;          // 512 TMEM columns / 16 output channels
+constexpr int kTmemCols = 512;
+constexpr int kBChunkBytes = 2 * kCout * 16;   // one MMA's B operand: 2 K-chunks x 16 rows x 16 bytes
+
+// B operand of the tcgen05 path, as it lies in shared memory: [chunk][k-chunk h][n][8 channel slots] bf16;
+// k-chunk h of chunk (kd, kh, q) is the voxel kw = 2q + h (zero for kw = 3 and for channel slots 4..7).
+__global__ void rt_conv_prepare_tc_kernel(const float *__restrict__ weight, __nv_bfloat16 *__restrict__ bop)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= kChunks * 2 * kCout * 8) return;
+    const int slot = idx & 7, n = (idx >> 3) & 15, h = (idx >> 7) & 1, chunk = idx >> 8;
+    const int kd = chunk / 6, kh = (chunk / 2) % 3, q = chunk & 1;
+    const int kw = 2 * q + h;
+    const float v = (slot < kCin && kw < 3) ? weight[(((n * kCin + slot) * 3 + kd) * 3 + kh) * 3 + kw] : 0.0f;
+    bop[idx] = __float2bfloat16(v);
+}
+
+__global__ void __launch_bounds__(kThreads, 1) rt_conv1_tc_kernel(ConvShape S, int n_samples, int chunks,
+                                                                  int pooled_per_chunk, const float *__restrict__ x,
+                                                                  const uint4 *__restrict__ bop,
+                                                                  const float *__restrict__ bias,
+                                                                  __nv_bfloat16 *__restrict__ out)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint4 *planes = reinterpret_cast<uint4 *>(smem_raw);                              // 3 x [plane_vox] x 16 B
+    __nv_bfloat16 *R = reinterpret_cast<__nv_bfloat16 *>(planes + 3 * (size_t)S.plane_vox);   // [Ho][Pw][16]
+    uint4 *bsm = reinterpret_cast<uint4 *>(R + (size_t)S.r_elems);                    // [18][512 B]
+    unsigned long long *mbars = reinterpret_cast<unsigned long long *>(bsm + kChunks * kBChunkBytes / 16);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(mbars + kTcMaxTiles);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int sample = blockIdx.x / chunks, chunk = blockIdx.x % chunks;
+
+    // depth range of this block: pooled planes [p_lo, p_hi) <- conv planes [d_lo, d_hi)
+    const int p_lo = chunk * pooled_per_chunk;
+    const int p_hi = min(S.Pd, p_lo + pooled_per_chunk);
+    const bool has_work = sample < n_samples && p_lo < p_hi;                          // block-uniform
+    const int d_lo = max(0, 2 * p_lo - S.pd);
+    const int d_hi = min(S.Do, 2 * p_hi - S.pd);
+
+    // one-time set-up: tensor memory, mbarriers, weights, zeroed planes
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 32) {
+        for (int i = 0; i < kTcMaxTiles; i++) tc::mbar_init(tc::smem_u32(&mbars[i]), 1);
+        tc::fence_mbar_init();
+    }
+    for (int i = tid; i < kChunks * kBChunkBytes / 16; i += kThreads) bsm[i] = __ldg(bop + i);
+    // the halo tail of a plane is read (times a zero weight, or for discarded rows): it must hold finite values
+    for (int i = tid; i < 3 * S.plane_vox; i += kThreads) planes[i] = make_uint4(0u, 0u, 0u, 0u);
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (has_work) {
+        const int HW = S.H * S.W;
+        const float *xs = x + (size_t)sample * kCin * S.D * HW;
+        auto load_plane = [&](int dz) {                // input depth plane dz -> buffer dz % 3, channels-last bf16
+            if (dz >= S.D) return;
+            uint4 *dst = planes + (size_t)(dz % 3) * S.plane_vox;
+            const float *src = xs + (size_t)dz * HW;
+            for (int v = tid; v < HW; v += kThreads) {
+                const float c0 = __ldg(src + v), c1 = __ldg(src + (size_t)S.D * HW + v);
+                const float c2 = __ldg(src + (size_t)2 * S.D * HW + v), c3 = __ldg(src + (size_t)3 * S.D * HW + v);
+                dst[v] = make_uint4(pack_bf16(c0, c1), pack_bf16(c2, c3), 0u, 0u);
+            }
+        };
+        load_plane(d_lo);
+        load_plane(d_lo + 1);
+        load_plane(d_lo + 2);
+
+        float bv[kCout];
+#pragma unroll
+        for (int c = 0; c < kCout; c++) bv[c] = bias[c];
+        const uint32_t planes_addr = tc::smem_u32(planes);
+        const uint32_t bsm_addr = tc::smem_u32(bsm);
+        const int pooled_elems = S.Ph * S.Pw * kCout;
+        float stash[kMaxStash];
+#pragma unroll
+        for (int i = 0; i < kMaxStash; i++) stash[i] = 0.0f;
+        const int grp = warp >> 2, quarter = warp & 3;
+        uint32_t phase = 0;
+
+        for (int d = d_lo; d < d_hi; d++) {
+            tc::fence_proxy_async();                   // this thread's plane writes are visible to the tensor core
+            __syncthreads();                           // planes d, d+1, d+2 are in shared memory; R is free
+            if (warp == 0) {
+                tc::fence_after_sync();
+                if (lane == 0) {
+                    for (int t = 0; t < S.tiles; t++) {
+#pragma unroll
+                        for (int c = 0; c < kChunks; c++) {
+                            const int kd = c / 6, kh = (c / 2) % 3, q = c & 1;
+                            const uint32_t a_addr = planes_addr +
+                                (uint32_t)((((d + kd) % 3) * S.plane_vox + t * kTcTileRows + kh * S.W + 2 * q) * 16);
+                            tc::mma_f16(tmem_base + (uint32_t)(t * kCout), tc::smem_desc(a_addr, 16, 128),
+                                        tc::smem_desc(bsm_addr + c * kBChunkBytes, kCout * 16, 128), c > 0 ? 1u : 0u);
+                        }
+                        tc::commit(tc::smem_u32(&mbars[t]));
+                    }
+                }
+                __syncwarp();
+            }
+            // drain: this warp's lane quarter of every second tile
+            for (int t = grp; t < S.tiles; t += 2) {
+                tc::mbar_wait(tc::smem_u32(&mbars[t]), phase);
+                tc::fence_after_sync();
+                uint32_t acc[16];
+                tc::tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(t * kCout), acc);
+                const int f = t * kTcTileRows + quarter * 32 + lane;
+                const int h = fastdiv(f, S.mW), w = f - h * S.W;
+                float v[kCout];
+#pragma unroll
+                for (int c = 0; c < kCout; c++) {
+                    v[c] = fmaxf(__uint_as_float(acc[c]) + bv[c], 0.0f);
+                    v[c] = fmaxf(v[c], __shfl_down_sync(0xffffffffu, v[c], 1));      // w pair: W and the tile base are even
+                }
+                if ((w & 1) == 0 && w < S.Wo && h < S.Ho) {
+                    uint4 *dst = reinterpret_cast<uint4 *>(R + ((size_t)h * S.Pw + (w >> 1)) * kCout);
+                    dst[0] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+                    dst[1] = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
+                }
+            }
+            tc::fence_before_sync();
+            __syncthreads();                           // R holds ReLU(conv) of plane d, max-pooled along w; TMEM is drained
+            tc::fence_after_sync();
+            load_plane(d + 3);                         // buffer d % 3 is free: its loads overlap the pooling below
+
+            // max over the h pair, then over the two planes of the depth window
+            const int pdx = (d + S.pd) >> 1;
+            const int first = 2 * pdx - S.pd;          // first conv plane of the window (may be -1)
+            const bool is_first = d == first;
+            const bool has_second = first + 1 < S.Do;
+            const bool has_first = first >= 0;
+#pragma unroll
+            for (int i = 0; i < kMaxStash; i++) {
+                const int e = tid + i * kThreads;
+                if (e < pooled_elems) {
+                    const int ch = fastdiv(e, S.mPhPw), rem = e - ch * (S.Ph * S.Pw);
+                    const int py = fastdiv(rem, S.mPw), px = rem - py * S.Pw;
+                    const int h0 = 2 * py - S.ph;
+                    float m = 0.0f;                    // every candidate is >= 0 after ReLU
+                    if (h0 >= 0 && h0 < S.Ho) m = __bfloat162float(R[((size_t)h0 * S.Pw + px) * kCout + ch]);
+                    if (h0 + 1 >= 0 && h0 + 1 < S.Ho) m = fmaxf(m, __bfloat162float(R[((size_t)(h0 + 1) * S.Pw + px) * kCout + ch]));
+                    if (is_first && has_second) {
+                        stash[i] = m;
+                    } else {
+                        if (!is_first && has_first) m = fmaxf(m, stash[i]);
+                        out[(((size_t)sample * kCout + ch) * S.Pd + pdx) * (S.Ph * S.Pw) + rem] = __float2bfloat16(m);
+                    }
+                }
+            }
+            phase ^= 1u;
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+}
+
 }  // namespace
 
 extern "C" {
@@ -272,21 +517,41 @@ int rt_conv1_relu_pool(const float *x_dev, const float *weight_dev, const float 
     S.mPw = magic(S.Pw);
     S.mPhPw = magic(S.Ph * S.Pw);
     if (S.tiles * 32 + 64 >= 65536 || S.Ph * S.Pw * kCout >= 65536) return RT_ERR_INVALID;
-    const size_t smem = (size_t)3 * S.plane_vox * 16 + (size_t)S.Ho * S.Pw * kCout * sizeof(__nv_bfloat16);
+    S.r_elems = (S.Ho * S.Pw * kCout + 63) / 64 * 64;
     int dev = 0, max_smem = 0, sms = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return RT_ERR_CUDA;
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (smem > (size_t)max_smem) return RT_ERR_INVALID;
-    if (cudaFuncSetAttribute(rt_conv1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return RT_ERR_CUDA;
-
-    uint32_t *frag = reinterpret_cast<uint32_t *>(scratch_dev);
-    rt_conv_prepare_kernel<<<(kChunks * 2 * 32 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(weight_dev, frag);
     // split the depth of a sample over several blocks when there are few samples
     int chunks = 1;
     while (n * chunks < 2 * sms && chunks < S.Pd) chunks++;
     const int per = (S.Pd + chunks - 1) / chunks;
     chunks = (S.Pd + per - 1) / per;
+
+    // tcgen05 path: 128-row tiles, all of a plane's tiles resident in tensor memory (RT_CONV_MMA_SYNC=1 selects
+    // the mma.sync kernel instead; shapes whose plane needs more than 32 tiles fall back to it as well)
+    static const bool force_sync = getenv("RT_CONV_MMA_SYNC") && atoi(getenv("RT_CONV_MMA_SYNC")) != 0;
+    const int tiles128 = (H * W + kTcTileRows - 1) / kTcTileRows;
+    ConvShape T = S;
+    T.tiles = tiles128;
+    T.plane_vox = (tiles128 * kTcTileRows + 2 * W + 8 + 7) / 8 * 8;
+    const size_t smem_tc = (size_t)3 * T.plane_vox * 16 + (size_t)T.r_elems * sizeof(__nv_bfloat16) +
+                           (size_t)kChunks * kBChunkBytes + kTcMaxTiles * 8 + 16;
+    if (!force_sync && tiles128 <= kTcMaxTiles && smem_tc <= (size_t)max_smem && (size_t)3 * T.plane_vox * 16 + 2 * W * 16 < (1u << 18)) {
+        if (cudaFuncSetAttribute(rt_conv1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc) != cudaSuccess) return RT_ERR_CUDA;
+        __nv_bfloat16 *bop = reinterpret_cast<__nv_bfloat16 *>(scratch_dev);
+        rt_conv_prepare_tc_kernel<<<(kChunks * 2 * kCout * 8 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(weight_dev, bop);
+        rt_conv1_tc_kernel<<<n * chunks, kThreads, smem_tc, (cudaStream_t)stream>>>(
+            T, n, chunks, per, x_dev, reinterpret_cast<const uint4 *>(bop), bias_dev, reinterpret_cast<__nv_bfloat16 *>(out_dev));
+        return cudaGetLastError() == cudaSuccess ? RT_OK : RT_ERR_CUDA;
+    }
+
+    const size_t smem = (size_t)3 * S.plane_vox * 16 + (size_t)S.Ho * S.Pw * kCout * sizeof(__nv_bfloat16);
+    if (smem > (size_t)max_smem) return RT_ERR_INVALID;
+    if (cudaFuncSetAttribute(rt_conv1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return RT_ERR_CUDA;
+
+    uint32_t *frag = reinterpret_cast<uint32_t *>(scratch_dev);
+    rt_conv_prepare_kernel<<<(kChunks * 2 * 32 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(weight_dev, frag);
     rt_conv1_kernel<<<n * chunks, kThreads, smem, (cudaStream_t)stream>>>(
         S, n, chunks, per, x_dev, frag, bias_dev, reinterpret_cast<__nv_bfloat16 *>(out_dev));
     return cudaGetLastError() == cudaSuccess ? RT_OK : RT_ERR_CUDA;
