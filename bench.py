@@ -101,6 +101,16 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def measured_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one step-kernel launch from the committed ncu capture
+    (profiles/step_traffic.json, written from the --set full report; cold-cache figures, per launch)."""
+    p = os.path.join(REPO, "profiles", "step_traffic.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return float(d["dram_read_bytes"]) + float(d["dram_write_bytes"])
+    return None
+
+
 def hbm_peak():
     p = os.path.join(REPO, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
@@ -181,6 +191,25 @@ def other_kernels(rt, dev, peak):
 
     out = []
     g = torch.Generator(device=dev).manual_seed(7)
+    # the step kernel again at 65,536 envs on this GPU (16 waves): its throughput once launch latency and the
+    # per-env dependent chain are amortised ("roofline fraction per kernel at large N")
+    n = 65536
+    se = rt.BatchedEpisodes(n, device=dev, seed=11)
+    se.reset()
+    acts = [torch.rand((n, 6), device=dev, generator=g) * 2 - 1 for _ in range(4)]
+    for i in range(30):
+        se.step(acts[i % 4], want_info=False)
+    k = [0]
+
+    def big_step():
+        se.step(acts[k[0] % 4], want_info=False)
+        k[0] += 1
+    s = timed(big_step, 40)
+    b = n * ALGO_BYTES_SECTOR
+    out.append({"kernel": "rt_step3_kernel", "workload": f"{n} envs (visionless sparse step)", "bytes": b, "us": s * 1e6,
+                "achieved": b / s / 1e9, "unit": "GB/s", "frac": b / s / 1e9 / peak, "env_steps_per_s": n / s})
+    se.close()
+    del acts
     # dense-mode step (BASELINE configs[4]): read + write every dose volume, 1,613,360 B per env-step
     n = 1024
     de = rt.BatchedEpisodes(n, device=dev, dense=True, seed=3)
@@ -358,8 +387,8 @@ def run_ours(args):
                       "bitmaps (13 MB) are L2-resident by design",
             },
             "roofline": {
-                "kernel": "rt_step_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "kernel": "rt_step3_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": measured_traffic() if E == 4096 else None, "peak_source": peak_src,
                 "bytes_per_env_step": ALGO_BYTES_SECTOR, "payload_bytes_per_env_step": ALGO_BYTES_PAYLOAD,
                 "avg_launch_us": launch_s * 1e6,
             },

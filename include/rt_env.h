@@ -183,9 +183,9 @@ RT_API int rt_gae(const float *rewards_dev, const float *values_dev, const float
 
 /* ---- FeaturesExtractor3D, first block (networks.py:15-24) ------------------------------------------ */
 /* Conv3d(4->16, k=3) + bias + ReLU + MaxPool3d(2, 2, padding=((D-2)%2, (H-2)%2, (W-2)%2)) fused in one tensor-core
- * kernel.  x_dev float32 [n][4][D][H][W] (the voxel observation), weight_dev float32 [16][4][3][3][3], bias_dev
- * float32 [16] -> out_dev bfloat16 [n][16][Pd][Ph][Pw] (NCDHW), P = (dim - 2 + pad - 2)/2 + 1.  scratch_dev: 9,216
- * bytes of device memory for the repacked weights.  W must be even (no pool padding on the last axis);
+ * kernel (tcgen05, accumulators in tensor memory).  x_dev float32 [n][4][D][H][W] (the voxel observation),
+ * weight_dev float32 [16][4][3][3][3], bias_dev float32 [16] -> out_dev bfloat16 [n][16][Pd][Ph][Pw] (NCDHW),
+ * P = (dim - 2 + pad - 2)/2 + 1.  scratch_dev: 16,384 bytes of device memory for the repacked weights.  W must be even (no pool padding on the last axis);
  * RT_ERR_INVALID is returned for shapes the kernel does not cover so that the caller can use its own path. */
 RT_API int rt_conv1_relu_pool(const float *x_dev, const float *weight_dev, const float *bias_dev, int n, int D, int H,
                               int W, void *out_dev, void *scratch_dev, void *stream);

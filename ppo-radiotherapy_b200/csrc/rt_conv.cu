@@ -250,18 +250,29 @@ __global__ void __launch_bounds__(kThreads, 1) rt_conv1_kernel(ConvShape S, int 
 // The same block on the 5th-generation tensor cores (tcgen05): accumulators in tensor memory, operands read
 // from shared memory through matrix descriptors, one thread issues the MMAs.
 //
-// A operand = the Toeplitz view of the channels-last planes, expressed directly in the shared-memory
-// descriptor: K-major, no swizzle, where a core matrix is 8 rows x 16 bytes with rows 16 bytes apart.  Row r of
-// a 128-position tile is voxel f0 + r (16 bytes = 8 bf16 channel slots), so consecutive rows are consecutive
-// voxels: the stride between 8-row groups (SBO) is 128 bytes and the second 8-wide K chunk of the row is the NEXT
-// voxel, i.e. the leading-dimension offset (LBO) is 16 bytes.  The core matrices overlap in memory; nothing is
-// gathered or copied.  One tcgen05.mma (M = 128, N = 16, K = 16) per (kd, kh, kw pair): 18 per tile, all into
-// the same 16 tensor-memory columns.  B operand (weights, 16 x 16 per MMA) sits in shared memory once per block.
+// Two conv planes at a time.  A pool window is the conv-plane pair (d0, d0+1), which reads the input planes
+// d0 .. d0+3.  Shared memory holds input planes in PAIRS, channels-last: a voxel is 16 bytes = [4 channels of
+// plane z | 4 channels of plane z+1] with z = d0, d0+2, ... (three pair buffers: two in use, one being loaded),
+// and the GEMM is  Y[f][o*16 + co],  N = 32 = two output planes x 16 channels, so every operand byte read from
+// shared memory serves both planes:
+//     output plane d0   takes  kd = 0, 1 from pair (d0, d0+1)   and  kd = 2 from the lower half of pair (d0+2, d0+3)
+//     output plane d0+1 takes  kd = 0 from the upper half of the first pair  and  kd = 1, 2 from the second pair
+// (the other weight blocks are zero).
 //
-// A plane of H*W positions is ceil(H*W/128) tiles; each tile owns 16 TMEM columns (32 tiles fit the 512 columns),
-// signals an mbarrier through tcgen05.commit when its 18 MMAs are done, and is drained by the warp that may
-// touch its lane quarter (warp % 4): tcgen05.ld 32x32b.x16 gives every thread one position x 16 channels, then
-// bias, ReLU, max over the w pair (neighbouring lane) and the bf16 row goes to R as before.
+// A operand = Toeplitz view of a pair buffer, expressed directly in the shared-memory descriptor: K-major, no
+// swizzle, where a core matrix is 8 rows x 16 bytes with rows 16 bytes apart.  Row r of a 128-position tile is
+// voxel f0 + r, so the stride between 8-row groups (SBO) is 128 bytes and the second 8-wide K chunk of a row is
+// simply ANOTHER VOXEL at a fixed distance: the leading-dimension offset (LBO) is W*16 bytes to pair the rows
+// kh = 0 and 1 of the stencil, or 16 bytes to pair kw and kw+1.  The 3x3 in-plane stencil is 5 MMAs
+// (M = 128, N = 32, K = 16) per pair buffer — (kh 0|1) x kw 0,1,2, then kh 2 x (kw 0|1) and (kw 2|pad) —
+// 10 per tile for two output planes, against 2 x 18 with one K chunk per (kd, kh, kw pair).  The core matrices
+// overlap in memory; nothing is gathered or copied.
+//
+// Warp roles (13 warps): warp 12 issues the MMAs, tile after tile, into a ring of 16 tensor-memory slots of 32
+// columns (tcgen05.commit -> full[slot]; empty[slot] comes back from the four warps that drained it);
+// warps 0-7 drain: tcgen05.ld gives every thread one position x 32 channels, then bias, ReLU, max over the two
+// planes and over the w pair (neighbouring lane), bf16 row to R; warps 8-11 meanwhile bring the next pair of
+// input planes from HBM.  Then all of them max over the h pair out of R and write the pooled plane.
 namespace tc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -269,6 +280,10 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t mbar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory");
 }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -291,13 +306,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity)
 // and stride byte offsets in 16-byte units, descriptor version 1 (Blackwell) at bit 46.
 __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes)
 {
-    return (uint64_t)((addr >> 4) & 0x3FFFu) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
-           (1ull << 46);
+    return (uint64_t)((addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
 }
 
 // kind::f16 instruction descriptor: D = f32 (bits 4-5 = 1), A = B = bf16 (bits 7-9, 10-12 = 1), both K-major,
 // N >> 3 at bit 17, M >> 4 at bit 24.
-constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((16u >> 3) << 17) | ((128u >> 4) << 24);
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
 
 __device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate)
 {
@@ -313,135 +328,182 @@ __device__ __forceinline__ void commit(uint32_t mbar)
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
 }
 
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16])
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t *v)
 {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
                    "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
                  : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 }  // namespace tc
 
 constexpr int kTcTileRows = 128;
-constexpr int kTcMaxTiles = 32;          // 512 TMEM columns / 16 output channels
-constexpr int kTmemCols = 512;
-constexpr int kBChunkBytes = 2 * kCout * 16;   // one MMA's B operand: 2 K-chunks x 16 rows x 16 bytes
+constexpr int kTcN = 2 * kCout;              // two output planes x 16 channels
+constexpr int kTcSlots = 16;                 // tensor-memory ring: 16 x 32 columns
+constexpr int kTmemCols = kTcSlots * kTcN;   // 512
+constexpr int kTcMmas = 10;                  // per tile: 5 per pair buffer
+constexpr int kBMmaBytes = 2 * kTcN * 16;    // one MMA's B operand: 2 K-chunks x 32 rows x 16 bytes
+constexpr int kTcDrainWarps = 8, kTcLoadWarps = 4;
+constexpr int kTcThreads = (kTcDrainWarps + kTcLoadWarps + 1) * 32;
+constexpr int kTcWorkers = (kTcDrainWarps + kTcLoadWarps) * 32;    // everybody but the MMA warp
 
-// B operand of the tcgen05 path, as it lies in shared memory: [chunk][k-chunk h][n][8 channel slots] bf16;
-// k-chunk h of chunk (kd, kh, q) is the voxel kw = 2q + h (zero for kw = 3 and for channel slots 4..7).
+// Stencil position of K chunk h of MMA m (within a pair buffer): (kh, kw); kw == 3 is padding.
+__host__ __device__ __forceinline__ void tc_tap(int m, int h, int &kh, int &kw)
+{
+    if (m < 3) { kh = h; kw = m; }
+    else if (m == 3) { kh = 2; kw = h; }
+    else { kh = 2; kw = 2 + h; }
+}
+
+// B operand of the tcgen05 path as it lies in shared memory: [mma = b*5 + m][K chunk h][n = o*16 + co][8 slots],
+// slot = u*4 + c: channel c of the lower (u = 0) / upper (u = 1) plane of pair buffer b, i.e. input plane
+// d0 + 2b + u, which output plane d0 + o sees as kd = 2b + u - o.
 __global__ void rt_conv_prepare_tc_kernel(const float *__restrict__ weight, __nv_bfloat16 *__restrict__ bop)
 {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= kChunks * 2 * kCout * 8) return;
-    const int slot = idx & 7, n = (idx >> 3) & 15, h = (idx >> 7) & 1, chunk = idx >> 8;
-    const int kd = chunk / 6, kh = (chunk / 2) % 3, q = chunk & 1;
-    const int kw = 2 * q + h;
-    const float v = (slot < kCin && kw < 3) ? weight[(((n * kCin + slot) * 3 + kd) * 3 + kh) * 3 + kw] : 0.0f;
+    if (idx >= kTcMmas * 2 * kTcN * 8) return;
+    const int slot = idx & 7, n = (idx >> 3) & 31, h = (idx >> 8) & 1, mma = idx >> 9;
+    const int b = mma / 5, m = mma % 5;
+    const int u = slot >> 2, c = slot & 3, o = n >> 4, co = n & 15;
+    const int kd = 2 * b + u - o;
+    int kh, kw;
+    tc_tap(m, h, kh, kw);
+    const float v = (kd >= 0 && kd <= 2 && kw < 3) ? weight[(((co * kCin + c) * 3 + kd) * 3 + kh) * 3 + kw] : 0.0f;
     bop[idx] = __float2bfloat16(v);
 }
 
-__global__ void __launch_bounds__(kThreads, 1) rt_conv1_tc_kernel(ConvShape S, int n_samples, int chunks,
-                                                                  int pooled_per_chunk, const float *__restrict__ x,
-                                                                  const uint4 *__restrict__ bop,
-                                                                  const float *__restrict__ bias,
-                                                                  __nv_bfloat16 *__restrict__ out)
+__global__ void __launch_bounds__(kTcThreads, 1) rt_conv1_tc_kernel(ConvShape S, int n_samples, int chunks,
+                                                                    int pooled_per_chunk, const float *__restrict__ x,
+                                                                    const uint4 *__restrict__ bop,
+                                                                    const float *__restrict__ bias,
+                                                                    __nv_bfloat16 *__restrict__ out)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    uint4 *planes = reinterpret_cast<uint4 *>(smem_raw);                              // 3 x [plane_vox] x 16 B
-    __nv_bfloat16 *R = reinterpret_cast<__nv_bfloat16 *>(planes + 3 * (size_t)S.plane_vox);   // [Ho][Pw][16]
-    uint4 *bsm = reinterpret_cast<uint4 *>(R + (size_t)S.r_elems);                    // [18][512 B]
-    unsigned long long *mbars = reinterpret_cast<unsigned long long *>(bsm + kChunks * kBChunkBytes / 16);
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(mbars + kTcMaxTiles);
+    uint4 *pairs = reinterpret_cast<uint4 *>(smem_raw);                               // 3 x [plane_vox] x 16 B
+    __nv_bfloat16 *R = reinterpret_cast<__nv_bfloat16 *>(pairs + 3 * (size_t)S.plane_vox);    // [Ho][Pw][16]
+    uint4 *bsm = reinterpret_cast<uint4 *>(R + (size_t)S.r_elems);                    // [10][1 KB]
+    unsigned long long *full = reinterpret_cast<unsigned long long *>(bsm + kTcMmas * kBMmaBytes / 16);
+    unsigned long long *empty = full + kTcSlots;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(empty + kTcSlots);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int sample = blockIdx.x / chunks, chunk = blockIdx.x % chunks;
+    const bool is_mma = warp == kTcDrainWarps + kTcLoadWarps;
+    const bool is_loader = warp >= kTcDrainWarps && !is_mma;
 
-    // depth range of this block: pooled planes [p_lo, p_hi) <- conv planes [d_lo, d_hi)
+    // pooled planes [p_lo, p_hi) of this block; pooled plane p is the max over conv planes 2p - pd and 2p - pd + 1
     const int p_lo = chunk * pooled_per_chunk;
     const int p_hi = min(S.Pd, p_lo + pooled_per_chunk);
     const bool has_work = sample < n_samples && p_lo < p_hi;                          // block-uniform
-    const int d_lo = max(0, 2 * p_lo - S.pd);
-    const int d_hi = min(S.Do, 2 * p_hi - S.pd);
+    const int iters = has_work ? p_hi - p_lo : 0;
+    const int z0 = 2 * p_lo - S.pd;                    // first input plane of pair 0 (may be -1)
 
-    // one-time set-up: tensor memory, mbarriers, weights, zeroed planes
-    if (warp == 0) {
+    // one-time set-up: tensor memory, mbarriers, weights, zeroed pair buffers
+    if (is_mma) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    if (tid == 32) {
-        for (int i = 0; i < kTcMaxTiles; i++) tc::mbar_init(tc::smem_u32(&mbars[i]), 1);
+    if (tid == 0) {
+        for (int i = 0; i < kTcSlots; i++) {
+            tc::mbar_init(tc::smem_u32(&full[i]), 1);
+            tc::mbar_init(tc::smem_u32(&empty[i]), 4);             // the four warps (lane quarters) that drain a slot
+        }
         tc::fence_mbar_init();
     }
-    for (int i = tid; i < kChunks * kBChunkBytes / 16; i += kThreads) bsm[i] = __ldg(bop + i);
-    // the halo tail of a plane is read (times a zero weight, or for discarded rows): it must hold finite values
-    for (int i = tid; i < 3 * S.plane_vox; i += kThreads) planes[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = tid; i < kTcMmas * kBMmaBytes / 16; i += kTcThreads) bsm[i] = __ldg(bop + i);
+    // the halo tail of a buffer is read (times a zero weight, or for discarded rows): it must hold finite values
+    for (int i = tid; i < 3 * S.plane_vox; i += kTcThreads) pairs[i] = make_uint4(0u, 0u, 0u, 0u);
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (has_work) {
-        const int HW = S.H * S.W;
-        const float *xs = x + (size_t)sample * kCin * S.D * HW;
-        auto load_plane = [&](int dz) {                // input depth plane dz -> buffer dz % 3, channels-last bf16
-            if (dz >= S.D) return;
-            uint4 *dst = planes + (size_t)(dz % 3) * S.plane_vox;
-            const float *src = xs + (size_t)dz * HW;
-            for (int v = tid; v < HW; v += kThreads) {
-                const float c0 = __ldg(src + v), c1 = __ldg(src + (size_t)S.D * HW + v);
-                const float c2 = __ldg(src + (size_t)2 * S.D * HW + v), c3 = __ldg(src + (size_t)3 * S.D * HW + v);
-                dst[v] = make_uint4(pack_bf16(c0, c1), pack_bf16(c2, c3), 0u, 0u);
-            }
-        };
-        load_plane(d_lo);
-        load_plane(d_lo + 1);
-        load_plane(d_lo + 2);
+    const int HW = S.H * S.W;
+    const float *xs = x + (size_t)sample * kCin * S.D * HW;
+    const size_t cstride = (size_t)S.D * HW;
+    // pair j = input planes (z0 + 2j, z0 + 2j + 1) -> buffer j % 3, channels-last bf16; planes outside [0, D) are zero
+    auto load_pair = [&](int j, int t0, int nt) {
+        const int za = z0 + 2 * j, zb = za + 1;
+        const bool ina = za >= 0 && za < S.D, inb = zb >= 0 && zb < S.D;
+        uint4 *dst = pairs + (size_t)(j % 3) * S.plane_vox;
+        const float *sa = xs + (size_t)(ina ? za : 0) * HW;
+        const float *sb = xs + (size_t)(inb ? zb : 0) * HW;
+#pragma unroll 2
+        for (int v = t0; v < HW; v += nt) {
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
+            if (ina) { a0 = __ldg(sa + v); a1 = __ldg(sa + cstride + v); a2 = __ldg(sa + 2 * cstride + v); a3 = __ldg(sa + 3 * cstride + v); }
+            if (inb) { b0 = __ldg(sb + v); b1 = __ldg(sb + cstride + v); b2 = __ldg(sb + 2 * cstride + v); b3 = __ldg(sb + 3 * cstride + v); }
+            dst[v] = make_uint4(pack_bf16(a0, a1), pack_bf16(a2, a3), pack_bf16(b0, b1), pack_bf16(b2, b3));
+        }
+    };
+    if (has_work && !is_mma) {
+        load_pair(0, tid, kTcWorkers);
+        load_pair(1, tid, kTcWorkers);
+        tc::fence_proxy_async();
+    }
 
-        float bv[kCout];
-#pragma unroll
-        for (int c = 0; c < kCout; c++) bv[c] = bias[c];
-        const uint32_t planes_addr = tc::smem_u32(planes);
-        const uint32_t bsm_addr = tc::smem_u32(bsm);
-        const int pooled_elems = S.Ph * S.Pw * kCout;
-        float stash[kMaxStash];
-#pragma unroll
-        for (int i = 0; i < kMaxStash; i++) stash[i] = 0.0f;
-        const int grp = warp >> 2, quarter = warp & 3;
-        uint32_t phase = 0;
+    const uint32_t pairs_addr = tc::smem_u32(pairs);
+    const uint32_t bsm_addr = tc::smem_u32(bsm);
+    const int pooled_plane = S.Ph * S.Pw * kCout;
+    const int grp = warp >> 2, quarter = warp & 3;     // drain warps only
 
-        for (int d = d_lo; d < d_hi; d++) {
-            tc::fence_proxy_async();                   // this thread's plane writes are visible to the tensor core
-            __syncthreads();                           // planes d, d+1, d+2 are in shared memory; R is free
-            if (warp == 0) {
+    for (int i = 0; i < iters; i++) {
+        __syncthreads();                               // pairs i, i+1 are in shared memory; R is free
+        const int d0 = z0 + 2 * i;                     // conv planes d0 (may be -1) and d0 + 1 (may be Do)
+        if (is_mma) {
+            tc::fence_after_sync();
+            const uint32_t buf0 = pairs_addr + (uint32_t)((i % 3) * S.plane_vox * 16);
+            const uint32_t buf1 = pairs_addr + (uint32_t)(((i + 1) % 3) * S.plane_vox * 16);
+            for (int t = 0; t < S.tiles; t++) {
+                const int g = i * S.tiles + t, slot = g % kTcSlots, use = g / kTcSlots;
+                tc::mbar_wait(tc::smem_u32(&empty[slot]), (uint32_t)((use & 1) ^ 1));
                 tc::fence_after_sync();
                 if (lane == 0) {
-                    for (int t = 0; t < S.tiles; t++) {
 #pragma unroll
-                        for (int c = 0; c < kChunks; c++) {
-                            const int kd = c / 6, kh = (c / 2) % 3, q = c & 1;
-                            const uint32_t a_addr = planes_addr +
-                                (uint32_t)((((d + kd) % 3) * S.plane_vox + t * kTcTileRows + kh * S.W + 2 * q) * 16);
-                            tc::mma_f16(tmem_base + (uint32_t)(t * kCout), tc::smem_desc(a_addr, 16, 128),
-                                        tc::smem_desc(bsm_addr + c * kBChunkBytes, kCout * 16, 128), c > 0 ? 1u : 0u);
-                        }
-                        tc::commit(tc::smem_u32(&mbars[t]));
+                    for (int q = 0; q < kTcMmas; q++) {
+                        const int b = q / 5, m = q % 5;
+                        int kh, kw;
+                        tc_tap(m, 0, kh, kw);
+                        const uint32_t a_addr = (b ? buf1 : buf0) + (uint32_t)((t * kTcTileRows + kh * S.W + kw) * 16);
+                        const uint32_t lbo = m < 3 ? (uint32_t)(S.W * 16) : 16u;
+                        tc::mma_f16(tmem_base + (uint32_t)(slot * kTcN), tc::smem_desc(a_addr, lbo, 128),
+                                    tc::smem_desc(bsm_addr + q * kBMmaBytes, kTcN * 16, 128), q > 0 ? 1u : 0u);
                     }
+                    tc::commit(tc::smem_u32(&full[slot]));
                 }
                 __syncwarp();
             }
-            // drain: this warp's lane quarter of every second tile
+        } else if (is_loader) {
+            if (i + 2 <= iters) {                      // pair i+2 is needed by iteration i+1
+                load_pair(i + 2, tid - kTcDrainWarps * 32, kTcLoadWarps * 32);
+                tc::fence_proxy_async();
+            }
+        } else {
+            float bv[kCout];
+#pragma unroll
+            for (int c = 0; c < kCout; c++) bv[c] = __ldg(bias + c);
+            const bool ok_a = d0 >= 0, ok_b = d0 + 1 < S.Do;
             for (int t = grp; t < S.tiles; t += 2) {
-                tc::mbar_wait(tc::smem_u32(&mbars[t]), phase);
+                const int g = i * S.tiles + t, slot = g % kTcSlots, use = g / kTcSlots;
+                tc::mbar_wait(tc::smem_u32(&full[slot]), (uint32_t)(use & 1));
                 tc::fence_after_sync();
-                uint32_t acc[16];
-                tc::tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(t * kCout), acc);
+                uint32_t acc[kTcN];
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(slot * kTcN);
+                tc::tmem_ld16(taddr, acc);
+                tc::tmem_ld16(taddr + 16, acc + 16);
+                tc::tmem_ld_wait();
+                tc::fence_before_sync();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(tc::smem_u32(&empty[slot]));
                 const int f = t * kTcTileRows + quarter * 32 + lane;
                 const int h = fastdiv(f, S.mW), w = f - h * S.W;
                 float v[kCout];
 #pragma unroll
                 for (int c = 0; c < kCout; c++) {
-                    v[c] = fmaxf(__uint_as_float(acc[c]) + bv[c], 0.0f);
+                    const float va = ok_a ? fmaxf(__uint_as_float(acc[c]) + bv[c], 0.0f) : 0.0f;
+                    const float vb = ok_b ? fmaxf(__uint_as_float(acc[kCout + c]) + bv[c], 0.0f) : 0.0f;
+                    v[c] = fmaxf(va, vb);              // depth pair; every candidate is >= 0 after ReLU
                     v[c] = fmaxf(v[c], __shfl_down_sync(0xffffffffu, v[c], 1));      // w pair: W and the tile base are even
                 }
                 if ((w & 1) == 0 && w < S.Wo && h < S.Ho) {
@@ -450,41 +512,26 @@ __global__ void __launch_bounds__(kThreads, 1) rt_conv1_tc_kernel(ConvShape S, i
                     dst[1] = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
                 }
             }
-            tc::fence_before_sync();
-            __syncthreads();                           // R holds ReLU(conv) of plane d, max-pooled along w; TMEM is drained
-            tc::fence_after_sync();
-            load_plane(d + 3);                         // buffer d % 3 is free: its loads overlap the pooling below
-
-            // max over the h pair, then over the two planes of the depth window
-            const int pdx = (d + S.pd) >> 1;
-            const int first = 2 * pdx - S.pd;          // first conv plane of the window (may be -1)
-            const bool is_first = d == first;
-            const bool has_second = first + 1 < S.Do;
-            const bool has_first = first >= 0;
-#pragma unroll
-            for (int i = 0; i < kMaxStash; i++) {
-                const int e = tid + i * kThreads;
-                if (e < pooled_elems) {
-                    const int ch = fastdiv(e, S.mPhPw), rem = e - ch * (S.Ph * S.Pw);
-                    const int py = fastdiv(rem, S.mPw), px = rem - py * S.Pw;
-                    const int h0 = 2 * py - S.ph;
-                    float m = 0.0f;                    // every candidate is >= 0 after ReLU
-                    if (h0 >= 0 && h0 < S.Ho) m = __bfloat162float(R[((size_t)h0 * S.Pw + px) * kCout + ch]);
-                    if (h0 + 1 >= 0 && h0 + 1 < S.Ho) m = fmaxf(m, __bfloat162float(R[((size_t)(h0 + 1) * S.Pw + px) * kCout + ch]));
-                    if (is_first && has_second) {
-                        stash[i] = m;
-                    } else {
-                        if (!is_first && has_first) m = fmaxf(m, stash[i]);
-                        out[(((size_t)sample * kCout + ch) * S.Pd + pdx) * (S.Ph * S.Pw) + rem] = __float2bfloat16(m);
-                    }
-                }
+        }
+        __syncthreads();                               // R holds the window's ReLU(conv), max-pooled along d and w
+        if (!is_mma) {
+            // max over the h pair -> pooled plane p
+            const int p = p_lo + i;
+            __nv_bfloat16 *op = out + ((size_t)sample * kCout * S.Pd + p) * (S.Ph * S.Pw);
+            for (int e = tid; e < pooled_plane; e += kTcWorkers) {
+                const int ch = fastdiv(e, S.mPhPw), rem = e - ch * (S.Ph * S.Pw);
+                const int py = fastdiv(rem, S.mPw), px = rem - py * S.Pw;
+                const int h0 = 2 * py - S.ph;
+                float m = 0.0f;
+                if (h0 >= 0 && h0 < S.Ho) m = __bfloat162float(R[((size_t)h0 * S.Pw + px) * kCout + ch]);
+                if (h0 + 1 >= 0 && h0 + 1 < S.Ho) m = fmaxf(m, __bfloat162float(R[((size_t)(h0 + 1) * S.Pw + px) * kCout + ch]));
+                op[(size_t)ch * S.Pd * (S.Ph * S.Pw) + rem] = __float2bfloat16(m);
             }
-            phase ^= 1u;
         }
     }
     tc::fence_before_sync();
     __syncthreads();
-    if (warp == 0)
+    if (is_mma)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
 }
 
@@ -494,7 +541,7 @@ extern "C" {
 
 // Fused Conv3d(4->16, k=3) + bias + ReLU + MaxPool3d(2, 2, padding=((D-2)%2, (H-2)%2, (W-2)%2)) — networks.py:15-24.
 // x_dev float32 [n][4][D][H][W]; weight_dev float32 [16][4][3][3][3]; bias_dev float32 [16];
-// out_dev bfloat16 [n][16][Pd][Ph][Pw] with P = (conv_out + pad - 2)/2 + 1; scratch_dev >= 9216 bytes.
+// out_dev bfloat16 [n][16][Pd][Ph][Pw] with P = (conv_out + pad - 2)/2 + 1; scratch_dev >= 16384 bytes.
 // Requires W even (pool padding 0 on the last axis) and a plane that fits shared memory.
 int rt_conv1_relu_pool(const float *x_dev, const float *weight_dev, const float *bias_dev, int n, int D, int H, int W,
                        void *out_dev, void *scratch_dev, void *stream)
@@ -528,20 +575,20 @@ int rt_conv1_relu_pool(const float *x_dev, const float *weight_dev, const float 
     const int per = (S.Pd + chunks - 1) / chunks;
     chunks = (S.Pd + per - 1) / per;
 
-    // tcgen05 path: 128-row tiles, all of a plane's tiles resident in tensor memory (RT_CONV_MMA_SYNC=1 selects
-    // the mma.sync kernel instead; shapes whose plane needs more than 32 tiles fall back to it as well)
+    // tcgen05 path: 128-row tiles through a ring of tensor-memory slots (RT_CONV_MMA_SYNC=1 selects the
+    // mma.sync kernel instead; planes too large for three pair buffers in shared memory fall back to it as well)
     static const bool force_sync = getenv("RT_CONV_MMA_SYNC") && atoi(getenv("RT_CONV_MMA_SYNC")) != 0;
     const int tiles128 = (H * W + kTcTileRows - 1) / kTcTileRows;
     ConvShape T = S;
     T.tiles = tiles128;
     T.plane_vox = (tiles128 * kTcTileRows + 2 * W + 8 + 7) / 8 * 8;
     const size_t smem_tc = (size_t)3 * T.plane_vox * 16 + (size_t)T.r_elems * sizeof(__nv_bfloat16) +
-                           (size_t)kChunks * kBChunkBytes + kTcMaxTiles * 8 + 16;
-    if (!force_sync && tiles128 <= kTcMaxTiles && smem_tc <= (size_t)max_smem && (size_t)3 * T.plane_vox * 16 + 2 * W * 16 < (1u << 18)) {
+                           (size_t)kTcMmas * kBMmaBytes + 2 * kTcSlots * 8 + 16;
+    if (!force_sync && smem_tc <= (size_t)max_smem && (size_t)3 * T.plane_vox * 16 < (1u << 18) && W * 16 < (1 << 18)) {
         if (cudaFuncSetAttribute(rt_conv1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc) != cudaSuccess) return RT_ERR_CUDA;
         __nv_bfloat16 *bop = reinterpret_cast<__nv_bfloat16 *>(scratch_dev);
-        rt_conv_prepare_tc_kernel<<<(kChunks * 2 * kCout * 8 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(weight_dev, bop);
-        rt_conv1_tc_kernel<<<n * chunks, kThreads, smem_tc, (cudaStream_t)stream>>>(
+        rt_conv_prepare_tc_kernel<<<(kTcMmas * 2 * kTcN * 8 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(weight_dev, bop);
+        rt_conv1_tc_kernel<<<n * chunks, kTcThreads, smem_tc, (cudaStream_t)stream>>>(
             T, n, chunks, per, x_dev, reinterpret_cast<const uint4 *>(bop), bias_dev, reinterpret_cast<__nv_bfloat16 *>(out_dev));
         return cudaGetLastError() == cudaSuccess ? RT_OK : RT_ERR_CUDA;
     }

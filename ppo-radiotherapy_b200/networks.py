@@ -100,7 +100,7 @@ class FeaturesExtractor3D(nn.Module):
         shape = (n, 16, (Do + 2 * pd - 2) // 2 + 1, (Ho + 2 * ph - 2) // 2 + 1, (Wo - 2) // 2 + 1)
         out = torch.empty(shape, dtype=torch.bfloat16, device=x.device)
         if getattr(self, "_conv_scratch", None) is None or self._conv_scratch.device != x.device:
-            self._conv_scratch = torch.empty(2304, dtype=torch.int32, device=x.device)
+            self._conv_scratch = torch.empty(4096, dtype=torch.int32, device=x.device)
         w = conv.weight.detach().float().contiguous()
         b = conv.bias.detach().float().contiguous()
         with torch.cuda.device(x.device):

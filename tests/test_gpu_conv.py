@@ -23,7 +23,7 @@ def _fused(x, w, b):
     pd, ph = Do % 2, Ho % 2
     out = torch.empty((n, 16, (Do + 2 * pd - 2) // 2 + 1, (Ho + 2 * ph - 2) // 2 + 1, (Wo - 2) // 2 + 1),
                       dtype=torch.bfloat16, device=x.device)
-    scratch = torch.empty(2304, dtype=torch.int32, device=x.device)
+    scratch = torch.empty(4096, dtype=torch.int32, device=x.device)
     rc = nat.lib().rt_conv1_relu_pool(C.c_void_p(x.data_ptr()), C.c_void_p(w.data_ptr()), C.c_void_p(b.data_ptr()), n, D, H, W,
                                       C.c_void_p(out.data_ptr()), C.c_void_p(scratch.data_ptr()),
                                       C.c_void_p(torch.cuda.current_stream().cuda_stream))
