@@ -268,11 +268,14 @@ __global__ void __launch_bounds__(kThreads, 1) rt_conv1_kernel(ConvShape S, int 
 // 10 per tile for two output planes, against 2 x 18 with one K chunk per (kd, kh, kw pair).  The core matrices
 // overlap in memory; nothing is gathered or copied.
 //
-// Warp roles (13 warps): warp 12 issues the MMAs, tile after tile, into a ring of 16 tensor-memory slots of 32
-// columns (tcgen05.commit -> full[slot]; empty[slot] comes back from the four warps that drained it);
-// warps 0-7 drain: tcgen05.ld gives every thread one position x 32 channels, then bias, ReLU, max over the two
-// planes and over the w pair (neighbouring lane), bf16 row to R; warps 8-11 meanwhile bring the next pair of
-// input planes from HBM.  Then all of them max over the h pair out of R and write the pooled plane.
+// Warp roles (13 warps), coupled by mbarriers only, so each runs ahead as far as its buffers allow:
+//   warps 8-11 load input-plane pairs from HBM into the ring of three pair buffers (pair_free -> pair_ready);
+//   warp 12 issues the MMAs, tile after tile, into a ring of 16 tensor-memory slots of 32 columns
+//      (tcgen05.commit -> full[slot]; empty[slot] comes back from the four warps that drained it) — while the
+//      drain warps pool one window it is already 16 tiles into the next;
+//   warps 0-7 drain: tcgen05.ld gives every thread one position x 32 channels, then bias, ReLU, max over the
+//      two planes and over the w pair (neighbouring lane), bf16 row to R; then max over the h pair out of R
+//      (8 channels per 16-byte read, bf16x2 max) and the pooled plane goes to HBM.
 namespace tc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -386,7 +389,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) rt_conv1_tc_kernel(ConvShape S,
     uint4 *bsm = reinterpret_cast<uint4 *>(R + (size_t)S.r_elems);                    // [10][1 KB]
     unsigned long long *full = reinterpret_cast<unsigned long long *>(bsm + kTcMmas * kBMmaBytes / 16);
     unsigned long long *empty = full + kTcSlots;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(empty + kTcSlots);
+    unsigned long long *pair_ready = empty + kTcSlots;             // [3] loader warps -> MMA warp
+    unsigned long long *pair_free = pair_ready + 3;                // [3] MMA warp (tcgen05.commit) -> loader warps
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(pair_free + 3);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int sample = blockIdx.x / chunks, chunk = blockIdx.x % chunks;
     const bool is_mma = warp == kTcDrainWarps + kTcLoadWarps;
@@ -409,49 +414,54 @@ __global__ void __launch_bounds__(kTcThreads, 1) rt_conv1_tc_kernel(ConvShape S,
             tc::mbar_init(tc::smem_u32(&full[i]), 1);
             tc::mbar_init(tc::smem_u32(&empty[i]), 4);             // the four warps (lane quarters) that drain a slot
         }
+        for (int i = 0; i < 3; i++) {
+            tc::mbar_init(tc::smem_u32(&pair_ready[i]), kTcLoadWarps);
+            tc::mbar_init(tc::smem_u32(&pair_free[i]), 1);
+        }
         tc::fence_mbar_init();
     }
     for (int i = tid; i < kTcMmas * kBMmaBytes / 16; i += kTcThreads) bsm[i] = __ldg(bop + i);
     // the halo tail of a buffer is read (times a zero weight, or for discarded rows): it must hold finite values
     for (int i = tid; i < 3 * S.plane_vox; i += kTcThreads) pairs[i] = make_uint4(0u, 0u, 0u, 0u);
+    tc::fence_proxy_async();
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
 
     const int HW = S.H * S.W;
-    const float *xs = x + (size_t)sample * kCin * S.D * HW;
-    const size_t cstride = (size_t)S.D * HW;
-    // pair j = input planes (z0 + 2j, z0 + 2j + 1) -> buffer j % 3, channels-last bf16; planes outside [0, D) are zero
-    auto load_pair = [&](int j, int t0, int nt) {
-        const int za = z0 + 2 * j, zb = za + 1;
-        const bool ina = za >= 0 && za < S.D, inb = zb >= 0 && zb < S.D;
-        uint4 *dst = pairs + (size_t)(j % 3) * S.plane_vox;
-        const float *sa = xs + (size_t)(ina ? za : 0) * HW;
-        const float *sb = xs + (size_t)(inb ? zb : 0) * HW;
-#pragma unroll 2
-        for (int v = t0; v < HW; v += nt) {
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
-            if (ina) { a0 = __ldg(sa + v); a1 = __ldg(sa + cstride + v); a2 = __ldg(sa + 2 * cstride + v); a3 = __ldg(sa + 3 * cstride + v); }
-            if (inb) { b0 = __ldg(sb + v); b1 = __ldg(sb + cstride + v); b2 = __ldg(sb + 2 * cstride + v); b3 = __ldg(sb + 3 * cstride + v); }
-            dst[v] = make_uint4(pack_bf16(a0, a1), pack_bf16(a2, a3), pack_bf16(b0, b1), pack_bf16(b2, b3));
-        }
-    };
-    if (has_work && !is_mma) {
-        load_pair(0, tid, kTcWorkers);
-        load_pair(1, tid, kTcWorkers);
-        tc::fence_proxy_async();
-    }
-
     const uint32_t pairs_addr = tc::smem_u32(pairs);
-    const uint32_t bsm_addr = tc::smem_u32(bsm);
-    const int pooled_plane = S.Ph * S.Pw * kCout;
-    const int grp = warp >> 2, quarter = warp & 3;     // drain warps only
 
-    for (int i = 0; i < iters; i++) {
-        __syncthreads();                               // pairs i, i+1 are in shared memory; R is free
-        const int d0 = z0 + 2 * i;                     // conv planes d0 (may be -1) and d0 + 1 (may be Do)
-        if (is_mma) {
+    if (is_loader) {
+        // ---- input-plane pairs: pair j = planes (z0 + 2j, z0 + 2j + 1) -> buffer j % 3, channels-last bf16;
+        //      planes outside [0, D) are zero.  Pairs 0 .. iters are needed (iteration i reads pairs i and i+1).
+        const float *xs = x + (size_t)sample * kCin * S.D * HW;
+        const size_t cstride = (size_t)S.D * HW;
+        const int t0 = tid - kTcDrainWarps * 32, nt = kTcLoadWarps * 32;
+        for (int j = 0; j <= iters && has_work; j++) {
+            if (j >= 3) tc::mbar_wait(tc::smem_u32(&pair_free[j % 3]), (uint32_t)((j / 3 - 1) & 1));   // MMAs of iteration j-3 done
+            const int za = z0 + 2 * j, zb = za + 1;
+            const bool ina = za >= 0 && za < S.D, inb = zb >= 0 && zb < S.D;
+            uint4 *dst = pairs + (size_t)(j % 3) * S.plane_vox;
+            const float *sa = xs + (size_t)(ina ? za : 0) * HW;
+            const float *sb = xs + (size_t)(inb ? zb : 0) * HW;
+#pragma unroll 2
+            for (int v = t0; v < HW; v += nt) {
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
+                if (ina) { a0 = __ldg(sa + v); a1 = __ldg(sa + cstride + v); a2 = __ldg(sa + 2 * cstride + v); a3 = __ldg(sa + 3 * cstride + v); }
+                if (inb) { b0 = __ldg(sb + v); b1 = __ldg(sb + cstride + v); b2 = __ldg(sb + 2 * cstride + v); b3 = __ldg(sb + 3 * cstride + v); }
+                dst[v] = make_uint4(pack_bf16(a0, a1), pack_bf16(a2, a3), pack_bf16(b0, b1), pack_bf16(b2, b3));
+            }
+            tc::fence_proxy_async();                   // this lane's writes are visible to the tensor core
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(tc::smem_u32(&pair_ready[j % 3]));
+        }
+    } else if (is_mma) {
+        // ---- MMA issue
+        const uint32_t bsm_addr = tc::smem_u32(bsm);
+        for (int i = 0; i < iters; i++) {
+            tc::mbar_wait(tc::smem_u32(&pair_ready[i % 3]), (uint32_t)((i / 3) & 1));
+            tc::mbar_wait(tc::smem_u32(&pair_ready[(i + 1) % 3]), (uint32_t)(((i + 1) / 3) & 1));
             tc::fence_after_sync();
             const uint32_t buf0 = pairs_addr + (uint32_t)((i % 3) * S.plane_vox * 16);
             const uint32_t buf1 = pairs_addr + (uint32_t)(((i + 1) % 3) * S.plane_vox * 16);
@@ -474,15 +484,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) rt_conv1_tc_kernel(ConvShape S,
                 }
                 __syncwarp();
             }
-        } else if (is_loader) {
-            if (i + 2 <= iters) {                      // pair i+2 is needed by iteration i+1
-                load_pair(i + 2, tid - kTcDrainWarps * 32, kTcLoadWarps * 32);
-                tc::fence_proxy_async();
-            }
-        } else {
-            float bv[kCout];
+            if (lane == 0) tc::commit(tc::smem_u32(&pair_free[i % 3]));     // buffer i % 3 may be reloaded once these MMAs are done
+            __syncwarp();
+        }
+    } else {
+        // ---- drain + pool
+        float bv[kCout];
 #pragma unroll
-            for (int c = 0; c < kCout; c++) bv[c] = __ldg(bias + c);
+        for (int c = 0; c < kCout; c++) bv[c] = __ldg(bias + c);
+        const int grp = warp >> 2, quarter = warp & 3;
+        const int PhPw = S.Ph * S.Pw;
+        for (int i = 0; i < iters; i++) {
+            const int d0 = z0 + 2 * i;                 // conv planes d0 (may be -1) and d0 + 1 (may be Do)
             const bool ok_a = d0 >= 0, ok_b = d0 + 1 < S.Do;
             for (int t = grp; t < S.tiles; t += 2) {
                 const int g = i * S.tiles + t, slot = g % kTcSlots, use = g / kTcSlots;
@@ -512,21 +525,31 @@ __global__ void __launch_bounds__(kTcThreads, 1) rt_conv1_tc_kernel(ConvShape S,
                     dst[1] = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
                 }
             }
-        }
-        __syncthreads();                               // R holds the window's ReLU(conv), max-pooled along d and w
-        if (!is_mma) {
-            // max over the h pair -> pooled plane p
+            asm volatile("bar.sync 1, %0;" ::"n"(kTcDrainWarps * 32) : "memory");     // R holds the window, pooled along d and w
+            // max over the h pair -> pooled plane p; an item is (8 channels, one pooled position)
             const int p = p_lo + i;
-            __nv_bfloat16 *op = out + ((size_t)sample * kCout * S.Pd + p) * (S.Ph * S.Pw);
-            for (int e = tid; e < pooled_plane; e += kTcWorkers) {
-                const int ch = fastdiv(e, S.mPhPw), rem = e - ch * (S.Ph * S.Pw);
-                const int py = fastdiv(rem, S.mPw), px = rem - py * S.Pw;
+            __nv_bfloat16 *op = out + ((size_t)sample * kCout * S.Pd + p) * PhPw;
+            for (int item = tid; item < 2 * PhPw; item += kTcDrainWarps * 32) {
+                const int half = item >= PhPw ? 1 : 0, pos = item - half * PhPw;
+                const int py = fastdiv(pos, S.mPw), px = pos - py * S.Pw;
                 const int h0 = 2 * py - S.ph;
-                float m = 0.0f;
-                if (h0 >= 0 && h0 < S.Ho) m = __bfloat162float(R[((size_t)h0 * S.Pw + px) * kCout + ch]);
-                if (h0 + 1 >= 0 && h0 + 1 < S.Ho) m = fmaxf(m, __bfloat162float(R[((size_t)(h0 + 1) * S.Pw + px) * kCout + ch]));
-                op[(size_t)ch * S.Pd * (S.Ph * S.Pw) + rem] = __float2bfloat16(m);
+                uint4 m = make_uint4(0u, 0u, 0u, 0u);  // every candidate is >= 0 after ReLU
+                if (h0 >= 0 && h0 < S.Ho) m = *reinterpret_cast<const uint4 *>(R + ((size_t)h0 * S.Pw + px) * kCout + half * 8);
+                if (h0 + 1 >= 0 && h0 + 1 < S.Ho) {
+                    const uint4 o = *reinterpret_cast<const uint4 *>(R + ((size_t)(h0 + 1) * S.Pw + px) * kCout + half * 8);
+                    auto mx = [](uint32_t a, uint32_t b) {
+                        const __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162 *>(&a), *reinterpret_cast<const __nv_bfloat162 *>(&b));
+                        return *reinterpret_cast<const uint32_t *>(&r);
+                    };
+                    m = make_uint4(mx(m.x, o.x), mx(m.y, o.y), mx(m.z, o.z), mx(m.w, o.w));
+                }
+                const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
+                unsigned short *o16 = reinterpret_cast<unsigned short *>(op) + (size_t)(half * 8) * S.Pd * PhPw + pos;
+#pragma unroll
+                for (int c = 0; c < 8; c++)
+                    o16[(size_t)c * S.Pd * PhPw] = (unsigned short)(c & 1 ? mw[c >> 1] >> 16 : mw[c >> 1] & 0xffffu);
             }
+            asm volatile("bar.sync 1, %0;" ::"n"(kTcDrainWarps * 32) : "memory");     // R is free again
         }
     }
     tc::fence_before_sync();
@@ -583,7 +606,7 @@ int rt_conv1_relu_pool(const float *x_dev, const float *weight_dev, const float 
     T.tiles = tiles128;
     T.plane_vox = (tiles128 * kTcTileRows + 2 * W + 8 + 7) / 8 * 8;
     const size_t smem_tc = (size_t)3 * T.plane_vox * 16 + (size_t)T.r_elems * sizeof(__nv_bfloat16) +
-                           (size_t)kTcMmas * kBMmaBytes + 2 * kTcSlots * 8 + 16;
+                           (size_t)kTcMmas * kBMmaBytes + (2 * kTcSlots + 6) * 8 + 16;
     if (!force_sync && smem_tc <= (size_t)max_smem && (size_t)3 * T.plane_vox * 16 < (1u << 18) && W * 16 < (1 << 18)) {
         if (cudaFuncSetAttribute(rt_conv1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc) != cudaSuccess) return RT_ERR_CUDA;
         __nv_bfloat16 *bop = reinterpret_cast<__nv_bfloat16 *>(scratch_dev);
