@@ -26,6 +26,7 @@
 
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
+#include <math_constants.h>
 #include <stdint.h>
 #include <stdlib.h>
 
@@ -511,18 +512,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) rt_conv1_tc_kernel(ConvShape S,
                 if (lane == 0) tc::mbar_arrive(tc::smem_u32(&empty[slot]));
                 const int f = t * kTcTileRows + quarter * 32 + lane;
                 const int h = fastdiv(f, S.mW), w = f - h * S.W;
-                float v[kCout];
+                // max over the depth pair first (ReLU and + bias are monotone), then bias, ReLU, bf16, and the w pair
+                // (W and the tile base are even: the odd position is the next lane) on packed bf16x2
+                uint32_t pk[kCout / 2];
 #pragma unroll
-                for (int c = 0; c < kCout; c++) {
-                    const float va = ok_a ? fmaxf(__uint_as_float(acc[c]) + bv[c], 0.0f) : 0.0f;
-                    const float vb = ok_b ? fmaxf(__uint_as_float(acc[kCout + c]) + bv[c], 0.0f) : 0.0f;
-                    v[c] = fmaxf(va, vb);              // depth pair; every candidate is >= 0 after ReLU
-                    v[c] = fmaxf(v[c], __shfl_down_sync(0xffffffffu, v[c], 1));      // w pair: W and the tile base are even
+                for (int c = 0; c < kCout; c += 2) {
+                    float v0 = ok_a ? __uint_as_float(acc[c]) : -CUDART_INF_F, v1 = ok_a ? __uint_as_float(acc[c + 1]) : -CUDART_INF_F;
+                    if (ok_b) { v0 = fmaxf(v0, __uint_as_float(acc[kCout + c])); v1 = fmaxf(v1, __uint_as_float(acc[kCout + c + 1])); }
+                    uint32_t mine = pack_bf16(fmaxf(v0 + bv[c], 0.0f), fmaxf(v1 + bv[c + 1], 0.0f));
+                    const uint32_t other = __shfl_down_sync(0xffffffffu, mine, 1);
+                    const __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162 *>(&mine), *reinterpret_cast<const __nv_bfloat162 *>(&other));
+                    pk[c / 2] = *reinterpret_cast<const uint32_t *>(&r);
                 }
                 if ((w & 1) == 0 && w < S.Wo && h < S.Ho) {
                     uint4 *dst = reinterpret_cast<uint4 *>(R + ((size_t)h * S.Pw + (w >> 1)) * kCout);
-                    dst[0] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-                    dst[1] = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
+                    dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
                 }
             }
             asm volatile("bar.sync 1, %0;" ::"n"(kTcDrainWarps * 32) : "memory");     // R holds the window, pooled along d and w
