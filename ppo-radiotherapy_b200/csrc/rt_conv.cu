@@ -269,9 +269,9 @@ __global__ void __launch_bounds__(kThreads, 1) rt_conv1_kernel(ConvShape S, int 
 // 10 per tile for two output planes, against 2 x 18 with one K chunk per (kd, kh, kw pair).  The core matrices
 // overlap in memory; nothing is gathered or copied.
 //
-// Warp roles (13 warps), coupled by mbarriers only, so each runs ahead as far as its buffers allow:
+// Warp roles (14 warps), coupled by mbarriers only, so each runs ahead as far as its buffers allow:
 //   warps 8-11 load input-plane pairs from HBM into the ring of three pair buffers (pair_free -> pair_ready);
-//   warp 12 issues the MMAs, tile after tile, into a ring of 16 tensor-memory slots of 32 columns
+//   warps 12-13 issue the MMAs (one thread each, alternate tiles) into a ring of 16 tensor-memory slots of 32 columns
 //      (tcgen05.commit -> full[slot]; empty[slot] comes back from the four warps that drained it) — while the
 //      drain warps pool one window it is already 16 tiles into the next;
 //   warps 0-7 drain: tcgen05.ld gives every thread one position x 32 channels, then bias, ReLU, max over the
@@ -349,9 +349,8 @@ constexpr int kTcSlots = 16;                 // tensor-memory ring: 16 x 32 colu
 constexpr int kTmemCols = kTcSlots * kTcN;   // 512
 constexpr int kTcMmas = 10;                  // per tile: 5 per pair buffer
 constexpr int kBMmaBytes = 2 * kTcN * 16;    // one MMA's B operand: 2 K-chunks x 32 rows x 16 bytes
-constexpr int kTcDrainWarps = 8, kTcLoadWarps = 4;
-constexpr int kTcThreads = (kTcDrainWarps + kTcLoadWarps + 1) * 32;
-constexpr int kTcWorkers = (kTcDrainWarps + kTcLoadWarps) * 32;    // everybody but the MMA warp
+constexpr int kTcDrainWarps = 8, kTcLoadWarps = 4, kTcMmaWarps = 2;
+constexpr int kTcThreads = (kTcDrainWarps + kTcLoadWarps + kTcMmaWarps) * 32;
 
 // Stencil position of K chunk h of MMA m (within a pair buffer): (kh, kw); kw == 3 is padding.
 __host__ __device__ __forceinline__ void tc_tap(int m, int h, int &kh, int &kw)
@@ -395,8 +394,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) rt_conv1_tc_kernel(ConvShape S,
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(pair_free + 3);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int sample = blockIdx.x / chunks, chunk = blockIdx.x % chunks;
-    const bool is_mma = warp == kTcDrainWarps + kTcLoadWarps;
+    const bool is_mma = warp >= kTcDrainWarps + kTcLoadWarps;
     const bool is_loader = warp >= kTcDrainWarps && !is_mma;
+    const int mma_rank = warp - (kTcDrainWarps + kTcLoadWarps);   // MMA warp r issues the tiles t = r (mod kTcMmaWarps)
 
     // pooled planes [p_lo, p_hi) of this block; pooled plane p is the max over conv planes 2p - pd and 2p - pd + 1
     const int p_lo = chunk * pooled_per_chunk;
@@ -406,7 +406,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rt_conv1_tc_kernel(ConvShape S,
     const int z0 = 2 * p_lo - S.pd;                    // first input plane of pair 0 (may be -1)
 
     // one-time set-up: tensor memory, mbarriers, weights, zeroed pair buffers
-    if (is_mma) {
+    if (is_mma && mma_rank == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -417,7 +417,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rt_conv1_tc_kernel(ConvShape S,
         }
         for (int i = 0; i < 3; i++) {
             tc::mbar_init(tc::smem_u32(&pair_ready[i]), kTcLoadWarps);
-            tc::mbar_init(tc::smem_u32(&pair_free[i]), 1);
+            tc::mbar_init(tc::smem_u32(&pair_free[i]), kTcMmaWarps);
         }
         tc::fence_mbar_init();
     }
@@ -466,7 +466,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rt_conv1_tc_kernel(ConvShape S,
             tc::fence_after_sync();
             const uint32_t buf0 = pairs_addr + (uint32_t)((i % 3) * S.plane_vox * 16);
             const uint32_t buf1 = pairs_addr + (uint32_t)(((i + 1) % 3) * S.plane_vox * 16);
-            for (int t = 0; t < S.tiles; t++) {
+            for (int t = mma_rank; t < S.tiles; t += kTcMmaWarps) {
                 const int g = i * S.tiles + t, slot = g % kTcSlots, use = g / kTcSlots;
                 tc::mbar_wait(tc::smem_u32(&empty[slot]), (uint32_t)((use & 1) ^ 1));
                 tc::fence_after_sync();
@@ -559,7 +559,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rt_conv1_tc_kernel(ConvShape S,
     }
     tc::fence_before_sync();
     __syncthreads();
-    if (is_mma)
+    if (is_mma && mma_rank == 0)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
 }
 
