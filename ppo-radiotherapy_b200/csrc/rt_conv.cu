@@ -446,12 +446,36 @@ __global__ void __launch_bounds__(kTcThreads, 1) rt_conv1_tc_kernel(ConvShape S,
             uint4 *dst = pairs + (size_t)(j % 3) * S.plane_vox;
             const float *sa = xs + (size_t)(ina ? za : 0) * HW;
             const float *sb = xs + (size_t)(inb ? zb : 0) * HW;
+            if ((HW & 1) == 0) {
+                // two voxels per thread and iteration: 8-byte loads (HW even keeps every plane 8-byte aligned),
+                // sixteen of them in flight per thread
+                const float2 z2 = make_float2(0.f, 0.f);
 #pragma unroll 2
-            for (int v = t0; v < HW; v += nt) {
-                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
-                if (ina) { a0 = __ldg(sa + v); a1 = __ldg(sa + cstride + v); a2 = __ldg(sa + 2 * cstride + v); a3 = __ldg(sa + 3 * cstride + v); }
-                if (inb) { b0 = __ldg(sb + v); b1 = __ldg(sb + cstride + v); b2 = __ldg(sb + 2 * cstride + v); b3 = __ldg(sb + 3 * cstride + v); }
-                dst[v] = make_uint4(pack_bf16(a0, a1), pack_bf16(a2, a3), pack_bf16(b0, b1), pack_bf16(b2, b3));
+                for (int v = 2 * t0; v < HW; v += 2 * nt) {
+                    float2 a0 = z2, a1 = z2, a2 = z2, a3 = z2, b0 = z2, b1 = z2, b2 = z2, b3 = z2;
+                    if (ina) {
+                        a0 = __ldg(reinterpret_cast<const float2 *>(sa + v));
+                        a1 = __ldg(reinterpret_cast<const float2 *>(sa + cstride + v));
+                        a2 = __ldg(reinterpret_cast<const float2 *>(sa + 2 * cstride + v));
+                        a3 = __ldg(reinterpret_cast<const float2 *>(sa + 3 * cstride + v));
+                    }
+                    if (inb) {
+                        b0 = __ldg(reinterpret_cast<const float2 *>(sb + v));
+                        b1 = __ldg(reinterpret_cast<const float2 *>(sb + cstride + v));
+                        b2 = __ldg(reinterpret_cast<const float2 *>(sb + 2 * cstride + v));
+                        b3 = __ldg(reinterpret_cast<const float2 *>(sb + 3 * cstride + v));
+                    }
+                    dst[v] = make_uint4(pack_bf16(a0.x, a1.x), pack_bf16(a2.x, a3.x), pack_bf16(b0.x, b1.x), pack_bf16(b2.x, b3.x));
+                    dst[v + 1] = make_uint4(pack_bf16(a0.y, a1.y), pack_bf16(a2.y, a3.y), pack_bf16(b0.y, b1.y), pack_bf16(b2.y, b3.y));
+                }
+            } else {
+#pragma unroll 2
+                for (int v = t0; v < HW; v += nt) {
+                    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
+                    if (ina) { a0 = __ldg(sa + v); a1 = __ldg(sa + cstride + v); a2 = __ldg(sa + 2 * cstride + v); a3 = __ldg(sa + 3 * cstride + v); }
+                    if (inb) { b0 = __ldg(sb + v); b1 = __ldg(sb + cstride + v); b2 = __ldg(sb + 2 * cstride + v); b3 = __ldg(sb + 3 * cstride + v); }
+                    dst[v] = make_uint4(pack_bf16(a0, a1), pack_bf16(a2, a3), pack_bf16(b0, b1), pack_bf16(b2, b3));
+                }
             }
             tc::fence_proxy_async();                   // this lane's writes are visible to the tensor core
             __syncwarp();
