@@ -434,6 +434,33 @@ def test_rng_tumour_choice_is_seeded_and_spread():
 
 
 # ------------------------------------------------------------------------------------ edge cases
+@pytest.mark.parametrize("kb", ["7", "14", "28", "0"])
+def test_step_kernel_block_shapes_vs_oracle(kb, monkeypatch):
+    """The step kernel exists for 7, 14 and 28 envs per block (picked from the env count in rt_create; RT_STEP_KB
+    overrides) and as the older two-role kernel (0).  Every variant, with a ragged last block, a full episode, the
+    autoreset call and the start of the next episode, against the CPU oracle."""
+    monkeypatch.setenv("RT_STEP_KB", kb)
+    n, T = 61, 112
+    rng = np.random.default_rng(11)
+    acts = rng.uniform(-1, 1, (T, n, 6)).astype(np.float32)
+    sched = np.stack([(np.arange(n) * 7919) % 1000, (np.arange(n) * 104729 + 17) % 1000]).astype(np.int32)
+    ref_out, ref_done = O.rollout(O.Phantom(), sched, acts, threads=8)
+    env = rt.RadiotherapyVectorEnv(n, device=DEV, tumour_ids=sched)
+    env.reset()
+    for t in range(T):
+        obs, reward, term, _, _ = env.step(_cuda(acts[t]))
+        info = env.engine.info.cpu().numpy()
+        stepped = info[:, nat.INFO_STEPPED] > 0
+        assert stepped.all() == (t != 100)
+        _compare_step(info, obs.cpu().numpy(), reward.cpu().numpy(), term.cpu().numpy(), ref_out[t], ref_done[t], stepped)
+    # bit-exact dose volume of the last env (last, partly filled block) in the second episode
+    o = O.OracleEnv(O.Phantom(), int(sched[1, n - 1]))
+    for t in range(101, T):
+        o.step(acts[t, n - 1])
+    assert np.array_equal(env.engine.dose(n - 1).cpu().numpy().view(np.uint32), o.dose.view(np.uint32))
+    env.close()
+
+
 @pytest.mark.parametrize("n", [1, 6, 7, 8, 13, 33])
 def test_ragged_env_counts(n):
     """Env counts that do not fill the kernel's 7-env blocks (and N = 1) behave like the oracle."""
