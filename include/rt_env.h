@@ -189,6 +189,16 @@ RT_API int rt_gae(const float *rewards_dev, const float *values_dev, const float
  * RT_ERR_INVALID is returned for shapes the kernel does not cover so that the caller can use its own path. */
 RT_API int rt_conv1_relu_pool(const float *x_dev, const float *weight_dev, const float *bias_dev, int n, int D, int H,
                               int W, void *out_dev, void *scratch_dev, void *stream);
+/* Same block with the output in the grouped channels-last layout the second block reads:
+ * out_dev bfloat16 [n][2 groups][Pd][Ph*Pw][8 channels] (channel = group*8 + c). */
+RT_API int rt_conv1_relu_pool_grouped(const float *x_dev, const float *weight_dev, const float *bias_dev, int n, int D,
+                                      int H, int W, void *out_dev, void *scratch_dev, void *stream);
+/* Second block (networks.py:25-27): Conv3d(16->16, k=3, groups=2) + bias + ReLU + MaxPool3d(2, 2) on tcgen05.
+ * x_dev bfloat16 [n][2][D][H*W][8] as written by rt_conv1_relu_pool_grouped, weight_dev float32 [16][8][3][3][3],
+ * bias_dev float32 [16] -> out_dev bfloat16 [n][16][(D-2)/2][(H-2)/2][(W-2)/2] (NCDHW).  scratch_dev: 65,536 bytes.
+ * W must be even; RT_ERR_INVALID for shapes the kernel does not cover. */
+RT_API int rt_conv2_relu_pool(const void *x_dev, const float *weight_dev, const float *bias_dev, int n, int D, int H,
+                              int W, void *out_dev, void *scratch_dev, void *stream);
 
 /* ---- instrumentation ----------------------------------------------------------------- */
 /* Number of kernels this library has launched since load (for bench.py's gpu_launches). */

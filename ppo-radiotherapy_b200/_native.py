@@ -115,6 +115,8 @@ _SIGNATURES = {
     "rt_apply_translation": (C.c_int, [_vp, _vp, C.c_int, C.POINTER(C.c_double), _vp, _vp, _vp]),
     "rt_gae": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_double, C.c_double, _vp, _vp, _vp]),
     "rt_conv1_relu_pool": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]),
+    "rt_conv1_relu_pool_grouped": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]),
+    "rt_conv2_relu_pool": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]),
     "rt_launch_count": (C.c_int64, []),
     "rt_set_stage_clock": (C.c_int, [_vp, _vp]),
 }

@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(kThreads, 1) rt_conv1_kernel(ConvShape S, int 
                                                                const float *__restrict__ bias,
                                                                __nv_bfloat16 *__restrict__ out)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     uint4 *planes = reinterpret_cast<uint4 *>(smem_raw);                              // 3 x [plane_vox] x 16 B
     __nv_bfloat16 *R = reinterpret_cast<__nv_bfloat16 *>(planes + 3 * (size_t)S.plane_vox);   // [Ho][Pw][16]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -377,6 +377,7 @@ __global__ void rt_conv_prepare_tc_kernel(const float *__restrict__ weight, __nv
     bop[idx] = __float2bfloat16(v);
 }
 
+template <bool kGroupedOut>
 __global__ void __launch_bounds__(kTcThreads, 1) rt_conv1_tc_kernel(ConvShape S, int n_samples, int chunks,
                                                                     int pooled_per_chunk, const float *__restrict__ x,
                                                                     const uint4 *__restrict__ bop,
@@ -572,13 +573,223 @@ __global__ void __launch_bounds__(kTcThreads, 1) rt_conv1_tc_kernel(ConvShape S,
                     };
                     m = make_uint4(mx(m.x, o.x), mx(m.y, o.y), mx(m.z, o.z), mx(m.w, o.w));
                 }
-                const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
-                unsigned short *o16 = reinterpret_cast<unsigned short *>(op) + (size_t)(half * 8) * S.Pd * PhPw + pos;
+                if (kGroupedOut) {
+                    // [n][group][Pd][Ph*Pw][8 channels]: the layout rt_conv2_tc_kernel bulk-copies into shared memory
+                    uint4 *og = reinterpret_cast<uint4 *>(out) + (((size_t)sample * 2 + half) * S.Pd + p) * PhPw + pos;
+                    *og = m;
+                } else {
+                    const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
+                    unsigned short *o16 = reinterpret_cast<unsigned short *>(op) + (size_t)(half * 8) * S.Pd * PhPw + pos;
+#pragma unroll
+                    for (int c = 0; c < 8; c++)
+                        o16[(size_t)c * S.Pd * PhPw] = (unsigned short)(c & 1 ? mw[c >> 1] >> 16 : mw[c >> 1] & 0xffffu);
+                }
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(kTcDrainWarps * 32) : "memory");     // R is free again
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (is_mma && mma_rank == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+}
+
+
+// ---------------------------------------------------------------------------------------------------------
+// Second block of FeaturesExtractor3D (networks.py:25-27): Conv3d(16 -> 16, k = 3, groups = 2) + bias + ReLU +
+// MaxPool3d(2, 2), same scheme as rt_conv1_tc_kernel.  The input is the first block's output in the grouped
+// channels-last layout [n][group][D][H*W][8 channels] bf16: a voxel of one group is exactly one 16-byte K chunk
+// (all 8 slots are real channels), a (plane, group) sub-plane is one contiguous run of H*W*16 bytes, and a
+// loader thread brings it to shared memory with a single cp.async.bulk — no conversion, no loader warps.
+// A pool window (conv planes 2p, 2p+1) reads input planes 2p .. 2p+3 = two pair buffers x 2 planes x 2 groups =
+// 8 sub-planes x 5 MMAs (M 128, N 32, K 16) per tile; N = 32 = [plane 2p | plane 2p+1] x [group 0 | group 1] x 8
+// channels, the weight blocks of the other group and of kd outside 0..2 are zero.
+constexpr int kC2Mmas = 40;
+constexpr int kC2Threads = (kTcDrainWarps + 1 + kTcMmaWarps) * 32;     // 8 drain warps, 1 loader warp, 2 MMA warps
+
+struct Conv2Shape {
+    int D, H, W;          // input planes
+    int Do, Ho, Wo;       // conv output = input - 2
+    int Pd, Ph, Pw;       // pooled output = floor(conv / 2)
+    int plane_vox;        // voxels per shared-memory sub-plane (tiles * 128 + halo reach)
+    int tiles;            // 128-position tiles per plane
+    int r_elems;
+    uint32_t mW, mPw;
+};
+
+// B operand: [mma = ((b*2 + u)*2 + g)*5 + m][K chunk h][n = o*16 + g'*8 + co][8 input channels of group g]
+__global__ void rt_conv2_prepare_kernel(const float *__restrict__ weight, __nv_bfloat16 *__restrict__ bop)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= kC2Mmas * 2 * kTcN * 8) return;
+    const int c = idx & 7, n = (idx >> 3) & 31, h = (idx >> 8) & 1, mma = idx >> 9;
+    const int m = mma % 5, src = mma / 5, g = src & 1, zi = src >> 1;     // zi = 2b + u: input plane d0 + zi
+    const int o = n >> 4, g2 = (n >> 3) & 1, co = n & 7;
+    const int kd = zi - o;
+    int kh, kw;
+    tc_tap(m, h, kh, kw);
+    const float v = (g2 == g && kd >= 0 && kd <= 2 && kw < 3) ? weight[((((g * 8 + co) * 8 + c) * 3 + kd) * 3 + kh) * 3 + kw] : 0.0f;
+    bop[idx] = __float2bfloat16(v);
+}
+
+__global__ void __launch_bounds__(kC2Threads, 1) rt_conv2_tc_kernel(Conv2Shape S, int n_samples, int chunks,
+                                                                    int pooled_per_chunk, const uint4 *__restrict__ x,
+                                                                    const uint4 *__restrict__ bop,
+                                                                    const float *__restrict__ bias,
+                                                                    __nv_bfloat16 *__restrict__ out)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint4 *pairs = reinterpret_cast<uint4 *>(smem_raw);                               // 3 x [2 planes][2 groups][plane_vox] x 16 B
+    const int sub = S.plane_vox;                       // voxels per sub-plane
+    __nv_bfloat16 *R = reinterpret_cast<__nv_bfloat16 *>(pairs + 3 * 4 * (size_t)sub);        // [Ho][Pw][16]
+    uint4 *bsm = reinterpret_cast<uint4 *>(R + (size_t)S.r_elems);                    // [40][1 KB]
+    unsigned long long *full = reinterpret_cast<unsigned long long *>(bsm + kC2Mmas * kBMmaBytes / 16);
+    unsigned long long *empty = full + kTcSlots;
+    unsigned long long *pair_ready = empty + kTcSlots;
+    unsigned long long *pair_free = pair_ready + 3;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(pair_free + 3);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int sample = blockIdx.x / chunks, chunk = blockIdx.x % chunks;
+    const bool is_mma = warp >= kTcDrainWarps + 1;
+    const bool is_loader = warp == kTcDrainWarps;
+    const int mma_rank = warp - (kTcDrainWarps + 1);
+
+    const int p_lo = chunk * pooled_per_chunk;
+    const int p_hi = min(S.Pd, p_lo + pooled_per_chunk);
+    const bool has_work = sample < n_samples && p_lo < p_hi;                          // block-uniform
+    const int iters = has_work ? p_hi - p_lo : 0;
+    const int z0 = 2 * p_lo;                           // first input plane of pair 0
+
+    if (is_mma && mma_rank == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) {
+        for (int i = 0; i < kTcSlots; i++) {
+            tc::mbar_init(tc::smem_u32(&full[i]), 1);
+            tc::mbar_init(tc::smem_u32(&empty[i]), 4);
+        }
+        for (int i = 0; i < 3; i++) {
+            tc::mbar_init(tc::smem_u32(&pair_ready[i]), 1);                // one arrive.expect_tx, then the bulk copies' bytes
+            tc::mbar_init(tc::smem_u32(&pair_free[i]), kTcMmaWarps);
+        }
+        tc::fence_mbar_init();
+    }
+    for (int i = tid; i < kC2Mmas * kBMmaBytes / 16; i += kC2Threads) bsm[i] = __ldg(bop + i);
+    // the halo tail of a sub-plane is read (times a zero weight, or for discarded rows): it must hold finite values
+    for (int i = tid; i < 3 * 4 * sub; i += kC2Threads) pairs[i] = make_uint4(0u, 0u, 0u, 0u);
+    tc::fence_proxy_async();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int HW = S.H * S.W;
+    const uint32_t pairs_addr = tc::smem_u32(pairs);
+
+    if (is_loader) {
+        if (lane == 0) {
+            const uint32_t bytes = (uint32_t)(HW * 16);
+            for (int j = 0; j <= iters && has_work; j++) {
+                if (j >= 3) tc::mbar_wait(tc::smem_u32(&pair_free[j % 3]), (uint32_t)((j / 3 - 1) & 1));
+                const uint32_t bar = tc::smem_u32(&pair_ready[j % 3]);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(4u * bytes) : "memory");
+#pragma unroll
+                for (int s4 = 0; s4 < 4; s4++) {
+                    const int u = s4 >> 1, g = s4 & 1, z = z0 + 2 * j + u;
+                    const uint4 *src = x + (((size_t)sample * 2 + g) * S.D + z) * HW;
+                    const uint32_t dst = pairs_addr + (uint32_t)((((j % 3) * 4 + s4) * sub) * 16);
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+                }
+            }
+        }
+    } else if (is_mma) {
+        const uint32_t bsm_addr = tc::smem_u32(bsm);
+        for (int i = 0; i < iters; i++) {
+            tc::mbar_wait(tc::smem_u32(&pair_ready[i % 3]), (uint32_t)((i / 3) & 1));
+            tc::mbar_wait(tc::smem_u32(&pair_ready[(i + 1) % 3]), (uint32_t)(((i + 1) / 3) & 1));
+            tc::fence_after_sync();
+            const uint32_t buf0 = pairs_addr + (uint32_t)(((i % 3) * 4 * sub) * 16);
+            const uint32_t buf1 = pairs_addr + (uint32_t)((((i + 1) % 3) * 4 * sub) * 16);
+            for (int t = mma_rank; t < S.tiles; t += kTcMmaWarps) {
+                const int g = i * S.tiles + t, slot = g % kTcSlots, use = g / kTcSlots;
+                tc::mbar_wait(tc::smem_u32(&empty[slot]), (uint32_t)((use & 1) ^ 1));
+                tc::fence_after_sync();
+                if (lane == 0) {
+#pragma unroll
+                    for (int q = 0; q < kC2Mmas; q++) {
+                        const int m = q % 5, src = q / 5, s4 = src & 3, b = src >> 2;     // src = (b*2 + u)*2 + g
+                        int kh, kw;
+                        tc_tap(m, 0, kh, kw);
+                        const uint32_t a_addr = (b ? buf1 : buf0) + (uint32_t)((s4 * sub + t * kTcTileRows + kh * S.W + kw) * 16);
+                        const uint32_t lbo = m < 3 ? (uint32_t)(S.W * 16) : 16u;
+                        tc::mma_f16(tmem_base + (uint32_t)(slot * kTcN), tc::smem_desc(a_addr, lbo, 128),
+                                    tc::smem_desc(bsm_addr + q * kBMmaBytes, kTcN * 16, 128), q > 0 ? 1u : 0u);
+                    }
+                    tc::commit(tc::smem_u32(&full[slot]));
+                }
+                __syncwarp();
+            }
+            if (lane == 0) tc::commit(tc::smem_u32(&pair_free[i % 3]));
+            __syncwarp();
+        }
+    } else {
+        float bv[kCout];
+#pragma unroll
+        for (int c = 0; c < kCout; c++) bv[c] = __ldg(bias + c);
+        const int grp = warp >> 2, quarter = warp & 3;
+        const int PhPw = S.Ph * S.Pw;
+        for (int i = 0; i < iters; i++) {
+            for (int t = grp; t < S.tiles; t += 2) {
+                const int g = i * S.tiles + t, slot = g % kTcSlots, use = g / kTcSlots;
+                tc::mbar_wait(tc::smem_u32(&full[slot]), (uint32_t)(use & 1));
+                tc::fence_after_sync();
+                uint32_t acc[kTcN];
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(slot * kTcN);
+                tc::tmem_ld16(taddr, acc);
+                tc::tmem_ld16(taddr + 16, acc + 16);
+                tc::tmem_ld_wait();
+                tc::fence_before_sync();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(tc::smem_u32(&empty[slot]));
+                const int f = t * kTcTileRows + quarter * 32 + lane;
+                const int h = fastdiv(f, S.mW), w = f - h * S.W;
+                uint32_t pk[kCout / 2];
+#pragma unroll
+                for (int c = 0; c < kCout; c += 2) {
+                    const float v0 = fmaxf(__uint_as_float(acc[c]), __uint_as_float(acc[kCout + c]));          // depth pair
+                    const float v1 = fmaxf(__uint_as_float(acc[c + 1]), __uint_as_float(acc[kCout + c + 1]));
+                    uint32_t mine = pack_bf16(fmaxf(v0 + bv[c], 0.0f), fmaxf(v1 + bv[c + 1], 0.0f));
+                    const uint32_t other = __shfl_down_sync(0xffffffffu, mine, 1);                             // w pair
+                    const __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162 *>(&mine), *reinterpret_cast<const __nv_bfloat162 *>(&other));
+                    pk[c / 2] = *reinterpret_cast<const uint32_t *>(&r);
+                }
+                if ((w & 1) == 0 && w < S.Wo && h < S.Ho) {
+                    uint4 *dst = reinterpret_cast<uint4 *>(R + ((size_t)h * S.Pw + (w >> 1)) * kCout);
+                    dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                }
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(kTcDrainWarps * 32) : "memory");
+            const int p = p_lo + i;
+            unsigned short *op = reinterpret_cast<unsigned short *>(out) + ((size_t)sample * kCout * S.Pd + p) * PhPw;
+            for (int item = tid; item < 2 * PhPw; item += kTcDrainWarps * 32) {
+                const int half = item >= PhPw ? 1 : 0, pos = item - half * PhPw;
+                const int py = fastdiv(pos, S.mPw), px = pos - py * S.Pw;
+                const uint4 a = *reinterpret_cast<const uint4 *>(R + ((size_t)(2 * py) * S.Pw + px) * kCout + half * 8);
+                const uint4 o = *reinterpret_cast<const uint4 *>(R + ((size_t)(2 * py + 1) * S.Pw + px) * kCout + half * 8);
+                auto mx = [](uint32_t u, uint32_t v) {
+                    const __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162 *>(&u), *reinterpret_cast<const __nv_bfloat162 *>(&v));
+                    return *reinterpret_cast<const uint32_t *>(&r);
+                };
+                const uint32_t mw[4] = {mx(a.x, o.x), mx(a.y, o.y), mx(a.z, o.z), mx(a.w, o.w)};
+                unsigned short *o16 = op + (size_t)(half * 8) * S.Pd * PhPw + pos;
 #pragma unroll
                 for (int c = 0; c < 8; c++)
                     o16[(size_t)c * S.Pd * PhPw] = (unsigned short)(c & 1 ? mw[c >> 1] >> 16 : mw[c >> 1] & 0xffffu);
             }
-            asm volatile("bar.sync 1, %0;" ::"n"(kTcDrainWarps * 32) : "memory");     // R is free again
+            asm volatile("bar.sync 1, %0;" ::"n"(kTcDrainWarps * 32) : "memory");
         }
     }
     tc::fence_before_sync();
@@ -595,8 +806,8 @@ extern "C" {
 // x_dev float32 [n][4][D][H][W]; weight_dev float32 [16][4][3][3][3]; bias_dev float32 [16];
 // out_dev bfloat16 [n][16][Pd][Ph][Pw] with P = (conv_out + pad - 2)/2 + 1; scratch_dev >= 16384 bytes.
 // Requires W even (pool padding 0 on the last axis) and a plane that fits shared memory.
-int rt_conv1_relu_pool(const float *x_dev, const float *weight_dev, const float *bias_dev, int n, int D, int H, int W,
-                       void *out_dev, void *scratch_dev, void *stream)
+static int conv1_launch(const float *x_dev, const float *weight_dev, const float *bias_dev, int n, int D, int H, int W,
+                        void *out_dev, void *scratch_dev, void *stream, bool grouped_out)
 {
     if (n == 0) return RT_OK;
     if (!x_dev || !weight_dev || !bias_dev || !out_dev || !scratch_dev || n < 0 || D < 3 || H < 3 || W < 4) return RT_ERR_INVALID;
@@ -637,13 +848,19 @@ int rt_conv1_relu_pool(const float *x_dev, const float *weight_dev, const float 
     const size_t smem_tc = (size_t)3 * T.plane_vox * 16 + (size_t)T.r_elems * sizeof(__nv_bfloat16) +
                            (size_t)kTcMmas * kBMmaBytes + (2 * kTcSlots + 6) * 8 + 16;
     if (!force_sync && smem_tc <= (size_t)max_smem && (size_t)3 * T.plane_vox * 16 < (1u << 18) && W * 16 < (1 << 18)) {
-        if (cudaFuncSetAttribute(rt_conv1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc) != cudaSuccess) return RT_ERR_CUDA;
+        if (cudaFuncSetAttribute(rt_conv1_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc) != cudaSuccess ||
+            cudaFuncSetAttribute(rt_conv1_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc) != cudaSuccess) return RT_ERR_CUDA;
         __nv_bfloat16 *bop = reinterpret_cast<__nv_bfloat16 *>(scratch_dev);
         rt_conv_prepare_tc_kernel<<<(kTcMmas * 2 * kTcN * 8 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(weight_dev, bop);
-        rt_conv1_tc_kernel<<<n * chunks, kTcThreads, smem_tc, (cudaStream_t)stream>>>(
-            T, n, chunks, per, x_dev, reinterpret_cast<const uint4 *>(bop), bias_dev, reinterpret_cast<__nv_bfloat16 *>(out_dev));
+        if (grouped_out)
+            rt_conv1_tc_kernel<true><<<n * chunks, kTcThreads, smem_tc, (cudaStream_t)stream>>>(
+                T, n, chunks, per, x_dev, reinterpret_cast<const uint4 *>(bop), bias_dev, reinterpret_cast<__nv_bfloat16 *>(out_dev));
+        else
+            rt_conv1_tc_kernel<false><<<n * chunks, kTcThreads, smem_tc, (cudaStream_t)stream>>>(
+                T, n, chunks, per, x_dev, reinterpret_cast<const uint4 *>(bop), bias_dev, reinterpret_cast<__nv_bfloat16 *>(out_dev));
         return cudaGetLastError() == cudaSuccess ? RT_OK : RT_ERR_CUDA;
     }
+    if (grouped_out) return RT_ERR_INVALID;                         // only the tcgen05 kernel writes the grouped layout
 
     const size_t smem = (size_t)3 * S.plane_vox * 16 + (size_t)S.Ho * S.Pw * kCout * sizeof(__nv_bfloat16);
     if (smem > (size_t)max_smem) return RT_ERR_INVALID;
@@ -653,6 +870,60 @@ int rt_conv1_relu_pool(const float *x_dev, const float *weight_dev, const float 
     rt_conv_prepare_kernel<<<(kChunks * 2 * 32 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(weight_dev, frag);
     rt_conv1_kernel<<<n * chunks, kThreads, smem, (cudaStream_t)stream>>>(
         S, n, chunks, per, x_dev, frag, bias_dev, reinterpret_cast<__nv_bfloat16 *>(out_dev));
+    return cudaGetLastError() == cudaSuccess ? RT_OK : RT_ERR_CUDA;
+}
+
+int rt_conv1_relu_pool(const float *x_dev, const float *weight_dev, const float *bias_dev, int n, int D, int H, int W,
+                       void *out_dev, void *scratch_dev, void *stream)
+{
+    return conv1_launch(x_dev, weight_dev, bias_dev, n, D, H, W, out_dev, scratch_dev, stream, false);
+}
+
+// Same block, output in the grouped channels-last layout [n][2][Pd][Ph*Pw][8] bf16 that rt_conv2_relu_pool reads.
+int rt_conv1_relu_pool_grouped(const float *x_dev, const float *weight_dev, const float *bias_dev, int n, int D, int H,
+                               int W, void *out_dev, void *scratch_dev, void *stream)
+{
+    return conv1_launch(x_dev, weight_dev, bias_dev, n, D, H, W, out_dev, scratch_dev, stream, true);
+}
+
+// Fused Conv3d(16->16, k=3, groups=2) + bias + ReLU + MaxPool3d(2, 2) — networks.py:25-27.
+// x_dev bfloat16 [n][2][D][H*W][8] (rt_conv1_relu_pool_grouped); weight_dev float32 [16][8][3][3][3]; bias_dev
+// float32 [16]; out_dev bfloat16 [n][16][(D-2)/2][(H-2)/2][(W-2)/2] (NCDHW); scratch_dev >= 65536 bytes.
+int rt_conv2_relu_pool(const void *x_dev, const float *weight_dev, const float *bias_dev, int n, int D, int H, int W,
+                       void *out_dev, void *scratch_dev, void *stream)
+{
+    if (n == 0) return RT_OK;
+    if (!x_dev || !weight_dev || !bias_dev || !out_dev || !scratch_dev || n < 0 || D < 4 || H < 4 || W < 4) return RT_ERR_INVALID;
+    if (W % 2) return RT_ERR_INVALID;                               // the w pair of the pool must not straddle a row
+    Conv2Shape S;
+    S.D = D; S.H = H; S.W = W;
+    S.Do = D - 2; S.Ho = H - 2; S.Wo = W - 2;
+    S.Pd = S.Do / 2; S.Ph = S.Ho / 2; S.Pw = S.Wo / 2;
+    if (S.Pd < 1 || S.Ph < 1 || S.Pw < 1) return RT_ERR_INVALID;
+    S.tiles = (H * W + kTcTileRows - 1) / kTcTileRows;
+    S.plane_vox = (S.tiles * kTcTileRows + 2 * W + 8 + 7) / 8 * 8;
+    S.r_elems = (S.Ho * S.Pw * kCout + 63) / 64 * 64;
+    auto magic = [](int d) { return d == 1 ? 0u : (uint32_t)(((1ull << 32) + (uint64_t)d - 1) / (uint64_t)d); };
+    S.mW = magic(W);
+    S.mPw = magic(S.Pw);
+    if (S.tiles * kTcTileRows + 64 >= 65536 || S.Ph * S.Pw * kCout >= 65536) return RT_ERR_INVALID;
+    int dev = 0, max_smem = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return RT_ERR_CUDA;
+    cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const size_t smem = (size_t)12 * S.plane_vox * 16 + (size_t)S.r_elems * sizeof(__nv_bfloat16) +
+                        (size_t)kC2Mmas * kBMmaBytes + (2 * kTcSlots + 6) * 8 + 16;
+    if (smem > (size_t)max_smem || (size_t)12 * S.plane_vox * 16 >= (1u << 18)) return RT_ERR_INVALID;
+    int chunks = 1;
+    while (n * chunks < 2 * sms && chunks < S.Pd) chunks++;
+    const int per = (S.Pd + chunks - 1) / chunks;
+    chunks = (S.Pd + per - 1) / per;
+    if (cudaFuncSetAttribute(rt_conv2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return RT_ERR_CUDA;
+    __nv_bfloat16 *bop = reinterpret_cast<__nv_bfloat16 *>(scratch_dev);
+    rt_conv2_prepare_kernel<<<(kC2Mmas * 2 * kTcN * 8 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(weight_dev, bop);
+    rt_conv2_tc_kernel<<<n * chunks, kC2Threads, smem, (cudaStream_t)stream>>>(
+        S, n, chunks, per, reinterpret_cast<const uint4 *>(x_dev), reinterpret_cast<const uint4 *>(bop), bias_dev,
+        reinterpret_cast<__nv_bfloat16 *>(out_dev));
     return cudaGetLastError() == cudaSuccess ? RT_OK : RT_ERR_CUDA;
 }
 

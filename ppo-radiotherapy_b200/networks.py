@@ -74,6 +74,7 @@ class FeaturesExtractor3D(nn.Module):
         self.observation_shape = observation_shape
         self.compute_dtype = compute_dtype
         self.fused_first_block = True       # rollout (no_grad) path: rt_conv1_relu_pool instead of cuDNN + 4 more kernels
+        self.fused_second_block = True      # ... and rt_conv2_relu_pool for cnn[3:6]
         pad = tuple((int(observation_shape[i + 1]) - 2) % 2 for i in range(3))
         self.cnn = nn.Sequential(
             nn.Conv3d(int(observation_shape[0]), 16, 3), nn.ReLU(), nn.MaxPool3d(2, 2, padding=pad),
@@ -113,9 +114,56 @@ class FeaturesExtractor3D(nn.Module):
         nat.check(rc, "rt_conv1_relu_pool")
         return out
 
+    def _fused_two_blocks(self, observations: torch.Tensor):
+        """cnn[0:6] — both Conv3d + ReLU + MaxPool3d blocks — as two tcgen05 kernels of librtenv_b200.so: the first
+        writes its activation in the grouped channels-last layout the second bulk-copies into shared memory
+        (inference only).  Returns None for shapes / dtypes the kernels do not cover."""
+        import ctypes as C
+        from . import _native as nat
+        conv1, pool1, conv2, pool2 = self.cnn[0], self.cnn[2], self.cnn[3], self.cnn[5]
+        x = observations
+        if (x.dtype != torch.float32 or x.dim() != 5 or x.shape[1] != 4 or conv1.out_channels != 16
+                or tuple(conv1.kernel_size) != (3, 3, 3) or x.shape[4] % 2 or not x.is_contiguous()
+                or conv2.groups != 2 or conv2.in_channels != 16 or conv2.out_channels != 16
+                or tuple(conv2.kernel_size) != (3, 3, 3) or pool2.padding not in (0, (0, 0, 0))):
+            return None
+        n, _, D, H, W = x.shape
+        Do, Ho, Wo = D - 2, H - 2, W - 2
+        pd, ph = Do % 2, Ho % 2
+        D1, H1, W1 = (Do + 2 * pd - 2) // 2 + 1, (Ho + 2 * ph - 2) // 2 + 1, (Wo - 2) // 2 + 1
+        if W1 % 2 or min(D1, H1, W1) < 4:
+            return None
+        act1 = torch.empty((n, 2, D1, H1 * W1, 8), dtype=torch.bfloat16, device=x.device)
+        out = torch.empty((n, 16, (D1 - 2) // 2, (H1 - 2) // 2, (W1 - 2) // 2), dtype=torch.bfloat16, device=x.device)
+        if getattr(self, "_conv_scratch2", None) is None or self._conv_scratch2.device != x.device:
+            self._conv_scratch = torch.empty(4096, dtype=torch.int32, device=x.device)
+            self._conv_scratch2 = torch.empty(16384, dtype=torch.int32, device=x.device)
+        w1, b1 = conv1.weight.detach().float().contiguous(), conv1.bias.detach().float().contiguous()
+        w2, b2 = conv2.weight.detach().float().contiguous(), conv2.bias.detach().float().contiguous()
+        stream = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+        with torch.cuda.device(x.device):
+            rc = nat.lib().rt_conv1_relu_pool_grouped(C.c_void_p(x.data_ptr()), C.c_void_p(w1.data_ptr()), C.c_void_p(b1.data_ptr()),
+                                                      n, D, H, W, C.c_void_p(act1.data_ptr()),
+                                                      C.c_void_p(self._conv_scratch.data_ptr()), stream)
+            if rc == -1:
+                return None
+            nat.check(rc, "rt_conv1_relu_pool_grouped")
+            rc = nat.lib().rt_conv2_relu_pool(C.c_void_p(act1.data_ptr()), C.c_void_p(w2.data_ptr()), C.c_void_p(b2.data_ptr()),
+                                              n, D1, H1, W1, C.c_void_p(out.data_ptr()),
+                                              C.c_void_p(self._conv_scratch2.data_ptr()), stream)
+        if rc == -1:
+            return None
+        nat.check(rc, "rt_conv2_relu_pool")
+        return out
+
     def forward(self, observations: torch.Tensor) -> torch.Tensor:
         if (self.compute_dtype == torch.bfloat16 and observations.is_cuda and not torch.is_grad_enabled()
                 and self.fused_first_block):
+            h = self._fused_two_blocks(observations) if self.fused_second_block else None
+            if h is not None:
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    h = self.cnn[6:](h)
+                return self.mlp(h.float())
             h = self._fused_first_block(observations)
             if h is not None:
                 with torch.autocast("cuda", dtype=torch.bfloat16):

@@ -65,6 +65,55 @@ def test_conv1_rejects_uncovered_shapes():
     assert rc == -1
 
 
+def _grouped_to_ncdhw(a, D, H, W):
+    """[n][2][D][H*W][8] -> [n][16][D][H][W]"""
+    n = a.shape[0]
+    return a.view(n, 2, D, H, W, 8).permute(0, 1, 5, 2, 3, 4).reshape(n, 16, D, H, W)
+
+
+@pytest.mark.parametrize("shape", [(2, 67, 43, 70), (3, 9, 12, 10), (1, 8, 11, 14)])
+def test_conv1_grouped_layout_equals_ncdhw(shape):
+    n, D, H, W = shape
+    g = torch.Generator(device=DEV).manual_seed(D + 7)
+    x = torch.rand((n, 4, D, H, W), device=DEV, generator=g)
+    w = torch.randn((16, 4, 3, 3, 3), device=DEV, generator=g) * 0.2
+    b = torch.randn(16, device=DEV, generator=g) * 0.1
+    rc, ref = _fused(x, w, b)
+    assert rc == 0
+    _, _, D1, H1, W1 = ref.shape
+    act = torch.empty((n, 2, D1, H1 * W1, 8), dtype=torch.bfloat16, device=DEV)
+    scratch = torch.empty(4096, dtype=torch.int32, device=DEV)
+    rc = nat.lib().rt_conv1_relu_pool_grouped(C.c_void_p(x.data_ptr()), C.c_void_p(w.data_ptr()), C.c_void_p(b.data_ptr()), n, D, H, W,
+                                              C.c_void_p(act.data_ptr()), C.c_void_p(scratch.data_ptr()),
+                                              C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert rc == 0
+    assert torch.equal(_grouped_to_ncdhw(act, D1, H1, W1), ref)
+
+
+@pytest.mark.parametrize("shape", [(2, 33, 21, 34), (3, 6, 7, 8), (1, 9, 12, 10), (70, 5, 4, 6)])
+def test_conv2_block_matches_torch(shape):
+    """Conv3d(16->16, k3, groups=2) + ReLU + MaxPool3d(2, 2) on tcgen05 against float32 torch on the same bf16 operands."""
+    n, D, H, W = shape
+    g = torch.Generator(device=DEV).manual_seed(D * 100 + W)
+    x = torch.rand((n, 16, D, H, W), device=DEV, generator=g).bfloat16()          # post-ReLU activations are >= 0
+    w = torch.randn((16, 8, 3, 3, 3), device=DEV, generator=g) * 0.1
+    b = torch.randn(16, device=DEV, generator=g) * 0.1
+    xg = x.view(n, 2, 8, D, H, W).permute(0, 1, 3, 4, 5, 2).reshape(n, 2, D, H * W, 8).contiguous()
+    out = torch.empty((n, 16, (D - 2) // 2, (H - 2) // 2, (W - 2) // 2), dtype=torch.bfloat16, device=DEV)
+    scratch = torch.empty(16384, dtype=torch.int32, device=DEV)
+    rc = nat.lib().rt_conv2_relu_pool(C.c_void_p(xg.data_ptr()), C.c_void_p(w.data_ptr()), C.c_void_p(b.data_ptr()), n, D, H, W,
+                                      C.c_void_p(out.data_ptr()), C.c_void_p(scratch.data_ptr()),
+                                      C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert rc == 0
+    torch.backends.cudnn.allow_tf32 = False
+    want = F.max_pool3d(F.relu(F.conv3d(x.float(), w.bfloat16().float(), b, groups=2)), 2, 2)
+    assert out.shape == want.shape
+    err = (out.float() - want).abs()
+    tol = want.abs() * 2.0 ** -7 + 2e-3
+    assert bool((err <= tol).all()), f"max err {float(err.max())} at {int(err.argmax())}"
+    assert float(out.float().max()) > 0.1
+
+
 def test_features_extractor_fused_path_matches_unfused():
     torch.manual_seed(0)
     fe = rt.FeaturesExtractor3D((4, 67, 43, 70), 64, compute_dtype=torch.bfloat16).to(DEV)
@@ -75,11 +124,15 @@ def test_features_extractor_fused_path_matches_unfused():
         obs, *_ = envs.step(a)
     with torch.no_grad():
         fe.fused_first_block = True
-        y1 = fe(obs)
+        y1 = fe(obs)                        # both blocks on tcgen05
+        fe.fused_second_block = False
+        y1b = fe(obs)                       # first block only
         fe.fused_first_block = False
         y2 = fe(obs)
+        fe.fused_first_block = fe.fused_second_block = True
     assert y1.shape == (6, 64)
     assert float((y1 - y2).abs().max()) <= 0.05 * float(y2.abs().max()) + 1e-2
+    assert float((y1b - y2).abs().max()) <= 0.05 * float(y2.abs().max()) + 1e-2
     # with autograd enabled the module takes the differentiable cuDNN path
     y3 = fe(obs)
     assert y3.requires_grad
