@@ -98,7 +98,9 @@ struct Tables {
     int bits_words;
     int pbits_words;
     int lung_words16;              // words of lungs_bits rounded up to a multiple of 4 (16-byte bulk copies)
-    long long *stage_clock;        // optional [N][8] clock64() stamps of the step kernel's stages (rt_set_stage_clock)
+    long long *stage_clock;        // optional [N][12] clock64() stamps of the step kernel's stages (rt_set_stage_clock)
+    int debug;                     // RT_STEP_DEBUG bits, honoured by the instrumented kernel only (what-if timing):
+                                   // 1 no zero fill / valid bits, 2 no voxel stores, 4 no dose loads, 8 no accumulation
 };
 
 #define RT_STAMP(slot)                                                                   \
@@ -1211,6 +1213,7 @@ int rt_create(rt_env **out, int device, int n_envs, uint32_t flags, const rt_pha
     e->T.gnorm = sqrt((double)(G.g0 * G.g0 + G.g1 * G.g1 + G.g2 * G.g2));
     e->T.n_tumours = ph->n_tumours;
     e->T.stage_clock = nullptr;
+    e->T.debug = getenv("RT_STEP_DEBUG") ? atoi(getenv("RT_STEP_DEBUG")) : 0;
 
     // tumour table: bbox, bbox-local bitmask, packed voxel coordinates
     std::vector<Tumour> tum(ph->n_tumours);

@@ -70,6 +70,13 @@ __device__ __forceinline__ void red_or(uint32_t *p, uint32_t v)
     asm volatile("red.global.or.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// one 32-byte sector of zeros with a single store (256-bit stores: sm_100, PTX 8.8): one write transaction
+// instead of two
+__device__ __forceinline__ void zero_sector(float *p)
+{
+    asm volatile("st.global.v8.f32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1};" ::"l"(p), "f"(0.0f) : "memory");
+}
+
 #define RT_STAMP3(env_, slot)                                                                    \
     do {                                                                                         \
         if (kClock) T.stage_clock[(size_t)(env_) * 12 + (slot)] = clock64();                     \
@@ -438,7 +445,7 @@ rt_step3_kernel(Tables T, Schedule S, EnvRec *rec, float *dose, uint32_t *valid,
                 sec[j] = l >> 3;
                 const bool fresh = inj && !((vsm[sec[j] >> 5] >> (sec[j] & 31)) & 1u);   // never written this episode: reads as zero
                 q.old[j] = 0.0f;
-                if (inj && !fresh) q.old[j] = vol[l];                      // re-touched sector: read from HBM / L2
+                if (inj && !fresh && !(kClock && (T.debug & 4))) q.old[j] = vol[l];   // re-touched sector: read from HBM / L2
                 freshm |= fresh ? 1u << j : 0u;
             }
             uint32_t drop;
@@ -477,11 +484,9 @@ rt_step3_kernel(Tables T, Schedule S, EnvRec *rec, float *dose, uint32_t *valid,
             const PassState &q = ps[c];
 #pragma unroll
             for (int j = 0; j < 4; j++)
-                if (q.flags & (16u << j)) {
+                if ((q.flags & (16u << j)) && !(kClock && (T.debug & 1))) {
                     const int sec = (q.base + (j >> 1) * g2 + (j & 1)) >> 3;
-                    float4 *sp = reinterpret_cast<float4 *>(vol + (sec << 3));
-                    sp[0] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    sp[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    zero_sector(vol + (sec << 3));
                     red_or(vbits + (sec >> 5), 1u << (sec & 31));
                 }
         }
@@ -494,20 +499,39 @@ rt_step3_kernel(Tables T, Schedule S, EnvRec *rec, float *dose, uint32_t *valid,
         for (int c = 0; c < kMaxPass; c++) {
             if (c * kWarp >= b.nslab) break;
             const PassState &q = ps[c];
+            float nd[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const float o = q.old[j];
+                nd[j] = fminf(__fadd_rn(o, __fmul_rn(q.w[j], 0.100000001490116119f)), 1.0f);   // clip(dose + beam*0.1, 0, 1), dose >= 0
+            }
+            // the two targets of a row are neighbours in memory: one 8-byte store when both are written and aligned
+#pragma unroll
+            for (int r = 0; r < 2; r++) {
+                const int l = q.base + r * g2;
+                const uint32_t both = (q.flags >> (2 * r)) & 3u;
+                if (!(kClock && (T.debug & 2))) {
+                    if (both == 3u && !(l & 1)) {
+                        *reinterpret_cast<float2 *>(vol + l) = make_float2(nd[2 * r], nd[2 * r + 1]);
+                    } else {
+                        if (both & 1u) vol[l] = nd[2 * r];
+                        if (both & 2u) vol[l + 1] = nd[2 * r + 1];
+                    }
+                }
+            }
 #pragma unroll
             for (int j = 0; j < 4; j++)
                 if (q.flags & (1u << j)) {
+                    if (kClock && (T.debug & 8)) continue;
                     const int l = q.base + (j >> 1) * g2 + (j & 1);
                     const float o = q.old[j];
-                    const float nd = fminf(__fadd_rn(o, __fmul_rn(q.w[j], 0.100000001490116119f)), 1.0f);   // clip(dose + beam*0.1, 0, 1), dose >= 0
-                    vol[l] = nd;
                     const bool in_t = q.flags & (256u << j);
                     const bool in_l = (slungs[l >> 5] >> (l & 31)) & 1u;
-                    const float delta = nd - o;
+                    const float delta = nd[j] - o;
                     d_tum += in_t ? delta : 0.0f;
                     d_lung += in_l ? delta : 0.0f;
                     // lungs_mask = lungs*(1-tumours); dose is monotone, so the count only grows (environment.py:174-177)
-                    d_cnt += (in_l && !in_t && !(o > 0.200000002980232239f) && nd > 0.200000002980232239f) ? 1 : 0;
+                    d_cnt += (in_l && !in_t && !(o > 0.200000002980232239f) && nd[j] > 0.200000002980232239f) ? 1 : 0;
                 }
         }
         if (lane == 0) RT_STAMP3(env, 6);
