@@ -1320,7 +1320,7 @@ int rt_create(rt_env **out, int device, int n_envs, uint32_t flags, const rt_pha
             if (kb == 0 || kb == 7 || kb == 14 || kb == 28) e->step_kb = kb;
         }
         const int kb = e->step_kb ? e->step_kb : kEnvsPerBlock;
-        e->step_smem = (size_t)kb * G.vwords * sizeof(uint32_t) + (e->step_kb ? (size_t)e->T.lung_words16 * sizeof(uint32_t) : 0);
+        e->step_smem = (size_t)kb * G.vwords * sizeof(uint32_t) + (e->step_kb >= 14 ? (size_t)e->T.lung_words16 * sizeof(uint32_t) : 0);
         cudaError_t ae = cudaSuccess;
         switch (e->step_kb) {
         case 0: ae = cudaFuncSetAttribute(rt_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->step_smem); break;

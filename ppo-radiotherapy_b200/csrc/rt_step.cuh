@@ -186,8 +186,10 @@ rt_step3_kernel(Tables T, Schedule S, EnvRec *rec, float *dose, uint32_t *valid,
     const int warp = threadIdx.x / kWarp;
     const int lane = threadIdx.x & (kWarp - 1);
     const int env0 = blockIdx.x * kB;
-    uint32_t *slungs = dyn_smem;
-    uint32_t *vsm_all = dyn_smem + T.lung_words16;
+    // blocks of 7 envs run four to an SM and read the lungs bitmask through L1 instead of staging it four times
+    constexpr bool kStageLungs = kB >= 14;
+    const uint32_t *slungs = kStageLungs ? dyn_smem : T.lungs_bits;
+    uint32_t *vsm_all = dyn_smem + (kStageLungs ? T.lung_words16 : 0);
 
     if (lane == 0) mbar_init(smem_u32(&mbars[warp]), 1);          // mbars[0]: lungs bitmask, mbars[1 + le]: env le's bitmap
     // Programmatic dependent launch: nothing the previous step wrote is read before this point; the trigger
@@ -199,7 +201,7 @@ rt_step3_kernel(Tables T, Schedule S, EnvRec *rec, float *dose, uint32_t *valid,
     if (warp == 0) {
         const int e = env0 + lane;
         const bool mine = lane < kB && e < n_envs;
-        if (lane == 0) bulk_load(smem_u32(slungs), T.lungs_bits, (uint32_t)(T.lung_words16 * sizeof(uint32_t)), smem_u32(&mbars[0]));
+        if (kStageLungs && lane == 0) bulk_load(smem_u32(dyn_smem), T.lungs_bits, (uint32_t)(T.lung_words16 * sizeof(uint32_t)), smem_u32(&mbars[0]));
         if (mine) RT_STAMP3(e, 0);
         EnvRec *my = rec + (mine ? e : 0);
         EnvShared &se = sh[lane < kB ? lane : 0];
@@ -308,7 +310,7 @@ rt_step3_kernel(Tables T, Schedule S, EnvRec *rec, float *dose, uint32_t *valid,
         const int nb = min(kB, n_envs - env0);                             // envs of this block
         __syncwarp();
         for (int i = lane; i < nb * RT_OBS_SIZE; i += kWarp) out.obs[(size_t)env0 * RT_OBS_SIZE + i] = s_obs[i];
-        mbar_wait(smem_u32(&mbars[0]), 0);                                 // the lungs copy must land before the block retires
+        if (kStageLungs) mbar_wait(smem_u32(&mbars[0]), 0);                // the lungs copy must land before the block retires
         __syncthreads();                                                   // ---- barrier 2
         if (stepping) {
             RT_STAMP3(e, 11);
@@ -408,7 +410,7 @@ rt_step3_kernel(Tables T, Schedule S, EnvRec *rec, float *dose, uint32_t *valid,
     __syncthreads();                                                       // ---- barrier 1
     if (active) mbar_wait(mbar, 0);                                        // the staged bitmap has landed
     if (stepping) {
-        mbar_wait(smem_u32(&mbars[0]), 0);                                 // and so has the lungs bitmask
+        if (kStageLungs) mbar_wait(smem_u32(&mbars[0]), 0);                // and so has the lungs bitmask
         if (lane == 0) RT_STAMP3(env, 3);
         // ---- dose deposition (environment.py:107-110): dose' = clip(dose + beam*0.1, 0, 1) on the voxels hit.
         // All (up to three) 32-slab passes of the beam go through each phase together, so the beam costs one
@@ -526,7 +528,7 @@ rt_step3_kernel(Tables T, Schedule S, EnvRec *rec, float *dose, uint32_t *valid,
                     const int l = q.base + (j >> 1) * g2 + (j & 1);
                     const float o = q.old[j];
                     const bool in_t = q.flags & (256u << j);
-                    const bool in_l = (slungs[l >> 5] >> (l & 31)) & 1u;
+                    const bool in_l = ((kStageLungs ? slungs[l >> 5] : __ldg(slungs + (l >> 5))) >> (l & 31)) & 1u;
                     const float delta = nd[j] - o;
                     d_tum += in_t ? delta : 0.0f;
                     d_lung += in_l ? delta : 0.0f;
