@@ -146,6 +146,20 @@ RT_API int rt_get_dose(rt_env *env, int env_index, float *dose_dev, void *stream
 /* Voxel observation, float32 [N][4][V] = clip(stack[lungs, tumours, dose, view], 0, 1)
  * (get_volumes, environment.py:245-257); envs [first, first+count). */
 RT_API int rt_assemble_volumes(rt_env *env, int first, int count, float *obs_dev, void *stream);
+/* Compressed voxel-observation records for rollout storage (train.py:110-112 keeps num_steps x num_envs float32
+ * observations: 3.2 MB each).  A record is the dose volume as bfloat16 [stride] (stride =
+ * rt_observation_record_stride(), V rounded up to 32), the pose float64 [6] and the tumour id; lungs, tumour and
+ * beam-view planes are regenerated from them.  rt_pack_observations writes the records of envs
+ * [first, first+count) to slots [slot0, slot0+count) of caller-owned arrays; rt_render_observations rebuilds
+ * float32 [count][4][V] for records index_dev[0..count) (or 0..count-1 when index_dev is NULL).  The dose plane of
+ * a rendered observation is the bfloat16-rounded dose, which is what a bf16 convolution reads anyway; the other
+ * three planes are identical to rt_assemble_volumes. */
+RT_API int rt_observation_record_stride(const rt_env *env);
+RT_API int rt_pack_observations(rt_env *env, int first, int count, int64_t slot0, void *dose_bf16_dev, double *pose_dev,
+                                int32_t *tumour_id_dev, void *stream);
+RT_API int rt_render_observations(rt_env *env, const void *dose_bf16_dev, const double *pose_dev,
+                                  const int32_t *tumour_id_dev, const int64_t *index_dev, int count, float *obs_dev,
+                                  void *stream);
 /* Recorded beams of one env (needs RT_FLAG_RECORD_BEAMS): float64 [100][6], returns count via n_dev. */
 RT_API int rt_get_beams(rt_env *env, int env_index, double *beams_dev, int32_t *n_dev, void *stream);
 

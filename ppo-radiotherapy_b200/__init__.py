@@ -18,7 +18,7 @@ include/rt_env.h).  There is no CPU fallback.
 from . import _native
 from ._native import RtError, build
 from .phantom import Phantom, default_phantom
-from .engine import BatchedEpisodes
+from .engine import BatchedEpisodes, ObservationStore
 from .geometry import (apply_rotation, apply_rotation_batch, apply_translation, apply_translation_batch,
                        beam_voxels, beam_voxels_batch, beam_voxels_dense_batch, compute_gae, pose_update_batch)
 from .vector_env import Box, RadiotherapyVectorEnv
@@ -27,7 +27,7 @@ from .networks import PPO, PPO_3DCNN, FeaturesExtractor3D
 from . import train as train          # noqa: F401  (ppo_radiotherapy_b200.train.train / main)
 
 __all__ = [
-    "RtError", "build", "Phantom", "default_phantom", "BatchedEpisodes", "RadiotherapyEnv",
+    "RtError", "build", "Phantom", "default_phantom", "BatchedEpisodes", "ObservationStore", "RadiotherapyEnv",
     "RadiotherapyVectorEnv", "Box", "beam_voxels", "beam_voxels_batch", "beam_voxels_dense_batch",
     "apply_rotation", "apply_rotation_batch", "apply_translation", "apply_translation_batch",
     "pose_update_batch", "compute_gae", "PPO", "PPO_3DCNN", "FeaturesExtractor3D", "train",

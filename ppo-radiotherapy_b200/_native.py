@@ -108,6 +108,9 @@ _SIGNATURES = {
     "rt_get_dose": (C.c_int, [_vp, C.c_int, _vp, _vp]),
     "rt_assemble_volumes": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp]),
     "rt_get_beams": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp]),
+    "rt_observation_record_stride": (C.c_int, [_vp]),
+    "rt_pack_observations": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int64, _vp, _vp, _vp, _vp]),
+    "rt_render_observations": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int, _vp, _vp]),
     "rt_beam_voxels": (C.c_int, [C.POINTER(C.c_int32), _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
     "rt_beam_voxels_dense": (C.c_int, [C.POINTER(C.c_int32), _vp, _vp, C.c_int, _vp, _vp, _vp]),
     "rt_pose_update": (C.c_int, [C.POINTER(C.c_int32), _vp, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp]),

@@ -18,6 +18,8 @@
 #include "../../include/rt_env.h"
 #include "rt_device.cuh"
 
+#include <cuda_bf16.h>
+
 #include <atomic>
 #include <cmath>
 #include <cstdio>
@@ -986,8 +988,20 @@ __global__ void rt_get_beams_kernel(const EnvRec *rec, const double *beams, int 
 // (V is even, so every channel plane stays 8-byte aligned).  4.03 MB of HBM traffic per env.
 constexpr int kVolThreads = 512;
 
+// kPacked = false: live envs [first, first + gridDim.x) (record, float32 dose, sector-valid bitmap).
+// kPacked = true: compressed observation records (rt_pack_observations): bfloat16 dose volume, pose and tumour id of
+// record index[blockIdx.x] (or blockIdx.x); the other three planes are regenerated, the dose plane is the stored
+// bfloat16 value — exactly what a bf16 convolution reads from the float32 observation.
+struct PackedObs {
+    const __nv_bfloat16 *dose;   // [records][vstride]
+    const double *pose;          // [records][6]
+    const int32_t *tid;          // [records]
+    const int64_t *index;        // [count] or nullptr
+};
+
+template <bool kPacked>
 __global__ void __launch_bounds__(kVolThreads) rt_volumes_kernel(Tables T, const EnvRec *rec, const float *dose,
-                                                                 const uint32_t *valid, int first, float *out)
+                                                                 const uint32_t *valid, int first, float *out, PackedObs P)
 {
     extern __shared__ uint32_t smem[];
     __shared__ RayWork view[2];
@@ -997,10 +1011,19 @@ __global__ void __launch_bounds__(kVolThreads) rt_volumes_kernel(Tables T, const
     uint32_t *tum_bits = smem + nwords;                         // [nwords] voxel belongs to the tumour
     int *hkeys = reinterpret_cast<int *>(smem + 2 * nwords);    // voxel -> current_beam + horizontal_beam_center
     float *hvals = reinterpret_cast<float *>(hkeys + kHashSlots);
-    const int env = first + blockIdx.x;
     const int lane = threadIdx.x & (kWarp - 1);
     const int warp = threadIdx.x / kWarp;
-    const EnvRec r = rec[env];
+    long long env;
+    EnvRec r;
+    if (kPacked) {
+        env = P.index ? P.index[blockIdx.x] : blockIdx.x;
+#pragma unroll
+        for (int i = 0; i < 3; i++) { r.pos[i] = P.pose[env * 6 + i]; r.dir[i] = P.pose[env * 6 + 3 + i]; }
+        r.tumour_id = P.tid[env];
+    } else {
+        env = first + blockIdx.x;
+        r = rec[env];
+    }
     const Tumour tm = T.tumours[r.tumour_id];
 
     for (int i = threadIdx.x; i < 2 * nwords; i += blockDim.x) smem[i] = 0u;
@@ -1029,8 +1052,9 @@ __global__ void __launch_bounds__(kVolThreads) rt_volumes_kernel(Tables T, const
         }
     }
     __syncthreads();
-    const float2 *vol2 = reinterpret_cast<const float2 *>(dose + (size_t)env * G.vstride);
-    const uint32_t *vbits = valid + (size_t)env * G.vwords;
+    const float2 *vol2 = kPacked ? nullptr : reinterpret_cast<const float2 *>(dose + (size_t)env * G.vstride);
+    const uint32_t *vbits = kPacked ? nullptr : valid + (size_t)env * G.vwords;
+    const __nv_bfloat162 *pk2 = kPacked ? reinterpret_cast<const __nv_bfloat162 *>(P.dose + (size_t)env * G.vstride) : nullptr;
     float *o = out + (size_t)blockIdx.x * 4 * G.nvox;
     float2 *o0 = reinterpret_cast<float2 *>(o), *o1 = reinterpret_cast<float2 *>(o + (size_t)G.nvox);
     float2 *o2 = reinterpret_cast<float2 *>(o + (size_t)2 * G.nvox), *o3 = reinterpret_cast<float2 *>(o + (size_t)3 * G.nvox);
@@ -1045,9 +1069,13 @@ __global__ void __launch_bounds__(kVolThreads) rt_volumes_kernel(Tables T, const
             ok[u] = false;
             d[u] = make_float2(0.f, 0.f);
             if (q < npairs) {
-                const int sec = q >> 2;                          // 2 voxels per pair, 8 per sector
-                ok[u] = (vbits[sec >> 5] >> (sec & 31)) & 1u;
-                if (ok[u]) d[u] = vol2[q];              // a sector never written this episode reads as zero
+                if (kPacked) {
+                    d[u] = __bfloat1622float2(pk2[q]);
+                } else {
+                    const int sec = q >> 2;                      // 2 voxels per pair, 8 per sector
+                    ok[u] = (vbits[sec >> 5] >> (sec & 31)) & 1u;
+                    if (ok[u]) d[u] = vol2[q];          // a sector never written this episode reads as zero
+                }
             }
         }
 #pragma unroll
@@ -1070,6 +1098,32 @@ __global__ void __launch_bounds__(kVolThreads) rt_volumes_kernel(Tables T, const
             o3[q] = (make_float2(fminf(fmaxf(view2[0], 0.0f), 1.0f), fminf(fmaxf(view2[1], 0.0f), 1.0f)));
         }
     }
+}
+
+// ---------------------------------------------------------------------------------
+// Compressed observation record of live envs [first, first + count): the dose volume as bfloat16 (sectors never
+// written this episode are zero), the pose and the tumour id.  806,784 B of float32 volume -> 403,392 B; with the
+// three regenerated planes a stored voxel observation costs 1/8 of its float32 [4][V] form.
+__global__ void __launch_bounds__(256) rt_pack_kernel(Grid G, const EnvRec *rec, const float *dose, const uint32_t *valid,
+                                                      int first, long long slot0, __nv_bfloat16 *out_dose, double *out_pose,
+                                                      int32_t *out_tid)
+{
+    const int env = first + blockIdx.y;
+    const long long slot = slot0 + blockIdx.y;
+    const float4 *vol4 = reinterpret_cast<const float4 *>(dose + (size_t)env * G.vstride);
+    const uint32_t *vbits = valid + (size_t)env * G.vwords;
+    uint2 *o = reinterpret_cast<uint2 *>(out_dose + (size_t)slot * G.vstride);
+    const int nquads = G.vstride / 4;
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nquads; q += gridDim.x * blockDim.x) {
+        const int sec = q >> 1;                                    // 4 voxels per quad, 8 per sector
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if ((vbits[sec >> 5] >> (sec & 31)) & 1u) v = vol4[q];
+        const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+        o[q] = make_uint2(*reinterpret_cast<const uint32_t *>(&a), *reinterpret_cast<const uint32_t *>(&b));
+    }
+    if (blockIdx.x == 0 && threadIdx.x < 6)
+        out_pose[slot * 6 + threadIdx.x] = threadIdx.x < 3 ? rec[env].pos[threadIdx.x] : rec[env].dir[threadIdx.x - 3];
+    if (blockIdx.x == 0 && threadIdx.x == 6) out_tid[slot] = rec[env].tumour_id;
 }
 
 // ---------------------------------------------------------------------------------
@@ -1575,12 +1629,52 @@ int rt_assemble_volumes(rt_env *e, int first, int count, float *obs_dev, void *s
     const size_t smem = (size_t)(2 * (e->T.G.vstride / 32)) * sizeof(uint32_t) + (size_t)kHashSlots * (sizeof(int) + sizeof(float));
     static bool attr_set = false;
     if (!attr_set) {
-        RT_CUDA(cudaFuncSetAttribute(rt_volumes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RT_CUDA(cudaFuncSetAttribute(rt_volumes_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RT_CUDA(cudaFuncSetAttribute(rt_volumes_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
-    rt_volumes_kernel<<<count, kVolThreads, smem, (cudaStream_t)stream>>>(e->T, e->rec, e->dose, e->valid, first,
-                                                                         obs_dev);
+    rt_volumes_kernel<false><<<count, kVolThreads, smem, (cudaStream_t)stream>>>(e->T, e->rec, e->dose, e->valid, first,
+                                                                                obs_dev, PackedObs{});
     RT_LAUNCH_CHECK("rt_volumes_kernel");
+    return RT_OK;
+}
+
+int rt_observation_record_stride(const rt_env *e) { return e ? e->T.G.vstride : 0; }
+
+int rt_pack_observations(rt_env *e, int first, int count, int64_t slot0, void *dose_bf16_dev, double *pose_dev,
+                         int32_t *tumour_id_dev, void *stream)
+{
+    if (!e || !dose_bf16_dev || !pose_dev || !tumour_id_dev) return fail(RT_ERR_INVALID, "rt_pack_observations: NULL argument");
+    if (count == 0) return RT_OK;
+    if (first < 0 || count < 0 || first + count > e->n || slot0 < 0)
+        return fail(RT_ERR_INVALID, "rt_pack_observations: env range out of bounds");
+    if (e->dense) return fail(RT_ERR_STATE, "rt_pack_observations: not available for dense-mode handles");
+    RT_CUDA(cudaSetDevice(e->device));
+    rt_pack_kernel<<<dim3(8, count), 256, 0, (cudaStream_t)stream>>>(e->T.G, e->rec, e->dose, e->valid, first, (long long)slot0,
+                                                                    reinterpret_cast<__nv_bfloat16 *>(dose_bf16_dev), pose_dev,
+                                                                    tumour_id_dev);
+    RT_LAUNCH_CHECK("rt_pack_kernel");
+    return RT_OK;
+}
+
+int rt_render_observations(rt_env *e, const void *dose_bf16_dev, const double *pose_dev, const int32_t *tumour_id_dev,
+                           const int64_t *index_dev, int count, float *obs_dev, void *stream)
+{
+    if (!e || !dose_bf16_dev || !pose_dev || !tumour_id_dev || !obs_dev)
+        return fail(RT_ERR_INVALID, "rt_render_observations: NULL argument");
+    if (count == 0) return RT_OK;
+    if (count < 0) return fail(RT_ERR_INVALID, "rt_render_observations: negative count");
+    RT_CUDA(cudaSetDevice(e->device));
+    if (e->T.G.nvox % 2) return fail(RT_ERR_INVALID, "rt_render_observations: the voxel count must be even");
+    const size_t smem = (size_t)(2 * (e->T.G.vstride / 32)) * sizeof(uint32_t) + (size_t)kHashSlots * (sizeof(int) + sizeof(float));
+    static bool attr_set = false;
+    if (!attr_set) {
+        RT_CUDA(cudaFuncSetAttribute(rt_volumes_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    PackedObs P{reinterpret_cast<const __nv_bfloat16 *>(dose_bf16_dev), pose_dev, tumour_id_dev, index_dev};
+    rt_volumes_kernel<true><<<count, kVolThreads, smem, (cudaStream_t)stream>>>(e->T, nullptr, nullptr, nullptr, 0, obs_dev, P);
+    RT_LAUNCH_CHECK("rt_volumes_kernel<packed>");
     return RT_OK;
 }
 

@@ -38,6 +38,7 @@ DEFAULTS = dict(
     num_minibatches=32, update_epochs=10, gamma=0.99, gae_lambda=0.95, norm_adv=True, clip_coef=0.1,
     clip_vloss=True, ent_coef=0.0, vf_coef=0.5, max_grad_norm=0.5, feature_dim=64, visionless=True,
     cuda_graph=True,     # replay one captured rollout step (policy + env + buffer writes) instead of ~50 launches
+    render_microbatch=256,   # vision mode: samples re-rendered from compressed records per gradient micro-batch
 )
 
 
@@ -115,9 +116,69 @@ def broadcast_parameters(module: nn.Module, src: int = 0):
 
 
 # --------------------------------------------------------------------------------------------
+def ppo_update_rendered(agent, optimizer, cfg, render, b_actions, b_logprobs, b_advantages, b_returns, b_values,
+                        sync_grads=None, generator: Optional[torch.Generator] = None):
+    """The same update (train.py:191-248) when observations are rendered on demand: a minibatch is processed in
+    micro-batches of cfg.render_microbatch samples whose gradients are accumulated (the losses are means over the
+    minibatch, so each micro-batch is weighted by its share of it; the advantage normalisation uses the statistics
+    of the whole minibatch like the reference)."""
+    n = b_actions.shape[0]
+    dev = b_actions.device
+    mb = max(1, n // cfg.num_minibatches)
+    micro = max(1, min(int(getattr(cfg, "render_microbatch", 256)), mb))
+    clipfracs = []
+    stats = {}
+    for _ in range(cfg.update_epochs):
+        perm = torch.randperm(n, device=dev, generator=generator)
+        for start in range(0, n - mb + 1, mb):
+            idx = perm[start:start + mb]
+            adv_all = b_advantages[idx]
+            if cfg.norm_adv:
+                adv_all = (adv_all - adv_all.mean()) / (adv_all.std() + 1e-8)
+            optimizer.zero_grad()
+            acc = torch.zeros(6, device=dev)          # pg, v, entropy, old_kl, kl, clipfrac (minibatch means)
+            for m0 in range(0, mb, micro):
+                sub = idx[m0:m0 + micro].contiguous()
+                share = sub.numel() / mb
+                obs = render(sub)
+                _, newlogprob, entropy, newvalue = agent.get_action_and_value(obs, b_actions[sub])
+                logratio = newlogprob - b_logprobs[sub]
+                ratio = logratio.exp()
+                adv = adv_all[m0:m0 + micro]
+                pg_loss = torch.max(-adv * ratio, -adv * torch.clamp(ratio, 1 - cfg.clip_coef, 1 + cfg.clip_coef)).mean()
+                newvalue = newvalue.view(-1)
+                if cfg.clip_vloss:
+                    v_unclipped = (newvalue - b_returns[sub]) ** 2
+                    v_clipped = b_values[sub] + torch.clamp(newvalue - b_values[sub], -cfg.clip_coef, cfg.clip_coef)
+                    v_loss = 0.5 * torch.max(v_unclipped, (v_clipped - b_returns[sub]) ** 2).mean()
+                else:
+                    v_loss = 0.5 * ((newvalue - b_returns[sub]) ** 2).mean()
+                entropy_loss = entropy.mean()
+                loss = (pg_loss - cfg.ent_coef * entropy_loss + v_loss * cfg.vf_coef) * share
+                loss.backward()
+                with torch.no_grad():
+                    acc += share * torch.stack([pg_loss, v_loss, entropy_loss, (-logratio).mean(),
+                                                ((ratio - 1) - logratio).mean(),
+                                                ((ratio - 1.0).abs() > cfg.clip_coef).float().mean()])
+                del obs
+            if sync_grads is not None:
+                sync_grads()
+            nn.utils.clip_grad_norm_(agent.parameters(), cfg.max_grad_norm)
+            optimizer.step()
+            clipfracs.append(acc[5])
+            stats = dict(pg_loss=acc[0], v_loss=acc[1], entropy=acc[2], old_approx_kl=acc[3], approx_kl=acc[4])
+    stats["clipfrac"] = torch.stack(clipfracs).mean() if clipfracs else torch.zeros((), device=dev)
+    return stats
+
+
 def ppo_update(agent, optimizer, cfg, b_obs, b_actions, b_logprobs, b_advantages, b_returns, b_values,
                sync_grads=None, generator: Optional[torch.Generator] = None):
-    """train.py:191-248 on device tensors.  Returns the last minibatch's statistics like the reference."""
+    """train.py:191-248 on device tensors.  Returns the last minibatch's statistics like the reference.
+    `b_obs` is the flattened observation tensor, or a callable idx -> observations (voxel observations are
+    re-rendered from compressed records, see ppo_update_rendered)."""
+    if callable(b_obs):
+        return ppo_update_rendered(agent, optimizer, cfg, b_obs, b_actions, b_logprobs, b_advantages, b_returns,
+                                   b_values, sync_grads, generator)
     n = b_obs.shape[0]
     mb = max(1, n // cfg.num_minibatches)
     clipfracs = []
@@ -179,7 +240,11 @@ def train(cfg, writer=None, device="cuda", output_dir: Optional[str] = None, run
     sync_grads = FlatGradAllReduce(agent.parameters()) if world > 1 else None
 
     T = cfg.num_steps
-    obs = torch.zeros((T, n_local) + obs_shape, device=device)
+    # visionless: the rollout keeps the observations (train.py:110).  Vision: a float32 voxel observation is 3.2 MB
+    # (422 GB for 1024 envs x 128 steps), so the rollout keeps compressed records (bfloat16 dose + pose + tumour
+    # id, 1/8 of that) and the update re-renders each micro-batch.
+    store = None if cfg.visionless else envs.engine.observation_store(T * n_local)
+    obs = torch.zeros((T, n_local) + obs_shape, device=device) if cfg.visionless else None
     actions = torch.zeros((T, n_local) + act_shape, device=device)
     logprobs = torch.zeros((T, n_local), device=device)
     rewards = torch.zeros((T, n_local), device=device)
@@ -197,10 +262,16 @@ def train(cfg, writer=None, device="cuda", output_dir: Optional[str] = None, run
     ep_cols = torch.tensor([nat.INFO_EPISODE_RETURN, nat.INFO_EPISODE_LENGTH, nat.INFO_REWARD_TUMOUR,
                             nat.INFO_REWARD_LUNG, nat.INFO_REWARD_DISTANCE, nat.INFO_REWARD_TOTAL], device=device)
 
+    rollout_pos = [0]
+
     def rollout_step():
         """train.py:139-158 for the step selected by the device-side counter `step_idx` (so that one captured
         CUDA graph serves every step of the rollout)."""
-        obs.index_copy_(0, step_idx, next_obs.unsqueeze(0))
+        if cfg.visionless:
+            obs.index_copy_(0, step_idx, next_obs.unsqueeze(0))
+        else:                                          # eager only (no CUDA graph in vision mode): host-side slot index
+            eng.pack_observations(store, rollout_pos[0] * n_local)
+            rollout_pos[0] += 1
         dones.index_copy_(0, step_idx, next_done.unsqueeze(0))
         with torch.no_grad():
             action, logprob, _, value = agent.get_action_and_value(next_obs)
@@ -245,6 +316,7 @@ def train(cfg, writer=None, device="cuda", output_dir: Optional[str] = None, run
             optimizer.param_groups[0]["lr"] = (1.0 - (iteration - 1.0) / cfg.num_iterations) * cfg.learning_rate
         ep.zero_()
         step_idx.zero_()
+        rollout_pos[0] = 0
         for step in range(T):
             global_step += cfg.num_envs
             if graph is not None:
@@ -256,8 +328,9 @@ def train(cfg, writer=None, device="cuda", output_dir: Optional[str] = None, run
             next_value = agent.get_value(next_obs).reshape(-1)
             advantages, returns = compute_gae(rewards, values, dones, next_value, next_done, cfg.gamma, cfg.gae_lambda)
 
+        b_obs = obs.reshape((-1,) + obs_shape) if cfg.visionless else (lambda idx: eng.render_observations(store, idx))
         stats = ppo_update(agent, optimizer, cfg,
-                           obs.reshape((-1,) + obs_shape), actions.reshape((-1,) + act_shape), logprobs.reshape(-1),
+                           b_obs, actions.reshape((-1,) + act_shape), logprobs.reshape(-1),
                            advantages.reshape(-1), returns.reshape(-1), values.reshape(-1), sync_grads)
 
         if world > 1:

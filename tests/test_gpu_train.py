@@ -69,3 +69,48 @@ def test_vision_agent_step():
         obs, reward, term, trunc, _ = envs.step(action)
         assert torch.isfinite(value).all() and obs.min() >= 0 and obs.max() <= 1
     envs.close()
+
+
+def test_observation_records_render_like_volumes():
+    """Compressed voxel-observation records (rt_pack_observations / rt_render_observations): lungs, tumour and
+    beam-view planes equal get_volumes bit for bit, the dose plane is the bfloat16-rounded dose; gathering by index
+    picks the right records."""
+    n = 12
+    eng = rt.BatchedEpisodes(n, device=DEV, seed=9)
+    eng.reset()
+    g = torch.Generator(device=DEV).manual_seed(3)
+    store = eng.observation_store(3 * n)
+    want = []
+    for k in range(3):
+        for _ in range(7):
+            eng.step(torch.rand((n, 6), device=DEV, generator=g) * 2 - 1, want_info=False)
+        eng.pack_observations(store, k * n)
+        want.append(eng.volumes().clone())
+    want = torch.cat(want)
+    got = eng.render_observations(store)
+    assert got.shape == want.shape == (3 * n, 4, 67, 43, 70)
+    for plane in (0, 1, 3):
+        assert torch.equal(got[:, plane], want[:, plane])
+    assert torch.equal(got[:, 2], want[:, 2].bfloat16().float())
+    assert float(got[:, 2].max()) > 0.05 and float(got[:, 3].max()) > 0.05
+    idx = torch.tensor([35, 0, 17, 17, 4], device=DEV, dtype=torch.int64)
+    sel = eng.render_observations(store, idx)
+    assert torch.equal(sel, got[idx])
+    assert store.nbytes < 0.13 * want.numel() * 4
+    # a record taken right after the autoreset call is the empty volume of the new episode
+    for _ in range(100 - 21 + 1):
+        eng.step(torch.rand((n, 6), device=DEV, generator=g) * 2 - 1, want_info=False)
+    eng.pack_observations(store, 0)
+    fresh = eng.render_observations(store, torch.arange(n, device=DEV))
+    assert float(fresh[:, 2].abs().sum()) == 0.0 and torch.equal(fresh, torch.cat([eng.volumes()[:, :2], fresh[:, 2:3], eng.volumes()[:, 3:]], 1))
+    eng.close()
+
+
+def test_train_vision_tiny():
+    """Vision-mode PPO with compressed rollout storage and re-rendered micro-batches runs and stays finite."""
+    cfg = load_config(None, num_envs=6, num_steps=10, num_minibatches=2, update_epochs=1, visionless=False,
+                      total_timesteps=6 * 10 * 2, num_saves=0, save_model=False, seed=5, render_microbatch=8)
+    torch.manual_seed(0)
+    agent = train(cfg, writer=None, device=DEV, output_dir=None, run_name="v", log=None)
+    h = agent.history
+    assert len(h) == 2 and all(np.isfinite(r["v_loss"]) and np.isfinite(r["pg_loss"]) for r in h)
