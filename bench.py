@@ -111,6 +111,16 @@ def measured_traffic():
     return None
 
 
+def tensor_peak():
+    p = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        for k in ("bf16_tflops_sustained", "bf16_tflops", "bf16_tflops_burst"):
+            if k in d:
+                return float(d[k])
+    return 2250.0
+
+
 def hbm_peak():
     p = os.path.join(REPO, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
@@ -251,6 +261,24 @@ def other_kernels(rt, dev, peak):
     b = T * N * 20
     out.append({"kernel": "rt_gae_kernel", "workload": f"T={T}, N={N}", "bytes": b, "us": s * 1e6,
                 "achieved": b / s / 1e9, "unit": "GB/s", "frac": b / s / 1e9 / peak})
+    del sets
+    # FeaturesExtractor3D (BASELINE configs[3], 1024 voxel observations): the tcgen05 blocks and the whole forward
+    n = 1024
+    tpeak = tensor_peak()
+    x = torch.rand((n, 4) + (67, 43, 70), device=dev, generator=g)
+    fe = rt.FeaturesExtractor3D((4, 67, 43, 70), 64, compute_dtype=torch.bfloat16).to(dev)
+    with torch.no_grad():
+        s = timed(lambda: fe._fused_first_block(x), 10)
+        fl = n * 2 * 313.0e6                                     # conv1 313 MMAC per sample
+        out.append({"kernel": "rt_conv1_tc_kernel (tcgen05)", "workload": f"{n} samples, Conv3d(4->16,k3)+ReLU+MaxPool fused",
+                    "flops": fl, "us": s * 1e6, "achieved": fl / s / 1e12, "unit": "TFLOP/s", "bound": "tensor",
+                    "frac": fl / s / 1e12 / tpeak, "peak": tpeak, "us_per_sample": s * 1e6 / n,
+                    "hbm_gbs": n * (4 * 201670 * 4 + 16 * 33 * 21 * 34 * 2) / s / 1e9})
+        s = timed(lambda: fe(x), 10)
+        fl = n * 0.761e9
+        out.append({"kernel": "FeaturesExtractor3D forward (conv1, conv2 on tcgen05; conv3, linear cuDNN/cuBLAS)",
+                    "workload": f"{n} samples", "flops": fl, "us": s * 1e6, "achieved": fl / s / 1e12, "unit": "TFLOP/s",
+                    "bound": "tensor", "frac": fl / s / 1e12 / tpeak, "peak": tpeak, "us_per_sample": s * 1e6 / n})
     return out
 
 

@@ -10,6 +10,7 @@ Public surface (mirrors the reference's module/function names for the hot path):
     compute_gae                train.py:164-181
     PPO, PPO_3DCNN             networks.py:54,107   (PyTorch; checkpoint-compatible)
     train.train / train.main   train.py:91,285      device-resident CleanRL loop, NCCL grad all-reduce
+    ppo_eval.evaluate          ppo_eval.py:5        evaluation of a saved policy
     Phantom                    environment.py:28-29,90-97 data, packed
 
 Everything computes in librtenv_b200.so (hand-written sm_100a CUDA behind the C ABI of
@@ -25,6 +26,7 @@ from .vector_env import Box, RadiotherapyVectorEnv
 from .environment import RadiotherapyEnv
 from .networks import PPO, PPO_3DCNN, FeaturesExtractor3D
 from . import train as train          # noqa: F401  (ppo_radiotherapy_b200.train.train / main)
+from . import ppo_eval as ppo_eval    # noqa: F401
 
 __all__ = [
     "RtError", "build", "Phantom", "default_phantom", "BatchedEpisodes", "ObservationStore", "RadiotherapyEnv",

@@ -114,3 +114,17 @@ def test_train_vision_tiny():
     agent = train(cfg, writer=None, device=DEV, output_dir=None, run_name="v", log=None)
     h = agent.history
     assert len(h) == 2 and all(np.isfinite(r["v_loss"]) and np.isfinite(r["pg_loss"]) for r in h)
+
+
+def test_evaluate_like_ppo_eval(tmp_path):
+    """ppo_eval.py:5-36 on the device-resident env: loads a reference-format checkpoint, returns one mean return per
+    batch of finished episodes."""
+    from ppo_radiotherapy_b200.ppo_eval import evaluate
+    envs = rt.RadiotherapyVectorEnv(32, visionless=True, device=DEV, seed=4)
+    torch.manual_seed(1)
+    model = rt.PPO(envs.single_observation_space.shape, envs.single_action_space.shape, 64)
+    path = tmp_path / "m.model"
+    torch.save(model.state_dict(), path)
+    out = evaluate(envs, 64, str(path), eval_episodes=2, Model=rt.PPO, device=torch.device(DEV), log=None)
+    assert len(out) == 2 and all(np.isfinite(r) and -200 < r < 200 for r in out)
+    envs.close()

@@ -11,8 +11,10 @@ world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCA
 torch.cuda.set_device(local); dev = torch.device("cuda", local)
 if world > 1: dist.init_process_group("nccl", device_id=dev)
 envs = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
-cfg = load_config(None, num_envs=envs * world, num_steps=128, num_minibatches=4, update_epochs=2,
-                  total_timesteps=envs * world * 128 * 3, num_saves=0, save_model=False, seed=1)
+vision = len(sys.argv) > 2 and sys.argv[2] == "vision"          # voxel observations + C3D, compressed rollout records
+steps = int(sys.argv[3]) if len(sys.argv) > 3 else (16 if vision else 128)
+cfg = load_config(None, num_envs=envs * world, num_steps=steps, num_minibatches=4, update_epochs=1 if vision else 2,
+                  total_timesteps=envs * world * steps * 3, num_saves=0, save_model=False, seed=1, visionless=not vision)
 torch.manual_seed(1 + local)
 t0 = time.time()
 agent = train(cfg, None, dev, None, "smoke", log=(print if local == 0 else None))
