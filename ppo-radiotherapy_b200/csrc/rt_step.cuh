@@ -488,8 +488,8 @@ rt_step3_kernel(Tables T, Schedule S, EnvRec *rec, float *dose, uint32_t *valid,
             for (int j = 0; j < 4; j++)
                 if ((q.flags & (16u << j)) && !(kClock && (T.debug & 1))) {
                     const int sec = (q.base + (j >> 1) * g2 + (j & 1)) >> 3;
-                    zero_sector(vol + (sec << 3));
-                    red_or(vbits + (sec >> 5), 1u << (sec & 31));
+                    if (!(kClock && (T.debug & 32))) zero_sector(vol + (sec << 3));
+                    if (!(kClock && (T.debug & 16))) red_or(vbits + (sec >> 5), 1u << (sec & 31));
                 }
         }
         __syncwarp();   // zero fill (any lane) is ordered before the voxel stores below
