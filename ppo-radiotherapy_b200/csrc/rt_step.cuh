@@ -160,7 +160,7 @@ __device__ __forceinline__ void slab_weights(const Beam &b, int k, const SlabCoo
 struct PassState {
     int base;          // linear index of target (dy, dz) = (0, 0)
     uint32_t flags;    // bit j: target j is written by this lane; 4+j: this lane zero-fills its (fresh) sector;
-                       // 8+j: voxel belongs to the tumour
+                       // 8+j: voxel belongs to the tumour; 12+j: to the lungs
     float w[4];        // summed splat weights
     float old[4];      // dose before the beam (0 for fresh sectors)
 };
@@ -438,13 +438,14 @@ rt_step3_kernel(Tables T, Schedule S, EnvRec *rec, float *dose, uint32_t *valid,
                                : b.dom == 1 ? slab_coords<1>(G, b, k, cur, q.base, inb, c0, c1, c2)
                                             : slab_coords<2>(G, b, k, cur, q.base, inb, c0, c1, c2);
             // the dose loads go out first (a voxel the previous slab owns is loaded for nothing: harmless)
-            uint32_t freshm = 0u;
+            uint32_t freshm = 0u, lungm = 0u;
             int sec[4];
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 const bool inj = (inb >> j) & 1u;
                 const int l = inj ? q.base + (j >> 1) * g2 + (j & 1) : 0;
                 sec[j] = l >> 3;
+                lungm |= (((kStageLungs ? slungs[l >> 5] : __ldg(slungs + (l >> 5))) >> (l & 31)) & 1u) << j;
                 const bool fresh = inj && !((vsm[sec[j] >> 5] >> (sec[j] & 31)) & 1u);   // never written this episode: reads as zero
                 q.old[j] = 0.0f;
                 if (inj && !fresh && !(kClock && (T.debug & 4))) q.old[j] = vol[l];   // re-touched sector: read from HBM / L2
@@ -474,7 +475,7 @@ rt_step3_kernel(Tables T, Schedule S, EnvRec *rec, float *dose, uint32_t *valid,
             uint32_t fill = freshm;
             if ((freshm & 3u) == 3u && sec[0] == sec[1]) fill &= ~2u;
             if ((freshm & 12u) == 12u && sec[2] == sec[3]) fill &= ~8u;
-            q.flags = ok | (fill << 4) | ((tmask & ok) << 8);
+            q.flags = ok | (fill << 4) | ((tmask & ok) << 8) | ((lungm & ok) << 12);
         }
         if (lane == 0) RT_STAMP3(env, 4);
         // First write to a sector this episode: materialise it as zeros and mark it valid for the next step.
@@ -521,20 +522,19 @@ rt_step3_kernel(Tables T, Schedule S, EnvRec *rec, float *dose, uint32_t *valid,
                     }
                 }
             }
+            if (!(kClock && (T.debug & 8))) {
+                const uint32_t tmask = (q.flags >> 8) & 15u, lmask = (q.flags >> 12) & 15u;
+                const uint32_t cmask = lmask & ~tmask;             // lungs_mask = lungs*(1-tumours) (environment.py:174)
 #pragma unroll
-            for (int j = 0; j < 4; j++)
-                if (q.flags & (1u << j)) {
-                    if (kClock && (T.debug & 8)) continue;
-                    const int l = q.base + (j >> 1) * g2 + (j & 1);
+                for (int j = 0; j < 4; j++) {
                     const float o = q.old[j];
-                    const bool in_t = q.flags & (256u << j);
-                    const bool in_l = ((kStageLungs ? slungs[l >> 5] : __ldg(slungs + (l >> 5))) >> (l & 31)) & 1u;
-                    const float delta = nd[j] - o;
-                    d_tum += in_t ? delta : 0.0f;
-                    d_lung += in_l ? delta : 0.0f;
-                    // lungs_mask = lungs*(1-tumours); dose is monotone, so the count only grows (environment.py:174-177)
-                    d_cnt += (in_l && !in_t && !(o > 0.200000002980232239f) && nd[j] > 0.200000002980232239f) ? 1 : 0;
+                    const float delta = (q.flags >> j) & 1u ? nd[j] - o : 0.0f;      // 0 for targets this lane does not write
+                    d_tum += (tmask >> j) & 1u ? delta : 0.0f;
+                    d_lung += (lmask >> j) & 1u ? delta : 0.0f;
+                    // dose is monotone, so the count only grows (environment.py:175-177)
+                    d_cnt += (int)((cmask >> j) & 1u) & (int)(!(o > 0.200000002980232239f) && nd[j] > 0.200000002980232239f);
                 }
+            }
         }
         if (lane == 0) RT_STAMP3(env, 6);
         // both sums in one butterfly: after the first exchange the lower half-warp carries the tumour sum, the
