@@ -485,13 +485,24 @@ rt_step3_kernel(Tables T, Schedule S, EnvRec *rec, float *dose, uint32_t *valid,
         for (int c = 0; c < kMaxPass; c++) {
             if (c * kWarp >= b.nslab) break;
             const PassState &q = ps[c];
+            // the lane's (at most four) fresh sectors usually fall into one or two words of the bitmap: one RED per word
+            int wrd[2] = {-1, -1};
+            uint32_t msk[2] = {0u, 0u};
 #pragma unroll
             for (int j = 0; j < 4; j++)
                 if ((q.flags & (16u << j)) && !(kClock && (T.debug & 1))) {
                     const int sec = (q.base + (j >> 1) * g2 + (j & 1)) >> 3;
                     if (!(kClock && (T.debug & 32))) zero_sector(vol + (sec << 3));
-                    if (!(kClock && (T.debug & 16))) red_or(vbits + (sec >> 5), 1u << (sec & 31));
+                    const int w = sec >> 5;
+                    const uint32_t bit = 1u << (sec & 31);
+                    if (wrd[0] < 0 || wrd[0] == w) { wrd[0] = w; msk[0] |= bit; }
+                    else if (wrd[1] < 0 || wrd[1] == w) { wrd[1] = w; msk[1] |= bit; }
+                    else red_or(vbits + w, bit);                           // a third word: rows far apart and straddling
                 }
+            if (!(kClock && (T.debug & 16))) {
+                if (wrd[0] >= 0) red_or(vbits + wrd[0], msk[0]);
+                if (wrd[1] >= 0) red_or(vbits + wrd[1], msk[1]);
+            }
         }
         __syncwarp();   // zero fill (any lane) is ordered before the voxel stores below
         if (lane == 0) RT_STAMP3(env, 5);
