@@ -51,6 +51,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-kernels", action="store_true", help="skip the dense / voxel-obs / GAE side measurements")
     ap.add_argument("--no-graph", action="store_true", help="launch every step from Python instead of CUDA graphs")
+    ap.add_argument("--action-pool", type=int, default=128, help="distinct device-resident action batches cycled through")
     return ap.parse_args()
 
 
@@ -309,7 +310,7 @@ def run_ours(args):
     eng.set_tumour_schedule(first[None, :])
     eng.reset()
     eng.set_tumour_schedule(None)                 # later episodes: device RNG
-    n_act = 128
+    n_act = max(GRAPH_CHUNK, args.action_pool) if not args.no_graph else max(1, args.action_pool)
     gen = torch.Generator(device=dev).manual_seed(rank)
     act_pool = torch.rand((n_act, E, 6), device=dev, generator=gen) * 2 - 1
     stream = torch.cuda.Stream(dev)

@@ -10,11 +10,12 @@
 //                          sector needs no read from HBM.
 //   lungs_bits, tumour table, tumour bbox bitmasks, packed voxel lists: < 1 MB, replicated.
 //
-// One warp advances one env per step (rt_step_kernel): pose update (f64) -> beam
-// clip + slab walk (bit-exact f32) -> merge duplicate splat targets by shuffle ->
-// sparse dose read-modify-write -> incremental tumour/lung accumulators -> reward,
-// termination, observation, episode statistics; NEXT_STEP autoreset happens in the
-// same kernel.
+// The sparse step is rt_step3_kernel (rt_step.cuh): per block one scalar warp (a thread per env: pose update in
+// float64, beam clip and the serial float32 slab walk, rewards, termination, observation, NEXT_STEP autoreset)
+// and one env warp per env (splat targets, sparse dose read-modify-write, tumour / lung deltas).  This file
+// holds the record / table definitions, the earlier two-role step kernel (still the first half of the dense-mode
+// step, and RT_STEP_KB=0 for A/B runs), reset, dense-mode, beam, pose, voxel-observation, observation-record and
+// GAE kernels, and the C ABI.
 #include "../../include/rt_env.h"
 #include "rt_device.cuh"
 
