@@ -627,6 +627,7 @@ __global__ void __launch_bounds__(kStepThreads, 4) rt_step_kernel(Tables T, Sche
 
 }  // namespace
 #include "rt_step.cuh"
+#include "rt_step_wide.cuh"
 namespace {
 
 // ---------------------------------------------------------------------------------
@@ -1373,12 +1374,13 @@ int rt_create(rt_env **out, int device, int n_envs, uint32_t flags, const rt_pha
         e->step_kb = per_sm <= 7 ? 7 : 14;
         if (const char *v = getenv("RT_STEP_KB")) {
             const int kb = atoi(v);
-            if (kb == 0 || kb == 7 || kb == 14 || kb == 28) e->step_kb = kb;
+            if (kb == 0 || kb == 7 || kb == 14 || kb == 28 || kb == -1) e->step_kb = kb;    // -1: thread-per-env kernel
         }
-        const int kb = e->step_kb ? e->step_kb : kEnvsPerBlock;
+        const int kb = e->step_kb > 0 ? e->step_kb : kEnvsPerBlock;
         e->step_smem = (size_t)kb * G.vwords * sizeof(uint32_t) + (e->step_kb >= 14 ? (size_t)e->T.lung_words16 * sizeof(uint32_t) : 0);
         cudaError_t ae = cudaSuccess;
         switch (e->step_kb) {
+        case -1: break;
         case 0: ae = cudaFuncSetAttribute(rt_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->step_smem); break;
         case 7: ae = cudaFuncSetAttribute(rt_step3_kernel<7, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->step_smem); break;
         case 14: ae = cudaFuncSetAttribute(rt_step3_kernel<14, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->step_smem); break;
@@ -1507,6 +1509,10 @@ int rt_step(rt_env *e, const float *actions_dev, float *obs_dev, double *reward_
         RT_LAUNCH_CHECK("rt_step_kernel<dense>");
         rt_dense_kernel<<<e->n, kDenseThreads, e->dense_smem, (cudaStream_t)stream>>>(e->T, e->rec, e->dose, e->dense, o);
         RT_LAUNCH_CHECK("rt_dense_kernel");
+    } else if (e->step_kb == -1) {
+        rt_step_wide_kernel<<<(e->n + kWideThreads - 1) / kWideThreads, kWideThreads, 0, (cudaStream_t)stream>>>(
+            e->T, e->S, e->rec, e->dose, e->valid, e->beams, e->n, actions_dev, o);
+        RT_LAUNCH_CHECK("rt_step_wide_kernel");
     } else {
         const int kb = e->step_kb ? e->step_kb : kEnvsPerBlock;
         cudaLaunchConfig_t cfg = {};
@@ -1565,7 +1571,7 @@ int rt_reset_host(rt_env *e, const uint8_t *mask_host, float *obs_host)
 int rt_set_stage_clock(rt_env *e, long long *stamps_dev)
 {
     if (!e) return fail(RT_ERR_INVALID, "rt_set_stage_clock: NULL handle");
-    if (stamps_dev && e->step_kb != 0 && e->step_kb != 28)
+    if (stamps_dev && e->step_kb != 28)
         return fail(RT_ERR_STATE, "rt_set_stage_clock: the instrumented step kernel exists for 28 envs per block only (RT_STEP_KB=28)");
     e->T.stage_clock = stamps_dev;
     return RT_OK;
