@@ -213,6 +213,12 @@ RT_API int rt_conv1_relu_pool_grouped(const float *x_dev, const float *weight_de
  * W must be even; RT_ERR_INVALID for shapes the kernel does not cover. */
 RT_API int rt_conv2_relu_pool(const void *x_dev, const float *weight_dev, const float *bias_dev, int n, int D, int H,
                               int W, void *out_dev, void *scratch_dev, void *stream);
+/* Tail (networks.py:28-45): Conv3d(16->16, k=3, groups=4) + ReLU + MaxPool3d(2, 2) + Flatten + Linear + ReLU, one
+ * kernel.  x_dev bfloat16 [n][16][D][H][W] (the second block's output), conv_w_dev float32 [16][4][3][3][3],
+ * conv_b_dev [16], lin_w_dev float32 [F][16*Pd*Ph*Pw] (P = (dim-2)/2; flatten order c, d, h, w), lin_b_dev [F], F <= 256
+ * -> out_dev float32 [n][F] (the features FeaturesExtractor3D.forward returns). */
+RT_API int rt_c3d_tail(const void *x_dev, const float *conv_w_dev, const float *conv_b_dev, const float *lin_w_dev,
+                       const float *lin_b_dev, int n, int D, int H, int W, int F, float *out_dev, void *stream);
 
 /* ---- instrumentation ----------------------------------------------------------------- */
 /* Number of kernels this library has launched since load (for bench.py's gpu_launches). */

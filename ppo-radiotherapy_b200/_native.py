@@ -120,6 +120,7 @@ _SIGNATURES = {
     "rt_conv1_relu_pool": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]),
     "rt_conv1_relu_pool_grouped": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]),
     "rt_conv2_relu_pool": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]),
+    "rt_c3d_tail": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "rt_launch_count": (C.c_int64, []),
     "rt_set_stage_clock": (C.c_int, [_vp, _vp]),
 }

@@ -798,6 +798,89 @@ __global__ void __launch_bounds__(kC2Threads, 1) rt_conv2_tc_kernel(Conv2Shape S
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Tail of FeaturesExtractor3D (networks.py:28-45): Conv3d(16 -> 16, k = 3, groups = 4) + bias + ReLU +
+// MaxPool3d(2, 2) + Flatten + Linear(n_flat -> F) + bias + ReLU, one block per sample.  2.3 MMAC per sample: too
+// small for the tensor pipe to matter; what matters is that the sample's activation (69 KB bf16) is read from HBM
+// once and nothing in between goes back.  A thread owns one pooled cell: the 2x2x2 conv outputs under it share a
+// 4x4x4 input window per input channel, so every window value and every weight is read from shared memory once
+// per cell (364 reads for 864 FMAs); then the 2016 features stay in shared memory for the linear layer.
+constexpr int kTailThreads = 256;
+constexpr int kTailMaxF = 256;
+
+__global__ void __launch_bounds__(kTailThreads) rt_c3d_tail_kernel(const __nv_bfloat16 *__restrict__ x, int D, int H, int W,
+                                                                   const float *__restrict__ w3, const float *__restrict__ b3,
+                                                                   const float *__restrict__ wl, const float *__restrict__ bl,
+                                                                   int F, float *__restrict__ out)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int DHW = D * H * W;
+    __nv_bfloat16 *xs = reinterpret_cast<__nv_bfloat16 *>(smem_raw);                   // [16][D][H][W]
+    float *ws = reinterpret_cast<float *>(xs + ((size_t)16 * DHW + 7) / 8 * 8);         // [16][4][27]
+    float *feat = ws + 16 * 4 * 27;                                                     // [16][Pd][Ph][Pw]
+    const int Pd = (D - 2) / 2, Ph = (H - 2) / 2, Pw = (W - 2) / 2;
+    const int cells = Pd * Ph * Pw, n_flat = 16 * cells;
+    const int tid = threadIdx.x;
+    const __nv_bfloat16 *xg = x + (size_t)blockIdx.x * 16 * DHW;
+    if ((16 * DHW) % 8 == 0) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(xg);
+        uint4 *dst = reinterpret_cast<uint4 *>(xs);
+        for (int i = tid; i < 16 * DHW / 8; i += kTailThreads) dst[i] = __ldg(src + i);
+    } else {
+        for (int i = tid; i < 16 * DHW; i += kTailThreads) xs[i] = xg[i];
+    }
+    for (int i = tid; i < 16 * 4 * 27; i += kTailThreads) ws[i] = __ldg(w3 + i);
+    __syncthreads();
+
+    for (int cell = tid; cell < n_flat; cell += kTailThreads) {
+        const int c = cell / cells, r = cell - c * cells;
+        const int pd = r / (Ph * Pw), r2 = r - pd * (Ph * Pw), ph = r2 / Pw, pw = r2 - ph * Pw;
+        const int g = c >> 2;
+        float acc[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) acc[i] = 0.0f;
+        for (int ci = 0; ci < 4; ci++) {
+            const __nv_bfloat16 *xc = xs + (size_t)(4 * g + ci) * DHW + ((2 * pd) * H + 2 * ph) * W + 2 * pw;
+            const float *wc = ws + (c * 4 + ci) * 27;
+            float win[4][4][4];                          // input window under the 2x2x2 conv outputs of this cell
+#pragma unroll
+            for (int a = 0; a < 4; a++)
+#pragma unroll
+                for (int b = 0; b < 4; b++)
+#pragma unroll
+                    for (int e = 0; e < 4; e++) win[a][b][e] = __bfloat162float(xc[(a * H + b) * W + e]);
+#pragma unroll
+            for (int kd = 0; kd < 3; kd++)
+#pragma unroll
+                for (int kh = 0; kh < 3; kh++)
+#pragma unroll
+                    for (int kw = 0; kw < 3; kw++) {
+                        const float wv = wc[(kd * 3 + kh) * 3 + kw];
+#pragma unroll
+                        for (int o = 0; o < 8; o++)
+                            acc[o] = fmaf(win[(o >> 2) + kd][((o >> 1) & 1) + kh][(o & 1) + kw], wv, acc[o]);
+                    }
+        }
+        float m = acc[0];
+#pragma unroll
+        for (int o = 1; o < 8; o++) m = fmaxf(m, acc[o]);
+        feat[cell] = fmaxf(m + __ldg(b3 + c), 0.0f);     // max, + bias and ReLU commute
+    }
+    __syncthreads();
+
+    // Linear + ReLU: warp w computes outputs w, w + 8, ...; lanes stride the features (coalesced weight rows)
+    const int lane = tid & 31, warp = tid >> 5;
+    for (int f = warp; f < F; f += kTailThreads / 32) {
+        const float *wr = wl + (size_t)f * n_flat;
+        float sum = 0.0f;
+        for (int i = lane; i < n_flat; i += 32) sum = fmaf(feat[i], __ldg(wr + i), sum);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        if (lane == 0) out[(size_t)blockIdx.x * F + f] = fmaxf(sum + __ldg(bl + f), 0.0f);
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -924,6 +1007,29 @@ int rt_conv2_relu_pool(const void *x_dev, const float *weight_dev, const float *
     rt_conv2_tc_kernel<<<n * chunks, kC2Threads, smem, (cudaStream_t)stream>>>(
         S, n, chunks, per, reinterpret_cast<const uint4 *>(x_dev), reinterpret_cast<const uint4 *>(bop), bias_dev,
         reinterpret_cast<__nv_bfloat16 *>(out_dev));
+    return cudaGetLastError() == cudaSuccess ? RT_OK : RT_ERR_CUDA;
+}
+
+// Tail of FeaturesExtractor3D (networks.py:28-45): Conv3d(16->16, k=3, groups=4) + ReLU + MaxPool3d(2, 2) + Flatten +
+// Linear(16*Pd*Ph*Pw -> F) + ReLU.  x_dev bfloat16 [n][16][D][H][W] (rt_conv2_relu_pool), conv_w float32 [16][4][3][3][3],
+// conv_b [16], lin_w float32 [F][16*Pd*Ph*Pw] (flatten order c, d, h, w), lin_b [F] -> out_dev float32 [n][F].
+int rt_c3d_tail(const void *x_dev, const float *conv_w_dev, const float *conv_b_dev, const float *lin_w_dev,
+                const float *lin_b_dev, int n, int D, int H, int W, int F, float *out_dev, void *stream)
+{
+    if (n == 0) return RT_OK;
+    if (!x_dev || !conv_w_dev || !conv_b_dev || !lin_w_dev || !lin_b_dev || !out_dev || n < 0 || D < 4 || H < 4 || W < 4 ||
+        F < 1 || F > kTailMaxF)
+        return RT_ERR_INVALID;
+    const int Pd = (D - 2) / 2, Ph = (H - 2) / 2, Pw = (W - 2) / 2;
+    const size_t smem = ((size_t)16 * D * H * W + 7) / 8 * 8 * sizeof(__nv_bfloat16) + (size_t)16 * 4 * 27 * sizeof(float) +
+                        (size_t)16 * Pd * Ph * Pw * sizeof(float);
+    int dev = 0, max_smem = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return RT_ERR_CUDA;
+    cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (smem > (size_t)max_smem) return RT_ERR_INVALID;
+    if (cudaFuncSetAttribute(rt_c3d_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return RT_ERR_CUDA;
+    rt_c3d_tail_kernel<<<n, kTailThreads, smem, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16 *>(x_dev), D, H, W,
+                                                                     conv_w_dev, conv_b_dev, lin_w_dev, lin_b_dev, F, out_dev);
     return cudaGetLastError() == cudaSuccess ? RT_OK : RT_ERR_CUDA;
 }
 

@@ -75,6 +75,7 @@ class FeaturesExtractor3D(nn.Module):
         self.compute_dtype = compute_dtype
         self.fused_first_block = True       # rollout (no_grad) path: rt_conv1_relu_pool instead of cuDNN + 4 more kernels
         self.fused_second_block = True      # ... and rt_conv2_relu_pool for cnn[3:6]
+        self.fused_tail = True              # ... and rt_c3d_tail for cnn[6:] + mlp: no library kernel left in the rollout
         pad = tuple((int(observation_shape[i + 1]) - 2) % 2 for i in range(3))
         self.cnn = nn.Sequential(
             nn.Conv3d(int(observation_shape[0]), 16, 3), nn.ReLU(), nn.MaxPool3d(2, 2, padding=pad),
@@ -156,11 +157,38 @@ class FeaturesExtractor3D(nn.Module):
         nat.check(rc, "rt_conv2_relu_pool")
         return out
 
+    def _fused_tail(self, h: torch.Tensor):
+        """cnn[6:] + mlp — Conv3d(16,16,3,groups=4) ReLU MaxPool3d(2,2) Flatten Linear ReLU — as one kernel
+        (rt_c3d_tail) on the second block's bfloat16 activation.  Returns None when the layers do not match."""
+        import ctypes as C
+        from . import _native as nat
+        conv3, pool3, lin = self.cnn[6], self.cnn[8], self.mlp[0]
+        n, c, D, H, W = h.shape
+        F = lin.out_features
+        if (h.dtype != torch.bfloat16 or c != 16 or not h.is_contiguous() or conv3.groups != 4 or conv3.in_channels != 16
+                or conv3.out_channels != 16 or tuple(conv3.kernel_size) != (3, 3, 3) or pool3.padding not in (0, (0, 0, 0))
+                or min(D, H, W) < 4 or F > 256 or lin.in_features != 16 * ((D - 2) // 2) * ((H - 2) // 2) * ((W - 2) // 2)):
+            return None
+        out = torch.empty((n, F), dtype=torch.float32, device=h.device)
+        w3, b3 = conv3.weight.detach().float().contiguous(), conv3.bias.detach().float().contiguous()
+        wl, bl = lin.weight.detach().float().contiguous(), lin.bias.detach().float().contiguous()
+        with torch.cuda.device(h.device):
+            rc = nat.lib().rt_c3d_tail(C.c_void_p(h.data_ptr()), C.c_void_p(w3.data_ptr()), C.c_void_p(b3.data_ptr()),
+                                       C.c_void_p(wl.data_ptr()), C.c_void_p(bl.data_ptr()), n, D, H, W, F,
+                                       C.c_void_p(out.data_ptr()), C.c_void_p(torch.cuda.current_stream(h.device).cuda_stream))
+        if rc == -1:
+            return None
+        nat.check(rc, "rt_c3d_tail")
+        return out
+
     def forward(self, observations: torch.Tensor) -> torch.Tensor:
         if (self.compute_dtype == torch.bfloat16 and observations.is_cuda and not torch.is_grad_enabled()
                 and self.fused_first_block):
             h = self._fused_two_blocks(observations) if self.fused_second_block else None
             if h is not None:
+                y = self._fused_tail(h) if self.fused_tail else None
+                if y is not None:
+                    return y
                 with torch.autocast("cuda", dtype=torch.bfloat16):
                     h = self.cnn[6:](h)
                 return self.mlp(h.float())

@@ -114,6 +114,31 @@ def test_conv2_block_matches_torch(shape):
     assert float(out.float().max()) > 0.1
 
 
+@pytest.mark.parametrize("shape", [(3, 15, 9, 16, 64), (2, 6, 5, 8, 10), (130, 4, 4, 4, 7)])
+def test_c3d_tail_matches_torch(shape):
+    """Conv3d(16->16, k3, groups=4) + ReLU + MaxPool3d(2,2) + Flatten + Linear + ReLU in one kernel."""
+    n, D, H, W, Fdim = shape
+    g = torch.Generator(device=DEV).manual_seed(D * 10 + W)
+    x = torch.rand((n, 16, D, H, W), device=DEV, generator=g).bfloat16()
+    w3 = torch.randn((16, 4, 3, 3, 3), device=DEV, generator=g) * 0.1
+    b3 = torch.randn(16, device=DEV, generator=g) * 0.1
+    n_flat = 16 * ((D - 2) // 2) * ((H - 2) // 2) * ((W - 2) // 2)
+    wl = torch.randn((Fdim, n_flat), device=DEV, generator=g) * (1.0 / n_flat ** 0.5)
+    bl = torch.randn(Fdim, device=DEV, generator=g) * 0.1
+    out = torch.empty((n, Fdim), dtype=torch.float32, device=DEV)
+    rc = nat.lib().rt_c3d_tail(C.c_void_p(x.data_ptr()), C.c_void_p(w3.data_ptr()), C.c_void_p(b3.data_ptr()),
+                               C.c_void_p(wl.data_ptr()), C.c_void_p(bl.data_ptr()), n, D, H, W, Fdim,
+                               C.c_void_p(out.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert rc == 0
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    y = F.max_pool3d(F.relu(F.conv3d(x.float(), w3, b3, groups=4)), 2, 2).flatten(1)
+    want = F.relu(F.linear(y, wl, bl))
+    assert out.shape == want.shape
+    assert float((out - want).abs().max()) <= 1e-4 * max(1.0, float(want.abs().max()))
+    assert float(out.max()) > 0.01
+
+
 def test_features_extractor_fused_path_matches_unfused():
     torch.manual_seed(0)
     fe = rt.FeaturesExtractor3D((4, 67, 43, 70), 64, compute_dtype=torch.bfloat16).to(DEV)
@@ -124,13 +149,16 @@ def test_features_extractor_fused_path_matches_unfused():
         obs, *_ = envs.step(a)
     with torch.no_grad():
         fe.fused_first_block = True
-        y1 = fe(obs)                        # both blocks on tcgen05
+        y1 = fe(obs)                        # both blocks on tcgen05 + fused tail
+        fe.fused_tail = False
+        y1a = fe(obs)                       # both blocks on tcgen05, cuDNN tail
         fe.fused_second_block = False
         y1b = fe(obs)                       # first block only
         fe.fused_first_block = False
         y2 = fe(obs)
-        fe.fused_first_block = fe.fused_second_block = True
+        fe.fused_first_block = fe.fused_second_block = fe.fused_tail = True
     assert y1.shape == (6, 64)
+    assert float((y1a - y2).abs().max()) <= 0.05 * float(y2.abs().max()) + 1e-2
     assert float((y1 - y2).abs().max()) <= 0.05 * float(y2.abs().max()) + 1e-2
     assert float((y1b - y2).abs().max()) <= 0.05 * float(y2.abs().max()) + 1e-2
     # with autograd enabled the module takes the differentiable cuDNN path
