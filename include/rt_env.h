@@ -207,6 +207,11 @@ RT_API int rt_conv1_relu_pool(const float *x_dev, const float *weight_dev, const
  * out_dev bfloat16 [n][2 groups][Pd][Ph*Pw][8 channels] (channel = group*8 + c). */
 RT_API int rt_conv1_relu_pool_grouped(const float *x_dev, const float *weight_dev, const float *bias_dev, int n, int D,
                                       int H, int W, void *out_dev, void *scratch_dev, void *stream);
+/* The first block computed straight from the state of envs [first, first+count): the voxel observation is generated
+ * inside the kernel and never written to HBM.  Output as rt_conv1_relu_pool_grouped, bit-identical to
+ * rt_assemble_volumes followed by it.  Sparse-mode handles only. */
+RT_API int rt_conv1_from_env(rt_env *env, int first, int count, const float *weight_dev, const float *bias_dev,
+                             void *out_dev, void *scratch_dev, void *stream);
 /* Second block (networks.py:25-27): Conv3d(16->16, k=3, groups=2) + bias + ReLU + MaxPool3d(2, 2) on tcgen05.
  * x_dev bfloat16 [n][2][D][H*W][8] as written by rt_conv1_relu_pool_grouped, weight_dev float32 [16][8][3][3][3],
  * bias_dev float32 [16] -> out_dev bfloat16 [n][16][(D-2)/2][(H-2)/2][(W-2)/2] (NCDHW).  scratch_dev: 65,536 bytes.

@@ -22,13 +22,11 @@
 // then max over the h pair and over the two planes of a depth window (the odd plane's partial result waits in
 // registers), written bf16 NCDHW.  ReLU and max commute, so pooling max(0, .) values equals the reference's
 // ReLU -> MaxPool; the implicit -inf padding of MaxPool3d is "ignore".
-#include "../../include/rt_env.h"
-
+// (included at the end of rt_env.cu: the from-env variant of the first block reads the env records, dose volumes
+// and tables defined there)
+#pragma once
 #include <cuda_bf16.h>
-#include <cuda_runtime.h>
 #include <math_constants.h>
-#include <stdint.h>
-#include <stdlib.h>
 
 namespace {
 
@@ -377,12 +375,24 @@ __global__ void rt_conv_prepare_tc_kernel(const float *__restrict__ weight, __nv
     bop[idx] = __float2bfloat16(v);
 }
 
-template <bool kGroupedOut>
+// Source of the first block's input when it is not a materialised observation tensor: the live env state.  The
+// loader warps then generate the four observation planes of environment.py:245-257 voxel by voxel — lungs bit,
+// tumour bit, dose (sector-valid bitmap applied), clip(current beam + horizontal beam, 0, 1) — exactly as
+// rt_volumes_kernel would have written them, and the 3.2 MB float32 observation never exists.
+struct EnvSource {
+    Tables T;
+    const EnvRec *rec;
+    const float *dose;
+    const uint32_t *valid;
+    int first;
+};
+
+template <bool kGroupedOut, bool kFromEnv>
 __global__ void __launch_bounds__(kTcThreads, 1) rt_conv1_tc_kernel(ConvShape S, int n_samples, int chunks,
                                                                     int pooled_per_chunk, const float *__restrict__ x,
                                                                     const uint4 *__restrict__ bop,
                                                                     const float *__restrict__ bias,
-                                                                    __nv_bfloat16 *__restrict__ out)
+                                                                    __nv_bfloat16 *__restrict__ out, EnvSource E)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint4 *pairs = reinterpret_cast<uint4 *>(smem_raw);                               // 3 x [plane_vox] x 16 B
@@ -393,6 +403,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) rt_conv1_tc_kernel(ConvShape S,
     unsigned long long *pair_ready = empty + kTcSlots;             // [3] loader warps -> MMA warp
     unsigned long long *pair_free = pair_ready + 3;                // [3] MMA warp (tcgen05.commit) -> loader warps
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(pair_free + 3);
+    int *hkeys = reinterpret_cast<int *>(tmem_slot + 4);           // kFromEnv: voxel -> beam-view weight (kHashSlots)
+    float *hvals = reinterpret_cast<float *>(hkeys + kHashSlots);
+    RayWork *view = reinterpret_cast<RayWork *>(hvals + kHashSlots);   // [2]
+    uint32_t *hit_sec = reinterpret_cast<uint32_t *>(view + 2);    // kFromEnv: 1 bit per dose sector touched by a view beam
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int sample = blockIdx.x / chunks, chunk = blockIdx.x % chunks;
     const bool is_mma = warp >= kTcDrainWarps + kTcLoadWarps;
@@ -434,7 +448,100 @@ __global__ void __launch_bounds__(kTcThreads, 1) rt_conv1_tc_kernel(ConvShape S,
     const int HW = S.H * S.W;
     const uint32_t pairs_addr = tc::smem_u32(pairs);
 
-    if (is_loader) {
+    if (is_loader && kFromEnv) {
+        // ---- the same pair buffers, generated from the env state (see EnvSource)
+        const int t0 = tid - kTcDrainWarps * 32, nt = kTcLoadWarps * 32, lw = warp - kTcDrainWarps;
+        const Grid &G = E.T.G;
+        const int env = E.first + sample;
+        if (has_work) {
+            const EnvRec *r = E.rec + env;
+            const int tumour_id = r->tumour_id;
+            // view planes (environment.py:246-250): beam along the current direction + beam along (1, 0, 0)
+            for (int i = t0; i < kHashSlots; i += nt) { hkeys[i] = -1; hvals[i] = 0.0f; }
+            for (int i = t0; i < G.vwords; i += nt) hit_sec[i] = 0u;
+            asm volatile("bar.sync 2, %0;" ::"n"(kTcLoadWarps * 32) : "memory");
+            if (lw < 2) {
+                const double pos[3] = {r->pos[0], r->pos[1], r->pos[2]};
+                const double dir[3] = {lw == 0 ? r->dir[0] : 1.0, lw == 0 ? r->dir[1] : 0.0, lw == 0 ? r->dir[2] : 0.0};
+                const Beam b = ray_prepare(G, pos, dir, lane, view[lw]);
+                for (int kbase = 0; kbase < b.nslab; kbase += kWarp) {
+                    int lin[4], c0, c1, c2;
+                    float w[4];
+                    slab_targets(G, b, view[lw].ys, view[lw].zs, kbase + lane, lin, w, c0, c1, c2);
+#pragma unroll
+                    for (int q = 0; q < 4; q++)
+                        if (lin[q] >= 0) {
+                            hash_add(hkeys, hvals, lin[q], w[q]);
+                            atomicOr(hit_sec + (lin[q] >> 8), 1u << ((lin[q] >> 3) & 31));
+                        }
+                }
+            }
+            asm volatile("bar.sync 2, %0;" ::"n"(kTcLoadWarps * 32) : "memory");
+            const Tumour tm = E.T.tumours[tumour_id];
+            const uint32_t *tb = E.T.tumour_pbits + (size_t)tumour_id * E.T.pbits_words;
+            const int pd1 = tm.dim[1] + 2, pd2 = tm.dim[2] + 2;
+            const float *vol = E.dose + (size_t)env * G.vstride;
+            const uint32_t *vbits = E.valid + (size_t)env * G.vwords;
+            // Work item = one 32-byte dose sector (8 consecutive voxels of the volume) of one plane of the pair: one
+            // bitmap word, two 16-byte dose loads when the sector holds data, one lungs word, one view-hit bit; the
+            // tumour and view tests only run for the few sectors that can contain such voxels.
+            for (int j = 0; j <= iters; j++) {
+                if (j >= 3) tc::mbar_wait(tc::smem_u32(&pair_free[j % 3]), (uint32_t)((j / 3 - 1) & 1));   // MMAs of iteration j-3 done
+                uint2 *dst = reinterpret_cast<uint2 *>(pairs + (size_t)(j % 3) * S.plane_vox);       // [voxel][lower | upper plane]
+#pragma unroll 1
+                for (int u = 0; u < 2; u++) {
+                    const int z = z0 + 2 * j + u;
+                    if (z < 0 || z >= S.D) {               // plane outside the volume: its half of every voxel is zero
+                        for (int v = t0; v < HW; v += nt) dst[2 * v + u] = make_uint2(0u, 0u);
+                        continue;
+                    }
+                    const int lin_lo = z * HW, lin_hi = lin_lo + HW;
+                    const bool z_in_tumour = (unsigned)(z - tm.lo[0]) < (unsigned)tm.dim[0];
+                    for (int sec = (lin_lo >> 3) + t0; sec <= (lin_hi - 1) >> 3; sec += nt) {
+                        const int l0 = sec << 3;
+                        float d[8];
+#pragma unroll
+                        for (int i = 0; i < 8; i++) d[i] = 0.0f;
+                        if ((__ldg(vbits + (sec >> 5)) >> (sec & 31)) & 1u) {
+                            const float4 q0 = __ldg(reinterpret_cast<const float4 *>(vol + l0));
+                            const float4 q1 = __ldg(reinterpret_cast<const float4 *>(vol + l0) + 1);
+                            d[0] = q0.x; d[1] = q0.y; d[2] = q0.z; d[3] = q0.w; d[4] = q1.x; d[5] = q1.y; d[6] = q1.z; d[7] = q1.w;
+                        }
+                        const uint32_t lung8 = (__ldg(E.T.lungs_bits + (l0 >> 5)) >> (l0 & 31)) & 255u;
+                        const bool view_hit = (hit_sec[sec >> 5] >> (sec & 31)) & 1u;
+                        int v = l0 - lin_lo;                                   // may be negative for the plane's first sector
+                        int h = v >= 0 ? fastdiv(v, S.mW) : 0, w = v - h * S.W;
+#pragma unroll
+                        for (int i = 0; i < 8; i++, v++, w++) {
+                            if (w == S.W) { w = 0; h++; }
+                            if (v < 0 || v >= HW) continue;                    // voxel of the neighbouring plane
+                            float tum = 0.0f, vw = 0.0f;
+                            if (z_in_tumour) {
+                                const int tj = h - tm.lo[1], tk = w - tm.lo[2];
+                                if ((unsigned)tj < (unsigned)tm.dim[1] && (unsigned)tk < (unsigned)tm.dim[2]) {
+                                    const int bit = ((z - tm.lo[0]) * pd1 + tj + 1) * pd2 + tk + 1;
+                                    tum = (__ldg(tb + (bit >> 5)) >> (bit & 31)) & 1u ? 1.0f : 0.0f;
+                                }
+                            }
+                            if (view_hit) {
+                                const int lin = l0 + i;
+                                for (int slot = hash_slot(lin);; slot = (slot + 1) & (kHashSlots - 1)) {
+                                    const int key = hkeys[slot];
+                                    if (key == lin) { vw = hvals[slot]; break; }
+                                    if (key == -1) break;
+                                }
+                            }
+                            dst[2 * v + u] = make_uint2(pack_bf16((lung8 >> i) & 1u ? 1.0f : 0.0f, tum),
+                                                        pack_bf16(fminf(fmaxf(d[i], 0.0f), 1.0f), fminf(fmaxf(vw, 0.0f), 1.0f)));
+                        }
+                    }
+                }
+                tc::fence_proxy_async();               // this lane's writes are visible to the tensor core
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(tc::smem_u32(&pair_ready[j % 3]));
+            }
+        }
+    } else if (is_loader) {
         // ---- input-plane pairs: pair j = planes (z0 + 2j, z0 + 2j + 1) -> buffer j % 3, channels-last bf16;
         //      planes outside [0, D) are zero.  Pairs 0 .. iters are needed (iteration i reads pairs i and i+1).
         const float *xs = x + (size_t)sample * kCin * S.D * HW;
@@ -814,7 +921,7 @@ __global__ void __launch_bounds__(kTailThreads) rt_c3d_tail_kernel(const __nv_bf
                                                                    const float *__restrict__ wl, const float *__restrict__ bl,
                                                                    int F, float *__restrict__ out)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const int DHW = D * H * W;
     __nv_bfloat16 *xs = reinterpret_cast<__nv_bfloat16 *>(smem_raw);                   // [16][D][H][W]
     float *ws = reinterpret_cast<float *>(xs + ((size_t)16 * DHW + 7) / 8 * 8);         // [16][4][27]
@@ -890,10 +997,10 @@ extern "C" {
 // out_dev bfloat16 [n][16][Pd][Ph][Pw] with P = (conv_out + pad - 2)/2 + 1; scratch_dev >= 16384 bytes.
 // Requires W even (pool padding 0 on the last axis) and a plane that fits shared memory.
 static int conv1_launch(const float *x_dev, const float *weight_dev, const float *bias_dev, int n, int D, int H, int W,
-                        void *out_dev, void *scratch_dev, void *stream, bool grouped_out)
+                        void *out_dev, void *scratch_dev, void *stream, bool grouped_out, const EnvSource *env_src = nullptr)
 {
     if (n == 0) return RT_OK;
-    if (!x_dev || !weight_dev || !bias_dev || !out_dev || !scratch_dev || n < 0 || D < 3 || H < 3 || W < 4) return RT_ERR_INVALID;
+    if ((!x_dev && !env_src) || !weight_dev || !bias_dev || !out_dev || !scratch_dev || n < 0 || D < 3 || H < 3 || W < 4) return RT_ERR_INVALID;
     ConvShape S;
     S.D = D; S.H = H; S.W = W;
     S.Do = D - 2; S.Ho = H - 2; S.Wo = W - 2;
@@ -929,21 +1036,26 @@ static int conv1_launch(const float *x_dev, const float *weight_dev, const float
     T.tiles = tiles128;
     T.plane_vox = (tiles128 * kTcTileRows + 2 * W + 8 + 7) / 8 * 8;
     const size_t smem_tc = (size_t)3 * T.plane_vox * 16 + (size_t)T.r_elems * sizeof(__nv_bfloat16) +
-                           (size_t)kTcMmas * kBMmaBytes + (2 * kTcSlots + 6) * 8 + 16;
+                           (size_t)kTcMmas * kBMmaBytes + (2 * kTcSlots + 6) * 8 + 16 +
+                           (size_t)kHashSlots * 8 + 2 * sizeof(RayWork) + 3328;    // + from-env: view hash, rays, hit-sector bits
     if (!force_sync && smem_tc <= (size_t)max_smem && (size_t)3 * T.plane_vox * 16 < (1u << 18) && W * 16 < (1 << 18)) {
-        if (cudaFuncSetAttribute(rt_conv1_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc) != cudaSuccess ||
-            cudaFuncSetAttribute(rt_conv1_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc) != cudaSuccess) return RT_ERR_CUDA;
+        if (cudaFuncSetAttribute(rt_conv1_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc) != cudaSuccess ||
+            cudaFuncSetAttribute(rt_conv1_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc) != cudaSuccess ||
+            cudaFuncSetAttribute(rt_conv1_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc) != cudaSuccess) return RT_ERR_CUDA;
         __nv_bfloat16 *bop = reinterpret_cast<__nv_bfloat16 *>(scratch_dev);
         rt_conv_prepare_tc_kernel<<<(kTcMmas * 2 * kTcN * 8 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(weight_dev, bop);
-        if (grouped_out)
-            rt_conv1_tc_kernel<true><<<n * chunks, kTcThreads, smem_tc, (cudaStream_t)stream>>>(
-                T, n, chunks, per, x_dev, reinterpret_cast<const uint4 *>(bop), bias_dev, reinterpret_cast<__nv_bfloat16 *>(out_dev));
+        if (env_src)
+            rt_conv1_tc_kernel<true, true><<<n * chunks, kTcThreads, smem_tc, (cudaStream_t)stream>>>(
+                T, n, chunks, per, nullptr, reinterpret_cast<const uint4 *>(bop), bias_dev, reinterpret_cast<__nv_bfloat16 *>(out_dev), *env_src);
+        else if (grouped_out)
+            rt_conv1_tc_kernel<true, false><<<n * chunks, kTcThreads, smem_tc, (cudaStream_t)stream>>>(
+                T, n, chunks, per, x_dev, reinterpret_cast<const uint4 *>(bop), bias_dev, reinterpret_cast<__nv_bfloat16 *>(out_dev), EnvSource{});
         else
-            rt_conv1_tc_kernel<false><<<n * chunks, kTcThreads, smem_tc, (cudaStream_t)stream>>>(
-                T, n, chunks, per, x_dev, reinterpret_cast<const uint4 *>(bop), bias_dev, reinterpret_cast<__nv_bfloat16 *>(out_dev));
+            rt_conv1_tc_kernel<false, false><<<n * chunks, kTcThreads, smem_tc, (cudaStream_t)stream>>>(
+                T, n, chunks, per, x_dev, reinterpret_cast<const uint4 *>(bop), bias_dev, reinterpret_cast<__nv_bfloat16 *>(out_dev), EnvSource{});
         return cudaGetLastError() == cudaSuccess ? RT_OK : RT_ERR_CUDA;
     }
-    if (grouped_out) return RT_ERR_INVALID;                         // only the tcgen05 kernel writes the grouped layout
+    if (grouped_out || env_src) return RT_ERR_INVALID;              // only the tcgen05 kernel writes the grouped layout / reads env state
 
     const size_t smem = (size_t)3 * S.plane_vox * 16 + (size_t)S.Ho * S.Pw * kCout * sizeof(__nv_bfloat16);
     if (smem > (size_t)max_smem) return RT_ERR_INVALID;
@@ -967,6 +1079,24 @@ int rt_conv1_relu_pool_grouped(const float *x_dev, const float *weight_dev, cons
                                int W, void *out_dev, void *scratch_dev, void *stream)
 {
     return conv1_launch(x_dev, weight_dev, bias_dev, n, D, H, W, out_dev, scratch_dev, stream, true);
+}
+
+// The first block computed straight from the state of envs [first, first+count) of a (sparse-mode) handle: the
+// observation of environment.py:245-257 is generated inside the kernel's loader warps instead of being assembled in
+// HBM first (rt_assemble_volumes).  Output in the grouped layout, bit-identical to
+// rt_assemble_volumes + rt_conv1_relu_pool_grouped.
+int rt_conv1_from_env(rt_env *e, int first, int count, const float *weight_dev, const float *bias_dev, void *out_dev,
+                      void *scratch_dev, void *stream)
+{
+    if (!e) return fail(RT_ERR_INVALID, "rt_conv1_from_env: NULL handle");
+    if (first < 0 || count < 0 || first + count > e->n) return fail(RT_ERR_INVALID, "rt_conv1_from_env: env range out of bounds");
+    if (e->dense) return fail(RT_ERR_STATE, "rt_conv1_from_env: not available for dense-mode handles");
+    if (cudaSetDevice(e->device) != cudaSuccess) return RT_ERR_CUDA;
+    EnvSource src{e->T, e->rec, e->dose, e->valid, first};
+    const Grid &G = e->T.G;
+    const int rc = conv1_launch(nullptr, weight_dev, bias_dev, count, G.g0, G.g1, G.g2, out_dev, scratch_dev, stream, true, &src);
+    if (rc == RT_OK && count > 0) g_launches.fetch_add(2, std::memory_order_relaxed);
+    return rc;
 }
 
 // Fused Conv3d(16->16, k=3, groups=2) + bias + ReLU + MaxPool3d(2, 2) — networks.py:25-27.

@@ -1836,3 +1836,6 @@ int rt_gae(const float *rewards_dev, const float *values_dev, const float *dones
 }
 
 }  // extern "C"
+
+// FeaturesExtractor3D kernels (tcgen05 conv blocks, tail) and their C ABI
+#include "rt_conv.cuh"

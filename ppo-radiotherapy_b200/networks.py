@@ -41,7 +41,10 @@ class _GaussianActorCritic(nn.Module):
         return self.critic(self.features(x))
 
     def get_action_and_value(self, x: torch.Tensor, action: torch.Tensor = None):
-        f = self.features(x)
+        return self.heads(self.features(x), action)
+
+    def heads(self, f: torch.Tensor, action: torch.Tensor = None):
+        """Actor and critic heads on already extracted features (networks.py:88-97,139-147)."""
         mean = self.actor_mean(f)
         # validate_args=False: the argument check synchronises with the host, which a CUDA-graph capture forbids
         dist = Normal(mean, torch.exp(self.actor_logstd.expand_as(mean)), validate_args=False)
@@ -157,6 +160,41 @@ class FeaturesExtractor3D(nn.Module):
         nat.check(rc, "rt_conv2_relu_pool")
         return out
 
+    def forward_from_env(self, engine, first: int = 0, count: int = None) -> torch.Tensor:
+        """Features of the current voxel observation of envs [first, first+count) of a BatchedEpisodes engine without
+        materialising the observation: the first block generates the four planes inside its loader warps
+        (rt_conv1_from_env), then rt_conv2_relu_pool and rt_c3d_tail.  Inference only; equals
+        forward(engine.volumes(first, count)) up to the summation order of crossing view beams."""
+        import ctypes as C
+        from . import _native as nat
+        count = engine.num_envs - first if count is None else count
+        conv1, conv2 = self.cnn[0], self.cnn[3]
+        D, H, W = engine.grid
+        Do, Ho, Wo = D - 2, H - 2, W - 2
+        pd, ph = Do % 2, Ho % 2
+        D1, H1, W1 = (Do + 2 * pd - 2) // 2 + 1, (Ho + 2 * ph - 2) // 2 + 1, (Wo - 2) // 2 + 1
+        dev = engine.device
+        act1 = torch.empty((count, 2, D1, H1 * W1, 8), dtype=torch.bfloat16, device=dev)
+        act2 = torch.empty((count, 16, (D1 - 2) // 2, (H1 - 2) // 2, (W1 - 2) // 2), dtype=torch.bfloat16, device=dev)
+        if getattr(self, "_conv_scratch2", None) is None or self._conv_scratch2.device != dev:
+            self._conv_scratch = torch.empty(4096, dtype=torch.int32, device=dev)
+            self._conv_scratch2 = torch.empty(16384, dtype=torch.int32, device=dev)
+        w1, b1 = conv1.weight.detach().float().contiguous(), conv1.bias.detach().float().contiguous()
+        w2, b2 = conv2.weight.detach().float().contiguous(), conv2.bias.detach().float().contiguous()
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        with torch.cuda.device(dev):
+            nat.check(nat.lib().rt_conv1_from_env(engine._h, int(first), int(count), C.c_void_p(w1.data_ptr()),
+                                                  C.c_void_p(b1.data_ptr()), C.c_void_p(act1.data_ptr()),
+                                                  C.c_void_p(self._conv_scratch.data_ptr()), stream), "rt_conv1_from_env")
+            nat.check(nat.lib().rt_conv2_relu_pool(C.c_void_p(act1.data_ptr()), C.c_void_p(w2.data_ptr()), C.c_void_p(b2.data_ptr()),
+                                                   count, D1, H1, W1, C.c_void_p(act2.data_ptr()),
+                                                   C.c_void_p(self._conv_scratch2.data_ptr()), stream), "rt_conv2_relu_pool")
+        y = self._fused_tail(act2)
+        if y is None:
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                y = self.mlp(self.cnn[6:](act2).float())
+        return y
+
     def _fused_tail(self, h: torch.Tensor):
         """cnn[6:] + mlp — Conv3d(16,16,3,groups=4) ReLU MaxPool3d(2,2) Flatten Linear ReLU — as one kernel
         (rt_c3d_tail) on the second block's bfloat16 activation.  Returns None when the layers do not match."""
@@ -216,6 +254,11 @@ class PPO_3DCNN(_GaussianActorCritic):
 
     def features(self, x: torch.Tensor) -> torch.Tensor:
         return self.features_extractor(x)
+
+    def get_action_and_value_from_env(self, engine, action: torch.Tensor = None):
+        """get_action_and_value on the engine's current voxel observations, which are never materialised."""
+        with torch.no_grad():
+            return self.heads(self.features_extractor.forward_from_env(engine), action)
 
     def summary(self):
         n = sum(p.numel() for p in self.parameters())

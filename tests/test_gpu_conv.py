@@ -139,6 +139,46 @@ def test_c3d_tail_matches_torch(shape):
     assert float(out.max()) > 0.01
 
 
+def test_conv1_from_env_equals_conv1_on_assembled_volumes():
+    """rt_conv1_from_env generates the observation planes in its loader warps: same activation as assembling the
+    float32 observation in HBM and convolving it (a voxel crossed by both view beams may differ in the last bit of
+    its float sum, hence a tolerance of one bf16 ulp on a handful of outputs)."""
+    n = 10
+    eng = rt.BatchedEpisodes(n, device=DEV, seed=21)
+    eng.reset()
+    g = torch.Generator(device=DEV).manual_seed(5)
+    for _ in range(25):
+        eng.step(torch.rand((n, 6), device=DEV, generator=g) * 2 - 1, want_info=False)
+    w = torch.randn((16, 4, 3, 3, 3), device=DEV, generator=g) * 0.2
+    b = torch.randn(16, device=DEV, generator=g) * 0.1
+    obs = eng.volumes()
+    D1, H1, W1 = 33, 21, 34
+    scratch = torch.empty(4096, dtype=torch.int32, device=DEV)
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    want = torch.empty((n, 2, D1, H1 * W1, 8), dtype=torch.bfloat16, device=DEV)
+    assert nat.lib().rt_conv1_relu_pool_grouped(C.c_void_p(obs.data_ptr()), C.c_void_p(w.data_ptr()), C.c_void_p(b.data_ptr()),
+                                                n, 67, 43, 70, C.c_void_p(want.data_ptr()), C.c_void_p(scratch.data_ptr()), stream) == 0
+    for first, count in ((0, n), (3, 4)):
+        got = torch.empty((count, 2, D1, H1 * W1, 8), dtype=torch.bfloat16, device=DEV)
+        nat.check(nat.lib().rt_conv1_from_env(eng._h, first, count, C.c_void_p(w.data_ptr()), C.c_void_p(b.data_ptr()),
+                                              C.c_void_p(got.data_ptr()), C.c_void_p(scratch.data_ptr()), stream))
+        ref = want[first:first + count].float()
+        diff = (got.float() - ref).abs()
+        assert bool((diff <= ref.abs() * 2.0 ** -7 + 1e-6).all())
+        assert float((diff > 0).float().mean()) < 1e-4
+    assert float(want.float().max()) > 0.1
+    # whole extractor and the policy heads through the env path
+    torch.manual_seed(0)
+    agent = rt.PPO_3DCNN((4, 67, 43, 70), (6,), 64, compute_dtype=torch.bfloat16).to(DEV)
+    with torch.no_grad():
+        f_env = agent.features_extractor.forward_from_env(eng)
+        f_obs = agent.features_extractor(obs)
+    assert f_env.shape == (n, 64) and float((f_env - f_obs).abs().max()) <= 1e-3 * max(1.0, float(f_obs.abs().max()))
+    a, lp, ent, v = agent.get_action_and_value_from_env(eng)
+    assert a.shape == (n, 6) and torch.isfinite(v).all()
+    eng.close()
+
+
 def test_features_extractor_fused_path_matches_unfused():
     torch.manual_seed(0)
     fe = rt.FeaturesExtractor3D((4, 67, 43, 70), 64, compute_dtype=torch.bfloat16).to(DEV)

@@ -38,3 +38,10 @@ def step():
     envs.step(action)
 s = timed(step)
 print(f"vision rollout step (policy + env + obs): {s*1e3:8.3f} ms  {n/s:10.0f} env-steps/s")
+
+def step_env():
+    with torch.no_grad():
+        action, logprob, _, value = agent.get_action_and_value_from_env(envs.engine)
+    envs.engine.step(action, want_info=False)
+s = timed(step_env)
+print(f"vision rollout step, observation never materialised (rt_conv1_from_env): {s*1e3:8.3f} ms  {n/s:10.0f} env-steps/s")
