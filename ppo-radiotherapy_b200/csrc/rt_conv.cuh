@@ -347,7 +347,7 @@ constexpr int kTcSlots = 16;                 // tensor-memory ring: 16 x 32 colu
 constexpr int kTmemCols = kTcSlots * kTcN;   // 512
 constexpr int kTcMmas = 10;                  // per tile: 5 per pair buffer
 constexpr int kBMmaBytes = 2 * kTcN * 16;    // one MMA's B operand: 2 K-chunks x 32 rows x 16 bytes
-constexpr int kTcDrainWarps = 8, kTcLoadWarps = 4, kTcMmaWarps = 2;
+constexpr int kTcDrainWarps = 8, kTcLoadWarps = 8, kTcMmaWarps = 2;
 constexpr int kTcThreads = (kTcDrainWarps + kTcLoadWarps + kTcMmaWarps) * 32;
 
 // Stencil position of K chunk h of MMA m (within a pair buffer): (kh, kw); kw == 3 is padding.
