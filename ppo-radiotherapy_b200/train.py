@@ -252,8 +252,14 @@ def train(cfg, writer=None, device="cuda", output_dir: Optional[str] = None, run
     values = torch.zeros((T, n_local), device=device)
 
     eng = envs.engine
-    next_obs, _ = envs.reset(seed=None, options={"backend": "torch"})
-    next_obs = next_obs.clone()
+    if cfg.visionless:
+        next_obs, _ = envs.reset(seed=None, options={"backend": "torch"})
+        next_obs = next_obs.clone()
+    else:
+        # vision mode never materialises the float32 observation during the rollout: the policy reads the env state
+        # through rt_conv1_from_env, the rollout buffer keeps compressed records
+        eng.reset()
+        next_obs = None
     next_done = torch.zeros(n_local, device=device)
     step_idx = torch.zeros(1, dtype=torch.long, device=device)
     # per-iteration episode statistics, reduced on the device: [finished, sum return, sum length,
@@ -274,14 +280,16 @@ def train(cfg, writer=None, device="cuda", output_dir: Optional[str] = None, run
             rollout_pos[0] += 1
         dones.index_copy_(0, step_idx, next_done.unsqueeze(0))
         with torch.no_grad():
-            action, logprob, _, value = agent.get_action_and_value(next_obs)
+            if cfg.visionless:
+                action, logprob, _, value = agent.get_action_and_value(next_obs)
+            else:
+                action, logprob, _, value = agent.get_action_and_value_from_env(eng)
         values.index_copy_(0, step_idx, value.reshape(1, -1))
         actions.index_copy_(0, step_idx, action.unsqueeze(0))
         logprobs.index_copy_(0, step_idx, logprob.unsqueeze(0))
         o, _, term, trunc, info = eng.step(action, want_info=True)              # train.py:151, on the device
-        if not cfg.visionless:
-            o = envs._volumes()
-        next_obs.copy_(o)
+        if cfg.visionless:
+            next_obs.copy_(o)
         rewards.index_copy_(0, step_idx, eng.reward_f32.unsqueeze(0))
         next_done.copy_((term | trunc).float())
         f64 = term.double()
@@ -325,7 +333,10 @@ def train(cfg, writer=None, device="cuda", output_dir: Optional[str] = None, run
                 rollout_step()
 
         with torch.no_grad():
-            next_value = agent.get_value(next_obs).reshape(-1)
+            if cfg.visionless:
+                next_value = agent.get_value(next_obs).reshape(-1)
+            else:
+                next_value = agent.critic(agent.features_extractor.forward_from_env(eng)).reshape(-1)
             advantages, returns = compute_gae(rewards, values, dones, next_value, next_done, cfg.gamma, cfg.gae_lambda)
 
         b_obs = obs.reshape((-1,) + obs_shape) if cfg.visionless else (lambda idx: eng.render_observations(store, idx))
