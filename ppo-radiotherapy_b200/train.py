@@ -320,6 +320,7 @@ def train(cfg, writer=None, device="cuda", output_dir: Optional[str] = None, run
     history = []
 
     for iteration in range(1, cfg.num_iterations + 1):
+        iter_start = time.time()
         if cfg.anneal_lr:
             optimizer.param_groups[0]["lr"] = (1.0 - (iteration - 1.0) / cfg.num_iterations) * cfg.learning_rate
         ep.zero_()
@@ -351,6 +352,7 @@ def train(cfg, writer=None, device="cuda", output_dir: Optional[str] = None, run
         var_y = torch.var(y_true)
         explained = float("nan") if float(var_y) == 0 else float(1 - torch.var(y_true - y_pred) / var_y)
         rec = dict(iteration=iteration, global_step=global_step, sps=global_step / max(time.time() - start, 1e-9),
+                   iter_sps=cfg.num_envs * T / max(time.time() - iter_start, 1e-9),   # this iteration alone (ep.cpu() above synchronised)
                    episodes=int(epc[0]), explained_variance=explained,
                    **{k: float(v) for k, v in stats.items()})
         if epc[0] > 0:
