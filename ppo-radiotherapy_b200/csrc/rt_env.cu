@@ -628,6 +628,7 @@ __global__ void __launch_bounds__(kStepThreads, 4) rt_step_kernel(Tables T, Sche
 }  // namespace
 #include "rt_step.cuh"
 #include "rt_step_wide.cuh"
+#include "rt_step_split.cuh"
 namespace {
 
 // ---------------------------------------------------------------------------------
@@ -1191,7 +1192,13 @@ struct rt_env {
     DenseWork *dense = nullptr;
     size_t dense_smem = 0;
     size_t step_smem = 0;
-    int step_kb = 0;          // envs per block of rt_step3_kernel (7, 14 or 28); 0 = the two-role kernel of rt_step_kernel
+    int step_kb = 0;          // envs per block of rt_step3_kernel (7, 14 or 28); 0 = the two-role kernel of rt_step_kernel;
+                              // -1 = thread-per-env kernel; -2 = pose + deposit kernels (rt_step_split.cuh)
+    int split_kw = 8;         // warps (= envs) per block of rt_split_deposit_kernel
+    BeamWork *work = nullptr; // split step: hand-over records and the slab walks
+    float2 *yzg = nullptr;
+    int yz_stride = 0;
+    size_t pose_smem = 0, deposit_smem = 0;
     bool use_pdl = true;      // RT_PDL=0 in the environment switches programmatic dependent launch off
     uint32_t *d_lungs = nullptr;
     Tumour *d_tumours = nullptr;
@@ -1374,13 +1381,37 @@ int rt_create(rt_env **out, int device, int n_envs, uint32_t flags, const rt_pha
         e->step_kb = per_sm <= 7 ? 7 : 14;
         if (const char *v = getenv("RT_STEP_KB")) {
             const int kb = atoi(v);
-            if (kb == 0 || kb == 7 || kb == 14 || kb == 28 || kb == -1) e->step_kb = kb;    // -1: thread-per-env kernel
+            if (kb == 0 || kb == 7 || kb == 14 || kb == 28 || kb == -1 || kb == -2) e->step_kb = kb;    // -1: thread-per-env kernel, -2: split
+        }
+        if (e->step_kb == -2) {
+            int gmax = G.g0 > G.g1 ? G.g0 : G.g1;
+            gmax = gmax > G.g2 ? gmax : G.g2;
+            e->yz_stride = (gmax + 1 + 1) & ~1;                               // a beam has at most max(G) + 1 slabs
+            if (const char *v = getenv("RT_SPLIT_KW")) {
+                const int kw = atoi(v);
+                if (kw == 4 || kw == 8 || kw == 12 || kw == 16) e->split_kw = kw;
+            }
+            if ((rc = dev_alloc(&e->work, (size_t)n_envs, &e->bytes)) ||
+                (rc = dev_alloc(&e->yzg, (size_t)n_envs * e->yz_stride, &e->bytes))) { rt_destroy(e); return rc; }
+            e->pose_smem = (size_t)kPoseThreads * ((e->yz_stride + 2) * sizeof(float2) + RT_OBS_SIZE * sizeof(float));
+            e->deposit_smem = ((size_t)e->T.lung_words16 + (size_t)e->split_kw * G.vwords) * sizeof(uint32_t);
+            cudaError_t se = cudaFuncSetAttribute(rt_split_pose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->pose_smem);
+            if (se == cudaSuccess) {
+                switch (e->split_kw) {
+                case 4: se = cudaFuncSetAttribute(rt_split_deposit_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->deposit_smem); break;
+                case 8: se = cudaFuncSetAttribute(rt_split_deposit_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->deposit_smem); break;
+                case 12: se = cudaFuncSetAttribute(rt_split_deposit_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->deposit_smem); break;
+                default: se = cudaFuncSetAttribute(rt_split_deposit_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->deposit_smem); break;
+                }
+            }
+            if (se != cudaSuccess) { rt_destroy(e); return fail(RT_ERR_CUDA, std::string("rt_split kernels smem: ") + cudaGetErrorString(se)); }
         }
         const int kb = e->step_kb > 0 ? e->step_kb : kEnvsPerBlock;
         e->step_smem = (size_t)kb * G.vwords * sizeof(uint32_t) + (e->step_kb >= 14 ? (size_t)e->T.lung_words16 * sizeof(uint32_t) : 0);
         cudaError_t ae = cudaSuccess;
         switch (e->step_kb) {
         case -1: break;
+        case -2: break;
         case 0: ae = cudaFuncSetAttribute(rt_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->step_smem); break;
         case 7: ae = cudaFuncSetAttribute(rt_step3_kernel<7, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->step_smem); break;
         case 14: ae = cudaFuncSetAttribute(rt_step3_kernel<14, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->step_smem); break;
@@ -1442,6 +1473,7 @@ int rt_destroy(rt_env *e)
     cudaSetDevice(e->device);
     cudaFree(e->d_lungs); cudaFree(e->d_tumours); cudaFree(e->d_tbits); cudaFree(e->d_ptbits); cudaFree(e->d_vox);
     cudaFree(e->rec); cudaFree(e->dose); cudaFree(e->valid); cudaFree(e->beams); cudaFree(e->dense); cudaFree(e->d_sched);
+    cudaFree(e->work); cudaFree(e->yzg);
     // the *_host staging buffers are device-visible pinned allocations of the same sizes
     cudaFreeHost(e->h_actions); cudaFreeHost(e->h_obs); cudaFreeHost(e->h_reward); cudaFreeHost(e->h_info);
     cudaFreeHost(e->h_term); cudaFreeHost(e->h_trunc); cudaFreeHost(e->h_mask);
@@ -1509,6 +1541,34 @@ int rt_step(rt_env *e, const float *actions_dev, float *obs_dev, double *reward_
         RT_LAUNCH_CHECK("rt_step_kernel<dense>");
         rt_dense_kernel<<<e->n, kDenseThreads, e->dense_smem, (cudaStream_t)stream>>>(e->T, e->rec, e->dose, e->dense, o);
         RT_LAUNCH_CHECK("rt_dense_kernel");
+    } else if (e->step_kb == -2) {
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = e->use_pdl ? 1 : 0;
+        cudaLaunchConfig_t cfg = {};
+        cfg.stream = (cudaStream_t)stream;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cfg.gridDim = dim3((e->n + kPoseThreads - 1) / kPoseThreads);
+        cfg.blockDim = dim3(kPoseThreads);
+        cfg.dynamicSmemBytes = e->pose_smem;
+        const int want_info = info_dev ? 1 : 0;
+        RT_CUDA(cudaLaunchKernelEx(&cfg, rt_split_pose_kernel, e->T, e->S, e->rec, e->beams, e->n, actions_dev, e->work, e->yzg,
+                                   e->yz_stride, obs_dev, want_info));
+        RT_LAUNCH_CHECK("rt_split_pose_kernel");
+        const int kw = e->split_kw;
+        cfg.gridDim = dim3((e->n + kw - 1) / kw);
+        cfg.blockDim = dim3(kw * kWarp);
+        cfg.dynamicSmemBytes = e->deposit_smem;
+        const BeamWork *wk = e->work;
+        const float2 *yz = e->yzg;
+        switch (kw) {
+        case 4: RT_CUDA(cudaLaunchKernelEx(&cfg, rt_split_deposit_kernel<4>, e->T, e->rec, e->dose, e->valid, e->n, wk, yz, e->yz_stride, o)); break;
+        case 8: RT_CUDA(cudaLaunchKernelEx(&cfg, rt_split_deposit_kernel<8>, e->T, e->rec, e->dose, e->valid, e->n, wk, yz, e->yz_stride, o)); break;
+        case 12: RT_CUDA(cudaLaunchKernelEx(&cfg, rt_split_deposit_kernel<12>, e->T, e->rec, e->dose, e->valid, e->n, wk, yz, e->yz_stride, o)); break;
+        default: RT_CUDA(cudaLaunchKernelEx(&cfg, rt_split_deposit_kernel<16>, e->T, e->rec, e->dose, e->valid, e->n, wk, yz, e->yz_stride, o)); break;
+        }
+        RT_LAUNCH_CHECK("rt_split_deposit_kernel");
     } else if (e->step_kb == -1) {
         rt_step_wide_kernel<<<(e->n + kWideThreads - 1) / kWideThreads, kWideThreads, 0, (cudaStream_t)stream>>>(
             e->T, e->S, e->rec, e->dose, e->valid, e->beams, e->n, actions_dev, o);

@@ -434,7 +434,7 @@ def test_rng_tumour_choice_is_seeded_and_spread():
 
 
 # ------------------------------------------------------------------------------------ edge cases
-@pytest.mark.parametrize("kb", ["7", "14", "28", "0", "-1"])
+@pytest.mark.parametrize("kb", ["7", "14", "28", "0", "-1", "-2"])
 def test_step_kernel_block_shapes_vs_oracle(kb, monkeypatch):
     """The step kernel exists for 7, 14 and 28 envs per block (picked from the env count in rt_create; RT_STEP_KB
     overrides) and as the older two-role kernel (0).  Every variant, with a ragged last block, a full episode, the
