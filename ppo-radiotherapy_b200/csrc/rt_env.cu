@@ -1197,6 +1197,8 @@ struct rt_env {
     int split_kw = 8;         // warps (= envs) per block of rt_split_deposit_kernel
     BeamWork *work = nullptr; // split step: hand-over records and the slab walks
     float2 *yzg = nullptr;
+    uint2 *brief = nullptr;
+    int split_blocks = 0, split_epb = 0;   // deposit kernel: blocks and envs per block
     int yz_stride = 0;
     size_t pose_smem = 0, deposit_smem = 0;
     bool use_pdl = true;      // RT_PDL=0 in the environment switches programmatic dependent launch off
@@ -1339,7 +1341,7 @@ int rt_create(rt_env **out, int device, int n_envs, uint32_t flags, const rt_pha
         const int pb = tm.dim[0] * (tm.dim[1] + 2) * (tm.dim[2] + 2);
         max_pbits = pb > max_pbits ? pb : max_pbits;
     }
-    e->T.pbits_words = (max_pbits + 31) / 32 + 1;
+    e->T.pbits_words = ((max_pbits + 31) / 32 + 1 + 3) & ~3;        // rows are bulk-copied: multiples of 16 bytes
     if (e->T.pbits_words > kMaxPTumourWords) {
         delete e;
         return fail(RT_ERR_INVALID, "rt_create: a tumour's padded bounding box exceeds 3040 voxels");
@@ -1356,11 +1358,22 @@ int rt_create(rt_env **out, int device, int n_envs, uint32_t flags, const rt_pha
         }
     }
 
+    // device copy of the voxel lists: every list starts at a multiple of four entries and is padded to one by
+    // repeating its last voxel (16-byte bulk copies; a repeated voxel does not change the minimum distance)
+    std::vector<uint32_t> vox_dev;
+    vox_dev.reserve(vox_xyz.size() + 4 * (size_t)ph->n_tumours);
+    for (int t = 0; t < ph->n_tumours; t++) {
+        tum[t].vox_off = (int)vox_dev.size();
+        for (int k = ph->vox_offsets[t]; k < ph->vox_offsets[t + 1]; k++) vox_dev.push_back(vox_xyz[k]);
+        while (vox_dev.size() % 4) vox_dev.push_back(vox_dev.back());
+    }
+    if (vox_dev.size() / 4 >= (1u << 24)) { delete e; return fail(RT_ERR_INVALID, "rt_create: voxel lists too long"); }
+
     int rc = RT_OK;
     const size_t lung_words = (size_t)(G.nvox + 31) / 32;
     e->T.lung_words16 = (int)((lung_words + 3) / 4 * 4);
     if ((rc = dev_alloc(&e->d_lungs, (size_t)e->T.lung_words16, &e->bytes)) || (rc = dev_alloc(&e->d_tumours, tum.size(), &e->bytes)) ||
-        (rc = dev_alloc(&e->d_tbits, tbits.size(), &e->bytes)) || (rc = dev_alloc(&e->d_ptbits, ptbits.size(), &e->bytes)) || (rc = dev_alloc(&e->d_vox, vox_xyz.size(), &e->bytes)) ||
+        (rc = dev_alloc(&e->d_tbits, tbits.size(), &e->bytes)) || (rc = dev_alloc(&e->d_ptbits, ptbits.size(), &e->bytes)) || (rc = dev_alloc(&e->d_vox, vox_dev.size(), &e->bytes)) ||
         (rc = dev_alloc(&e->rec, (size_t)n_envs, &e->bytes)) ||
         (rc = dev_alloc(&e->dose, (size_t)n_envs * G.vstride, &e->bytes)) ||
         (rc = dev_alloc(&e->valid, (size_t)n_envs * G.vwords, &e->bytes))) {
@@ -1386,22 +1399,27 @@ int rt_create(rt_env **out, int device, int n_envs, uint32_t flags, const rt_pha
         if (e->step_kb == -2) {
             int gmax = G.g0 > G.g1 ? G.g0 : G.g1;
             gmax = gmax > G.g2 ? gmax : G.g2;
-            e->yz_stride = (gmax + 1 + 1) & ~1;                               // a beam has at most max(G) + 1 slabs
+            e->yz_stride = (gmax + 1 + 3) & ~3;                               // a beam has at most max(G) + 1 slabs; 32-byte rows
+            e->split_kw = 28;
             if (const char *v = getenv("RT_SPLIT_KW")) {
                 const int kw = atoi(v);
-                if (kw == 4 || kw == 8 || kw == 12 || kw == 16) e->split_kw = kw;
+                if (kw == 14 || kw == 28) e->split_kw = kw;
             }
-            if ((rc = dev_alloc(&e->work, (size_t)n_envs, &e->bytes)) ||
+            if (ph->n_tumours > 65535) { rt_destroy(e); return fail(RT_ERR_INVALID, "rt_create: the split step supports at most 65535 tumours"); }
+            if ((rc = dev_alloc(&e->work, (size_t)n_envs, &e->bytes)) || (rc = dev_alloc(&e->brief, (size_t)n_envs, &e->bytes)) ||
                 (rc = dev_alloc(&e->yzg, (size_t)n_envs * e->yz_stride, &e->bytes))) { rt_destroy(e); return rc; }
-            e->pose_smem = (size_t)kPoseThreads * ((e->yz_stride + 2) * sizeof(float2) + RT_OBS_SIZE * sizeof(float));
-            e->deposit_smem = ((size_t)e->T.lung_words16 + (size_t)e->split_kw * G.vwords) * sizeof(uint32_t);
+            // persistent deposit kernel: one block of 32 warps per SM (or two of 14 / 16), consecutive envs per block
+            const int blocks_max = sms * (kSplitWarpsPerSM / e->split_kw);
+            e->split_epb = (n_envs + blocks_max - 1) / blocks_max;
+            e->split_blocks = (n_envs + e->split_epb - 1) / e->split_epb;
+            e->pose_smem = (size_t)kPoseThreads * RT_OBS_SIZE * sizeof(float);
+            e->deposit_smem = (size_t)e->T.lung_words16 * sizeof(uint32_t) +
+                              (size_t)e->split_kw * (sizeof(DepositWarp) + G.vwords * sizeof(uint32_t) + 2 * e->yz_stride * sizeof(float2));
             cudaError_t se = cudaFuncSetAttribute(rt_split_pose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->pose_smem);
             if (se == cudaSuccess) {
                 switch (e->split_kw) {
-                case 4: se = cudaFuncSetAttribute(rt_split_deposit_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->deposit_smem); break;
-                case 8: se = cudaFuncSetAttribute(rt_split_deposit_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->deposit_smem); break;
-                case 12: se = cudaFuncSetAttribute(rt_split_deposit_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->deposit_smem); break;
-                default: se = cudaFuncSetAttribute(rt_split_deposit_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->deposit_smem); break;
+                case 14: se = cudaFuncSetAttribute(rt_split_deposit_kernel<14>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->deposit_smem); break;
+                default: se = cudaFuncSetAttribute(rt_split_deposit_kernel<28>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->deposit_smem); break;
                 }
             }
             if (se != cudaSuccess) { rt_destroy(e); return fail(RT_ERR_CUDA, std::string("rt_split kernels smem: ") + cudaGetErrorString(se)); }
@@ -1439,7 +1457,7 @@ int rt_create(rt_env **out, int device, int n_envs, uint32_t flags, const rt_pha
     chk(cudaMemcpy(e->d_tumours, tum.data(), tum.size() * sizeof(Tumour), cudaMemcpyHostToDevice));
     chk(cudaMemcpy(e->d_tbits, tbits.data(), tbits.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     chk(cudaMemcpy(e->d_ptbits, ptbits.data(), ptbits.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-    chk(cudaMemcpy(e->d_vox, vox_xyz.data(), vox_xyz.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    chk(cudaMemcpy(e->d_vox, vox_dev.data(), vox_dev.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     chk(cudaMemset(e->rec, 0, (size_t)n_envs * sizeof(EnvRec)));
     chk(cudaMemset(e->valid, 0, (size_t)n_envs * G.vwords * sizeof(uint32_t)));
     // dose is deliberately left uninitialised: a sector is only read once its valid bit is set
@@ -1473,7 +1491,7 @@ int rt_destroy(rt_env *e)
     cudaSetDevice(e->device);
     cudaFree(e->d_lungs); cudaFree(e->d_tumours); cudaFree(e->d_tbits); cudaFree(e->d_ptbits); cudaFree(e->d_vox);
     cudaFree(e->rec); cudaFree(e->dose); cudaFree(e->valid); cudaFree(e->beams); cudaFree(e->dense); cudaFree(e->d_sched);
-    cudaFree(e->work); cudaFree(e->yzg);
+    cudaFree(e->work); cudaFree(e->yzg); cudaFree(e->brief);
     // the *_host staging buffers are device-visible pinned allocations of the same sizes
     cudaFreeHost(e->h_actions); cudaFreeHost(e->h_obs); cudaFreeHost(e->h_reward); cudaFreeHost(e->h_info);
     cudaFreeHost(e->h_term); cudaFreeHost(e->h_trunc); cudaFreeHost(e->h_mask);
@@ -1553,20 +1571,19 @@ int rt_step(rt_env *e, const float *actions_dev, float *obs_dev, double *reward_
         cfg.blockDim = dim3(kPoseThreads);
         cfg.dynamicSmemBytes = e->pose_smem;
         const int want_info = info_dev ? 1 : 0;
-        RT_CUDA(cudaLaunchKernelEx(&cfg, rt_split_pose_kernel, e->T, e->S, e->rec, e->beams, e->n, actions_dev, e->work, e->yzg,
-                                   e->yz_stride, obs_dev, want_info));
+        RT_CUDA(cudaLaunchKernelEx(&cfg, rt_split_pose_kernel, e->T, e->S, e->rec, e->beams, e->n, actions_dev, e->work, e->brief,
+                                   e->yzg, e->yz_stride, obs_dev, want_info));
         RT_LAUNCH_CHECK("rt_split_pose_kernel");
         const int kw = e->split_kw;
-        cfg.gridDim = dim3((e->n + kw - 1) / kw);
+        cfg.gridDim = dim3(e->split_blocks);
         cfg.blockDim = dim3(kw * kWarp);
         cfg.dynamicSmemBytes = e->deposit_smem;
         const BeamWork *wk = e->work;
+        const uint2 *br = e->brief;
         const float2 *yz = e->yzg;
         switch (kw) {
-        case 4: RT_CUDA(cudaLaunchKernelEx(&cfg, rt_split_deposit_kernel<4>, e->T, e->rec, e->dose, e->valid, e->n, wk, yz, e->yz_stride, o)); break;
-        case 8: RT_CUDA(cudaLaunchKernelEx(&cfg, rt_split_deposit_kernel<8>, e->T, e->rec, e->dose, e->valid, e->n, wk, yz, e->yz_stride, o)); break;
-        case 12: RT_CUDA(cudaLaunchKernelEx(&cfg, rt_split_deposit_kernel<12>, e->T, e->rec, e->dose, e->valid, e->n, wk, yz, e->yz_stride, o)); break;
-        default: RT_CUDA(cudaLaunchKernelEx(&cfg, rt_split_deposit_kernel<16>, e->T, e->rec, e->dose, e->valid, e->n, wk, yz, e->yz_stride, o)); break;
+        case 14: RT_CUDA(cudaLaunchKernelEx(&cfg, rt_split_deposit_kernel<14>, e->T, e->rec, e->dose, e->valid, e->n, e->split_epb, wk, br, yz, e->yz_stride, o)); break;
+        default: RT_CUDA(cudaLaunchKernelEx(&cfg, rt_split_deposit_kernel<28>, e->T, e->rec, e->dose, e->valid, e->n, e->split_epb, wk, br, yz, e->yz_stride, o)); break;
         }
         RT_LAUNCH_CHECK("rt_split_deposit_kernel");
     } else if (e->step_kb == -1) {
