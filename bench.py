@@ -205,21 +205,34 @@ def other_kernels(rt, dev, peak):
     # the step kernel again at 65,536 envs on this GPU (16 waves): its throughput once launch latency and the
     # per-env dependent chain are amortised ("roofline fraction per kernel at large N")
     n = 65536
-    se = rt.BatchedEpisodes(n, device=dev, seed=11)
-    se.reset()
     acts = [torch.rand((n, 6), device=dev, generator=g) * 2 - 1 for _ in range(4)]
-    for i in range(30):
-        se.step(acts[i % 4], want_info=False)
-    k = [0]
-
-    def big_step():
-        se.step(acts[k[0] % 4], want_info=False)
-        k[0] += 1
-    s = timed(big_step, 40)
     b = n * ALGO_BYTES_SECTOR
-    out.append({"kernel": "rt_step3_kernel", "workload": f"{n} envs (visionless sparse step)", "bytes": b, "us": s * 1e6,
-                "achieved": b / s / 1e9, "unit": "GB/s", "frac": b / s / 1e9 / peak, "env_steps_per_s": n / s})
-    se.close()
+    # ... and the two-kernel variant of the step (rt_step_split.cuh, RT_STEP_KB=-2: thread-per-env pose kernel +
+    # persistent warp-per-env deposit kernel), which exists for this regime
+    for name, kb in (("rt_step3_kernel", None), ("rt_split_pose_kernel + rt_split_deposit_kernel (RT_STEP_KB=-2)", "-2")):
+        old_kb = os.environ.get("RT_STEP_KB")
+        if kb is not None:
+            os.environ["RT_STEP_KB"] = kb
+        try:
+            se = rt.BatchedEpisodes(n, device=dev, seed=11)
+        finally:
+            if kb is not None:
+                if old_kb is None:
+                    del os.environ["RT_STEP_KB"]
+                else:
+                    os.environ["RT_STEP_KB"] = old_kb
+        se.reset()
+        for i in range(30):
+            se.step(acts[i % 4], want_info=False)
+        k = [0]
+
+        def big_step():
+            se.step(acts[k[0] % 4], want_info=False)
+            k[0] += 1
+        s = timed(big_step, 40)
+        out.append({"kernel": name, "workload": f"{n} envs (visionless sparse step)", "bytes": b, "us": s * 1e6,
+                    "achieved": b / s / 1e9, "unit": "GB/s", "frac": b / s / 1e9 / peak, "env_steps_per_s": n / s})
+        se.close()
     del acts
     # dense-mode step (BASELINE configs[4]): read + write every dose volume, 1,613,360 B per env-step
     n = 1024
@@ -365,8 +378,14 @@ def run_ours(args):
         barrier()
         ms = ev0.elapsed_time(ev1)
         eager_launches = nat.launch_count() - launches0
-        # rt_step is one kernel per call; graph replays re-issue the captured launches
-        gpu_launches = K
+        # kernels per rt_step call (1 for the fused step kernel, 2 for the pose + deposit variant), counted by the
+        # library on one eager call after the timed region; graph replays re-issue the captured launches
+        l0 = nat.launch_count()
+        eager(1)
+        stream.synchronize()
+        per_step = nat.launch_count() - l0
+        gpu_launches = K * per_step
+        step_kernel = "rt_step3_kernel" if per_step == 1 else "rt_split_pose_kernel + rt_split_deposit_kernel"
 
         # ---- e2e: host buffers through rt_step_host, every step --------------------------------
         Ke = args.e2e_steps or min(K, 500)
@@ -416,7 +435,7 @@ def run_ours(args):
                       "bitmaps (13 MB) are L2-resident by design",
             },
             "roofline": {
-                "kernel": "rt_step3_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "kernel": step_kernel, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": measured_traffic() if E == 4096 else None, "peak_source": peak_src,
                 "bytes_per_env_step": ALGO_BYTES_SECTOR, "payload_bytes_per_env_step": ALGO_BYTES_PAYLOAD,
                 "avg_launch_us": launch_s * 1e6,
