@@ -24,7 +24,7 @@
 //
 // Both are launched with programmatic stream serialization; the pose kernel triggers only after its own
 // cudaGridDependencySynchronize, so nothing of call t+1 starts before the deposit kernel of call t has completed.
-// Same arithmetic as rt_step3_kernel, same results (tests/test_gpu_parity.py runs every variant against the oracle).
+// Same arithmetic as rt_step3_kernel, same results (tests/test_gpu_parity.py runs every variant on the same episodes).
 #pragma once
 
 namespace {
