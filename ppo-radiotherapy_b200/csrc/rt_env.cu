@@ -1409,7 +1409,11 @@ int rt_create(rt_env **out, int device, int n_envs, uint32_t flags, const rt_pha
             if ((rc = dev_alloc(&e->work, (size_t)n_envs, &e->bytes)) || (rc = dev_alloc(&e->brief, (size_t)n_envs, &e->bytes)) ||
                 (rc = dev_alloc(&e->yzg, (size_t)n_envs * e->yz_stride, &e->bytes))) { rt_destroy(e); return rc; }
             // persistent deposit kernel: one block of 32 warps per SM (or two of 14 / 16), consecutive envs per block
-            const int blocks_max = sms * (kSplitWarpsPerSM / e->split_kw);
+            int blocks_max = sms * (kSplitWarpsPerSM / e->split_kw);
+            if (const char *v = getenv("RT_SPLIT_BLOCKS")) {                  // tests: many envs per warp at small env counts
+                const int bm = atoi(v);
+                if (bm >= 1 && bm < blocks_max) blocks_max = bm;
+            }
             e->split_epb = (n_envs + blocks_max - 1) / blocks_max;
             e->split_blocks = (n_envs + e->split_epb - 1) / e->split_epb;
             e->pose_smem = (size_t)kPoseThreads * RT_OBS_SIZE * sizeof(float);

@@ -132,7 +132,7 @@ def test_transform_dropins_vs_oracle():
 
 
 # ------------------------------------------------------------------------------------ step
-def _compare_step(info, obs, reward, term, rec, done, mask=None):
+def _compare_step(info, obs, reward, term, rec, done, mask=None, overshoot_atol=None):
     if mask is not None:
         info, obs, reward, term, rec, done = info[mask], obs[mask], reward[mask], term[mask], rec[mask], done[mask]
     np.testing.assert_allclose(obs, rec[:, 0:9].astype(np.float32), rtol=0, atol=OBS_ATOL)
@@ -140,7 +140,8 @@ def _compare_step(info, obs, reward, term, rec, done, mask=None):
     np.testing.assert_allclose(info[:, 0:4], rec[:, 9:13], rtol=REW_RTOL, atol=REW_ATOL)
     np.testing.assert_allclose(info[:, 4:6], rec[:, 13:15], rtol=REW_RTOL, atol=REW_ATOL)
     assert np.array_equal(info[:, nat.INFO_OVERSHOOT_T0:nat.INFO_OVERSHOOT_T0 + 3], rec[:, 15:18])
-    np.testing.assert_allclose(info[:, nat.INFO_OVERSHOOT_R], rec[:, 18], rtol=0, atol=OVERSHOOT_ATOL)
+    np.testing.assert_allclose(info[:, nat.INFO_OVERSHOOT_R], rec[:, 18], rtol=0,
+                               atol=OVERSHOOT_ATOL if overshoot_atol is None else overshoot_atol)
     assert np.array_equal(info[:, nat.INFO_LUNG_COUNT], rec[:, 19])
     assert np.array_equal(term.astype(np.int8), done)
 
@@ -458,6 +459,40 @@ def test_step_kernel_block_shapes_vs_oracle(kb, monkeypatch):
     for t in range(101, T):
         o.step(acts[t, n - 1])
     assert np.array_equal(env.engine.dose(n - 1).cpu().numpy().view(np.uint32), o.dose.view(np.uint32))
+    env.close()
+
+
+@pytest.mark.parametrize("blocks,kw", [("2", "28"), ("3", "14")])
+def test_split_step_persistent_loop_vs_oracle(blocks, kw, monkeypatch):
+    """The two-kernel step (RT_STEP_KB=-2) with its deposit kernel squeezed into a few blocks, so that every warp
+    works through 20-30 envs: the staged hand-over (slots alternate, bitmap buffer reused), the 16-env tail flush,
+    multi-pass beams, a full episode, the autoreset call and the next episode, against the CPU oracle; final dose
+    volumes of three envs bit for bit."""
+    monkeypatch.setenv("RT_STEP_KB", "-2")
+    monkeypatch.setenv("RT_SPLIT_KW", kw)
+    monkeypatch.setenv("RT_SPLIT_BLOCKS", blocks)
+    n, T = 1501, 106
+    rng = np.random.default_rng(23)
+    acts = rng.uniform(-1, 1, (T, n, 6)).astype(np.float32)
+    acts[:, 7, :] = 0.0                                     # an env that never moves: same sectors every step
+    sched = np.stack([(np.arange(n) * 7919) % 1000, (np.arange(n) * 104729 + 17) % 1000]).astype(np.int32)
+    ref_out, ref_done = O.rollout(O.Phantom(), sched, acts, threads=8)
+    env = rt.RadiotherapyVectorEnv(n, device=DEV, tumour_ids=sched)
+    env.reset()
+    for t in range(T):
+        obs, reward, term, _, _ = env.step(_cuda(acts[t]))
+        info = env.engine.info.cpu().numpy()
+        stepped = info[:, nat.INFO_STEPPED] > 0
+        assert stepped.all() == (t != 100)
+        # rotation overshoot (info only) = max(0, pi/4 - acos(z)): for a direction within 1e-3 of the axis the 1e-12
+        # pose tolerance is amplified a thousandfold by acos; 150,000 random steps do get that close
+        _compare_step(info, obs.cpu().numpy(), reward.cpu().numpy(), term.cpu().numpy(), ref_out[t], ref_done[t], stepped,
+                      overshoot_atol=1e-7)
+    for e in (0, 7, n - 1):
+        o = O.OracleEnv(O.Phantom(), int(sched[1, e]))
+        for t in range(101, T):
+            o.step(acts[t, e])
+        assert np.array_equal(env.engine.dose(e).cpu().numpy().view(np.uint32), o.dose.view(np.uint32))
     env.close()
 
 
