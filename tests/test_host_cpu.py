@@ -119,3 +119,25 @@ def test_build_infos_merging():
     assert "episode" not in build_infos(info, np.zeros(n, np.uint8), 0.0)
     info[:, nat.INFO_STEPPED] = 0
     assert build_infos(info, term, 0.0) == {}
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU leg the driver times beside the CUDA arm): one JSON line with the same
+    metric / unit as the CUDA arm on rank 0, nothing and exit status 0 on the other ranks."""
+    import json
+    import subprocess
+    import sys
+    bench = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py")
+    env = dict(os.environ, RANK="0", WORLD_SIZE="1")
+    out = subprocess.run([sys.executable, bench, "--impl", "reference", "--steps", "2", "--warmup", "1"],
+                         capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "env-steps/sec" and line["unit"] == "env-steps/s"
+    assert line["higher_is_better"] is True and line["value"] > 0 and line["steps"] == 2 and line["warmup"] == 1
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    env["RANK"] = "1"
+    out = subprocess.run([sys.executable, bench, "--impl", "reference", "--gpus", "2", "--steps", "2", "--warmup", "1"],
+                         capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0 and out.stdout.strip() == ""
