@@ -102,7 +102,7 @@ struct Tables {
     int pbits_words;
     int lung_words16;              // words of lungs_bits rounded up to a multiple of 4 (16-byte bulk copies)
     long long *stage_clock;        // optional [N][12] clock64() stamps of the step kernel's stages (rt_set_stage_clock)
-    int debug;                     // RT_STEP_DEBUG bits, honoured by the instrumented kernel only (what-if timing):
+    int debug;                     // RT_STEP_DEBUG bits, honoured by the instrumented kernel and by rt_split_deposit_kernel (what-if timing):
                                    // 1 no zero fill / valid bits, 2 no voxel stores, 4 no dose loads, 8 no accumulation,
                                    // 16 no valid-bit RED, 32 no zero-fill store
 };

@@ -195,8 +195,7 @@ struct __align__(16) DepositWarp {
     uint32_t tb[2][kMaxPTumourWords];        // padded tumour bitmasks: this env, next env
     uint32_t vox[2][kVoxStage];              // first entries of the tumours' voxel lists: this env, next env
     SplitResult res[kTailCap];               // results waiting for the tail
-    unsigned long long mbar_a[2], mbar_b;    // record + walk + tumour bits of slot 0 / 1; sector-valid bitmap
-    unsigned long long pad_;
+    unsigned long long mbar_a[2];            // everything staged for the env in slot 0 / 1 (the bitmap included)
 };
 
 __device__ __forceinline__ void mbar_expect(uint32_t mbar, uint32_t bytes)
@@ -230,8 +229,8 @@ rt_split_deposit_kernel(Tables T, EnvRec *rec, float *dose, uint32_t *valid, int
     float2 *yzs = reinterpret_cast<float2 *>(dyn_smem + T.lung_words16 + kW * (sizeof(DepositWarp) / 4) + (size_t)kW * G.vwords) +
                   (size_t)le * 2 * yz_stride;
     const uint32_t mb_a[2] = {smem_u32(&dw.mbar_a[0]), smem_u32(&dw.mbar_a[1])};
-    const uint32_t mb_b = smem_u32(&dw.mbar_b), mb_l = smem_u32(&mbar_lungs);
-    if (lane == 0) { mbar_init(mb_a[0], 1); mbar_init(mb_a[1], 1); mbar_init(mb_b, 1); }
+    const uint32_t mb_l = smem_u32(&mbar_lungs);
+    if (lane == 0) { mbar_init(mb_a[0], 1); mbar_init(mb_a[1], 1); }
     if (threadIdx.x == 0) {
         mbar_init(mb_l, 1);
         s_next = 0;
@@ -243,6 +242,7 @@ rt_split_deposit_kernel(Tables T, EnvRec *rec, float *dose, uint32_t *valid, int
     const int blk0 = blockIdx.x * envs_per_block;
     const int blk_n = min(envs_per_block, n_envs - blk0);
     const uint32_t pbits_bytes = (uint32_t)(T.pbits_words * sizeof(uint32_t));
+    const uint32_t bitmap_bytes = (uint32_t)(G.vwords * sizeof(uint32_t));
 
     const uint32_t next_addr = smem_u32(&s_next);
     auto grab = [&]() -> int {                                             // next env of the block, or -1
@@ -251,25 +251,26 @@ rt_split_deposit_kernel(Tables T, EnvRec *rec, float *dose, uint32_t *valid, int
         v = __shfl_sync(kFull, v, 0);
         return v < blk_n ? blk0 + v : -1;
     };
+    // Everything of an env arrives on ONE mbarrier (slot = parity of the env's position in the warp's sequence): the
+    // transaction count announced here covers the sector-valid bitmap as well, whose copy is issued later (issue_b),
+    // when the previous env's target phase has released the single bitmap buffer.
     auto issue_a = [&](int env, uint2 br2, int slot) {                     // record + walk + tumour bits + voxel list -> slot
         if (lane == 0) {
             const uint32_t br = br2.x;
             const uint32_t yzb = (((br & 255u) + 1u) >> 1) * 16u;
             const bool st = (br >> 8) & 1u;
             const uint32_t vxb = st ? (br2.y >> 24) * 16u : 0u;
-            mbar_expect(mb_a[slot], (uint32_t)sizeof(BeamWork) + yzb + (st ? pbits_bytes : 0u) + vxb);
+            mbar_expect(mb_a[slot], (uint32_t)sizeof(BeamWork) + yzb + (st ? pbits_bytes + bitmap_bytes : 0u) + vxb);
             bulk_copy(smem_u32(&dw.wk[slot]), work + env, (uint32_t)sizeof(BeamWork), mb_a[slot]);
             if (yzb) bulk_copy(smem_u32(yzs + (size_t)slot * yz_stride), yzg + (size_t)env * yz_stride, yzb, mb_a[slot]);
             if (st) bulk_copy(smem_u32(dw.tb[slot]), T.tumour_pbits + (size_t)(br >> 16) * T.pbits_words, pbits_bytes, mb_a[slot]);
             if (vxb) bulk_copy(smem_u32(dw.vox[slot]), T.vox_xyz + (size_t)(br2.y & 0xffffffu) * 4, vxb, mb_a[slot]);
-            // the env's sector-valid bitmap can only be staged once the current env's target phase is over (one
-            // buffer per warp): bring it from HBM to L2 meanwhile
-            if (st) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(valid + (size_t)env * G.vwords),
-                                 "r"((uint32_t)(G.vwords * sizeof(uint32_t))) : "memory");
+            // bring the bitmap from HBM to L2 meanwhile
+            if (st) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(valid + (size_t)env * G.vwords), "r"(bitmap_bytes) : "memory");
         }
     };
-    auto issue_b = [&](int env) {                                          // sector-valid bitmap
-        if (lane == 0) bulk_load(smem_u32(vsm), valid + (size_t)env * G.vwords, (uint32_t)(G.vwords * sizeof(uint32_t)), mb_b);
+    auto issue_b = [&](int env, int slot) {                                // sector-valid bitmap, on the env's barrier
+        if (lane == 0) bulk_copy(smem_u32(vsm), valid + (size_t)env * G.vwords, bitmap_bytes, mb_a[slot]);
     };
     // thread per env: rewards, termination, episode statistics, record update (environment.py:158-191, 214-243)
     auto tail = [&](int cnt) {
@@ -337,13 +338,13 @@ rt_split_deposit_kernel(Tables T, EnvRec *rec, float *dose, uint32_t *valid, int
     }
     uint2 cur_br = brief[cur_env];
     issue_a(cur_env, cur_br, 0);
-    if ((cur_br.x >> 8) & 1u) issue_b(cur_env);
+    if ((cur_br.x >> 8) & 1u) issue_b(cur_env, 0);
     int nxt_env = grab();
     uint2 nxt_br = nxt_env >= 0 ? brief[nxt_env] : make_uint2(0u, 0u);
     mbar_wait(mb_l, 0);                                                    // the lungs bitmask has landed
     int cnt = 0;
-    uint32_t phase_b = 0;
     const int g2 = G.g2;
+    const int dbg = T.debug;                                               // RT_STEP_DEBUG what-if bits (timing experiments: results are wrong by construction)
     for (int it = 0; cur_env >= 0; it++) {
         const int slot = it & 1;
         if (nxt_env >= 0) issue_a(nxt_env, nxt_br, slot ^ 1);              // that slot's env finished in the previous iteration
@@ -371,8 +372,6 @@ rt_split_deposit_kernel(Tables T, EnvRec *rec, float *dose, uint32_t *valid, int
             const int nv = w.n_vox;
             const uint32_t *vx = T.vox_xyz + w.vox_off;
             const uint32_t *vxs = dw.vox[slot];                            // its first kVoxStage entries, staged
-            mbar_wait(mb_b, phase_b);                                      // the staged bitmap has landed
-            phase_b ^= 1u;
             // One 32-slab pass at a time (not unrolled: with every warp of the SM at a different point of the loop
             // the code has to fit the instruction cache).  A later pass must see what an earlier one did to a sector
             // they share: fresh sectors are also marked in the staged bitmap, and a warp barrier orders the stores
@@ -401,7 +400,7 @@ rt_split_deposit_kernel(Tables T, EnvRec *rec, float *dose, uint32_t *valid, int
                     lungm |= ((slungs[l >> 5] >> (l & 31)) & 1u) << j;
                     const bool fresh = inj && !((vsm[sec[j] >> 5] >> (sec[j] & 31)) & 1u);   // never written this episode: reads as zero
                     q.old[j] = 0.0f;
-                    if (inj && !fresh) q.old[j] = vol[l];                  // re-touched sector: read from HBM / L2
+                    if (inj && !fresh && !(dbg & 4)) q.old[j] = vol[l];                  // re-touched sector: read from HBM / L2
                     freshm |= fresh ? 1u << j : 0u;
                 }
                 uint32_t drop;
@@ -429,7 +428,7 @@ rt_split_deposit_kernel(Tables T, EnvRec *rec, float *dose, uint32_t *valid, int
                 __syncwarp();                                              // every lane has done its bitmap lookups
                 if (last) {
                     // the copy engine may overwrite the staged bitmap with the next env's
-                    if (nxt_steps) issue_b(nxt_env);
+                    if (nxt_steps) issue_b(nxt_env, slot ^ 1);
                 }
                 if (c0s == 0) {
                     // distance_to_tumour_reward (environment.py:150-162): min over the tumour's voxel list (the staged
@@ -439,13 +438,26 @@ rt_split_deposit_kernel(Tables T, EnvRec *rec, float *dose, uint32_t *valid, int
                     const float q0 = (float)w.p[0], q1 = (float)w.p[1], q2 = (float)w.p[2];
                     float bestf = CUDART_INF_F;
                     uint32_t bestv = 0u;
-                    for (int k0 = 0; k0 < nv; k0 += kWarp) {
+                    for (int k0 = 0; k0 < nv && k0 < kVoxStage; k0 += kWarp) {
                         const int kq = k0 + lane;
-                        const int kc = kq < nv ? kq : 0;                   // a repeated voxel does not change the minimum
-                        const uint32_t pk = k0 < kVoxStage ? vxs[kc] : __ldg(vx + kc);
+                        const uint32_t pk = vxs[kq < nv ? kq : 0];         // a repeated voxel does not change the minimum
                         const float dx = (float)(pk & 255u) - q0, dy = (float)((pk >> 8) & 255u) - q1, dz = (float)(pk >> 16) - q2;
                         const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
                         if (d2 < bestf) { bestf = d2; bestv = pk; }
+                    }
+                    for (int k0 = kVoxStage; k0 < nv; k0 += 4 * kWarp) {   // the rest of a large tumour: four loads in flight
+                        uint32_t pk[4];
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            const int kq = k0 + u * kWarp + lane;
+                            pk[u] = __ldg(vx + (kq < nv ? kq : 0));
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            const float dx = (float)(pk[u] & 255u) - q0, dy = (float)((pk[u] >> 8) & 255u) - q1, dz = (float)(pk[u] >> 16) - q2;
+                            const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                            if (d2 < bestf) { bestf = d2; bestv = pk[u]; }
+                        }
                     }
                     const float mf = __reduce_min_sync(kFull, __float_as_uint(bestf)) == __float_as_uint(bestf) ? 0.0f : 1.0f;   // d2 >= 0: uint order = float order
                     const uint32_t win = __ballot_sync(kFull, mf == 0.0f);
@@ -462,17 +474,17 @@ rt_split_deposit_kernel(Tables T, EnvRec *rec, float *dose, uint32_t *valid, int
                     uint32_t msk[2] = {0u, 0u};
 #pragma unroll
                     for (int j = 0; j < 4; j++)
-                        if (q.flags & (16u << j)) {
+                        if ((q.flags & (16u << j)) && !(dbg & 1)) {
                             const int sc2 = (q.base + (j >> 1) * g2 + (j & 1)) >> 3;
-                            zero_sector(vol + (sc2 << 3));
+                            if (!(dbg & 32)) zero_sector(vol + (sc2 << 3));
                             const int wd = sc2 >> 5;
                             const uint32_t bit = 1u << (sc2 & 31);
                             if (wrd[0] < 0 || wrd[0] == wd) { wrd[0] = wd; msk[0] |= bit; }
                             else if (wrd[1] < 0 || wrd[1] == wd) { wrd[1] = wd; msk[1] |= bit; }
-                            else { red_or(vbits + wd, bit); if (!last) atomicOr(vsm + wd, bit); }
+                            else { if (!(dbg & 16)) red_or(vbits + wd, bit); if (!last) atomicOr(vsm + wd, bit); }
                         }
-                    if (wrd[0] >= 0) { red_or(vbits + wrd[0], msk[0]); if (!last) atomicOr(vsm + wrd[0], msk[0]); }
-                    if (wrd[1] >= 0) { red_or(vbits + wrd[1], msk[1]); if (!last) atomicOr(vsm + wrd[1], msk[1]); }
+                    if (wrd[0] >= 0) { if (!(dbg & 16)) red_or(vbits + wrd[0], msk[0]); if (!last) atomicOr(vsm + wrd[0], msk[0]); }
+                    if (wrd[1] >= 0) { if (!(dbg & 16)) red_or(vbits + wrd[1], msk[1]); if (!last) atomicOr(vsm + wrd[1], msk[1]); }
                 }
                 __syncwarp();   // zero fill (any lane) is ordered before the voxel stores below
                 float nd[4];
@@ -483,6 +495,7 @@ rt_split_deposit_kernel(Tables T, EnvRec *rec, float *dose, uint32_t *valid, int
                 for (int r = 0; r < 2; r++) {
                     const int l = q.base + r * g2;
                     const uint32_t both = (q.flags >> (2 * r)) & 3u;
+                    if (dbg & 2) continue;
                     if (both == 3u && !(l & 1)) {
                         *reinterpret_cast<float2 *>(vol + l) = make_float2(nd[2 * r], nd[2 * r + 1]);
                     } else {
@@ -505,7 +518,7 @@ rt_split_deposit_kernel(Tables T, EnvRec *rec, float *dose, uint32_t *valid, int
             }
             if (nslab <= 0) {
                 // an empty beam (it missed the volume): only the distance term, and the bitmap buffer is free
-                if (nxt_steps) issue_b(nxt_env);
+                if (nxt_steps) issue_b(nxt_env, slot ^ 1);
                 const double p0 = w.p[0], p1 = w.p[1], p2 = w.p[2];
                 double best = CUDART_INF;
                 for (int kq = lane; kq < nv; kq += kWarp) {
@@ -534,7 +547,7 @@ rt_split_deposit_kernel(Tables T, EnvRec *rec, float *dose, uint32_t *valid, int
             uint4 *vw = reinterpret_cast<uint4 *>(valid + (size_t)env * G.vwords);
             for (int i = lane; i < G.vwords / 4; i += kWarp) vw[i] = make_uint4(0u, 0u, 0u, 0u);
             if (lane == 0) dw.res[cnt].env = env;
-            if (nxt_steps) issue_b(nxt_env);                               // nobody is reading the staged bitmap
+            if (nxt_steps) issue_b(nxt_env, slot ^ 1);                               // nobody is reading the staged bitmap
         }
         if (++cnt == kTailCap) { tail(cnt); cnt = 0; }
         __syncwarp();                                                      // slot's buffers are free for the copy engine
