@@ -205,7 +205,10 @@ def other_kernels(rt, dev, peak):
     # the step kernel again at 65,536 envs on this GPU (16 waves): its throughput once launch latency and the
     # per-env dependent chain are amortised ("roofline fraction per kernel at large N")
     n = 65536
-    acts = [torch.rand((n, 6), device=dev, generator=g) * 2 - 1 for _ in range(4)]
+    # one distinct action batch per call of an episode cycle: a short repeating pool would walk every beam into the
+    # bounds of the volume (a lighter workload than the uniform-random policy the algorithmic bytes were counted on)
+    n_pool = 104
+    acts = [torch.rand((n, 6), device=dev, generator=g) * 2 - 1 for _ in range(n_pool)]
     b = n * ALGO_BYTES_SECTOR
     # ... and the two-kernel variant of the step (rt_step_split.cuh, RT_STEP_KB=-2: thread-per-env pose kernel +
     # persistent warp-per-env deposit kernel), which exists for this regime
@@ -223,11 +226,11 @@ def other_kernels(rt, dev, peak):
                     os.environ["RT_STEP_KB"] = old_kb
         se.reset()
         for i in range(127):                       # into the second episode (timed() adds three more warm-up calls)
-            se.step(acts[i % 4], want_info=False)
+            se.step(acts[i % n_pool], want_info=False)
         k = [0]
 
         def big_step():
-            se.step(acts[k[0] % 4], want_info=False)
+            se.step(acts[k[0] % n_pool], want_info=False)
             k[0] += 1
         s = timed(big_step, 101)                   # one full episode cycle incl. the autoreset call: steady-state mix of
                                                    # fresh and re-touched sectors
