@@ -195,6 +195,32 @@ RT_API int rt_gae(const float *rewards_dev, const float *values_dev, const float
                   const float *next_value_dev, const float *next_done_dev, int T, int N,
                   double gamma, double gae_lambda, float *advantages_dev, float *returns_dev, void *stream);
 
+/* ---- rollout side of the PPO loop (train.py:139-161, networks.py:107-147), SURVEY.md 8f-1 ------------------ */
+/* Device pointers to the parameters of the reference's MLP agent `PPO` (networks.py:107-130; state-dict keys
+ * critic.{0,2,4}.{weight,bias}, actor_mean.{0,2,4}.{weight,bias}, actor_logstd), torch Linear layout weight [out][in].
+ * Supported: n_obs <= 16, hidden == 64 (feature_dim of configs/*.yaml.template), n_act <= 6. */
+typedef struct rt_mlp_params {
+    const float *critic_w0, *critic_b0, *critic_w1, *critic_b1, *critic_w2, *critic_b2;
+    const float *actor_w0, *actor_b0, *actor_w1, *actor_b1, *actor_w2, *actor_b2;
+    const float *actor_logstd;
+    int32_t n_obs, hidden, n_act;
+} rt_mlp_params;
+/* train.py:139-149 in one kernel: row t = counters_dev[0] of the rollout buffers obs [T][n][n_obs], dones [T][n] receives
+ * obs_dev / next_done_dev; `agent.get_action_and_value(next_obs)` (networks.py:132-147, no_grad) is evaluated in float32;
+ * action = mean + exp(logstd) * N(0,1) from Philox4x32-10 keyed by (seed, env, counters_dev[1]); values [T][n],
+ * actions [T][n][n_act], logprobs [T][n] receive row t; action_out_dev [n][n_act] is the input of rt_step.  Any rollout
+ * buffer may be NULL.  `p` is a HOST struct of device pointers. */
+RT_API int rt_ppo_act(const rt_mlp_params *p, const float *obs_dev, const float *next_done_dev, int n, uint64_t seed,
+                      const int64_t *counters_dev, float *obs_buf_dev, float *dones_buf_dev, float *values_buf_dev,
+                      float *actions_buf_dev, float *logprobs_buf_dev, float *action_out_dev, void *stream);
+/* train.py:153-161 after rt_step: rewards [T][n] row t = counters_dev[0] <- reward_f32_dev, next_done_dev [n] <-
+ * terminated | truncated, and for the envs that terminated the episode statistics train.py:42-66 logs
+ * (episode_stats_dev float64 [7]: finished, sum of episode returns, lengths, last-step tumour / lung / distance / total
+ * reward; accumulated, the caller zeroes it) from info_dev [n][RT_INFO_SIZE].  truncated, info, rewards, stats may be NULL. */
+RT_API int rt_ppo_record(const float *reward_f32_dev, const uint8_t *terminated_dev, const uint8_t *truncated_dev,
+                         const double *info_dev, int n, const int64_t *counters_dev, float *rewards_buf_dev,
+                         float *next_done_dev, double *episode_stats_dev, void *stream);
+
 /* ---- FeaturesExtractor3D, first block (networks.py:15-24) ------------------------------------------ */
 /* Conv3d(4->16, k=3) + bias + ReLU + MaxPool3d(2, 2, padding=((D-2)%2, (H-2)%2, (W-2)%2)) fused in one tensor-core
  * kernel (tcgen05, accumulators in tensor memory).  x_dev float32 [n][4][D][H][W] (the voxel observation),

@@ -25,6 +25,7 @@ from .geometry import (apply_rotation, apply_rotation_batch, apply_translation, 
 from .vector_env import Box, RadiotherapyVectorEnv
 from .environment import RadiotherapyEnv
 from .networks import PPO, PPO_3DCNN, FeaturesExtractor3D
+from .rollout import FusedRollout
 from . import train as train          # noqa: F401  (ppo_radiotherapy_b200.train.train / main)
 from . import ppo_eval as ppo_eval    # noqa: F401
 
@@ -32,5 +33,5 @@ __all__ = [
     "RtError", "build", "Phantom", "default_phantom", "BatchedEpisodes", "ObservationStore", "RadiotherapyEnv",
     "RadiotherapyVectorEnv", "Box", "beam_voxels", "beam_voxels_batch", "beam_voxels_dense_batch",
     "apply_rotation", "apply_rotation_batch", "apply_translation", "apply_translation_batch",
-    "pose_update_batch", "compute_gae", "PPO", "PPO_3DCNN", "FeaturesExtractor3D", "train",
+    "pose_update_batch", "compute_gae", "PPO", "PPO_3DCNN", "FeaturesExtractor3D", "FusedRollout", "train",
 ]

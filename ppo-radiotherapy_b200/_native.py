@@ -74,6 +74,14 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB_PATH
 
 
+class MlpParams(C.Structure):
+    """rt_mlp_params: device pointers to the parameters of the reference's MLP agent (include/rt_env.h)."""
+    _fields_ = [(name, C.c_void_p) for name in (
+        "critic_w0", "critic_b0", "critic_w1", "critic_b1", "critic_w2", "critic_b2",
+        "actor_w0", "actor_b0", "actor_w1", "actor_b1", "actor_w2", "actor_b2", "actor_logstd")] + [
+        ("n_obs", C.c_int32), ("hidden", C.c_int32), ("n_act", C.c_int32)]
+
+
 class PhantomDesc(C.Structure):
     _fields_ = [
         ("grid", C.c_int32 * 3),
@@ -122,6 +130,8 @@ _SIGNATURES = {
     "rt_conv1_from_env": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp]),
     "rt_conv2_relu_pool": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]),
     "rt_c3d_tail": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
+    "rt_ppo_act": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_uint64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "rt_ppo_record": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp]),
     "rt_launch_count": (C.c_int64, []),
     "rt_set_stage_clock": (C.c_int, [_vp, _vp]),
 }

@@ -30,6 +30,7 @@ import torch.optim as optim
 from . import _native as nat
 from .geometry import compute_gae
 from .networks import PPO, PPO_3DCNN
+from .rollout import FusedRollout, supported as fused_rollout_supported
 from .vector_env import RadiotherapyVectorEnv
 
 DEFAULTS = dict(
@@ -38,6 +39,7 @@ DEFAULTS = dict(
     num_minibatches=32, update_epochs=10, gamma=0.99, gae_lambda=0.95, norm_adv=True, clip_coef=0.1,
     clip_vloss=True, ent_coef=0.0, vf_coef=0.5, max_grad_norm=0.5, feature_dim=64, visionless=True,
     cuda_graph=True,     # replay one captured rollout step (policy + env + buffer writes) instead of ~50 launches
+    fused_rollout=True,  # MLP agent: rt_ppo_act + rt_step + rt_ppo_record per rollout step (rollout.py) instead of PyTorch ops
     render_microbatch=256,   # vision mode: samples re-rendered from compressed records per gradient micro-batch
 )
 
@@ -252,6 +254,13 @@ def train(cfg, writer=None, device="cuda", output_dir: Optional[str] = None, run
     values = torch.zeros((T, n_local), device=device)
 
     eng = envs.engine
+    # visionless MLP agent: the whole rollout step is three hand-written kernels (policy forward + sampling + buffer
+    # writes, env step, reward / done / episode statistics); the rollout buffers are the FusedRollout's own
+    fused = None
+    if cfg.visionless and getattr(cfg, "fused_rollout", True) and fused_rollout_supported(agent):
+        fused = FusedRollout(agent, n_local, T, seed=cfg.seed * 7919 + rank)
+        obs, actions, logprobs, rewards, dones, values = (fused.obs, fused.actions, fused.logprobs, fused.rewards,
+                                                          fused.dones, fused.values)
     if cfg.visionless:
         next_obs, _ = envs.reset(seed=None, options={"backend": "torch"})
         next_obs = next_obs.clone()
@@ -262,9 +271,11 @@ def train(cfg, writer=None, device="cuda", output_dir: Optional[str] = None, run
         next_obs = None
     next_done = torch.zeros(n_local, device=device)
     step_idx = torch.zeros(1, dtype=torch.long, device=device)
+    if fused is not None:
+        next_obs, next_done, step_idx = eng.obs, fused.next_done, fused.counters[:1]     # views of the kernels' own state
     # per-iteration episode statistics, reduced on the device: [finished, sum return, sum length,
     # sum of last-step reward components (tumour, lung, distance, total)] (train.py:42-66)
-    ep = torch.zeros(7, dtype=torch.float64, device=device)
+    ep = torch.zeros(7, dtype=torch.float64, device=device) if fused is None else fused.episode_stats
     ep_cols = torch.tensor([nat.INFO_EPISODE_RETURN, nat.INFO_EPISODE_LENGTH, nat.INFO_REWARD_TUMOUR,
                             nat.INFO_REWARD_LUNG, nat.INFO_REWARD_DISTANCE, nat.INFO_REWARD_TOTAL], device=device)
 
@@ -273,6 +284,12 @@ def train(cfg, writer=None, device="cuda", output_dir: Optional[str] = None, run
     def rollout_step():
         """train.py:139-158 for the step selected by the device-side counter `step_idx` (so that one captured
         CUDA graph serves every step of the rollout)."""
+        if fused is not None:
+            fused.act(eng.obs)                                                   # train.py:139-149
+            eng.step(fused.action, want_info=True)                               # train.py:151
+            fused.record(eng)                                                    # train.py:153-161
+            fused.advance()
+            return
         if cfg.visionless:
             obs.index_copy_(0, step_idx, next_obs.unsqueeze(0))
         else:                                          # eager only (no CUDA graph in vision mode): host-side slot index

@@ -128,3 +128,80 @@ def test_evaluate_like_ppo_eval(tmp_path):
     out = evaluate(envs, 64, str(path), eval_episodes=2, Model=rt.PPO, device=torch.device(DEV), log=None)
     assert len(out) == 2 and all(np.isfinite(r) and -200 < r < 200 for r in out)
     envs.close()
+
+
+def test_fused_rollout_policy_matches_torch():
+    """rt_ppo_act against `PPO.get_action_and_value` (networks.py:132-147) on the same parameters: value and
+    log-probability of the kernel's own action in float32 tolerance, rollout rows written, the noise standard normal
+    and fresh every step; a ragged env count (not a multiple of the 64-env tile)."""
+    torch.manual_seed(1)
+    dev = torch.device(DEV)
+    agent = rt.PPO((9,), (6,), 64).to(dev)
+    with torch.no_grad():
+        agent.actor_logstd.copy_(torch.linspace(-0.7, 0.4, 6, device=dev).reshape(1, 6))
+        agent.actor_mean[4].weight.mul_(30.0)
+        agent.actor_mean[4].bias.uniform_(-0.3, 0.3)
+        agent.critic[4].bias.fill_(0.25)
+    n, T = 4099, 3
+    fr = rt.FusedRollout(agent, n, T, seed=5)
+    zs = []
+    for t in range(T):
+        obs = torch.rand((n, 9), device=dev) * 2 - 1
+        fr.next_done.copy_((torch.rand(n, device=dev) < 0.1).float())
+        a = fr.act(obs).clone()
+        with torch.no_grad():
+            mean = agent.actor_mean(obs)
+            _, lp, _, v = agent.get_action_and_value(obs, a)
+        assert torch.equal(fr.obs[t], obs) and torch.equal(fr.actions[t], a) and torch.equal(fr.dones[t], fr.next_done)
+        torch.testing.assert_close(fr.values[t], v.flatten(), rtol=1e-5, atol=2e-6)
+        torch.testing.assert_close(fr.logprobs[t], lp, rtol=1e-5, atol=2e-4)
+        zs.append(((a - mean) / torch.exp(agent.actor_logstd)).detach().cpu().numpy())
+        fr.advance()
+    assert fr.counters.cpu().tolist() == [T, T]
+    z = np.stack(zs)
+    assert abs(z.mean()) < 0.02 and abs(z.std() - 1.0) < 0.02
+    assert abs(np.mean(z ** 3)) < 0.05 and abs(np.mean(z ** 4) - 3.0) < 0.15            # skewness, kurtosis of N(0,1)
+    assert np.abs(np.corrcoef(z[0].ravel(), z[1].ravel())[0, 1]) < 0.02                 # fresh noise every step
+    assert np.abs(np.corrcoef(z[0][:, 0], z[0][:, 1])[0, 1]) < 0.05                     # ... and per action component
+    # the same (seed, env, step) gives the same noise
+    fr2 = rt.FusedRollout(agent, n, T, seed=5)
+    obs = torch.zeros((n, 9), device=dev)
+    assert torch.equal(fr2.act(obs), rt.FusedRollout(agent, n, T, seed=5).act(obs))
+
+
+def test_fused_rollout_record_and_train():
+    """rt_ppo_record against the tensor expressions of the PyTorch path, then the training loop with the fused rollout
+    step (CUDA graph) and without it: same env trajectories up to the sampled actions, finite losses, same statistics."""
+    from ppo_radiotherapy_b200 import _native as nat
+    dev = torch.device(DEV)
+    n = 300
+    eng = rt.BatchedEpisodes(n, device=dev, seed=2)
+    eng.reset()
+    agent = rt.PPO((9,), (6,), 64).to(dev)
+    fr = rt.FusedRollout(agent, n, 8, seed=1)
+    eng.step(torch.rand((n, 6), device=dev) * 2 - 1, want_info=True)
+    eng.terminated[::7] = 1                                                   # pretend some envs finished
+    fr.counters[0] = 3
+    fr.record(eng)
+    torch.cuda.synchronize()
+    assert torch.equal(fr.rewards[3], eng.reward_f32) and fr.rewards[:3].abs().sum() == 0
+    assert torch.equal(fr.next_done, eng.terminated.float())
+    f64 = eng.terminated.double()
+    cols = [nat.INFO_EPISODE_RETURN, nat.INFO_EPISODE_LENGTH, nat.INFO_REWARD_TUMOUR, nat.INFO_REWARD_LUNG,
+            nat.INFO_REWARD_DISTANCE, nat.INFO_REWARD_TOTAL]
+    want = torch.cat([f64.sum().reshape(1), (eng.info[:, cols] * f64.unsqueeze(1)).sum(0)])
+    torch.testing.assert_close(fr.episode_stats, want, rtol=1e-12, atol=1e-12)
+    eng.close()
+    hist = {}
+    for fused in (True, False):
+        cfg = load_config(None, num_envs=128, num_steps=100, num_minibatches=4, update_epochs=2,
+                          total_timesteps=128 * 100 * 2, num_saves=0, save_model=False, seed=4, fused_rollout=fused)
+        torch.manual_seed(0)
+        hist[fused] = train(cfg, writer=None, device=DEV, output_dir=None, run_name="f", log=None).history
+    for fused in (True, False):
+        h = hist[fused]
+        assert len(h) == 2 and all(np.isfinite(r["v_loss"]) and np.isfinite(r["pg_loss"]) for r in h)
+        assert h[0]["episodes"] == 128 and abs(h[0]["episodic_length"] - 100) < 1e-9
+        assert -200 < h[0]["episodic_return"] < 200
+    # first-iteration policy is the same initial network: approx_kl of the first minibatches is tiny in both paths
+    assert abs(hist[True][0]["approx_kl"]) < 0.05 and abs(hist[False][0]["approx_kl"]) < 0.05
