@@ -22,6 +22,7 @@ constexpr int kPolTile = 64;         // envs per block
 constexpr int kPolThreads = 256;
 constexpr int kPolStride = kPolTile + 4;   // activation rows [unit][env]: 16-byte aligned, conflict-free 128-bit stores
 constexpr int kPolMaxObs = 16;
+constexpr int kPolWStride = kPolHidden + 1;   // transposed weight rows [k][unit]: conflict-free both for the transposing store and the unit-wise read
 constexpr int kPolOut = 8;           // output columns: actor means 0..n_act-1 (n_act <= 6), critic value 6, unused 7
 
 struct PolicyNet {
@@ -49,7 +50,7 @@ __device__ __forceinline__ void policy_layer(const float *wT, const float *bias,
     for (int j = 0; j < 16; j++) acc[j] = b;
 #pragma unroll 4
     for (int k = 0; k < K; k++) {
-        const float w = wT[k * kPolHidden + u];
+        const float w = wT[k * kPolWStride + u];
         const float4 *x = reinterpret_cast<const float4 *>(in + k * kPolStride + e0);
 #pragma unroll
         for (int j = 0; j < 4; j++) {
@@ -72,10 +73,10 @@ __global__ void __launch_bounds__(kPolThreads) rt_ppo_act_kernel(PolicyArgs A)
     extern __shared__ __align__(16) float psm[];
     const int n_obs = A.n_obs, n_act = A.n_act;
     // shared-memory plan (floats)
-    float *w0T = psm;                                             // [2][n_obs][64]
-    float *b0 = w0T + 2 * kPolMaxObs * kPolHidden;                // [2][64]
-    float *w1T = b0 + 2 * kPolHidden;                             // [2][64][64]
-    float *b1 = w1T + 2 * kPolHidden * kPolHidden;                // [2][64]
+    float *w0T = psm;                                             // [2][kPolMaxObs][65]
+    float *b0 = w0T + 2 * kPolMaxObs * kPolWStride;               // [2][64]
+    float *w1T = b0 + 2 * kPolHidden;                             // [2][64][65]
+    float *b1 = w1T + 2 * kPolHidden * kPolWStride;               // [2][64]
     float *w2T = b1 + 2 * kPolHidden;                             // [64][8]: column o of the output layer
     float *b2 = w2T + kPolHidden * kPolOut;                       // [8]
     float *sigma = b2 + kPolOut;                                  // [8] exp(logstd), then [8] logstd
@@ -90,11 +91,11 @@ __global__ void __launch_bounds__(kPolThreads) rt_ppo_act_kernel(PolicyArgs A)
         const PolicyNet &P = net ? A.actor : A.critic;
         for (int i = t; i < kPolHidden * n_obs; i += kPolThreads) {           // w0 [64][n_obs]
             const int u = i / n_obs, k = i - u * n_obs;
-            w0T[(net * kPolMaxObs + k) * kPolHidden + u] = __ldg(P.w0 + i);
+            w0T[(net * kPolMaxObs + k) * kPolWStride + u] = __ldg(P.w0 + i);
         }
         for (int i = t; i < kPolHidden * kPolHidden; i += kPolThreads) {      // w1 [64][64]
             const int u = i >> 6, k = i & 63;
-            w1T[(net * kPolHidden + k) * kPolHidden + u] = __ldg(P.w1 + i);
+            w1T[(net * kPolHidden + k) * kPolWStride + u] = __ldg(P.w1 + i);
         }
         if (t < kPolHidden) {
             b0[net * kPolHidden + t] = __ldg(P.b0 + t);
@@ -134,9 +135,9 @@ __global__ void __launch_bounds__(kPolThreads) rt_ppo_act_kernel(PolicyArgs A)
         if (t < nb && A.dones_buf) A.dones_buf[(size_t)row * A.n + env0 + t] = A.next_done[env0 + t];   // train.py:141
         __syncthreads();
         for (int net = 0; net < 2; net++) {
-            policy_layer<true>(w0T + net * kPolMaxObs * kPolHidden, b0 + net * kPolHidden, xin, n_obs, h1, u, e0);
+            policy_layer<true>(w0T + net * kPolMaxObs * kPolWStride, b0 + net * kPolHidden, xin, n_obs, h1, u, e0);
             __syncthreads();
-            policy_layer<true>(w1T + net * kPolHidden * kPolHidden, b1 + net * kPolHidden, h1, kPolHidden,
+            policy_layer<true>(w1T + net * kPolHidden * kPolWStride, b1 + net * kPolHidden, h1, kPolHidden,
                                h2 + net * kPolHidden * kPolStride, u, e0);
             __syncthreads();
         }
@@ -215,7 +216,7 @@ __global__ void __launch_bounds__(256) rt_ppo_record_kernel(RecordArgs A)
     }
 }
 
-constexpr size_t kPolSmemFloats = 2 * kPolMaxObs * kPolHidden + 2 * kPolHidden + 2 * kPolHidden * kPolHidden + 2 * kPolHidden +
+constexpr size_t kPolSmemFloats = 2 * kPolMaxObs * kPolWStride + 2 * kPolHidden + 2 * kPolHidden * kPolWStride + 2 * kPolHidden +
                                   kPolHidden * kPolOut + kPolOut + 2 * kPolOut + kPolMaxObs * kPolStride +
                                   kPolHidden * kPolStride + 2 * kPolHidden * kPolStride + 4 * kPolTile;
 
