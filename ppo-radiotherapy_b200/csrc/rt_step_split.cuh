@@ -1,6 +1,6 @@
 // rt_step_split.cuh — the sparse environment step (RadiotherapyEnv.step, environment.py:193-243) as two
-// kernels, for env counts of several waves per GPU (selected in rt_create; RT_STEP_KB=-2 forces it), included by
-// rt_env.cu after rt_step.cuh.
+// kernels, an experiment for env counts of many waves per GPU (selected with RT_STEP_KB=-2 only: it ties with the
+// fused kernel at 65,536 envs and loses below), included by rt_env.cu after rt_step.cuh.
 //
 // rt_step3_kernel couples a scalar warp (thread per env: pose, beam set-up, walk, rewards) and kB env warps (warp
 // per env: deposition) with three block barriers.  With one wave of blocks that is the shortest dependent chain;
@@ -10,16 +10,17 @@
 //
 //   rt_split_pose_kernel    one THREAD per env, 64 per block: record + action load, float64 translation and
 //        rotation (transforms.py:7-69), beam clip / set-up and the serial float32 slab walk (draw_line.py:19-66,
-//        98-99), observation (environment.py:259-268), the NEXT_STEP autoreset of the record.  Leaves a 128-byte
-//        BeamWork record and the (intery, interz) of every slab in global memory (written row-contiguously from a
-//        shared-memory stage; they stay in L2).
+//        98-99), observation (environment.py:259-268), the NEXT_STEP autoreset of the record.  Leaves a 192-byte
+//        BeamWork record, an 8-byte brief (sizes of the deposit kernel's bulk copies) and the (intery, interz) of
+//        every slab in global memory (one 32-byte store per four slabs; they stay in L2).
 //   rt_split_deposit_kernel one WARP per env at a time, PERSISTENT: a block owns a run of consecutive envs and its
 //        warps take them one by one from a shared-memory counter; no block barrier.  While a warp works on an env
 //        the copy engine (cp.async.bulk on mbarriers) brings the next env's hand-over record, walk values, padded
 //        tumour bitmask and sector-valid bitmap to shared memory, so the only load a warp waits for is the dose of
-//        re-touched sectors.  Per env: dose deposition exactly as in rt_step3_kernel (environment.py:107-110: all
-//        passes of a beam through one HBM round trip), distance-to-tumour minimum (environment.py:150-162) in the
-//        shadow of the dose loads, warp reductions.  Rewards, termination, episode statistics and the record update
+//        re-touched sectors.  Per env: dose deposition with the arithmetic of rt_step3_kernel (environment.py:107-110),
+//        one 32-slab pass at a time (the rolled loop has to fit the instruction cache: the SM's warps are all at
+//        different points of it), distance-to-tumour minimum (environment.py:150-162) in the shadow of the dose
+//        loads, warp reductions.  Rewards, termination, episode statistics and the record update
 //        (environment.py:158-191, 214-243) are done one THREAD per env for up to 16 finished envs of the warp at once.
 //
 // Both are launched with programmatic stream serialization; the pose kernel triggers only after its own
