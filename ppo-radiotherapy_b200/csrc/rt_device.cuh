@@ -236,6 +236,18 @@ struct Beam {
     float sgy, sgz;  // gradient * step (:65-66, 98-99)
 };
 
+// a / b in float32, round to nearest, for a FINITE NON-ZERO b: the same value as __fdiv_rn.  A zero numerator — a beam
+// position clamped to the lower bound of the volume (transforms.py:66), which under a random policy some env of every
+// warp has — sends __fdiv_rn's range check (FCHK) into its ~100-instruction slow path; the quotient is a signed zero
+// that needs no division at all.
+__device__ __forceinline__ float fdiv_rn_zero_num(float a, float b)
+{
+    const bool z = a == 0.0f;
+    const float q = __fdiv_rn(z ? 1.0f : a, b);
+    const float sz = __int_as_float((__float_as_int(a) ^ __float_as_int(b)) & (int)0x80000000);   // sign(a) xor sign(b), magnitude 0
+    return z ? sz : q;
+}
+
 __device__ __forceinline__ Beam beam_setup(const Grid &G, const double pd[3], const double dd[3])
 {
     const float eps = 9.99999997475242708e-07f;   // float32(1e-6)
@@ -252,7 +264,7 @@ __device__ __forceinline__ Beam beam_setup(const Grid &G, const double pd[3], co
     float norm = __fsqrt_rn(__double2float_rn(acc));
     if (norm < eps) { b.nslab = -1; return b; }                        // :23-24
 #pragma unroll
-    for (int i = 0; i < 3; i++) v[i] = __fdiv_rn(v[i], norm);          // :25
+    for (int i = 0; i < 3; i++) v[i] = fdiv_rn_zero_num(v[i], norm);   // :25
 
     const int gsz[3] = {G.g0, G.g1, G.g2};
     float t_entry = -CUDART_INF_F, t_exit = CUDART_INF_F;
@@ -262,8 +274,8 @@ __device__ __forceinline__ Beam beam_setup(const Grid &G, const double pd[3], co
         float gm1 = (float)(gsz[i] - 1);
         float te, tx;
         if (fabsf(v[i]) > eps) {
-            float t1 = __fdiv_rn(-p[i], v[i]);
-            float t2 = __fdiv_rn(__fsub_rn(gm1, p[i]), v[i]);
+            float t1 = fdiv_rn_zero_num(-p[i], v[i]);
+            float t2 = fdiv_rn_zero_num(__fsub_rn(gm1, p[i]), v[i]);
             te = t1 < t2 ? t1 : t2;
             tx = t1 < t2 ? t2 : t1;
         } else {
@@ -295,8 +307,8 @@ __device__ __forceinline__ Beam beam_setup(const Grid &G, const double pd[3], co
     b.y0 = __fadd_rn(p0, __fmul_rn(t_entry, v0));                      // :62
     b.z0 = __fadd_rn(p1, __fmul_rn(t_entry, v1));                      // :63
     float den = __fadd_rn(vd, eps);                                    // :65-66
-    float gy = __fdiv_rn(v0, den);
-    float gz = __fdiv_rn(v1, den);
+    float gy = fdiv_rn_zero_num(v0, den);
+    float gz = fdiv_rn_zero_num(v1, den);
     b.sgy = step > 0 ? gy : -gy;                                       // gradient * step, exact
     b.sgz = step > 0 ? gz : -gz;
     b.dom = dom; b.o0 = o0; b.o1 = o1; b.step = step; b.x0 = x0;
@@ -318,6 +330,21 @@ __device__ __forceinline__ void beam_walk(const Beam &b, float *ys, float *zs)
     for (int k = 0; k < b.nslab; k++) {
         ys[k] = y;
         zs[k] = z;
+        y = __fadd_rn(y, b.sgy);
+        z = __fadd_rn(z, b.sgz);
+    }
+}
+
+// Same walk for the lanes of a warp that each hold a beam (one thread per env): every participating lane runs as many
+// steps as the longest beam among them, so the loop has one trip count, no per-lane exit test, and unrolls cleanly.
+// Entries past a lane's own nslab are written (the row must hold `cap` >= every nslab) and never read.
+__device__ __forceinline__ void beam_walk2_uniform(const Beam &b, float2 *yz)
+{
+    const int nmax = __reduce_max_sync(__activemask(), b.nslab);
+    float y = b.y0, z = b.z0;
+#pragma unroll 8
+    for (int k = 0; k < nmax; k++) {
+        yz[k] = make_float2(y, z);
         y = __fadd_rn(y, b.sgy);
         z = __fadd_rn(z, b.sgz);
     }

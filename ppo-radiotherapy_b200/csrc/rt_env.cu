@@ -565,7 +565,7 @@ __global__ void __launch_bounds__(kStepThreads, 4) rt_step_kernel(Tables T, Sche
 
     // rewards, termination (environment.py:158-191, 214-220)
     const float tsum_f32 = (float)tumour_dose;                                   // np.sum(dose*tumours) float32
-    const float ratio = __fdiv_rn(tsum_f32, tm.tumour_sum);
+    const float ratio = fdiv_rn_zero_num(tsum_f32, tm.tumour_sum);   // no dose on the tumour yet: the common case
     const float r_tumour = __fmul_rn(ratio, 10.0f);
     const double r_lung = __dmul_rn(__ddiv_rn((double)lung_count, (double)tm.lung_mask_sum), -1.0);
     const double r_dist = sc.r_dist;
@@ -762,7 +762,7 @@ __global__ void __launch_bounds__(kDenseThreads) rt_dense_kernel(Tables T, EnvRe
     EnvRec *my = rec + env;
     const int t = dw.t;
     const float tsum_f32 = (float)tumour_dose;
-    const float ratio = __fdiv_rn(tsum_f32, tm.tumour_sum);
+    const float ratio = fdiv_rn_zero_num(tsum_f32, tm.tumour_sum);   // no dose on the tumour yet: the common case
     const float r_tumour = __fmul_rn(ratio, 10.0f);
     const double r_lung = __dmul_rn(__ddiv_rn((double)lung_count, (double)tm.lung_mask_sum), -1.0);
     const double r_dist = __dmul_rn(__ddiv_rn(sqrt(dw.best), T.gnorm), -1.0);

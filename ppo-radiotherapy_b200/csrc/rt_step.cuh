@@ -247,7 +247,7 @@ rt_step3_kernel(Tables T, Schedule S, EnvRec *rec, float *dose, uint32_t *valid,
             if (kClock) T.stage_clock[(size_t)e * 12 + 9] = clock64() + (long long)(s.d[0] * 0.0);
             const Beam b = beam_setup(G, s.p, s.d);                        // draw_line.py:19-66
             if (kClock) T.stage_clock[(size_t)e * 12 + 10] = clock64() + (b.nslab < -5);
-            beam_walk2(b, yz[lane]);                                       // draw_line.py:98-99
+            beam_walk2_uniform(b, yz[lane]);                               // draw_line.py:98-99 (rows hold kMaxSlabs + 1 entries)
             se.beam = b;
             RT_STAMP3(e, 1);
         }
@@ -319,7 +319,7 @@ rt_step3_kernel(Tables T, Schedule S, EnvRec *rec, float *dose, uint32_t *valid,
             lung_count += se.d_cnt;
             // rewards, termination (environment.py:158-191, 214-220)
             const float tsum_f32 = (float)tumour_dose;                      // np.sum(dose*tumours) float32
-            const float ratio = __fdiv_rn(tsum_f32, tm.tumour_sum);
+            const float ratio = fdiv_rn_zero_num(tsum_f32, tm.tumour_sum);   // no dose on the tumour yet: the common case
             const float r_tumour = __fmul_rn(ratio, 10.0f);
             const double r_lung = __dmul_rn(div_shared((double)lung_count, mask_sum, rcp_mask), -1.0);
             const double reward = __dadd_rn(__dadd_rn((double)r_tumour, r_lung), r_dist);

@@ -294,7 +294,7 @@ rt_split_deposit_kernel(Tables T, EnvRec *rec, float *dose, uint32_t *valid, int
                 const int n_beams = we->n_beams;
                 const double r_dist = __dmul_rn(__ddiv_rn(sqrt(rs.best), T.gnorm), -1.0);   // environment.py:158-162
                 const float tsum_f32 = (float)tumour_dose;                 // np.sum(dose*tumours) float32
-                const float ratio = __fdiv_rn(tsum_f32, we->tumour_sum);
+                const float ratio = fdiv_rn_zero_num(tsum_f32, we->tumour_sum);
                 const float r_tumour = __fmul_rn(ratio, 10.0f);
                 const double r_lung = __dmul_rn(__ddiv_rn((double)lung_count, (double)we->lung_mask_sum), -1.0);
                 reward = __dadd_rn(__dadd_rn((double)r_tumour, r_lung), r_dist);

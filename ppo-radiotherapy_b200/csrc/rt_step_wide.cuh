@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(kWideThreads) rt_step_wide_kernel(Tables T, Sc
     const int lung_count = my->lung_count + d_cnt;
     const int t = my->t + 1, n_beams = my->n_beams;
     const float tsum_f32 = (float)tumour_dose;
-    const float ratio = __fdiv_rn(tsum_f32, __ldg(&tg->tumour_sum));
+    const float ratio = fdiv_rn_zero_num(tsum_f32, __ldg(&tg->tumour_sum));
     const float r_tumour = __fmul_rn(ratio, 10.0f);
     const double r_lung = __dmul_rn(__ddiv_rn((double)lung_count, (double)__ldg(&tg->lung_mask_sum)), -1.0);
     const double r_dist = __dmul_rn(__ddiv_rn(sqrt(best), T.gnorm), -1.0);
