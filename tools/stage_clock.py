@@ -33,3 +33,11 @@ for k in order:
     v = rel[:, :, k][ok]
     print(f"  {k:2d} {names[k]:30s} {v.mean():9.0f} {np.percentile(v,50):9.0f} {np.percentile(v,99):9.0f}")
 eng.close()
+# the block that finishes last decides the kernel: per step, the largest "end" over all envs
+end = np.where(ok, rel[:, :, 7], 0.0)
+mx = end.max(axis=1)
+am = end.argmax(axis=1)
+print(f"  slowest block per step (cycles): mean {mx.mean():.0f}  min {mx.min():.0f}  max {mx.max():.0f}")
+for k in order:
+    v = np.array([rel[i, am[i], k] for i in range(rel.shape[0])])
+    print(f"     slowest env's stamp {k:2d} {names[k]:30s} mean {v.mean():9.0f}")
