@@ -297,6 +297,20 @@ def other_kernels(rt, dev, peak):
         out.append({"kernel": "FeaturesExtractor3D forward (conv1, conv2 on tcgen05; conv3, linear cuDNN/cuBLAS)",
                     "workload": f"{n} samples", "flops": fl, "us": s * 1e6, "achieved": fl / s / 1e12, "unit": "TFLOP/s",
                     "bound": "tensor", "frac": fl / s / 1e12 / tpeak, "peak": tpeak, "us_per_sample": s * 1e6 / n})
+    # rollout body of the PPO loop for the MLP agent (train.py:139-149): policy + value forward, sampling, log-prob and
+    # rollout-buffer rows in one kernel; float32 FFMA, 2 * 10,061 flop per env against the FFMA peak of the SMs
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    fpeak = sms * 128 * 2 * 1.965e9 / 1e12
+    agent = rt.PPO((9,), (6,), 64).to(dev)
+    for n in (8192, 65536):
+        fr = rt.FusedRollout(agent, n, 4, seed=1)
+        o = torch.rand((n, 9), device=dev, generator=g) * 2 - 1
+        s = timed(lambda: fr.act(o), 50)
+        fl = n * 2.0 * 10061
+        out.append({"kernel": "rt_ppo_act_kernel", "workload": f"{n} envs, PPO MLP 9-64-64-{{6,1}} forward + Gaussian sample + log-prob",
+                    "flops": fl, "us": s * 1e6, "achieved": fl / s / 1e12, "unit": "TFLOP/s", "bound": "fp32",
+                    "frac": fl / s / 1e12 / fpeak, "peak": fpeak, "peak_source": "SMs x 128 FFMA x 2 x 1.965 GHz"})
+        del fr
     return out
 
 

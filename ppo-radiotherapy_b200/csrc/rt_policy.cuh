@@ -257,7 +257,13 @@ int rt_ppo_act(const rt_mlp_params *p, const float *obs_dev, const float *next_d
     A.obs_buf = obs_buf_dev; A.dones_buf = dones_buf_dev; A.values_buf = values_buf_dev;
     A.actions_buf = actions_buf_dev; A.logprobs_buf = logprobs_buf_dev; A.action_out = action_out_dev;
     const int tiles = (n + kPolTile - 1) / kPolTile;
-    rt_ppo_act_kernel<<<tiles < 1184 ? tiles : 1184, kPolThreads, smem, (cudaStream_t)stream>>>(A);
+    // two blocks fit an SM (97 KB of shared memory each): beyond that a block takes several tiles and stages the
+    // parameters once
+    int sms = 148, dev_id = 0;
+    cudaGetDevice(&dev_id);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev_id);
+    const int max_blocks = 2 * sms;
+    rt_ppo_act_kernel<<<tiles < max_blocks ? tiles : max_blocks, kPolThreads, smem, (cudaStream_t)stream>>>(A);
     RT_LAUNCH_CHECK("rt_ppo_act_kernel");
     return RT_OK;
 }
