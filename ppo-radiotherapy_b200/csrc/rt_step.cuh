@@ -359,6 +359,20 @@ rt_step3_kernel(Tables T, Schedule S, EnvRec *rec, float *dose, uint32_t *valid,
         }
         if (out.info)
             for (int i = lane; i < nb * RT_INFO_SIZE; i += kWarp) out.info[(size_t)env0 * RT_INFO_SIZE + i] = s_info[i];
+        if (out.done_flag) {
+            // host-buffer path: this warp wrote all of the block's outputs; make them visible to the host, count the
+            // block, and let the last block of the grid raise the host's flag
+            __threadfence_system();
+            __syncwarp();
+            if (lane == 0) {
+                const unsigned int prev = atomicAdd(out.done_counter, 1u);
+                if (prev == gridDim.x - 1) {
+                    *out.done_counter = 0u;                                // next launch counts from zero
+                    __threadfence_system();
+                    *out.done_flag = out.done_value;
+                }
+            }
+        }
         return;
     }
 

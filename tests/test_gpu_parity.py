@@ -640,3 +640,36 @@ def test_full_size_rollout_vs_oracle_4096_envs():
             worst = max(worst, float(np.abs(reward.cpu().numpy() - ref_out[t, :, 9]).max()))
     assert worst < 1e-5
     env.close()
+
+
+@pytest.mark.parametrize("flag", ["1", "0"])
+def test_host_buffer_step_matches_device_step(flag, monkeypatch):
+    """rt_step_host (pinned and pageable host buffers; completion flag polled by the host, or the stream waited for)
+    gives bit for bit what rt_step gives on device buffers: a full episode, the autoreset call and the next steps."""
+    monkeypatch.setenv("RT_HOST_FLAG", flag)
+    n, T = 333, 106
+    rng = np.random.default_rng(31)
+    acts = rng.uniform(-1, 1, (T, n, 6)).astype(np.float32)
+    sched = np.stack([(np.arange(n) * 7919) % 1000, (np.arange(n) * 104729 + 17) % 1000]).astype(np.int32)
+    a = rt.BatchedEpisodes(n, device=DEV); a.set_tumour_schedule(sched); a.reset()
+    b = rt.BatchedEpisodes(n, device=DEV); b.set_tumour_schedule(sched); b.reset()
+    pin = lambda *s, dt=torch.float32: torch.empty(s, dtype=dt, pin_memory=True)
+    h_act, h_obs, h_rew = pin(n, 6), pin(n, 9), pin(n, dt=torch.float64)
+    h_term, h_trunc, h_info = pin(n, dt=torch.uint8), pin(n, dt=torch.uint8), pin(n, nat.INFO_SIZE, dt=torch.float64)
+    p_obs, p_rew = np.empty((n, 9), np.float32), np.empty(n, np.float64)          # pageable: staged by the library
+    p_term, p_trunc = np.empty(n, np.uint8), np.empty(n, np.uint8)
+    for t in range(T):
+        obs, rew, term, trunc, info = a.step(_cuda(acts[t]), want_info=True)
+        if t % 2 == 0:
+            h_act.copy_(torch.from_numpy(acts[t]))
+            b.step_host(h_act.numpy(), h_obs.numpy(), h_rew.numpy(), h_term.numpy(), h_trunc.numpy(), h_info.numpy())
+            got = (h_obs.numpy(), h_rew.numpy(), h_term.numpy(), h_trunc.numpy())
+            assert np.array_equal(h_info.numpy().view(np.uint64), info.cpu().numpy().view(np.uint64))
+        else:
+            b.step_host(acts[t], p_obs, p_rew, p_term, p_trunc)
+            got = (p_obs, p_rew, p_term, p_trunc)
+        assert np.array_equal(got[0].view(np.uint32), obs.cpu().numpy().view(np.uint32))
+        assert np.array_equal(got[1].view(np.uint64), rew.cpu().numpy().view(np.uint64))
+        assert np.array_equal(got[2], term.cpu().numpy()) and np.array_equal(got[3], trunc.cpu().numpy())
+    assert np.array_equal(a.dose(n - 1).cpu().numpy().view(np.uint32), b.dose(n - 1).cpu().numpy().view(np.uint32))
+    a.close(); b.close()
