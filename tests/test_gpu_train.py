@@ -205,3 +205,22 @@ def test_fused_rollout_record_and_train():
         assert -200 < h[0]["episodic_return"] < 200
     # first-iteration policy is the same initial network: approx_kl of the first minibatches is tiny in both paths
     assert abs(hist[True][0]["approx_kl"]) < 0.05 and abs(hist[False][0]["approx_kl"]) < 0.05
+
+
+@pytest.mark.parametrize("n_obs,n_act,n", [(12, 4, 130), (3, 1, 64), (16, 6, 1)])
+def test_fused_rollout_other_shapes(n_obs, n_act, n):
+    """rt_ppo_act for observation / action sizes other than the radiotherapy env's (9, 6), env counts below and at a tile."""
+    torch.manual_seed(2)
+    dev = torch.device(DEV)
+    agent = rt.PPO((n_obs,), (n_act,), 64).to(dev)
+    with torch.no_grad():
+        agent.actor_logstd.uniform_(-0.5, 0.5)
+        agent.actor_mean[4].weight.mul_(20.0)
+    fr = rt.FusedRollout(agent, n, 2, seed=9)
+    obs = torch.randn((n, n_obs), device=dev)
+    a = fr.act(obs).clone()
+    with torch.no_grad():
+        _, lp, _, v = agent.get_action_and_value(obs, a)
+    torch.testing.assert_close(fr.values[0], v.flatten(), rtol=1e-5, atol=2e-6)
+    torch.testing.assert_close(fr.logprobs[0], lp, rtol=1e-5, atol=2e-4)
+    assert torch.equal(fr.actions[0], a) and torch.equal(fr.obs[0], obs) and a.shape == (n, n_act)
