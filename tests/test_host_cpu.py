@@ -141,3 +141,20 @@ def test_bench_reference_arm_contract():
     out = subprocess.run([sys.executable, bench, "--impl", "reference", "--gpus", "2", "--steps", "2", "--warmup", "1"],
                          capture_output=True, text=True, env=env, timeout=300)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_mlp_params_struct_matches_header():
+    """rt_mlp_params (include/rt_env.h) and its ctypes mirror: same fields in the same order, same size; the fused
+    rollout refuses agents the kernel does not cover (and anything on the CPU)."""
+    header = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "rt_env.h")).read()
+    body = re.search(r"typedef struct rt_mlp_params \{(.*?)\} rt_mlp_params;", header, re.S).group(1)
+    ptrs = [n for line in re.findall(r"const float \*([^;]+);", body) for n in re.split(r",\s*\*", line)]
+    ints = [n.strip() for n in re.search(r"int32_t ([^;]+);", body).group(1).split(",")]
+    assert [f[0] for f in nat.MlpParams._fields_] == ptrs + ints
+    assert ctypes.sizeof(nat.MlpParams) == 13 * 8 + 16
+    from ppo_radiotherapy_b200 import rollout
+    assert not rollout.supported(rt.PPO((9,), (6,), 64))            # CPU tensors: there is no CPU path
+    assert not rollout.supported(rt.PPO((9,), (6,), 32))
+    assert not rollout.supported(torch.nn.Linear(3, 3))
+    with pytest.raises(nat.RtError):
+        rt.FusedRollout(rt.PPO((9,), (6,), 64), 8, 4)
