@@ -341,7 +341,10 @@ def run_ours(args):
     eng.set_tumour_schedule(first[None, :])
     eng.reset()
     eng.set_tumour_schedule(None)                 # later episodes: device RNG
-    n_act = max(GRAPH_CHUNK, args.action_pool) if not args.no_graph else max(1, args.action_pool)
+    # steps per captured graph: 50, or all K timed steps when fewer are asked for (so that a short run is not measured
+    # on eager launches)
+    chunk = GRAPH_CHUNK if args.steps >= GRAPH_CHUNK else max(1, args.steps)
+    n_act = max(chunk, args.action_pool) if not args.no_graph else max(1, args.action_pool)
     gen = torch.Generator(device=dev).manual_seed(rank)
     act_pool = torch.rand((n_act, E, 6), device=dev, generator=gen) * 2 - 1
     stream = torch.cuda.Stream(dev)
@@ -359,25 +362,39 @@ def run_ours(args):
         eager(min(W, 8))
         stream.synchronize()
         if not args.no_graph:
-            n_graphs = max(1, n_act // GRAPH_CHUNK)
+            n_graphs = max(1, n_act // chunk)
             for gi in range(n_graphs):
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g, stream=stream):
-                    for j in range(GRAPH_CHUNK):
-                        eng.step(act_pool[(gi * GRAPH_CHUNK + j) % n_act], want_info=False)
+                    for j in range(chunk):
+                        eng.step(act_pool[(gi * chunk + j) % n_act], want_info=False)
                 graphs.append(g)
+            # the K % chunk steps left over at the end of the timed region get a graph of their own
+            rem_graph = None
+            if K % chunk:
+                rem_graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(rem_graph, stream=stream):
+                    for j in range(K % chunk):
+                        eng.step(act_pool[j % n_act], want_info=False)
+            # first replay of a graph uploads it: do that outside the timed region (these steps add to the warm-up)
+            for g in graphs + ([rem_graph] if rem_graph is not None else []):
+                g.replay()
+            stream.synchronize()
 
-        def run_steps(k):
+        def run_steps(k, timed=False):
             nonlocal step_idx
             if not graphs:
                 eager(k)
                 return k
             launched, gi = 0, 0
-            while k - launched >= GRAPH_CHUNK:
+            while k - launched >= chunk:
                 graphs[gi % len(graphs)].replay()
                 gi += 1
-                launched += GRAPH_CHUNK
-            eager(k - launched)
+                launched += chunk
+            if timed and rem_graph is not None and k - launched == K % chunk:
+                rem_graph.replay()
+            else:
+                eager(k - launched)
             return k
 
         run_steps(W)
@@ -390,7 +407,7 @@ def run_ours(args):
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         ev0.record(stream)
-        run_steps(K)
+        run_steps(K, timed=True)
         ev1.record(stream)
         stream.synchronize()
         barrier()
@@ -447,7 +464,7 @@ def run_ours(args):
                 "workload": f"visionless vector-env, {E} envs/GPU resident in HBM (BASELINE.json configs[1]), "
                             "uniform(-1,1) actions, autoreset included",
                 "envs_per_gpu": E, "total_envs": E * world, "parallelism": f"env-sharded x{world}, no data-path collective",
-                "launch": "eager" if not graphs else f"CUDA graphs of {GRAPH_CHUNK} steps",
+                "launch": "eager" if not graphs else f"CUDA graphs of {chunk} steps",
                 "l2": f"no flush: dose state {eng.device_bytes / 1e9:.2f} GB/GPU >> 126 MB L2 and every step writes "
                       "sectors not touched before in the episode; the env records (0.5 MB) and the sector-valid "
                       "bitmaps (13 MB) are L2-resident by design",
