@@ -15,8 +15,13 @@ envs are sharded with no data-path collective (weak scaling: E per GPU fixed).
            in, pinned host obs/reward/flags out, every step, copies inside the timed region.
 `roofline` — step kernel: algorithmic bytes (SURVEY.md §8d sector-granular S per env-step x E)
            over the average launch duration, against MEASURED_PEAKS.json hbm_gbs.
-`cpu_baseline` / --impl reference — the CPU oracle port of the reference path (oracle/rt_oracle.c,
-           the Python reference cannot travel to the GPU box) on all host cores, bounded sample.
+`cpu_baseline` / --impl reference — the UNMODIFIED Python reference (oracle/_ref, copied by oracle/build_ref.py;
+           one process per host core, one env each) on a bounded sample, `kind: "reference"`; the C port
+           (oracle/rt_oracle.c) is timed beside it (`port`).  Without oracle/_ref the port alone, `kind: "port"`.
+`ppo`    — BASELINE.json configs[2]: PPO (MLP agent) on 8,192 envs per GPU x 128 steps per iteration, fused rollout,
+           NCCL flat-gradient all-reduce per optimiser step when N > 1; steady-state env-steps/s, CUDA-event time per
+           all_reduce call, rollout / update split, replicas_identical.
+`dense`  — BASELINE.json configs[4]: RT_FLAG_DENSE full-volume dose update at 1,024 envs per GPU, HBM fraction.
 """
 import argparse
 import json
@@ -50,6 +55,8 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-buffer leg (default min(steps, 500))")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-kernels", action="store_true", help="skip the dense / voxel-obs / GAE side measurements")
+    ap.add_argument("--no-ppo", action="store_true", help="skip the PPO leg (BASELINE configs[2])")
+    ap.add_argument("--no-dense", action="store_true", help="skip the dense-mode leg (BASELINE configs[4])")
     ap.add_argument("--no-graph", action="store_true", help="launch every step from Python instead of CUDA graphs")
     ap.add_argument("--action-pool", type=int, default=128, help="distinct device-resident action batches cycled through")
     return ap.parse_args()
@@ -143,7 +150,19 @@ def cpu_rate(n_envs: int, T: int, threads: int, seed: int = 0):
     return n_envs * T / dt, dt
 
 
-def cpu_baseline(target_s: float = 15.0):
+def workload_config(E: int, world: int, dose_gb=None):
+    """The `config` object of the JSON line: the same dict in both arms (ours / reference)."""
+    return {
+        "workload": f"visionless vector-env, {E} envs/GPU resident in HBM (BASELINE.json configs[1]), "
+                    "uniform(-1,1) actions, tumour id (i*7919) mod 1000 then seeded RNG, NEXT_STEP autoreset calls "
+                    "counted in autoreset_calls_in_timed_region",
+        "envs_per_gpu": E, "total_envs": E * world, "parallelism": f"env-sharded x{world}, no data-path collective",
+        "l2": "no flush: the dose state (3.3 GB/GPU at 4096 envs) >> 126 MB L2 and every step touches sectors not "
+              "touched before in the episode; the 0.5 MB of env records are L2-resident by design",
+    }
+
+
+def port_baseline(target_s: float = 8.0):
     cores = os.cpu_count() or 1
     rate, _ = cpu_rate(cores, 20, cores)                       # calibration
     T = 101
@@ -155,28 +174,77 @@ def cpu_baseline(target_s: float = 15.0):
                       f"holds them), {dt:.1f} s on {cores} threads"}
 
 
+def reference_rate(processes: int, n_steps: int, warm: int = 3, envs_per_process: int = 1):
+    """The unmodified Python reference: `processes` vector-env loops side by side (SURVEY.md 8d CPU baseline)."""
+    from oracle import ref_runtime as R
+    rate, wall, resets = R.measure(processes, n_steps, warm=warm, envs_per_process=envs_per_process)
+    return rate, wall, resets
+
+
+def cpu_baseline(target_s: float = 12.0):
+    """Bounded CPU sample for the `cpu_baseline` key of our line: the Python reference on every host core (and on
+    one), the C port beside it."""
+    from oracle import ref_runtime as R
+    cores = os.cpu_count() or 1
+    port = port_baseline()
+    if not R.available():
+        port["note"] = "oracle/_ref (Python reference) or SciPy absent on this box: C port only"
+        return port
+    r1, w1, _ = reference_rate(1, 300)                          # reference single-env CPU path
+    n_steps = int(max(101, min(2000, r1 * 0.6 * target_s)))     # per process; all cores are slower per core than one
+    rp, wp, resets = reference_rate(cores, n_steps)
+    return {"value": rp, "unit": "env-steps/s", "cores": cores, "kind": "reference",
+            "sample": f"unmodified environment.py/draw_line.py/transforms.py (oracle/_ref): {cores} processes x 1 env x "
+                      f"{n_steps} vector-env calls incl. {resets} autoreset calls, {wp:.1f} s; BLAS threads 1",
+            "single_process": {"value": r1, "cores": 1, "sample": f"1 process x 1 env x 300 calls, {w1:.1f} s"},
+            "port": port}
+
+
 def run_reference(args):
-    """--impl reference: the reference's CPU path (oracle port) on all host cores; rank 0 only."""
+    """--impl reference: the reference's own CPU implementation of the path on all host cores; rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    from oracle import ref_runtime as R
     cores = os.cpu_count() or 1
     K, W = args.steps, args.warmup
-    rate, _ = cpu_rate(cores, 20, cores)
-    # K timed "steps", each over a bounded sample of n envs of the 4096-env workload, sized for <= ~120 s
-    n = int(max(cores, min(args.envs_per_gpu, rate * 120.0 / max(K + W, 1))))
-    n = max(cores, (n // cores) * cores)
-    cpu_rate(n, max(W, 1), cores, seed=2)                      # warm-up (page-in, thread pool)
-    rate, dt = cpu_rate(n, K, cores, seed=3)
-    sample = (f"{n} of {args.envs_per_gpu} envs per step x {K} steps (oracle/rt_oracle.c port of environment.py/"
-              f"draw_line.py/transforms.py; the Python reference cannot travel to the GPU box)")
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    if R.available():
+        # a "step" = one vector-env call over a bounded sample of n = cores x m envs of the 4096-env workload (each
+        # process steps its m envs serially, as SyncVectorEnv does); m and the timed steps are sized for ~30 s
+        r1, _, _ = reference_rate(1, 200)
+        per_proc = r1 * 0.5                                       # all cores busy: slower per core than one process
+        m = int(max(1, min(32, per_proc * 30.0 / max(K + W, 1))))
+        k_run = int(max(1, min(K, per_proc * 100.0 / m)))
+        rate, wall, resets = reference_rate(cores, k_run, warm=max(1, min(W, 20)), envs_per_process=m)
+        kind = "reference"
+        n = cores * m
+        sample = (f"unmodified Python reference (oracle/_ref: environment.py, draw_line.py, transforms.py): {n} of "
+                  f"{args.envs_per_gpu} envs per step ({cores} processes, one per host core, x {m} envs), {k_run} of {K} "
+                  f"steps timed ({resets} autoreset calls), {wall:.1f} s")
+        port = port_baseline()
+        dt_per_step = wall / k_run
+    else:
+        rate0, _ = cpu_rate(cores, 20, cores)
+        n = int(max(cores, min(args.envs_per_gpu, rate0 * 120.0 / max(K + W, 1))))
+        n = max(cores, (n // cores) * cores)
+        cpu_rate(n, max(W, 1), cores, seed=2)                  # warm-up (page-in, thread pool)
+        rate, dt = cpu_rate(n, K, cores, seed=3)
+        kind, port = "port", None
+        sample = (f"{n} of {args.envs_per_gpu} envs per step x {K} steps (oracle/rt_oracle.c port of environment.py/"
+                  f"draw_line.py/transforms.py; oracle/_ref or SciPy absent on this box)")
+        dt_per_step = dt / K
+    cb = {"value": rate, "unit": "env-steps/s", "cores": cores, "kind": kind, "sample": sample}
+    if port is not None:
+        cb["port"] = port
     line = {
         "impl": "reference", "metric": "env-steps/sec", "value": rate, "unit": "env-steps/s", "n_gpus": args.gpus,
-        "steps": K, "warmup": W, "ms_per_step": dt / K * 1e3, "higher_is_better": True, "scaling": "weak",
+        "steps": K, "warmup": W, "ms_per_step": dt_per_step * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32/f64", "data": "synthetic",
-        "config": {"workload": "visionless vector-env, 4096 envs/GPU (BASELINE.json configs[1]); CPU port on a "
-                               f"bounded sample of {n} envs per step", "envs_per_step_sample": n},
-        "cpu_baseline": {"value": rate, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": workload_config(args.envs_per_gpu, world),
+        "envs_per_step_sample": n,
+        "note": "one host runs this arm whatever N is: at N > 1 the ratio compares N GPUs x 4096 envs with the CPUs of one box",
+        "cpu_baseline": cb,
         "e2e": {"value": rate, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -314,15 +382,93 @@ def other_kernels(rt, dev, peak):
     return out
 
 
+def ppo_leg(rt, torch, dist, dev, world, rank, envs_per_gpu=8192, num_steps=128, iterations=8, steady=5):
+    """BASELINE.json configs[2]: CleanRL-style PPO (reference train.py:91-282) with the MLP agent on `envs_per_gpu`
+    envs per rank x `num_steps` steps per iteration, fused rollout step, one NCCL all-reduce of the flat gradient per
+    optimiser step (reference train.py:246-247 is where it goes).  Steady state = the last `steady` iterations, timed
+    with CUDA events from the first rollout step to the last optimiser step, max over ranks."""
+    from ppo_radiotherapy_b200.train import load_config, train
+    total = envs_per_gpu * world
+    cfg = load_config(None, num_envs=total, num_steps=num_steps, num_minibatches=4, update_epochs=2,
+                      total_timesteps=total * num_steps * iterations, num_saves=0, save_model=False, seed=1, visionless=True)
+    torch.manual_seed(1 + rank)
+    prof = {}
+    agent = train(cfg, None, dev, None, "bench", log=None, profile=prof)
+    flat = torch.cat([p.detach().reshape(-1) for p in agent.parameters()])
+    same = True
+    if world > 1:
+        ref = flat.clone()
+        dist.broadcast(ref, 0)
+        t = torch.tensor([int(torch.equal(ref, flat))], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        same = bool(t.item())
+    it = torch.tensor([sum(prof["iter_ms"][-steady:]), sum(prof["rollout_ms"][-steady:]), sum(prof["update_ms"][-steady:])],
+                      dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(it, op=dist.ReduceOp.MAX)
+    ar = sorted(prof["allreduce_us"][len(prof["allreduce_us"]) // 2:])
+    h = agent.history
+    out = {
+        "workload": f"PPO, MLP agent, {total} envs = {world} x {envs_per_gpu}, {num_steps} steps per iteration, 2 epochs x 4 "
+                    f"minibatches (BASELINE.json configs[2]); {steady} steady iterations of {iterations}",
+        "value": steady * total * num_steps / (float(it[0]) * 1e-3), "unit": "env-steps/s",
+        "iter_ms": float(it[0]) / steady, "rollout_ms": float(it[1]) / steady, "update_ms": float(it[2]) / steady,
+        "fused_rollout": bool(prof.get("fused_rollout")),
+        "allreduce": None if world == 1 else {
+            "calls_per_iteration": len(prof["allreduce_us"]) // max(1, iterations), "elements": int(flat.numel()),
+            "bytes": int(flat.numel()) * 4, "us_median": ar[len(ar) // 2] if ar else None,
+            "us_p90": ar[int(len(ar) * 0.9)] if ar else None, "backend": "nccl", "timed": "CUDA events around dist.all_reduce"},
+        "replicas_identical": same,
+        "episodic_return_first_last": [h[0].get("episodic_return"), h[-1].get("episodic_return")],
+    }
+    del agent
+    return out
+
+
+def dense_leg(rt, torch, dist, dev, world, rank, peak, n=1024, reps=20):
+    """BASELINE.json configs[4]: dose-grid stress — RT_FLAG_DENSE handles read and write every dose volume every step
+    (the reference's own dataflow, environment.py:107-110, 164-191), random tumours from the bundled table, `n` envs
+    per GPU, no collective.  CUDA events, max over ranks."""
+    de = rt.BatchedEpisodes(n, device=dev, dense=True, seed=3 + rank)
+    de.reset()
+    g = torch.Generator(device=dev).manual_seed(100 + rank)
+    acts = [torch.rand((n, 6), device=dev, generator=g) * 2 - 1 for _ in range(8)]
+    for i in range(3):
+        de.step(acts[i], want_info=False)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(reps):
+        de.step(acts[i % 8], want_info=False)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    s = float(t[0]) * 1e-3 / reps
+    b = n * 2 * de.nvox * 4
+    de.close()
+    return {"workload": f"dense mode (RT_FLAG_DENSE), {n} envs/GPU x {world} GPUs, full-volume dose update + from-scratch "
+                        "reductions every step (BASELINE.json configs[4])",
+            "value": n * world / s, "unit": "env-steps/s", "us_per_step": s * 1e6, "bytes_per_gpu_step": b,
+            "achieved_gbs_per_gpu": b / s / 1e9, "frac": b / s / 1e9 / peak, "working_set": f"{b / 2e9:.2f} GB/GPU >> L2"}
+
+
 def run_ours(args):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    # the CPU arm forks worker processes: run it before this process creates a CUDA context
+    cpu_line = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_line = cpu_baseline()
+
     import torch
     import torch.distributed as dist
     import ppo_radiotherapy_b200 as rt
     from ppo_radiotherapy_b200 import _native as nat
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl ours needs a CUDA device (there is no CPU fallback)")
     torch.cuda.set_device(local)
@@ -399,6 +545,7 @@ def run_ours(args):
 
         run_steps(W)
         barrier()
+        episodes0 = int(eng.counters()[:, 3].sum().item())
         sampler = ClockSampler(local)
         if rank == 0:
             sampler.start()
@@ -413,6 +560,8 @@ def run_ours(args):
         barrier()
         ms = ev0.elapsed_time(ev1)
         eager_launches = nat.launch_count() - launches0
+        # every autoreset call of an env starts an episode: calls of the timed region that were resets, per env
+        autoreset_calls = (int(eng.counters()[:, 3].sum().item()) - episodes0) / float(E)
         # kernels per rt_step call (1 for the fused step kernel, 2 for the pose + deposit variant), counted by the
         # library on one eager call after the timed region; graph replays re-issue the captured launches
         l0 = nat.launch_count()
@@ -420,7 +569,7 @@ def run_ours(args):
         stream.synchronize()
         per_step = nat.launch_count() - l0
         gpu_launches = K * per_step
-        step_kernel = "rt_step3_kernel" if per_step == 1 else "rt_split_pose_kernel + rt_split_deposit_kernel"
+        step_kernel = "rt_step3_kernel"
 
         # ---- e2e: host buffers through rt_step_host, every step --------------------------------
         Ke = args.e2e_steps or min(K, 500)
@@ -460,15 +609,10 @@ def run_ours(args):
             "metric": "env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32/f64", "data": "synthetic",
-            "config": {
-                "workload": f"visionless vector-env, {E} envs/GPU resident in HBM (BASELINE.json configs[1]), "
-                            "uniform(-1,1) actions, autoreset included",
-                "envs_per_gpu": E, "total_envs": E * world, "parallelism": f"env-sharded x{world}, no data-path collective",
-                "launch": "eager" if not graphs else f"CUDA graphs of {chunk} steps",
-                "l2": f"no flush: dose state {eng.device_bytes / 1e9:.2f} GB/GPU >> 126 MB L2 and every step writes "
-                      "sectors not touched before in the episode; the env records (0.5 MB) and the sector-valid "
-                      "bitmaps (13 MB) are L2-resident by design",
-            },
+            "config": workload_config(E, world),
+            "launch": "eager" if not graphs else f"CUDA graphs of {chunk} steps",
+            "autoreset_calls_in_timed_region": autoreset_calls,
+            "state_gb_per_gpu": eng.device_bytes / 1e9,
             "roofline": {
                 "kernel": step_kernel, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": measured_traffic() if E == 4096 else None, "peak_source": peak_src,
@@ -481,10 +625,18 @@ def run_ours(args):
             "gpu_launches": gpu_launches,
             "clocks": clocks,
         }
-        if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline()
+        if cpu_line is not None:
+            line["cpu_baseline"] = cpu_line
     eng.close()
+    del act_pool, graphs
+    torch.cuda.empty_cache()
+    peak_all, _ = hbm_peak()
+    # BASELINE.json configs[2] and configs[4] at this N (every rank takes part; rank 0 reports)
+    ppo = None if args.no_ppo else ppo_leg(rt, torch, dist, dev, world, rank)
+    dense = None if args.no_dense else dense_leg(rt, torch, dist, dev, world, rank, peak_all)
     if rank == 0:
+        line["ppo"] = ppo
+        line["dense"] = dense
         if world == 1 and not args.no_other_kernels:
             line["other_kernels"] = other_kernels(rt, dev, peak)
         print(json.dumps(line))

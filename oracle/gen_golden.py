@@ -13,6 +13,9 @@ file).  Re-run:  python oracle/gen_golden.py
   tiny.npz        synthetic few-voxel tumours that terminate early (full irradiation)
   resets.npz (G4) reset observation for every tumour
   gae.npz    (G3) train.py:164-181 on random tensors (CPU torch)
+  stress.npz      240 synthetic 16-64-voxel tumours with homing actions: the dose ratio crosses the 0.9
+                  termination threshold (environment.py:184-191) on most of them, many within a few ulp
+  trajectory.npz  RadiotherapyEnv.export_trajectory (environment.py:69-75): keys, shapes, dtypes, content
 """
 import os
 import sys
@@ -311,6 +314,120 @@ def gen_tiny(ns, T=100):
     print("tiny.npz: lengths", length.tolist())
 
 
+def stress_tumours(n=240, seed=5):
+    """Tube-shaped tumours in the plane of the start beam (axis-0 index 33; the beam starts at (33.5, 21.5, 35)
+    pointing along axis 1 and, through the axis quirk of draw_line.py:88-90, deposits on plane 33 only): L columns
+    along axis 1 times 2-4 rows along axis 2, some thinned out; 16-64 voxels each."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for e in range(n):
+        L = int(rng.integers(8, 33))
+        y0 = int(rng.integers(1, 43 - L - 1))
+        rows = [35, 36] if e % 3 else [34, 35, 36, 37][:int(rng.integers(2, 5))]
+        idx = sorted(set(((33 * 43 + y) * 70 + c) for y in range(y0, y0 + L) for c in rows))
+        if e % 5 == 0:
+            idx = sorted(set(idx[::2] + idx[1::4]))
+        if len(idx) > 64:
+            idx = idx[:64]
+        out.append(np.array(idx, dtype=np.int32))
+    return out
+
+
+def gen_stress(ns, T=48):
+    """The termination threshold under stress: the reference's own `done` flags and rewards on
+    tumours of 16-64 voxels whose dose ratio climbs by ~0.05 per beam and crosses 0.9 around beam 18 — for the
+    parked beams exactly at the knife edge (ratios 0.8999999 / 0.9 / 0.90000004), where a different summation
+    order of np.sum(dose * tumours) (environment.py:166,186) flips the flag."""
+    import shutil
+    import tempfile
+    lungs = np.load(os.path.join(ref_harness.REF_ROOT, "data", "lungs.npy"))
+    tumours = stress_tumours()
+    E = len(tumours)
+    root = tempfile.mkdtemp(prefix="rt_stress_")
+    os.makedirs(os.path.join(root, "data", "tumours"))
+    np.save(os.path.join(root, "data", "lungs.npy"), lungs)
+    rng = np.random.default_rng(17)
+    acts = np.zeros((E, T, 6), dtype=np.float32)
+    rec = np.zeros((E, T, 20))
+    done = np.zeros((E, T), dtype=np.int8)
+    length = np.zeros(E, dtype=np.int32)
+    ratio = np.zeros((E, T), dtype=np.float32)
+    old_root = ref_harness.REF_ROOT
+    near = 0
+    try:
+        for e, lin in enumerate(tumours):
+            t = np.zeros(int(np.prod(G)), dtype=np.float32)
+            t[lin] = 1.0
+            fname = f"0.0_0.0_0.0_0.01_stress{e}.npy"
+            np.save(os.path.join(root, "data", "tumours", fname), t.reshape(tuple(G)))
+            ref_harness.REF_ROOT = root
+            try:
+                env = ref_harness.RefEnv(visionless=True, tumour_name=fname)
+                env.reset()
+            finally:
+                ref_harness.REF_ROOT = old_root
+            for s in range(T):
+                p = env.env.beam_position
+                a = np.zeros(6, dtype=np.float32)
+                target = 35.0 + rng.uniform(0.05, 0.95)          # stay between rows 35 and 36 of axis 2
+                a[2] = np.float32((target - p[2]) / 14.0)
+                if e % 2:
+                    a[3] = np.float32(rng.uniform(-0.004, 0.004))    # tilt the beam in the plane
+                if e % 7 == 3:
+                    a[1] = np.float32(rng.uniform(-0.01, 0.01))
+                acts[e, s] = a
+                obs, reward, dn, _, info = env.step(a)
+                r = rec[e, s]
+                r[0:9] = obs
+                r[9] = reward
+                rc = info["reward_components"]
+                r[10], r[11], r[12] = rc["tumour"], rc["lung"], rc["distance_to_tumour"]
+                r[13], r[14] = info["doses"]["tumour"], info["doses"]["lung"]
+                r[15:18] = info["overshoot"]["translation"]
+                r[18] = info["overshoot"]["rotation"]
+                inner = env.env
+                mask = inner.lungs * (1 - inner.tumours)
+                r[19] = np.sum(inner.dose * mask > inner.LUNG_DOSE_THRESHOLD)
+                ratio[e, s] = np.sum(inner.dose * inner.tumours) / np.sum(inner.tumours)   # environment.py:186-189
+                near += int(abs(float(ratio[e, s]) - 0.9) < 2e-6)
+                done[e, s] = dn
+                length[e] = s + 1
+                if dn:
+                    break
+    finally:
+        shutil.rmtree(root, ignore_errors=True)
+    off = np.concatenate([[0], np.cumsum([len(v) for v in tumours])]).astype(np.int32)
+    np.savez_compressed(os.path.join(OUT, "stress.npz"), vox_off=off, vox=np.concatenate(tumours), actions=acts,
+                        rec=rec, done=done, length=length, ratio=ratio, versions=versions())
+    early = int((done.sum(axis=1) > 0).sum())
+    print(f"stress.npz: {E} tumours, {early} terminate before step {T}, {near} steps within 2e-6 of the threshold; "
+          f"length histogram {np.bincount(length).tolist()}")
+
+
+def gen_trajectory(ns, phantom_names, steps=12):
+    """environment.py:69-75 export_trajectory after `steps` beams: what the reference writes."""
+    import tempfile
+    tid = 123
+    rng = np.random.default_rng(23)
+    acts = rng.uniform(-1, 1, (steps, 6)).astype(np.float32)
+    env = ref_harness.RefEnv(visionless=True, tumour_name=phantom_names[tid])
+    env.reset()
+    for a in acts:
+        env.step(a)
+    path = os.path.join(tempfile.mkdtemp(prefix="rt_traj_"), "traj.npz")
+    env.env.export_trajectory(path)
+    z = np.load(path)
+    keys = sorted(z.files)
+    dose = z["dose"].reshape(-1)
+    nz = np.flatnonzero(dose)
+    np.savez_compressed(os.path.join(OUT, "trajectory.npz"), tumour_id=np.int32(tid), actions=acts,
+                        keys=np.array(keys), shapes=np.array([str(tuple(z[k].shape)) for k in keys]),
+                        dtypes=np.array([str(z[k].dtype) for k in keys]), beams=z["beams"],
+                        tumours_nz=np.flatnonzero(z["tumours"].reshape(-1)).astype(np.int32),
+                        dose_idx=nz.astype(np.int32), dose_val=dose[nz], versions=versions())
+    print("trajectory.npz:", keys, [tuple(z[k].shape) for k in keys], [str(z[k].dtype) for k in keys])
+
+
 def gen_resets(ns, phantom_names):
     obs = np.zeros((len(phantom_names), 9))
     env = ref_harness.RefEnv(visionless=True, tumour_name=phantom_names[0])
@@ -360,7 +477,7 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     ns = ref_harness.load()
     names = [str(x) for x in np.load(os.path.join(REPO, "ppo-radiotherapy_b200", "data", "phantom.npz"))["names"]]
-    which = sys.argv[1:] or ["beams", "poses", "steps", "tiny", "resets", "gae"]
+    which = sys.argv[1:] or ["beams", "poses", "steps", "tiny", "resets", "gae", "stress", "trajectory"]
     if "beams" in which:
         gen_beams(ns)
     if "poses" in which:
@@ -373,6 +490,10 @@ def main():
         gen_resets(ns, names)
     if "gae" in which:
         gen_gae()
+    if "stress" in which:
+        gen_stress(ns)
+    if "trajectory" in which:
+        gen_trajectory(ns, names)
 
 
 if __name__ == "__main__":

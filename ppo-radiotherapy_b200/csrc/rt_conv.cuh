@@ -9,19 +9,9 @@
 //
 // Implicit GEMM without im2col.  Per sample and output depth d the GEMM is
 //     Y[f][co] = sum_{kd,kh,kw,c} X[d+kd][h+kh][w+kw][c] * Wt[co][c][kd][kh][kw],      f = h*W + w
-// Input depth planes live in shared memory channels-last with the 4 channels padded to 8 bf16 = 16 bytes per
-// voxel.  Row f of the A operand for the K-slice (kd, kh, kw in {2q, 2q+1}) is then the 32 contiguous bytes
-// of voxels f + kh*W + 2q and +1 of plane d+kd: consecutive rows are consecutive 16-byte chunks, so ldmatrix
-// fetches A straight out of the plane (a Toeplitz view of it) and nothing is ever gathered.  K per (kd, kh)
-// is 2 chunks x 16 (kw = 0,1 | kw = 2 and a zero-weight column), 18 chunks in all.  Flattening (h, w) into f
-// makes positions with w >= W-2 or h >= H-2 wrap around; they are computed and discarded (7 %).
-// mma.sync m16n8k16 bf16 with float32 accumulation; the kernel is bound by shared-memory operand reads
-// (N = 16 output channels is too narrow for the MMA itself to matter).
-//
-// Epilogue in registers: + bias, ReLU, max over the w pair by shuffle, staged per plane in shared memory,
-// then max over the h pair and over the two planes of a depth window (the odd plane's partial result waits in
-// registers), written bf16 NCDHW.  ReLU and max commute, so pooling max(0, .) values equals the reference's
-// ReLU -> MaxPool; the implicit -inf padding of MaxPool3d is "ignore".
+// Flattening (h, w) into f makes positions with w >= W-2 or h >= H-2 wrap around; they are computed and discarded
+// (7 %).  ReLU and max commute, so pooling max(0, .) values equals the reference's ReLU -> MaxPool; the implicit
+// -inf padding of MaxPool3d is "ignore".  The kernel is described where it is defined (rt_conv1_tc_kernel).
 // (included at the end of rt_env.cu: the from-env variant of the first block reads the env records, dose volumes
 // and tables defined there)
 #pragma once
@@ -30,11 +20,7 @@
 
 namespace {
 
-constexpr int kThreads = 256;
-constexpr int kWarps = kThreads / 32;
 constexpr int kCin = 4, kCout = 16;
-constexpr int kChunks = 18;            // (kd, kh) x {kw 0-1, kw 2-pad}
-constexpr int kMaxStash = 48;          // pooled elements per thread kept across the two planes of a depth window
 
 struct ConvShape {
     int D, H, W;          // input
@@ -56,197 +42,8 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b)
     return *reinterpret_cast<uint32_t *>(&v);
 }
 
-// B fragments of mma.m16n8k16 (col-major K x N), one K-chunk of 16 = 2 voxels x 8 channel slots:
-// frag[chunk][ntile][lane][2]; b0 holds k = (lane%4)*2 + {0,1}, b1 holds k + 8; n = ntile*8 + lane/4.
-__global__ void rt_conv_prepare_kernel(const float *__restrict__ weight, uint32_t *__restrict__ frag)
-{
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= kChunks * 2 * 32) return;
-    const int lane = idx & 31, ntile = (idx >> 5) & 1, chunk = idx >> 6;
-    const int kd = chunk / 6, kh = (chunk / 2) % 3, q = chunk & 1;
-    const int n = ntile * 8 + lane / 4;
-    uint32_t regs[2];
-#pragma unroll
-    for (int half = 0; half < 2; half++) {              // b0: first voxel of the pair (kw = 2q), b1: second (kw = 2q+1)
-        const int kw = 2 * q + half;
-        float v[2];
-#pragma unroll
-        for (int e = 0; e < 2; e++) {
-            const int c = (lane % 4) * 2 + e;           // channel slot 0..7, slots 4..7 are zero padding
-            v[e] = (c < kCin && kw < 3) ? weight[(((n * kCin + c) * 3 + kd) * 3 + kh) * 3 + kw] : 0.0f;
-        }
-        regs[half] = pack_bf16(v[0], v[1]);
-    }
-    frag[idx * 2 + 0] = regs[0];
-    frag[idx * 2 + 1] = regs[1];
-}
-
-__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t smem_addr)
-{
-    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];\n"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
-                 : "r"(smem_addr));
-}
-
-__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1)
-{
-    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
-                 "{%0, %1, %2, %3};\n"
-                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-
-// One block per (sample, chunk of pooled depth planes).
-__global__ void __launch_bounds__(kThreads, 1) rt_conv1_kernel(ConvShape S, int n_samples, int chunks,
-                                                               int pooled_per_chunk, const float *__restrict__ x,
-                                                               const uint32_t *__restrict__ wfrag,
-                                                               const float *__restrict__ bias,
-                                                               __nv_bfloat16 *__restrict__ out)
-{
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    uint4 *planes = reinterpret_cast<uint4 *>(smem_raw);                              // 3 x [plane_vox] x 16 B
-    __nv_bfloat16 *R = reinterpret_cast<__nv_bfloat16 *>(planes + 3 * (size_t)S.plane_vox);   // [Ho][Pw][16]
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int sample = blockIdx.x / chunks, chunk = blockIdx.x % chunks;
-    if (sample >= n_samples) return;
-
-    // depth range of this block: pooled planes [p_lo, p_hi) <- conv planes [d_lo, d_hi)
-    const int p_lo = chunk * pooled_per_chunk;
-    const int p_hi = min(S.Pd, p_lo + pooled_per_chunk);
-    if (p_lo >= p_hi) return;
-    const int d_lo = max(0, 2 * p_lo - S.pd);
-    const int d_hi = min(S.Do, 2 * p_hi - S.pd);
-
-    uint32_t breg[kChunks][2][2];
-#pragma unroll
-    for (int c = 0; c < kChunks; c++)
-#pragma unroll
-        for (int nt = 0; nt < 2; nt++) {
-            const uint2 v = *reinterpret_cast<const uint2 *>(wfrag + ((size_t)(c * 2 + nt) * 32 + lane) * 2);
-            breg[c][nt][0] = v.x;
-            breg[c][nt][1] = v.y;
-        }
-    float bv[2][2];                                    // bias of this lane's 4 channels
-#pragma unroll
-    for (int nt = 0; nt < 2; nt++)
-#pragma unroll
-        for (int e = 0; e < 2; e++) bv[nt][e] = bias[nt * 8 + (lane % 4) * 2 + e];
-
-    const int HW = S.H * S.W;
-    const float *xs = x + (size_t)sample * kCin * S.D * HW;
-    // zero the buffers once: the halo tail of a plane is read (times a zero weight, or for discarded rows)
-    for (int i = tid; i < 3 * S.plane_vox; i += kThreads) planes[i] = make_uint4(0u, 0u, 0u, 0u);
-    __syncthreads();
-
-    auto load_plane = [&](int dz) {                    // input depth plane dz -> buffer dz % 3, channels-last bf16
-        uint4 *dst = planes + (size_t)(dz % 3) * S.plane_vox;
-        const float *src = xs + (size_t)dz * HW;
-        for (int v = tid; v < HW; v += kThreads) {
-            const float c0 = __ldg(src + v), c1 = __ldg(src + (size_t)S.D * HW + v);
-            const float c2 = __ldg(src + (size_t)2 * S.D * HW + v), c3 = __ldg(src + (size_t)3 * S.D * HW + v);
-            dst[v] = make_uint4(pack_bf16(c0, c1), pack_bf16(c2, c3), 0u, 0u);
-        }
-    };
-    load_plane(d_lo);
-    load_plane(d_lo + 1);
-
-    const uint32_t planes_addr = (uint32_t)__cvta_generic_to_shared(planes);
-    const int pooled_elems = S.Ph * S.Pw * kCout;
-    float stash[kMaxStash];
-#pragma unroll
-    for (int i = 0; i < kMaxStash; i++) stash[i] = 0.0f;
-    // ldmatrix row of this lane: matrix j = lane/8 -> rows (j&1)*8 + lane%8 of the m16 tile, voxel shift j>>1
-    const int lrow = ((lane >> 3) & 1) * 8 + (lane & 7);
-    const int lshift = lane >> 4;
-
-    for (int d = d_lo; d < d_hi; d++) {
-        load_plane(d + 2);
-        __syncthreads();                               // planes d, d+1, d+2 are in shared memory; R is free
-
-        for (int t = warp; t < S.tiles; t += kWarps) {
-            float acc[2][2][4];
-#pragma unroll
-            for (int mi = 0; mi < 2; mi++)
-#pragma unroll
-                for (int nt = 0; nt < 2; nt++)
-#pragma unroll
-                    for (int e = 0; e < 4; e++) acc[mi][nt][e] = 0.0f;
-            const int f0 = t * 32;
-#pragma unroll
-            for (int c = 0; c < kChunks; c++) {
-                const int kd = c / 6, kh = (c / 2) % 3, q = c & 1;
-                const uint32_t base = planes_addr +
-                                      (uint32_t)((((d + kd) % 3) * S.plane_vox + f0 + kh * S.W + 2 * q + lrow + lshift) * 16);
-#pragma unroll
-                for (int mi = 0; mi < 2; mi++) {
-                    uint32_t a[4];
-                    ldmatrix_x4(a, base + mi * 16 * 16);
-                    mma_bf16(acc[mi][0], a, breg[c][0][0], breg[c][0][1]);
-                    mma_bf16(acc[mi][1], a, breg[c][1][0], breg[c][1][1]);
-                }
-            }
-            // epilogue: rows lane/4 (+8) of each m16 tile, channels nt*8 + (lane%4)*2 + {0,1}
-#pragma unroll
-            for (int mi = 0; mi < 2; mi++)
-#pragma unroll
-                for (int half = 0; half < 2; half++) {
-                    const int f = f0 + mi * 16 + half * 8 + lane / 4;
-                    const int h = fastdiv(f, S.mW), w = f - h * S.W;
-                    float v[2][2];
-#pragma unroll
-                    for (int nt = 0; nt < 2; nt++)
-#pragma unroll
-                        for (int e = 0; e < 2; e++) v[nt][e] = fmaxf(acc[mi][nt][half * 2 + e] + bv[nt][e], 0.0f);
-                    // max over the w pair (w even, w+1): the odd position is 4 lanes up (W is even, f0 is even)
-#pragma unroll
-                    for (int nt = 0; nt < 2; nt++)
-#pragma unroll
-                        for (int e = 0; e < 2; e++) {
-                            const float o = __shfl_down_sync(0xffffffffu, v[nt][e], 4);
-                            if (w + 1 < S.Wo) v[nt][e] = fmaxf(v[nt][e], o);
-                        }
-                    if ((w & 1) == 0 && w < S.Wo && h < S.Ho) {
-                        __nv_bfloat16 *dst = R + ((size_t)h * S.Pw + (w >> 1)) * kCout + (lane % 4) * 2;
-                        *reinterpret_cast<uint32_t *>(dst) = pack_bf16(v[0][0], v[0][1]);
-                        *reinterpret_cast<uint32_t *>(dst + 8) = pack_bf16(v[1][0], v[1][1]);
-                    }
-                }
-        }
-        __syncthreads();                               // R holds ReLU(conv) of plane d, max-pooled along w
-
-        // max over the h pair, then over the two planes of the depth window
-        const int pdx = (d + S.pd) >> 1;
-        const int first = 2 * pdx - S.pd;              // first conv plane of the window (may be -1)
-        const bool is_first = d == first;
-        const bool has_second = first + 1 < S.Do;
-        const bool has_first = first >= 0;
-#pragma unroll
-        for (int i = 0; i < kMaxStash; i++) {
-            const int e = tid + i * kThreads;
-            if (e < pooled_elems) {
-                const int ch = fastdiv(e, S.mPhPw), rem = e - ch * (S.Ph * S.Pw);
-                const int py = fastdiv(rem, S.mPw), px = rem - py * S.Pw;
-                const int h0 = 2 * py - S.ph;
-                float m = 0.0f;                        // every candidate is >= 0 after ReLU
-                if (h0 >= 0 && h0 < S.Ho) m = __bfloat162float(R[((size_t)h0 * S.Pw + px) * kCout + ch]);
-                if (h0 + 1 >= 0 && h0 + 1 < S.Ho) m = fmaxf(m, __bfloat162float(R[((size_t)(h0 + 1) * S.Pw + px) * kCout + ch]));
-                if (is_first && has_second) {
-                    stash[i] = m;
-                } else {
-                    if (!is_first && has_first) m = fmaxf(m, stash[i]);
-                    out[(((size_t)sample * kCout + ch) * S.Pd + pdx) * (S.Ph * S.Pw) + rem] = __float2bfloat16(m);
-                }
-            }
-        }
-        // the next iteration's load_plane(d + 3) overwrites buffer d % 3 and the tiles overwrite R: both are
-        // only touched after the __syncthreads() that follows that load, and every thread is past its reads here
-        __syncthreads();
-    }
-}
-
-
 // ---------------------------------------------------------------------------------------------------------
-// The same block on the 5th-generation tensor cores (tcgen05): accumulators in tensor memory, operands read
+// The block on the 5th-generation tensor cores (tcgen05): accumulators in tensor memory, operands read
 // from shared memory through matrix descriptors, one thread issues the MMAs.
 //
 // Two conv planes at a time.  A pool window is the conv-plane pair (d0, d0+1), which reads the input planes
@@ -1011,7 +808,6 @@ static int conv1_launch(const float *x_dev, const float *weight_dev, const float
     S.Pw = (S.Wo - 2) / 2 + 1;
     S.tiles = (H * W + 31) / 32;
     S.plane_vox = S.tiles * 32 + 2 * W + 8;                         // rows read up to f + 2W + 3 (+1 for the voxel pair)
-    if (S.Ph * S.Pw * kCout > kMaxStash * kThreads) return RT_ERR_INVALID;
     auto magic = [](int d) { return d == 1 ? 0u : (uint32_t)(((1ull << 32) + (uint64_t)d - 1) / (uint64_t)d); };
     S.mW = magic(W);
     S.mPw = magic(S.Pw);
@@ -1028,9 +824,8 @@ static int conv1_launch(const float *x_dev, const float *weight_dev, const float
     const int per = (S.Pd + chunks - 1) / chunks;
     chunks = (S.Pd + per - 1) / per;
 
-    // tcgen05 path: 128-row tiles through a ring of tensor-memory slots (RT_CONV_MMA_SYNC=1 selects the
-    // mma.sync kernel instead; planes too large for three pair buffers in shared memory fall back to it as well)
-    static const bool force_sync = getenv("RT_CONV_MMA_SYNC") && atoi(getenv("RT_CONV_MMA_SYNC")) != 0;
+    // 128-row tiles through a ring of tensor-memory slots; a plane too large for three pair buffers in shared memory
+    // is not covered (RT_ERR_INVALID: the caller decides what to do, there is no second kernel)
     const int tiles128 = (H * W + kTcTileRows - 1) / kTcTileRows;
     ConvShape T = S;
     T.tiles = tiles128;
@@ -1038,7 +833,8 @@ static int conv1_launch(const float *x_dev, const float *weight_dev, const float
     const size_t smem_tc = (size_t)3 * T.plane_vox * 16 + (size_t)T.r_elems * sizeof(__nv_bfloat16) +
                            (size_t)kTcMmas * kBMmaBytes + (2 * kTcSlots + 6) * 8 + 16 +
                            (size_t)kHashSlots * 8 + 2 * sizeof(RayWork) + 3328;    // + from-env: view hash, rays, hit-sector bits
-    if (!force_sync && smem_tc <= (size_t)max_smem && (size_t)3 * T.plane_vox * 16 < (1u << 18) && W * 16 < (1 << 18)) {
+    if (smem_tc > (size_t)max_smem || (size_t)3 * T.plane_vox * 16 >= (1u << 18) || W * 16 >= (1 << 18)) return RT_ERR_INVALID;
+    {
         if (cudaFuncSetAttribute(rt_conv1_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc) != cudaSuccess ||
             cudaFuncSetAttribute(rt_conv1_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc) != cudaSuccess ||
             cudaFuncSetAttribute(rt_conv1_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc) != cudaSuccess) return RT_ERR_CUDA;
@@ -1055,17 +851,6 @@ static int conv1_launch(const float *x_dev, const float *weight_dev, const float
                 T, n, chunks, per, x_dev, reinterpret_cast<const uint4 *>(bop), bias_dev, reinterpret_cast<__nv_bfloat16 *>(out_dev), EnvSource{});
         return cudaGetLastError() == cudaSuccess ? RT_OK : RT_ERR_CUDA;
     }
-    if (grouped_out || env_src) return RT_ERR_INVALID;              // only the tcgen05 kernel writes the grouped layout / reads env state
-
-    const size_t smem = (size_t)3 * S.plane_vox * 16 + (size_t)S.Ho * S.Pw * kCout * sizeof(__nv_bfloat16);
-    if (smem > (size_t)max_smem) return RT_ERR_INVALID;
-    if (cudaFuncSetAttribute(rt_conv1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return RT_ERR_CUDA;
-
-    uint32_t *frag = reinterpret_cast<uint32_t *>(scratch_dev);
-    rt_conv_prepare_kernel<<<(kChunks * 2 * 32 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(weight_dev, frag);
-    rt_conv1_kernel<<<n * chunks, kThreads, smem, (cudaStream_t)stream>>>(
-        S, n, chunks, per, x_dev, frag, bias_dev, reinterpret_cast<__nv_bfloat16 *>(out_dev));
-    return cudaGetLastError() == cudaSuccess ? RT_OK : RT_ERR_CUDA;
 }
 
 int rt_conv1_relu_pool(const float *x_dev, const float *weight_dev, const float *bias_dev, int n, int D, int H, int W,

@@ -191,8 +191,7 @@ class FeaturesExtractor3D(nn.Module):
                                                    C.c_void_p(self._conv_scratch2.data_ptr()), stream), "rt_conv2_relu_pool")
         y = self._fused_tail(act2)
         if y is None:
-            with torch.autocast("cuda", dtype=torch.bfloat16):
-                y = self.mlp(self.cnn[6:](act2).float())
+            raise nat.RtError("FeaturesExtractor3D.forward_from_env: rt_c3d_tail does not cover this layer configuration")
         return y
 
     def _fused_tail(self, h: torch.Tensor):
@@ -219,22 +218,37 @@ class FeaturesExtractor3D(nn.Module):
         nat.check(rc, "rt_c3d_tail")
         return out
 
+    def _not_covered(self, what: str, observations: torch.Tensor):
+        from . import _native as nat
+        return nat.RtError(
+            f"FeaturesExtractor3D: {what} does not cover input shape {tuple(observations.shape)} / this layer configuration "
+            "(the hand-written kernels implement networks.py:22-45 of the reference: Conv3d(4->16,k3), groups 2 and 4, even "
+            "last extent).  There is no silent fallback: set fused_first_block = False on the module to run the "
+            "PyTorch/cuDNN layers explicitly.")
+
     def forward(self, observations: torch.Tensor) -> torch.Tensor:
+        """Inference (no_grad, bfloat16, CUDA): the hand-written kernels, and an error for shapes they do not cover.
+        Training (autograd enabled) and modules with fused_first_block = False: the PyTorch layers."""
         if (self.compute_dtype == torch.bfloat16 and observations.is_cuda and not torch.is_grad_enabled()
                 and self.fused_first_block):
-            h = self._fused_two_blocks(observations) if self.fused_second_block else None
-            if h is not None:
-                y = self._fused_tail(h) if self.fused_tail else None
-                if y is not None:
+            if self.fused_second_block:
+                h = self._fused_two_blocks(observations)
+                if h is None:
+                    raise self._not_covered("rt_conv1_relu_pool_grouped + rt_conv2_relu_pool", observations)
+                if self.fused_tail:
+                    y = self._fused_tail(h)
+                    if y is None:
+                        raise self._not_covered("rt_c3d_tail", observations)
                     return y
-                with torch.autocast("cuda", dtype=torch.bfloat16):
+                with torch.autocast("cuda", dtype=torch.bfloat16):       # fused_tail = False: explicit opt-out
                     h = self.cnn[6:](h)
                 return self.mlp(h.float())
-            h = self._fused_first_block(observations)
-            if h is not None:
-                with torch.autocast("cuda", dtype=torch.bfloat16):
-                    h = self.cnn[3:](h)
-                return self.mlp(h.float())
+            h = self._fused_first_block(observations)                    # fused_second_block = False: explicit opt-out
+            if h is None:
+                raise self._not_covered("rt_conv1_relu_pool", observations)
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                h = self.cnn[3:](h)
+            return self.mlp(h.float())
         if self.compute_dtype is not None and observations.is_cuda:
             with torch.autocast("cuda", dtype=self.compute_dtype):
                 x = self.cnn(observations)

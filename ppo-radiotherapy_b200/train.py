@@ -1,8 +1,11 @@
 """CleanRL-style PPO on the device-resident vector env — the reference's train.py:91-282 with the
 host round trips removed.
 
-    python -m torch.distributed.run --nproc-per-node 8 -m ppo_radiotherapy_b200.train --config-file cfg.yaml --output-dir out
-    python ppo_radiotherapy_b200_train.py ...   (single GPU)
+    python -m torch.distributed.run --nproc-per-node 8 ppo_radiotherapy_b200_train.py --config-file cfg.yaml --output-dir out
+    python ppo_radiotherapy_b200_train.py --config-file cfg.yaml --output-dir out      (single GPU)
+
+(`ppo_radiotherapy_b200_train.py` at the repo root is the launcher: the package directory has a hyphen in its name, so
+`python -m` cannot address this module.)
 
 What stays as in the reference: config field names (configs/default.yaml.template), the agent classes and
 their checkpoint layout, the loss (clipped surrogate, clipped value loss, per-minibatch advantage
@@ -80,9 +83,10 @@ def shard_range(total: int, world_size: int, rank: int):
 class FlatGradAllReduce:
     """One all-reduce of the flattened gradient per optimiser step, averaged over ranks."""
 
-    def __init__(self, params, group=None):
+    def __init__(self, params, group=None, events: Optional[list] = None):
         self.params = [p for p in params if p.requires_grad]
         self.group = group
+        self.events = events       # profiling: (start, end) CUDA event pairs around every all_reduce call
         n = sum(p.numel() for p in self.params)
         ref = self.params[0]
         self.flat = torch.zeros(n, dtype=ref.dtype, device=ref.device)
@@ -99,7 +103,14 @@ class FlatGradAllReduce:
             else:
                 self.flat[off:off + n].copy_(p.grad.reshape(-1))
             off += n
-        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+        if self.events is not None and self.flat.is_cuda:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+            e1.record()
+            self.events.append((e0, e1))
+        else:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
         self.flat.div_(self.world)
         off = 0
         for p in self.params:
@@ -221,8 +232,11 @@ def ppo_update(agent, optimizer, cfg, b_obs, b_actions, b_logprobs, b_advantages
     return stats
 
 
-def train(cfg, writer=None, device="cuda", output_dir: Optional[str] = None, run_name: str = "run", log=print):
-    """The reference's train(cfg, writer, device) (train.py:91) on one rank's env shard."""
+def train(cfg, writer=None, device="cuda", output_dir: Optional[str] = None, run_name: str = "run", log=print,
+          profile: Optional[dict] = None):
+    """The reference's train(cfg, writer, device) (train.py:91) on one rank's env shard.
+    `profile` (a dict) asks for CUDA-event timings per iteration: it receives `rollout_ms`, `update_ms`, `iter_ms`
+    (lists, one entry per iteration) and `allreduce_us` (one entry per NCCL all-reduce call)."""
     world = dist.get_world_size() if dist.is_initialized() else 1
     rank = dist.get_rank() if dist.is_initialized() else 0
     finalize_config(cfg, world)
@@ -239,7 +253,9 @@ def train(cfg, writer=None, device="cuda", output_dir: Optional[str] = None, run
         agent = PPO_3DCNN(obs_shape, act_shape, cfg.feature_dim, compute_dtype=torch.bfloat16).to(device)
     broadcast_parameters(agent)
     optimizer = optim.Adam(agent.parameters(), lr=cfg.learning_rate, eps=1e-5)
-    sync_grads = FlatGradAllReduce(agent.parameters()) if world > 1 else None
+    ar_events = [] if profile is not None else None
+    sync_grads = FlatGradAllReduce(agent.parameters(), events=ar_events) if world > 1 else None
+    iter_events = []
 
     T = cfg.num_steps
     # visionless: the rollout keeps the observations (train.py:110).  Vision: a float32 voxel observation is 3.2 MB
@@ -343,6 +359,9 @@ def train(cfg, writer=None, device="cuda", output_dir: Optional[str] = None, run
         ep.zero_()
         step_idx.zero_()
         rollout_pos[0] = 0
+        if profile is not None:
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            ev[0].record()
         for step in range(T):
             global_step += cfg.num_envs
             if graph is not None:
@@ -356,11 +375,16 @@ def train(cfg, writer=None, device="cuda", output_dir: Optional[str] = None, run
             else:
                 next_value = agent.critic(agent.features_extractor.forward_from_env(eng)).reshape(-1)
             advantages, returns = compute_gae(rewards, values, dones, next_value, next_done, cfg.gamma, cfg.gae_lambda)
+        if profile is not None:
+            ev[1].record()
 
         b_obs = obs.reshape((-1,) + obs_shape) if cfg.visionless else (lambda idx: eng.render_observations(store, idx))
         stats = ppo_update(agent, optimizer, cfg,
                            b_obs, actions.reshape((-1,) + act_shape), logprobs.reshape(-1),
                            advantages.reshape(-1), returns.reshape(-1), values.reshape(-1), sync_grads)
+        if profile is not None:
+            ev[2].record()
+            iter_events.append(ev)
 
         if world > 1:
             dist.all_reduce(ep, op=dist.ReduceOp.SUM)
@@ -400,6 +424,13 @@ def train(cfg, writer=None, device="cuda", output_dir: Optional[str] = None, run
                 torch.save(agent.state_dict(), path)                           # train.py:270-279
                 if log is not None:
                     log(f"model saved to {path}")
+    if profile is not None:
+        torch.cuda.synchronize(device)
+        profile["rollout_ms"] = [e[0].elapsed_time(e[1]) for e in iter_events]      # rollout + GAE
+        profile["update_ms"] = [e[1].elapsed_time(e[2]) for e in iter_events]
+        profile["iter_ms"] = [e[0].elapsed_time(e[2]) for e in iter_events]
+        profile["allreduce_us"] = [a.elapsed_time(b) * 1e3 for a, b in (ar_events or [])]
+        profile["fused_rollout"] = fused is not None
     envs.close()
     agent.history = history
     return agent

@@ -205,3 +205,44 @@ def test_features_extractor_fused_path_matches_unfused():
     y3 = fe(obs)
     assert y3.requires_grad
     envs.close()
+
+
+def test_features_extractor_against_float32_reference_module():
+    """the fused bfloat16 forward (three hand-written kernels) against the reference's
+    FeaturesExtractor3D evaluated in plain float32 (networks.py:8-45: the same torch layers and weights, no autocast)
+    on real voxel observations.  Stated bound: |y_fused - y_fp32| <= 3e-2 * max|y_fp32| + 5e-3 (operands are rounded to
+    bfloat16, 8 significant bits, once per layer; accumulation is float32); the observed error is printed."""
+    torch.manual_seed(3)
+    fe = rt.FeaturesExtractor3D((4, 67, 43, 70), 64, compute_dtype=torch.bfloat16).to(DEV)
+    envs = rt.RadiotherapyVectorEnv(8, visionless=False, device=DEV, seed=9)
+    obs, _ = envs.reset(options={"backend": "torch"})
+    g = torch.Generator(device=DEV).manual_seed(1)
+    for _ in range(30):
+        obs, *_ = envs.step(torch.rand((8, 6), device=DEV, generator=g) * 2 - 1)
+    with torch.no_grad():
+        y = fe(obs)
+        old = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+        try:
+            y32 = fe.mlp(fe.cnn(obs.float()))                     # the reference forward, float32 end to end
+        finally:
+            torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    err = float((y - y32).abs().max())
+    scale = float(y32.abs().max())
+    print(f"C3D fused bf16 vs float32 reference: max abs err {err:.3e}, max |y| {scale:.3e}, relative {err / scale:.3e}")
+    assert err <= 3e-2 * scale + 5e-3
+    envs.close()
+
+
+def test_features_extractor_refuses_uncovered_shapes():
+    """No silent cuDNN fallback under no_grad: a shape the kernels do not cover raises; the
+    PyTorch layers run only when asked for (fused_first_block = False) or under autograd."""
+    fe = rt.FeaturesExtractor3D((4, 35, 27, 37), 64, compute_dtype=torch.bfloat16).to(DEV)     # odd last extent
+    x = torch.rand((2, 4, 35, 27, 37), device=DEV)
+    with torch.no_grad():
+        with pytest.raises(nat.RtError, match="does not cover"):
+            fe(x)
+        fe.fused_first_block = False
+        assert fe(x).shape == (2, 64)
+    fe.fused_first_block = True
+    assert fe(x).requires_grad                                   # autograd enabled: the differentiable PyTorch path

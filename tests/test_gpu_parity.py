@@ -235,6 +235,92 @@ def test_tiny_tumours_early_termination_and_autoreset(golden):
     env.close()
 
 
+def test_termination_threshold_under_stress(golden):
+    """240 synthetic 16-64-voxel tumours with homing actions, the reference's own traces
+    (stress.npz).  The dose ratio crosses 0.9 on 159 of them, 49 steps lie within 2e-6 of the threshold (ratios
+    0.8999999 / 0.9 / 0.90000004) where the summation order of np.sum(dose * tumours) (environment.py:166,186)
+    decides `done`.  The terminal step index of every env equals the reference's: 0 flips."""
+    g = golden("stress")
+    E, T = g["actions"].shape[:2]
+    lungs = rt.default_phantom().lungs_volume()
+    vols = []
+    for e in range(E):
+        v = np.zeros(lungs.size, dtype=np.float32)
+        v[g["vox"][g["vox_off"][e]:g["vox_off"][e + 1]]] = 1.0
+        vols.append(v.reshape(lungs.shape))
+    ph = rt.Phantom.from_volumes(lungs, vols, names=[f"stress{e}" for e in range(E)])
+    env = rt.RadiotherapyVectorEnv(E, device=DEV, phantom=ph, tumour_ids=np.arange(E, dtype=np.int32)[None, :])
+    env.reset()
+    length = g["length"]
+    alive = np.ones(E, dtype=bool)
+    flips = 0
+    early = 0
+    for t in range(T):
+        obs, reward, term, trunc, infos = env.step(_cuda(g["actions"][:, t]))
+        term = term.cpu().numpy().astype(bool)
+        info = env.engine.info.cpu().numpy()
+        m = alive & (t < length)
+        flips += int((term[m] != g["done"][m, t].astype(bool)).sum())
+        np.testing.assert_allclose(reward.cpu().numpy()[m], g["rec"][m, t, 9], rtol=REW_RTOL, atol=REW_ATOL)
+        np.testing.assert_allclose(info[m, nat.INFO_DOSE_TUMOUR], g["rec"][m, t, 13], rtol=REW_RTOL, atol=REW_ATOL)
+        assert np.array_equal(info[m, nat.INFO_LUNG_COUNT], g["rec"][m, t, 19])
+        early += int((term & m).sum())
+        alive &= ~(g["done"][:, t].astype(bool) | term)          # past its (reference) terminal step an env is not compared
+    print(f"stress: {early} early terminations, {flips} done flips")
+    assert flips == 0
+    assert early >= 150
+    env.close()
+
+
+def test_reset_observation_all_tumours(golden):
+    """reset observation of all 1000 bundled tumours on the GPU against the reference's
+    (resets.npz; environment.py:86-97, 145-148, 259-268)."""
+    g = golden("resets")
+    n = g["obs"].shape[0]
+    env = rt.RadiotherapyVectorEnv(n, device=DEV, tumour_ids=np.arange(n, dtype=np.int32)[None, :])
+    obs, _ = env.reset()
+    np.testing.assert_allclose(obs, g["obs"].astype(np.float32), rtol=0, atol=OBS_ATOL)
+    assert np.array_equal(obs[:, 6:9], g["obs"][:, 6:9].astype(np.float32))     # centroid: a per-tumour constant, exact
+    # ... and through the autoreset path: terminate every env, the next call resets it to the next tumour
+    sched = np.stack([np.arange(n), (np.arange(n) + 1) % n]).astype(np.int32)
+    env.engine.set_tumour_schedule(sched)
+    env.reset()
+    a = torch.zeros((n, 6), device=DEV)
+    for _ in range(100):
+        _, _, term, _, _ = env.step(a)
+    assert term.all()
+    obs, reward, term, _, _ = env.step(a)
+    np.testing.assert_allclose(obs.cpu().numpy(), np.roll(g["obs"], -1, axis=0).astype(np.float32), rtol=0, atol=OBS_ATOL)
+    assert (reward == 0).all() and not term.any()
+    env.close()
+
+
+def test_export_trajectory_matches_reference_file(golden, tmp_path):
+    """export_trajectory (environment.py:69-75) writes the reference's npz: keys tumours, dose,
+    beams with its shapes and dtypes; dose bit-exact, beams as (position, direction) pairs."""
+    g = golden("trajectory")
+    env = rt.RadiotherapyVectorEnv(1, device=DEV, tumour_ids=np.array([[int(g["tumour_id"])]], dtype=np.int32), record_beams=True)
+    env.reset()
+    for a in g["actions"]:
+        env.step(_cuda(a[None, :]))
+    path = str(tmp_path / "traj.npz")
+    env.envs[0].export_trajectory(path)
+    z = np.load(path)
+    keys = sorted(z.files)
+    assert keys == [str(k) for k in g["keys"]]
+    assert [str(tuple(z[k].shape)) for k in keys] == [str(x) for x in g["shapes"]]
+    assert [str(z[k].dtype) for k in keys] == [str(x) for x in g["dtypes"]]
+    assert np.array_equal(np.flatnonzero(z["tumours"].reshape(-1)), g["tumours_nz"])
+    assert set(np.unique(z["tumours"]).tolist()) == {0.0, 1.0}
+    dose = z["dose"].reshape(-1)
+    nz = np.flatnonzero(dose)
+    assert np.array_equal(nz, g["dose_idx"])
+    assert np.array_equal(dose[nz].view(np.uint32), g["dose_val"].view(np.uint32))
+    assert np.array_equal(z["beams"][:, 0], g["beams"][:, 0])                   # positions: exact IEEE
+    np.testing.assert_allclose(z["beams"][:, 1], g["beams"][:, 1], rtol=0, atol=POSE_ATOL)
+    env.close()
+
+
 @pytest.mark.parametrize("kind", ["uniform", "normal"])
 def test_rollout_vs_oracle_256_envs(kind):
     """SURVEY §8d C2 at reduced width: tumour id (i*7919) mod 1000, T = 101 calls (a full episode plus
@@ -617,12 +703,14 @@ def test_full_size_properties_4096_envs():
     assert run() == run()
 
 
-def test_full_size_rollout_vs_oracle_4096_envs():
+@pytest.mark.parametrize("kind", ["uniform", "normal"])
+def test_full_size_rollout_vs_oracle_4096_envs(kind):
     """SURVEY §8d C2 in full: 4096 envs, tumour id (i*7919) mod 1000, T = 101 calls (one whole episode plus the
-    autoreset call) = 409,600 beams, every output of every step against the CPU oracle."""
+    autoreset call) = 409,600 beams, every output of every step against the CPU oracle; uniform(-1,1) actions and
+    N(0,1) actions (the initial policy: actor_logstd = 0; a third of the components are clipped at +-1)."""
     n, T = 4096, 101
-    rng = np.random.default_rng(0)
-    acts = rng.uniform(-1, 1, (T, n, 6)).astype(np.float32)
+    rng = np.random.default_rng(0 if kind == "uniform" else 1)
+    acts = (rng.uniform(-1, 1, (T, n, 6)) if kind == "uniform" else rng.standard_normal((T, n, 6))).astype(np.float32)
     tids = ((np.arange(n) * 7919) % 1000).astype(np.int32)[None, :]
     import os
     ref_out, ref_done = O.rollout(O.Phantom(), tids, acts, threads=os.cpu_count() or 8)

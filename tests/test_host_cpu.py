@@ -135,7 +135,11 @@ def test_bench_reference_arm_contract():
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["metric"] == "env-steps/sec" and line["unit"] == "env-steps/s"
     assert line["higher_is_better"] is True and line["value"] > 0 and line["steps"] == 2 and line["warmup"] == 1
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    from oracle import ref_runtime
+    # the unmodified Python reference (oracle/_ref, copied by oracle/build_ref.py) when it is there, else the C port
+    assert line["cpu_baseline"]["kind"] == ("reference" if ref_runtime.available() else "port")
+    assert line["cpu_baseline"]["cores"] >= 1 and line["cpu_baseline"]["value"] == line["value"]
+    assert set(line["config"]) == {"workload", "envs_per_gpu", "total_envs", "parallelism", "l2"}
     assert line["e2e"] == {"value": line["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     env["RANK"] = "1"
     out = subprocess.run([sys.executable, bench, "--impl", "reference", "--gpus", "2", "--steps", "2", "--warmup", "1"],

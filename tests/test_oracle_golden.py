@@ -128,6 +128,31 @@ def test_tiny_tumours_terminate_early(golden, phantom):
         assert bool(g["done"][e, lengths[e] - 1])
 
 
+def test_termination_threshold_under_stress(golden, phantom):
+    """stress.npz: 240 synthetic 16-64-voxel tumours whose dose ratio crosses 0.9 (environment.py:184-191), 49 steps
+    within 2e-6 of the threshold: the oracle's NumPy-order float32 sums reproduce every `done` flag and the float32
+    ratio bit for bit."""
+    g = golden("stress")
+    ph = O.Phantom()
+    ph.vox_offsets = np.ascontiguousarray(g["vox_off"].astype(np.int32))
+    ph.vox = np.ascontiguousarray(g["vox"].astype(np.int32))
+    lengths = g["length"]
+    assert (g["done"].sum(axis=1) > 0).sum() >= 150
+    near = 0
+    for e in range(len(lengths)):
+        env = O.OracleEnv(ph, e)
+        n_vox = int(g["vox_off"][e + 1] - g["vox_off"][e])
+        for t in range(int(lengths[e])):
+            out, dn = env.step(g["actions"][e, t])
+            assert dn == bool(g["done"][e, t]), (e, t)
+            ratio = np.float32(out[13]) / np.float32(n_vox)              # info doses.tumour / sum(tumours)
+            assert ratio == g["ratio"][e, t], (e, t)
+            near += int(abs(float(ratio) - 0.9) < 2e-6)
+            np.testing.assert_allclose(out[9:15], g["rec"][e, t, 9:15], rtol=RTOL, atol=1e-7)
+            assert out[19] == g["rec"][e, t, 19]
+    assert near >= 40
+
+
 def test_reset_obs_all_tumours(golden, phantom):
     g = golden("resets")
     env = O.OracleEnv(phantom, 0)
