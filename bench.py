@@ -157,7 +157,7 @@ def workload_config(E: int, world: int, dose_gb=None):
                     "uniform(-1,1) actions, tumour id (i*7919) mod 1000 then seeded RNG, NEXT_STEP autoreset calls "
                     "counted in autoreset_calls_in_timed_region",
         "envs_per_gpu": E, "total_envs": E * world, "parallelism": f"env-sharded x{world}, no data-path collective",
-        "l2": "no flush: the dose state (3.3 GB/GPU at 4096 envs) >> 126 MB L2 and every step touches sectors not "
+        "l2": "no flush: the dose state (6.6 GB/GPU at 4096 envs) >> 126 MB L2 and every step touches cells not "
               "touched before in the episode; the 0.5 MB of env records are L2-resident by design",
     }
 
@@ -278,20 +278,8 @@ def other_kernels(rt, dev, peak):
     n_pool = 104
     acts = [torch.rand((n, 6), device=dev, generator=g) * 2 - 1 for _ in range(n_pool)]
     b = n * ALGO_BYTES_SECTOR
-    # ... and the two-kernel variant of the step (rt_step_split.cuh, RT_STEP_KB=-2: thread-per-env pose kernel +
-    # persistent warp-per-env deposit kernel), which exists for this regime
-    for name, kb in (("rt_step3_kernel", None), ("rt_split_pose_kernel + rt_split_deposit_kernel (RT_STEP_KB=-2)", "-2")):
-        old_kb = os.environ.get("RT_STEP_KB")
-        if kb is not None:
-            os.environ["RT_STEP_KB"] = kb
-        try:
-            se = rt.BatchedEpisodes(n, device=dev, seed=11)
-        finally:
-            if kb is not None:
-                if old_kb is None:
-                    del os.environ["RT_STEP_KB"]
-                else:
-                    os.environ["RT_STEP_KB"] = old_kb
+    for name in ("rt_step_kernel",):
+        se = rt.BatchedEpisodes(n, device=dev, seed=11)
         se.reset()
         for i in range(127):                       # into the second episode (timed() adds three more warm-up calls)
             se.step(acts[i % n_pool], want_info=False)
@@ -301,9 +289,10 @@ def other_kernels(rt, dev, peak):
             se.step(acts[k[0] % n_pool], want_info=False)
             k[0] += 1
         s = timed(big_step, 101)                   # one full episode cycle incl. the autoreset call: steady-state mix of
-                                                   # fresh and re-touched sectors
+                                                   # first-touched and re-touched cells
         out.append({"kernel": name, "workload": f"{n} envs (visionless sparse step)", "bytes": b, "us": s * 1e6,
-                    "achieved": b / s / 1e9, "unit": "GB/s", "frac": b / s / 1e9 / peak, "env_steps_per_s": n / s})
+                    "achieved": b / s / 1e9, "unit": "GB/s", "frac": b / s / 1e9 / peak, "env_steps_per_s": n / s,
+                    "state_gb": se.device_bytes / 1e9})
         se.close()
     del acts
     # dense-mode step (BASELINE configs[4]): read + write every dose volume, 1,613,360 B per env-step
@@ -569,7 +558,6 @@ def run_ours(args):
         stream.synchronize()
         per_step = nat.launch_count() - l0
         gpu_launches = K * per_step
-        step_kernel = "rt_step3_kernel"
 
         # ---- e2e: host buffers through rt_step_host, every step --------------------------------
         Ke = args.e2e_steps or min(K, 500)
@@ -614,7 +602,7 @@ def run_ours(args):
             "autoreset_calls_in_timed_region": autoreset_calls,
             "state_gb_per_gpu": eng.device_bytes / 1e9,
             "roofline": {
-                "kernel": step_kernel, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "kernel": "rt_step_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": measured_traffic() if E == 4096 else None, "peak_source": peak_src,
                 "bytes_per_env_step": ALGO_BYTES_SECTOR, "payload_bytes_per_env_step": ALGO_BYTES_PAYLOAD,
                 "avg_launch_us": launch_s * 1e6,

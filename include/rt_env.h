@@ -10,9 +10,12 @@
  *   - pointers named *_dev are DEVICE pointers owned by the caller (e.g. PyTorch
  *     allocations); calls taking a `stream` are asynchronous and stream-ordered and
  *     never synchronise the host; `stream` is a cudaStream_t passed as void*;
- *   - pointers named *_host are HOST pointers (pinned memory recommended); the
- *     *_host calls copy host->device, run the same kernels, copy device->host and
- *     return after the stream has drained;
+ *   - pointers named *_host are HOST pointers; the *_host calls run the same kernels on the
+ *     handle's own stream and return after it has drained.  Page-locked buffers are mapped
+ *     into the kernel (zero-copy), pageable ones are staged through the handle's pinned
+ *     buffers.  A *_host call that follows device-pointer calls on the same handle waits for
+ *     them first.  The pinned-or-not answer is cached per address: do not free a pinned
+ *     buffer and pass a pageable array that reuses its address while a handle lives;
  *   - one handle drives one device and is not thread-safe.
  *
  * Array layouts are C-order.  G = grid = (67, 43, 70) for the bundled phantom,
@@ -34,7 +37,7 @@ extern "C" {
 #define RT_API
 #endif
 
-#define RT_ABI_VERSION 1
+#define RT_ABI_VERSION 2
 
 typedef enum {
     RT_OK = 0,
@@ -255,11 +258,14 @@ RT_API int rt_c3d_tail(const void *x_dev, const float *conv_w_dev, const float *
 /* Number of kernels this library has launched since load (for bench.py's gpu_launches). */
 RT_API int64_t rt_launch_count(void);
 /* Developer aid: when stamps_dev (int64 [N][12], device) is non-NULL the step kernel records clock64()
- * at its stage boundaries per env (0 producer start, 1 producer done, 2 env warp ready, 3 past the
- * barrier, 4 splat + bitmap loads issued, 5 dose loads / zero fill done, 6 stores issued, 7 end;
- * 8 state loaded, 9 pose updated, 10 beam set up — producer sub-stages).
- * NULL (the default) switches it off. */
+ * at its stage boundaries per env (scalar warp: 0 start, 8 state loaded and translated, 9 pose updated,
+ * 10 beam set up, 1 walk done, 11 past barrier 2, 7 end; env warp: 2 tumour entry + distance done, 3 past
+ * barrier 1, 4 first pass's cell loads issued, 6 all passes stored).  Sparse-mode handles with more than
+ * 7 envs per SM only.  NULL (the default) switches it off. */
 RT_API int rt_set_stage_clock(rt_env *env, long long *stamps_dev);
+/* Measurement aid: consecutive rt_step launches overlap through programmatic dependent launch (the next
+ * launch's blocks are scheduled while the previous one drains).  enabled = 0 switches that off for A/B timing. */
+RT_API int rt_set_pdl(rt_env *env, int enabled);
 
 #ifdef __cplusplus
 }

@@ -16,7 +16,7 @@ LIB_DIR = os.path.join(_PKG, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "librtenv_b200.so")
 HEADER = os.path.join(_REPO, "include", "rt_env.h")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 ACTION_SIZE = 6
 OBS_SIZE = 9
 MAX_TIME_STEPS = 100
@@ -134,6 +134,7 @@ _SIGNATURES = {
     "rt_ppo_record": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp]),
     "rt_launch_count": (C.c_int64, []),
     "rt_set_stage_clock": (C.c_int, [_vp, _vp]),
+    "rt_set_pdl": (C.c_int, [_vp, C.c_int]),
 }
 
 EXPORTS = tuple(_SIGNATURES)

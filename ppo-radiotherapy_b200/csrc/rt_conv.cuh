@@ -179,8 +179,7 @@ __global__ void rt_conv_prepare_tc_kernel(const float *__restrict__ weight, __nv
 struct EnvSource {
     Tables T;
     const EnvRec *rec;
-    const float *dose;
-    const uint32_t *valid;
+    const uint2 *cells;      // sparse-mode dose cells {dose, generation}
     int first;
 };
 
@@ -253,9 +252,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) rt_conv1_tc_kernel(ConvShape S,
         if (has_work) {
             const EnvRec *r = E.rec + env;
             const int tumour_id = r->tumour_id;
+            const uint32_t gen = r->gen;
             // view planes (environment.py:246-250): beam along the current direction + beam along (1, 0, 0)
             for (int i = t0; i < kHashSlots; i += nt) { hkeys[i] = -1; hvals[i] = 0.0f; }
-            for (int i = t0; i < G.vwords; i += nt) hit_sec[i] = 0u;
+            for (int i = t0; i < (G.vstride / 8 + 31) / 32; i += nt) hit_sec[i] = 0u;     // one bit per 8 voxels
             asm volatile("bar.sync 2, %0;" ::"n"(kTcLoadWarps * 32) : "memory");
             if (lw < 2) {
                 const double pos[3] = {r->pos[0], r->pos[1], r->pos[2]};
@@ -277,11 +277,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) rt_conv1_tc_kernel(ConvShape S,
             const Tumour tm = E.T.tumours[tumour_id];
             const uint32_t *tb = E.T.tumour_pbits + (size_t)tumour_id * E.T.pbits_words;
             const int pd1 = tm.dim[1] + 2, pd2 = tm.dim[2] + 2;
-            const float *vol = E.dose + (size_t)env * G.vstride;
-            const uint32_t *vbits = E.valid + (size_t)env * G.vwords;
-            // Work item = one 32-byte dose sector (8 consecutive voxels of the volume) of one plane of the pair: one
-            // bitmap word, two 16-byte dose loads when the sector holds data, one lungs word, one view-hit bit; the
-            // tumour and view tests only run for the few sectors that can contain such voxels.
+            const uint2 *vol = E.cells + (size_t)env * G.vstride;
+            // Work item = 8 consecutive voxels of the volume (64 bytes of cells) of one plane of the pair: four 16-byte
+            // cell loads (a cell of another generation reads as zero), one lungs word, one view-hit bit; the tumour and
+            // view tests only run for the few groups that can contain such voxels.
             for (int j = 0; j <= iters; j++) {
                 if (j >= 3) tc::mbar_wait(tc::smem_u32(&pair_free[j % 3]), (uint32_t)((j / 3 - 1) & 1));   // MMAs of iteration j-3 done
                 uint2 *dst = reinterpret_cast<uint2 *>(pairs + (size_t)(j % 3) * S.plane_vox);       // [voxel][lower | upper plane]
@@ -298,11 +297,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) rt_conv1_tc_kernel(ConvShape S,
                         const int l0 = sec << 3;
                         float d[8];
 #pragma unroll
-                        for (int i = 0; i < 8; i++) d[i] = 0.0f;
-                        if ((__ldg(vbits + (sec >> 5)) >> (sec & 31)) & 1u) {
-                            const float4 q0 = __ldg(reinterpret_cast<const float4 *>(vol + l0));
-                            const float4 q1 = __ldg(reinterpret_cast<const float4 *>(vol + l0) + 1);
-                            d[0] = q0.x; d[1] = q0.y; d[2] = q0.z; d[3] = q0.w; d[4] = q1.x; d[5] = q1.y; d[6] = q1.z; d[7] = q1.w;
+                        for (int i = 0; i < 4; i++) {
+                            const uint4 c = __ldg(reinterpret_cast<const uint4 *>(vol + l0) + i);
+                            d[2 * i] = c.y == gen ? __uint_as_float(c.x) : 0.0f;
+                            d[2 * i + 1] = c.w == gen ? __uint_as_float(c.z) : 0.0f;
                         }
                         const uint32_t lung8 = (__ldg(E.T.lungs_bits + (l0 >> 5)) >> (l0 & 31)) & 255u;
                         const bool view_hit = (hit_sec[sec >> 5] >> (sec & 31)) & 1u;
@@ -832,7 +830,8 @@ static int conv1_launch(const float *x_dev, const float *weight_dev, const float
     T.plane_vox = (tiles128 * kTcTileRows + 2 * W + 8 + 7) / 8 * 8;
     const size_t smem_tc = (size_t)3 * T.plane_vox * 16 + (size_t)T.r_elems * sizeof(__nv_bfloat16) +
                            (size_t)kTcMmas * kBMmaBytes + (2 * kTcSlots + 6) * 8 + 16 +
-                           (size_t)kHashSlots * 8 + 2 * sizeof(RayWork) + 3328;    // + from-env: view hash, rays, hit-sector bits
+                           (size_t)kHashSlots * 8 + 2 * sizeof(RayWork) +       // + from-env: view hash, rays, hit bits (1 per 8 voxels)
+                           (size_t)((((size_t)D * H * W + 31) / 32 * 32 / 8 + 31) / 32 * 4 + 128);
     if (smem_tc > (size_t)max_smem || (size_t)3 * T.plane_vox * 16 >= (1u << 18) || W * 16 >= (1 << 18)) return RT_ERR_INVALID;
     {
         if (cudaFuncSetAttribute(rt_conv1_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc) != cudaSuccess ||
@@ -877,7 +876,7 @@ int rt_conv1_from_env(rt_env *e, int first, int count, const float *weight_dev, 
     if (first < 0 || count < 0 || first + count > e->n) return fail(RT_ERR_INVALID, "rt_conv1_from_env: env range out of bounds");
     if (e->dense) return fail(RT_ERR_STATE, "rt_conv1_from_env: not available for dense-mode handles");
     if (cudaSetDevice(e->device) != cudaSuccess) return RT_ERR_CUDA;
-    EnvSource src{e->T, e->rec, e->dose, e->valid, first};
+    EnvSource src{e->T, e->rec, e->cells, first};
     const Grid &G = e->T.G;
     const int rc = conv1_launch(nullptr, weight_dev, bias_dev, count, G.g0, G.g1, G.g2, out_dev, scratch_dev, stream, true, &src);
     if (rc == RT_OK && count > 0) g_launches.fetch_add(2, std::memory_order_relaxed);

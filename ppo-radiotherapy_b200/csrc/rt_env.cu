@@ -1,21 +1,19 @@
 // rt_env.cu — kernels and C ABI (include/rt_env.h) of the batched environment step.
 //
 // HBM layout per handle (N envs, V voxels):
-//   rec     [N]            128-byte env record: pose f64, accumulators, counters
-//   dose    [N][vstride]   float32 dose volumes, vstride = V rounded up to 32 floats
-//   valid   [N][vwords]    1 bit per 32-byte dose sector: "written this episode".
-//                          A sector whose bit is clear reads as zero, so reset never
-//                          touches the 807 KB volume: it clears 3.2 KB of bitmap
-//                          (L2-resident for thousands of envs) and the first write to a
-//                          sector needs no read from HBM.
-//   lungs_bits, tumour table, tumour bbox bitmasks, packed voxel lists: < 1 MB, replicated.
+//   rec     [N]            128-byte env record: pose f64, accumulators, counters, dose generation
+//   cells   [N][vstride]   sparse mode: one 8-byte cell per voxel {float32 dose, uint32 generation}, vstride = V
+//                          rounded up to 32 cells.  A cell of another generation than its env's reads as zero, so
+//                          reset never touches the 1.6 MB volume (it bumps EnvRec::gen) and a beam needs no
+//                          validity bitmap: every voxel it hits is one 8-byte load and one 8-byte store.
+//   dose    [N][vstride]   dense mode (RT_FLAG_DENSE): plain float32 volumes, streamed whole every step
+//   lungs bitmask, tumour table, tumour bbox bitmasks, packed voxel lists: < 1 MB, replicated.
 //
-// The sparse step is rt_step3_kernel (rt_step.cuh): per block one scalar warp (a thread per env: pose update in
-// float64, beam clip and the serial float32 slab walk, rewards, termination, observation, NEXT_STEP autoreset)
-// and one env warp per env (splat targets, sparse dose read-modify-write, tumour / lung deltas).  This file
-// holds the record / table definitions, the earlier two-role step kernel (still the first half of the dense-mode
-// step, and RT_STEP_KB=0 for A/B runs), reset, dense-mode, beam, pose, voxel-observation, observation-record and
-// GAE kernels, and the C ABI.
+// The step is rt_step_kernel (rt_step.cuh): per block one scalar warp (a thread per env: pose update in float64,
+// beam clip and the serial float32 slab walk, rewards, termination, observation, NEXT_STEP autoreset) and one env
+// warp per env (splat targets, sparse dose read-modify-write, tumour / lung deltas).  This file holds the record /
+// table definitions, reset, dense-mode, beam, pose, voxel-observation, observation-record and GAE kernels, and the
+// C ABI.
 #include "../../include/rt_env.h"
 #include "rt_device.cuh"
 
@@ -37,6 +35,7 @@ namespace {
 
 thread_local std::string g_err;
 std::atomic<long long> g_launches{0};
+std::atomic<unsigned> g_alias_epoch{0};      // bumped whenever this library frees pinned memory (see pinned_alias)
 
 int fail(int code, const std::string &msg)
 {
@@ -71,7 +70,9 @@ struct __align__(128) EnvRec {
     int32_t episode;        // episodes started since rt_reset (indexes the tumour schedule)
     int32_t needs_reset;    // terminated on the previous call (NEXT_STEP autoreset)
     int32_t n_beams;
-    int32_t pad[8];
+    uint32_t gen;           // dose generation: cells stamped with another value read as zero; bumped by every reset
+    int32_t pad;
+    double dn[3];           // dir / |dir| as the NEXT step's transforms.py:23 computes it (off that step's critical path)
 };
 static_assert(sizeof(EnvRec) == 128, "EnvRec must be one 128-byte line");
 
@@ -93,7 +94,8 @@ constexpr int kMaxPTumourWords = 96;  // same for the bitmask padded by one voxe
 struct Tables {
     Grid G;
     double gnorm;                  // np.linalg.norm(LUNG_SHAPE), environment.py:161
-    const uint32_t *lungs_bits;
+    const uint32_t *lungs_bits;    // bit v = lungs.flat[v]  (= lungs_pad + kLungPadBits / 32)
+    const uint32_t *lungs_pad;     // the same mask with kLungPadBits zero bits in front (bit_pair lookups, bulk copies)
     const Tumour *tumours;
     const uint32_t *tumour_bits;   // [n_tumours][bits_words] bbox-local occupancy
     const uint32_t *vox_xyz;       // packed i | j<<8 | k<<16 per tumour voxel
@@ -101,17 +103,9 @@ struct Tables {
     int n_tumours;
     int bits_words;
     int pbits_words;
-    int lung_words16;              // words of lungs_bits rounded up to a multiple of 4 (16-byte bulk copies)
+    int lung_words16;              // words of lungs_pad (padding included) rounded up to a multiple of 4 (16-byte bulk copies)
     long long *stage_clock;        // optional [N][12] clock64() stamps of the step kernel's stages (rt_set_stage_clock)
-    int debug;                     // RT_STEP_DEBUG bits, honoured by the instrumented kernel and by rt_split_deposit_kernel (what-if timing):
-                                   // 1 no zero fill / valid bits, 2 no voxel stores, 4 no dose loads, 8 no accumulation,
-                                   // 16 no valid-bit RED, 32 no zero-fill store
 };
-
-#define RT_STAMP(slot)                                                                   \
-    do {                                                                                 \
-        if (T.stage_clock && lane == 0) T.stage_clock[(size_t)stamp_env * 12 + (slot)] = clock64(); \
-    } while (0)
 
 struct Schedule {
     const int32_t *ids;     // [n_episodes][N] or nullptr
@@ -126,12 +120,6 @@ struct StepOut {
     uint8_t *terminated;
     uint8_t *truncated;
     double *info;
-    // completion signal of the host-buffer path (rt_step_host): every block counts itself on done_counter (device
-    // memory) once its outputs are written; the last one stores done_value to done_flag (pinned host memory), which
-    // the host polls instead of waiting for the stream.  All three zero / NULL otherwise.
-    unsigned int *done_counter;
-    volatile unsigned int *done_flag;
-    unsigned int done_value;
 };
 
 // Dense mode (RT_FLAG_DENSE): hand-over from the step kernel to rt_dense_kernel, one per env in HBM.
@@ -177,26 +165,23 @@ __device__ __forceinline__ void write_obs(const Tables &T, const Tumour &tm, con
     }
 }
 
-// environment.py:77-105 for the warp's env: new tumour, centred pose, empty dose (= clear the
-// sector-valid bitmap), zero counters.
-__device__ __forceinline__ int reset_env(const Tables &T, const Schedule &S, EnvRec *rec, uint32_t *valid,
-                                         int env, int n_envs, int episode, int lane, float *obs, bool dense = false)
+// environment.py:77-105 for the warp's env: new tumour, centred pose, empty dose (= a new generation: every cell
+// written before reads as zero from now on), zero counters.
+__device__ __forceinline__ int reset_env(const Tables &T, const Schedule &S, EnvRec *rec, int env, int n_envs, int episode,
+                                         int lane, float *obs)
 {
     const int tid = pick_tumour(T, S, env, n_envs, episode);
-    uint4 *vw = reinterpret_cast<uint4 *>(valid + (size_t)env * T.G.vwords);
-    // sparse mode: no sector is valid (reads as zero); dense mode: the volume itself is zeroed, all valid
-    const uint32_t fill = dense ? 0xffffffffu : 0u;
-    for (int i = lane; i < T.G.vwords / 4; i += kWarp) vw[i] = make_uint4(fill, fill, fill, fill);
     const double p[3] = {(double)T.G.g0 / 2.0, (double)T.G.g1 / 2.0, (double)T.G.g2 / 2.0};
     const double d[3] = {0.0, 1.0, 0.0};
     if (lane == 0) {
         EnvRec r;
         r.pos[0] = p[0]; r.pos[1] = p[1]; r.pos[2] = p[2];
         r.dir[0] = d[0]; r.dir[1] = d[1]; r.dir[2] = d[2];
+        r.dn[0] = d[0]; r.dn[1] = d[1]; r.dn[2] = d[2];             // (0, 1, 0) / 1
         r.tumour_dose = 0.0; r.lung_dose = 0.0; r.ep_return = 0.0;
         r.t = 0; r.tumour_id = tid; r.lung_count = 0; r.episode = episode; r.needs_reset = 0; r.n_beams = 0;
-#pragma unroll
-        for (int i = 0; i < 8; i++) r.pad[i] = 0;
+        r.gen = rec[env].gen + 1u;
+        r.pad = 0;
         rec[env] = r;
     }
     const Tumour tm = T.tumours[tid];
@@ -205,9 +190,8 @@ __device__ __forceinline__ int reset_env(const Tables &T, const Schedule &S, Env
 }
 
 // ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) rt_reset_kernel(Tables T, Schedule S, EnvRec *rec, uint32_t *valid,
-                                                       int n_envs, const uint8_t *mask, float *obs,
-                                                       DenseWork *dense)
+__global__ void __launch_bounds__(256) rt_reset_kernel(Tables T, Schedule S, EnvRec *rec, int n_envs,
+                                                       const uint8_t *mask, float *obs, DenseWork *dense)
 {
     const int env = (blockIdx.x * blockDim.x + threadIdx.x) / kWarp;
     const int lane = threadIdx.x & (kWarp - 1);
@@ -215,7 +199,7 @@ __global__ void __launch_bounds__(256) rt_reset_kernel(Tables T, Schedule S, Env
     const bool mine = mask == nullptr || mask[env];
     if (dense && lane == 0) dense[env].mode = mine ? 1 : 2;
     if (mine) {
-        reset_env(T, S, rec, valid, env, n_envs, 0, lane, obs, dense != nullptr);
+        reset_env(T, S, rec, env, n_envs, 0, lane, obs);
     } else if (obs) {
         const EnvRec r = rec[env];
         const Tumour tm = T.tumours[r.tumour_id];
@@ -223,419 +207,8 @@ __global__ void __launch_bounds__(256) rt_reset_kernel(Tables T, Schedule S, Env
     }
 }
 
-// ---------------------------------------------------------------------------------
-// The step.  A block of 8 warps advances kEnvsPerBlock = 7 envs:
-//   producer warp, one THREAD per env: the float64 rotation (sincos/acos/div/sqrt chain), beam
-//      clip/setup and the serial float32 slab walk, left in shared memory.  Scalar latency-bound
-//      work is issued once per env instead of once per lane.
-//   7 env warps, one WARP per env: while the producer runs they load the env record and tumour
-//      entry, apply the translation and reduce the distance-to-tumour term; after the barrier,
-//      lane = (slab, splat target): sparse dose read-modify-write, tumour/lung accumulators,
-//      warp-shuffle reductions, reward, termination, observation, episode statistics and the
-//      NEXT_STEP autoreset.
-// 4 blocks x 256 threads x 64 registers fill an SM; 586 blocks cover 4096 envs in one wave of 592 slots.
-constexpr int kEnvsPerBlock = 7;
-constexpr int kStepThreads = (kEnvsPerBlock + 1) * kWarp;
-
-struct EnvScalars {           // env-warp values parked in shared memory while the dose loop runs
-    double px, py, pz;
-    double os_t[3];
-    double tumour_dose, lung_dose, ep_return, best, r_dist;
-    float obs_p[3];
-    int t, lung_count, n_beams;
-};
-
-struct EnvWork {
-    Beam beam;
-    double dir[3];           // direction after the rotation
-    double os_r;             // rotation overshoot (environment.py:239), published after the barrier
-    int os_ready;            // set by the producer once os_r is valid
-    int pad_;
-    float ys[kMaxSlabs], zs[kMaxSlabs];
-};
-
-template <bool kDense>
-__global__ void __launch_bounds__(kStepThreads, 4) rt_step_kernel(Tables T, Schedule S, EnvRec *rec, float *dose,
-                                                                  uint32_t *valid, double *beams, int n_envs,
-                                                                  const float *__restrict__ actions, StepOut out,
-                                                                  DenseWork *dense)
-{
-    __shared__ EnvWork work[kEnvsPerBlock];
-    __shared__ Tumour tum[kEnvsPerBlock];
-    __shared__ EnvScalars park[kEnvsPerBlock];
-    __shared__ uint32_t tbits[kEnvsPerBlock][kMaxTumourWords];
-    // the env's sector-valid bitmap (3.2 KB), staged while the producer runs: the first-touch test after the
-    // barrier is a shared-memory lookup and dose values are only loaded for sectors that hold data
-    extern __shared__ uint32_t vsm_all[];
-    const Grid &G = T.G;
-    const int warp = threadIdx.x / kWarp;
-    const int lane = threadIdx.x & (kWarp - 1);
-    const int env0 = blockIdx.x * kEnvsPerBlock;
-
-    // Programmatic dependent launch: when this launch follows another step in the stream its blocks may be
-    // scheduled while that step drains; nothing of the previous step's state is read before this point.
-    // The trigger lets the NEXT launch do the same with respect to this one.
-    cudaGridDependencySynchronize();
-    cudaTriggerProgrammaticLaunchCompletion();
-
-    // ---- producer warp ---------------------------------------------------------------------
-    if (warp == kEnvsPerBlock) {
-        const int e = env0 + lane;
-        if (T.stage_clock && lane < kEnvsPerBlock && e < n_envs) T.stage_clock[(size_t)e * 12 + 0] = clock64();
-        const bool mine = lane < kEnvsPerBlock && e < n_envs;
-        double zc = 0.0;
-        bool stepped = false;
-        if (mine) {
-            EnvWork &wk = work[lane];
-            const EnvRec *my = rec + e;
-            // every load is issued before the first use: one round trip to L2
-            const int needs_reset = my->needs_reset;
-            Pose s;
-            float a[6];
-#pragma unroll
-            for (int i = 0; i < 3; i++) { s.p[i] = my->pos[i]; s.d[i] = my->dir[i]; }
-#pragma unroll
-            for (int i = 0; i < 6; i++) a[i] = __ldg(actions + (size_t)e * RT_ACTION_SIZE + i);
-            wk.beam.nslab = 0;
-            wk.os_ready = 0;
-            if (!needs_reset) {
-                stepped = true;
-                if (T.stage_clock) T.stage_clock[(size_t)e * 12 + 8] = clock64() + (long long)(s.d[0] * 0.0);
-                const double gs[3] = {(double)G.g0, (double)G.g1, (double)G.g2};
-                double os_t[3], rv[3];
-#pragma unroll
-                for (int i = 0; i < 3; i++)                                 // environment.py:122-125, transforms.py:65-67
-                    s.p[i] = translate_axis(s.p[i], __dmul_rn(__dmul_rn((double)clip1(a[i]), gs[i]), 0.2), gs[i], os_t[i]);
-                map_rotation(a, rv);
-                zc = rotate_env(s.d, rv);                                   // transforms.py:7-55
-                if (T.stage_clock) T.stage_clock[(size_t)e * 12 + 9] = clock64() + (long long)(s.d[0] * 0.0);
-                const Beam b = beam_setup(G, s.p, s.d);                     // draw_line.py:19-66
-                if (T.stage_clock) T.stage_clock[(size_t)e * 12 + 10] = clock64() + (b.nslab < -5);
-                beam_walk(b, wk.ys, wk.zs);                                 // draw_line.py:98-99
-                wk.beam = b;
-#pragma unroll
-                for (int i = 0; i < 3; i++) wk.dir[i] = s.d[i];
-            }
-            if (T.stage_clock) T.stage_clock[(size_t)e * 12 + 1] = clock64();
-        }
-        __syncthreads();
-        if (stepped) {                                                      // off the env warps' critical path
-            volatile EnvWork &wk = work[lane];
-            wk.os_r = overshoot_from_z(zc);                                 // transforms.py:29-33, 57
-            __threadfence_block();
-            wk.os_ready = 1;
-        }
-        return;
-    }
-
-    // ---- env warps, before the barrier (overlaps the producer) ------------------------------
-    const int env = env0 + warp;
-    const bool active = env < n_envs;
-    EnvRec *my = rec + (active ? env : 0);
-    Tumour &tm = tum[warp];
-    EnvScalars &sc = park[warp];
-    uint32_t *vsm = vsm_all + (size_t)warp * G.vwords;
-    bool needs_reset = false;
-    int tid = 0;
-    if (active) {
-        needs_reset = my->needs_reset != 0;
-        if (!needs_reset) {
-            tid = my->tumour_id;
-            if (!kDense) {
-                const uint4 *src = reinterpret_cast<const uint4 *>(valid + (size_t)env * G.vwords);
-                uint4 *dst = reinterpret_cast<uint4 *>(vsm);
-                for (int i = lane; i < G.vwords / 4; i += kWarp) dst[i] = src[i];
-            }
-            if (lane < kTumourWords)
-                reinterpret_cast<uint32_t *>(&tm)[lane] = __ldg(reinterpret_cast<const uint32_t *>(T.tumours + tid) + lane);
-            for (int i = lane; i < T.bits_words; i += kWarp)                    // bits_words <= kMaxTumourWords (rt_create)
-                tbits[warp][i] = __ldg(T.tumour_bits + (size_t)tid * T.bits_words + i);
-            // translation (environment.py:122-125, transforms.py:65-67): same operations as the producer
-            const double gs[3] = {(double)G.g0, (double)G.g1, (double)G.g2};
-            double p[3], os_t[3];
-#pragma unroll
-            for (int i = 0; i < 3; i++) {
-                const float ai = __ldg(actions + (size_t)env * RT_ACTION_SIZE + i);
-                const double tr = __dmul_rn(__dmul_rn((double)clip1(ai), gs[i]), 0.2);
-                p[i] = translate_axis(my->pos[i], tr, gs[i], os_t[i]);
-            }
-            if (lane < 3) {                                                     // environment.py:260
-                const double pl = lane == 0 ? p[0] : (lane == 1 ? p[1] : p[2]);
-                const double gl = lane == 0 ? gs[0] : (lane == 1 ? gs[1] : gs[2]);
-                sc.obs_p[lane] = (float)__dsub_rn(__dmul_rn(__ddiv_rn(pl, gl), 2.0), 1.0);
-                sc.os_t[lane] = lane == 0 ? os_t[0] : (lane == 1 ? os_t[1] : os_t[2]);
-            }
-            if (lane == 0) {
-                sc.px = p[0]; sc.py = p[1]; sc.pz = p[2];
-                sc.tumour_dose = my->tumour_dose; sc.lung_dose = my->lung_dose; sc.ep_return = my->ep_return;
-                sc.t = my->t + 1;                                               // environment.py:194
-                sc.lung_count = my->lung_count; sc.n_beams = my->n_beams;
-            }
-            __syncwarp();
-            // distance_to_tumour_reward (environment.py:150-162): min over the tumour's voxel list
-            double best = CUDART_INF;
-            const int nv = tm.n_vox, off = tm.vox_off;
-            for (int k = lane; k < nv; k += kWarp) {
-                const uint32_t pk = __ldg(T.vox_xyz + off + k);
-                const double dx = __dsub_rn((double)(pk & 255u), p[0]);
-                const double dy = __dsub_rn((double)((pk >> 8) & 255u), p[1]);
-                const double dz = __dsub_rn((double)(pk >> 16), p[2]);
-                double d2 = __dmul_rn(dx, dx);
-                d2 = __dadd_rn(d2, __dmul_rn(dy, dy));
-                d2 = __dadd_rn(d2, __dmul_rn(dz, dz));
-                best = fmin(best, d2);
-            }
-            best = warp_min(best);
-            if (lane == 0) {
-                sc.best = best;
-                sc.r_dist = __dmul_rn(__ddiv_rn(sqrt(best), T.gnorm), -1.0);     // environment.py:158-162
-            }
-        }
-    }
-    const int stamp_env = active ? env : 0;
-    if (active) RT_STAMP(2);
-    __syncthreads();
-    if (!active) return;
-    RT_STAMP(3);
-
-    if (needs_reset) {
-        // gymnasium 1.0.0 NEXT_STEP: the call after a terminal step resets and reports reward 0.
-        const int episode = my->episode + 1;
-        __syncwarp();
-        const int new_tid = reset_env(T, S, rec, valid, env, n_envs, episode, lane, out.obs, kDense);
-        if (kDense && lane == 0) dense[env].mode = 1;
-        if (lane == 0) {
-            if (out.reward) out.reward[env] = 0.0;
-            if (out.reward_f32) out.reward_f32[env] = 0.0f;
-            if (out.terminated) out.terminated[env] = 0;
-            if (out.truncated) out.truncated[env] = 0;
-        }
-        if (out.info && lane < RT_INFO_SIZE)
-            out.info[(size_t)env * RT_INFO_SIZE + lane] = lane == RT_INFO_TUMOUR_ID ? (double)new_tid : 0.0;
-        return;
-    }
-
-    // ---- env warps, after the barrier: dose deposition (environment.py:107-110) --------------
-    // dose' = clip(dose + beam*0.1, 0, 1) changes only the voxels the beam hits.
-    const EnvWork &wk = work[warp];
-    const Beam b = wk.beam;
-    if (kDense) {
-        // Dense mode: publish the beam (distinct voxels + weights) and the pose; rt_dense_kernel streams the
-        // whole volume, recomputes the reductions from scratch and finishes the step.
-        DenseWork &dw = dense[env];
-        int base = 0;
-        for (int kbase = 0; kbase < b.nslab; kbase += kWarp) {
-            int lin[4], c0, c1, c2;
-            float w[4];
-            slab_targets(G, b, wk.ys, wk.zs, kbase + lane, lin, w, c0, c1, c2);
-            int mine = 0;
-#pragma unroll
-            for (int j = 0; j < 4; j++) mine += lin[j] >= 0;
-            int incl = mine;
-#pragma unroll
-            for (int o = 1; o < kWarp; o <<= 1) {
-                const int v = __shfl_up_sync(kFull, incl, o);
-                if (lane >= o) incl += v;
-            }
-            int at = base + incl - mine;
-#pragma unroll
-            for (int j = 0; j < 4; j++)
-                if (lin[j] >= 0 && at < RT_BEAM_CAP) {
-                    dw.lin[at] = lin[j];
-                    dw.w[at] = w[j];
-                    at++;
-                }
-            base += __shfl_sync(kFull, incl, kWarp - 1);
-        }
-        if (lane == 0) {
-            dw.mode = 0;
-            dw.n_hits = base < RT_BEAM_CAP ? base : RT_BEAM_CAP;
-            dw.tid = tid; dw.t = sc.t; dw.n_beams = sc.n_beams;
-            dw.best = sc.best;
-            dw.os_t[0] = sc.os_t[0]; dw.os_t[1] = sc.os_t[1]; dw.os_t[2] = sc.os_t[2];
-            while (reinterpret_cast<const volatile EnvWork &>(wk).os_ready == 0) {}
-            __threadfence_block();
-            dw.os_r = reinterpret_cast<const volatile EnvWork &>(wk).os_r;
-            dw.ep_return = sc.ep_return;
-            my->pos[0] = sc.px; my->pos[1] = sc.py; my->pos[2] = sc.pz;
-            my->dir[0] = wk.dir[0]; my->dir[1] = wk.dir[1]; my->dir[2] = wk.dir[2];
-            my->t = sc.t;
-            my->n_beams = sc.n_beams + 1;
-        }
-        if (lane < 9) {                                                          // environment.py:259-268
-            float v;
-            if (lane >= 6) v = tm.obs_c[lane - 6];
-            else if (lane >= 3) v = (float)wk.dir[lane - 3];
-            else v = sc.obs_p[lane];
-            out.obs[(size_t)env * RT_OBS_SIZE + lane] = v;
-        }
-        if (beams && lane < 6 && sc.n_beams < RT_MAX_TIME_STEPS) {
-            const double pv = lane == 0 ? sc.px : (lane == 1 ? sc.py : sc.pz);
-            beams[((size_t)env * RT_MAX_TIME_STEPS + sc.n_beams) * 6 + lane] = lane < 3 ? pv : wk.dir[lane - 3];
-        }
-        return;
-    }
-    float *vol = dose + (size_t)env * G.vstride;
-    uint32_t *vbits = valid + (size_t)env * G.vwords;
-    double d_tum = 0.0, d_lung = 0.0;
-    int d_cnt = 0;
-    const int li0 = tm.lo[0], li1 = tm.lo[1], li2 = tm.lo[2];
-    const int td0 = tm.dim[0], td1 = tm.dim[1], td2 = tm.dim[2];
-    // One slab per lane; kPass chunks of 32 slabs are staged together so that their bitmap loads, then
-    // their dose loads, are all in flight at once (a beam has 37 slabs on average, 71 at most).
-    constexpr int kPass = 1;
-    for (int kbase = 0; kbase < b.nslab; kbase += kPass * kWarp) {
-        int lin[kPass][4], c0[kPass], c1[kPass], c2[kPass];
-        float w[kPass][4], old[kPass][4];
-        uint32_t lw[kPass][4];
-        bool use[kPass];
-#pragma unroll
-        for (int c = 0; c < kPass; c++) {
-            use[c] = kbase + c * kWarp < b.nslab;                       // warp-uniform
-#pragma unroll
-            for (int j = 0; j < 4; j++) { lin[c][j] = -1; w[c][j] = 0.0f; }
-            c0[c] = c1[c] = c2[c] = 0;
-            if (use[c]) slab_targets(G, b, wk.ys, wk.zs, kbase + c * kWarp + lane, lin[c], w[c], c0[c], c1[c], c2[c]);
-        }
-        bool fresh[kPass][4];
-#pragma unroll
-        for (int c = 0; c < kPass; c++)
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                lw[c][j] = 0u;
-                old[c][j] = 0.0f;
-                fresh[c][j] = false;
-                if (lin[c][j] >= 0) {
-                    const int sec = lin[c][j] >> 3;
-                    fresh[c][j] = !((vsm[sec >> 5] >> (sec & 31)) & 1u);        // never written this episode: reads as zero
-                    lw[c][j] = __ldg(T.lungs_bits + (lin[c][j] >> 5));
-                    if (!fresh[c][j]) old[c][j] = vol[lin[c][j]];               // re-touched sector: read from HBM/L2
-                }
-            }
-        if (kbase == 0) RT_STAMP(4);
-        __syncwarp();   // every lane has sampled the bitmap before any lane updates it
-        // first write to a sector this episode: materialise it as zeros and mark it valid (shared copy for the
-        // next pass of this warp, global copy for the next step).  Targets 2q and 2q+1 of a slab are neighbours
-        // in memory, so the second one usually shares the first one's sector and skips the fill.
-#pragma unroll
-        for (int c = 0; c < kPass; c++)
-#pragma unroll
-            for (int j = 0; j < 4; j++)
-                if (fresh[c][j]) {
-                    const int sec = lin[c][j] >> 3;
-                    if ((j & 1) && fresh[c][j - 1] && (lin[c][j - 1] >> 3) == sec) continue;
-                    float4 *sp = reinterpret_cast<float4 *>(vol + (sec << 3));
-                    sp[0] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    sp[1] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    atomicOr(vsm + (sec >> 5), 1u << (sec & 31));
-                    atomicOr(vbits + (sec >> 5), 1u << (sec & 31));
-                }
-        __syncwarp();   // zero fill (any lane) is ordered before the voxel stores below
-        if (kbase == 0) RT_STAMP(5);
-#pragma unroll
-        for (int c = 0; c < kPass; c++) {
-            if (!use[c]) continue;
-            // tumour membership of the slab's 2x2 block: bbox test on the shared coordinates, then the bitmask
-            const int ti = c0[c] - li0, tj = c1[c] - li1, tk = c2[c] - li2;
-            const bool near_t = (unsigned)ti < (unsigned)td0 && tj >= -1 && tj < td1 && tk >= -1 && tk < td2;
-#pragma unroll
-            for (int j = 0; j < 4; j++)
-                if (lin[c][j] >= 0) {
-                    const int dy = j >> 1, dz = j & 1;
-                    const float o = old[c][j];
-                    float nd = __fadd_rn(o, __fmul_rn(w[c][j], 0.100000001490116119f));   // beam * BEAM_DOSE, then +
-                    nd = fminf(fmaxf(nd, 0.0f), 1.0f);                                     // np.clip(., 0, 1)
-                    vol[lin[c][j]] = nd;
-                    bool in_t = false;
-                    if (near_t && (unsigned)(tj + dy) < (unsigned)td1 && (unsigned)(tk + dz) < (unsigned)td2) {
-                        const int bit = (ti * td1 + tj + dy) * td2 + tk + dz;
-                        in_t = (tbits[warp][bit >> 5] >> (bit & 31)) & 1u;
-                    }
-                    const bool in_l = (lw[c][j] >> (lin[c][j] & 31)) & 1u;
-                    if (in_t || in_l) {
-                        const double delta = (double)nd - (double)o;
-                        if (in_t) d_tum += delta;
-                        if (in_l) d_lung += delta;
-                        // lungs_mask = lungs*(1-tumours); dose is monotone, so the count only grows (environment.py:174-177)
-                        if (!in_t && !(o > 0.200000002980232239f) && nd > 0.200000002980232239f) d_cnt++;
-                    }
-                }
-        }
-        __syncwarp();
-    }
-    RT_STAMP(6);
-    __syncwarp();
-    const double tumour_dose = sc.tumour_dose + warp_sum(d_tum);
-    const double lung_dose = sc.lung_dose + warp_sum(d_lung);
-    const int lung_count = sc.lung_count + __reduce_add_sync(kFull, d_cnt);
-    const int t = sc.t, n_beams = sc.n_beams;
-
-    // rewards, termination (environment.py:158-191, 214-220)
-    const float tsum_f32 = (float)tumour_dose;                                   // np.sum(dose*tumours) float32
-    const float ratio = fdiv_rn_zero_num(tsum_f32, tm.tumour_sum);   // no dose on the tumour yet: the common case
-    const float r_tumour = __fmul_rn(ratio, 10.0f);
-    const double r_lung = __dmul_rn(__ddiv_rn((double)lung_count, (double)tm.lung_mask_sum), -1.0);
-    const double r_dist = sc.r_dist;
-    const double reward = __dadd_rn(__dadd_rn((double)r_tumour, r_lung), r_dist);
-    const bool done = (ratio >= 0.899999976158142090f) || (t >= RT_MAX_TIME_STEPS);
-    const double ep_return = sc.ep_return + reward;
-
-    if (lane == 0) {
-        my->pos[0] = sc.px; my->pos[1] = sc.py; my->pos[2] = sc.pz;
-        my->dir[0] = wk.dir[0]; my->dir[1] = wk.dir[1]; my->dir[2] = wk.dir[2];
-        my->tumour_dose = tumour_dose; my->lung_dose = lung_dose; my->ep_return = ep_return;
-        my->t = t; my->lung_count = lung_count;
-        my->needs_reset = done ? 1 : 0;
-        my->n_beams = n_beams + 1;
-        if (out.reward) out.reward[env] = reward;
-        if (out.reward_f32) out.reward_f32[env] = (float)reward;
-        if (out.terminated) out.terminated[env] = done ? 1 : 0;
-        if (out.truncated) out.truncated[env] = 0;
-    }
-    if (lane < 9) {                                                              // environment.py:259-268
-        float v;
-        if (lane >= 6) v = tm.obs_c[lane - 6];
-        else if (lane >= 3) v = (float)wk.dir[lane - 3];
-        else v = sc.obs_p[lane];
-        out.obs[(size_t)env * RT_OBS_SIZE + lane] = v;
-    }
-    if (beams && lane < 6 && n_beams < RT_MAX_TIME_STEPS) {                      // environment.py:110
-        const double pv = lane == 0 ? sc.px : (lane == 1 ? sc.py : sc.pz);
-        beams[((size_t)env * RT_MAX_TIME_STEPS + n_beams) * 6 + lane] = lane < 3 ? pv : wk.dir[lane - 3];
-    }
-    if (out.info && lane < RT_INFO_SIZE) {
-        double v;
-        switch (lane) {
-        case RT_INFO_REWARD_TOTAL: v = reward; break;
-        case RT_INFO_REWARD_TUMOUR: v = (double)r_tumour; break;
-        case RT_INFO_REWARD_LUNG: v = r_lung; break;
-        case RT_INFO_REWARD_DISTANCE: v = r_dist; break;
-        case RT_INFO_DOSE_TUMOUR: v = (double)tsum_f32; break;
-        case RT_INFO_DOSE_LUNG: v = (double)(float)lung_dose; break;
-        case RT_INFO_OVERSHOOT_T0: v = sc.os_t[0]; break;
-        case RT_INFO_OVERSHOOT_T0 + 1: v = sc.os_t[1]; break;
-        case RT_INFO_OVERSHOOT_T0 + 2: v = sc.os_t[2]; break;
-        case RT_INFO_OVERSHOOT_R:
-            while (reinterpret_cast<const volatile EnvWork &>(wk).os_ready == 0) {}   // long since published
-            __threadfence_block();
-            v = reinterpret_cast<const volatile EnvWork &>(wk).os_r;
-            break;
-        case RT_INFO_EPISODE_RETURN: v = ep_return; break;
-        case RT_INFO_EPISODE_LENGTH: v = (double)t; break;
-        case RT_INFO_LUNG_COUNT: v = (double)lung_count; break;
-        case RT_INFO_STEPPED: v = 1.0; break;
-        case RT_INFO_TUMOUR_ID: v = (double)tid; break;
-        default: v = (double)t; break;
-        }
-        out.info[(size_t)env * RT_INFO_SIZE + lane] = v;
-    }
-    RT_STAMP(7);
-}
-
 }  // namespace
 #include "rt_step.cuh"
-#include "rt_step_wide.cuh"
-#include "rt_step_split.cuh"
 namespace {
 
 // ---------------------------------------------------------------------------------
@@ -768,13 +341,21 @@ __global__ void __launch_bounds__(kDenseThreads) rt_dense_kernel(Tables T, EnvRe
 
     EnvRec *my = rec + env;
     const int t = dw.t;
-    const float tsum_f32 = (float)tumour_dose;
-    const float ratio = fdiv_rn_zero_num(tsum_f32, tm.tumour_sum);   // no dose on the tumour yet: the common case
+    float tsum_f32 = (float)tumour_dose;
+    float ratio = fdiv_rn_zero_num(tsum_f32, tm.tumour_sum);         // no dose on the tumour yet: the common case
+    if (fabsf(ratio - kDoneRatio) < kDoneWindow) {                   // on the termination threshold: NumPy's summation order decides
+        __threadfence_block();
+        const float *vol = dose + (size_t)env * G.vstride;
+        if (lane == 0)
+            tsum_f32 = np_pairwise_sparse(G.nvox, T.vox_xyz + tm.vox_off, tm.n_vox, G, [&](int lin) { return __ldcg(vol + lin); });
+        tsum_f32 = __shfl_sync(kFull, tsum_f32, 0);
+        ratio = __fdiv_rn(tsum_f32, tm.tumour_sum);
+    }
     const float r_tumour = __fmul_rn(ratio, 10.0f);
     const double r_lung = __dmul_rn(__ddiv_rn((double)lung_count, (double)tm.lung_mask_sum), -1.0);
     const double r_dist = __dmul_rn(__ddiv_rn(sqrt(dw.best), T.gnorm), -1.0);
     const double reward = __dadd_rn(__dadd_rn((double)r_tumour, r_lung), r_dist);
-    const bool done = (ratio >= 0.899999976158142090f) || (t >= RT_MAX_TIME_STEPS);
+    const bool done = (ratio >= kDoneRatio) || (t >= RT_MAX_TIME_STEPS);
     const double ep_return = dw.ep_return + reward;
     if (lane == 0) {
         my->tumour_dose = tumour_dose; my->lung_dose = lung_dose; my->ep_return = ep_return;
@@ -964,6 +545,11 @@ __global__ void rt_set_pose_kernel(EnvRec *rec, int n, const double *pose)
     const int e = k / 6, c = k % 6;
     if (c < 3) rec[e].pos[c] = pose[k];
     else rec[e].dir[c - 3] = pose[k];
+    if (c == 0) {                                   // dir / |dir| for the next step (transforms.py:23)
+        double a = pose[6 * e + 3], b = pose[6 * e + 4], d = pose[6 * e + 5];
+        normalize3(a, b, d);
+        rec[e].dn[0] = a; rec[e].dn[1] = b; rec[e].dn[2] = d;
+    }
 }
 
 __global__ void rt_get_counters_kernel(const EnvRec *rec, int n, int32_t *out)
@@ -975,14 +561,23 @@ __global__ void rt_get_counters_kernel(const EnvRec *rec, int n, int32_t *out)
     o[0] = r.t; o[1] = r.tumour_id; o[2] = r.lung_count; o[3] = r.episode; o[4] = r.needs_reset; o[5] = r.n_beams;
 }
 
-// dense dose of one env: a sector that was never written this episode reads as zero
-__global__ void rt_get_dose_kernel(Grid G, const float *dose, const uint32_t *valid, int env, float *out)
+// Source of an env's dose volume: sparse-mode cells {dose, generation} or a dense-mode float32 volume.
+struct DoseSrc {
+    const uint2 *cells;      // [N][vstride] or nullptr
+    const float *dense;      // [N][vstride] or nullptr
+};
+
+// dense float32 dose of one env: a cell of another generation reads as zero
+__global__ void rt_get_dose_kernel(Grid G, const EnvRec *rec, DoseSrc D, int env, float *out)
 {
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= G.nvox) return;
-    const int sec = v >> 3;
-    const bool ok = (valid[(size_t)env * G.vwords + (sec >> 5)] >> (sec & 31)) & 1u;
-    out[v] = ok ? dose[(size_t)env * G.vstride + v] : 0.0f;
+    if (D.cells) {
+        const uint2 c = D.cells[(size_t)env * G.vstride + v];
+        out[v] = c.y == rec[env].gen ? __uint_as_float(c.x) : 0.0f;
+    } else {
+        out[v] = D.dense[(size_t)env * G.vstride + v];
+    }
 }
 
 __global__ void rt_get_beams_kernel(const EnvRec *rec, const double *beams, int env, double *out, int32_t *n_out)
@@ -999,7 +594,7 @@ __global__ void rt_get_beams_kernel(const EnvRec *rec, const double *beams, int 
 // (V is even, so every channel plane stays 8-byte aligned).  4.03 MB of HBM traffic per env.
 constexpr int kVolThreads = 512;
 
-// kPacked = false: live envs [first, first + gridDim.x) (record, float32 dose, sector-valid bitmap).
+// kPacked = false: live envs [first, first + gridDim.x) (record, dose cells or dense float32 volume).
 // kPacked = true: compressed observation records (rt_pack_observations): bfloat16 dose volume, pose and tumour id of
 // record index[blockIdx.x] (or blockIdx.x); the other three planes are regenerated, the dose plane is the stored
 // bfloat16 value — exactly what a bf16 convolution reads from the float32 observation.
@@ -1011,8 +606,8 @@ struct PackedObs {
 };
 
 template <bool kPacked>
-__global__ void __launch_bounds__(kVolThreads) rt_volumes_kernel(Tables T, const EnvRec *rec, const float *dose,
-                                                                 const uint32_t *valid, int first, float *out, PackedObs P)
+__global__ void __launch_bounds__(kVolThreads) rt_volumes_kernel(Tables T, const EnvRec *rec, DoseSrc D, int first,
+                                                                 float *out, PackedObs P)
 {
     extern __shared__ uint32_t smem[];
     __shared__ RayWork view[2];
@@ -1063,8 +658,9 @@ __global__ void __launch_bounds__(kVolThreads) rt_volumes_kernel(Tables T, const
         }
     }
     __syncthreads();
-    const float2 *vol2 = kPacked ? nullptr : reinterpret_cast<const float2 *>(dose + (size_t)env * G.vstride);
-    const uint32_t *vbits = kPacked ? nullptr : valid + (size_t)env * G.vwords;
+    const float2 *vol2 = kPacked || !D.dense ? nullptr : reinterpret_cast<const float2 *>(D.dense + (size_t)env * G.vstride);
+    const uint4 *cell2 = kPacked || !D.cells ? nullptr : reinterpret_cast<const uint4 *>(D.cells + (size_t)env * G.vstride);
+    const uint32_t gen = kPacked ? 0u : r.gen;
     const __nv_bfloat162 *pk2 = kPacked ? reinterpret_cast<const __nv_bfloat162 *>(P.dose + (size_t)env * G.vstride) : nullptr;
     float *o = out + (size_t)blockIdx.x * 4 * G.nvox;
     float2 *o0 = reinterpret_cast<float2 *>(o), *o1 = reinterpret_cast<float2 *>(o + (size_t)G.nvox);
@@ -1073,19 +669,18 @@ __global__ void __launch_bounds__(kVolThreads) rt_volumes_kernel(Tables T, const
     constexpr int kUnroll = 4;
     for (int q0 = threadIdx.x; q0 < npairs; q0 += kUnroll * kVolThreads) {
         float2 d[kUnroll];
-        bool ok[kUnroll];
 #pragma unroll
         for (int u = 0; u < kUnroll; u++) {
             const int q = q0 + u * kVolThreads;
-            ok[u] = false;
             d[u] = make_float2(0.f, 0.f);
             if (q < npairs) {
                 if (kPacked) {
                     d[u] = __bfloat1622float2(pk2[q]);
+                } else if (cell2) {
+                    const uint4 c = __ldcs(cell2 + q);           // two cells; another generation reads as zero
+                    d[u] = make_float2(c.y == gen ? __uint_as_float(c.x) : 0.0f, c.w == gen ? __uint_as_float(c.z) : 0.0f);
                 } else {
-                    const int sec = q >> 2;                      // 2 voxels per pair, 8 per sector
-                    ok[u] = (vbits[sec >> 5] >> (sec & 31)) & 1u;
-                    if (ok[u]) d[u] = vol2[q];          // a sector never written this episode reads as zero
+                    d[u] = __ldcs(vol2 + q);
                 }
             }
         }
@@ -1112,24 +707,23 @@ __global__ void __launch_bounds__(kVolThreads) rt_volumes_kernel(Tables T, const
 }
 
 // ---------------------------------------------------------------------------------
-// Compressed observation record of live envs [first, first + count): the dose volume as bfloat16 (sectors never
-// written this episode are zero), the pose and the tumour id.  806,784 B of float32 volume -> 403,392 B; with the
-// three regenerated planes a stored voxel observation costs 1/8 of its float32 [4][V] form.
-__global__ void __launch_bounds__(256) rt_pack_kernel(Grid G, const EnvRec *rec, const float *dose, const uint32_t *valid,
-                                                      int first, long long slot0, __nv_bfloat16 *out_dose, double *out_pose,
-                                                      int32_t *out_tid)
+// Compressed observation record of live envs [first, first + count): the dose volume as bfloat16 (cells of an earlier
+// generation are zero), the pose and the tumour id: 403,392 B; with the three regenerated planes a stored voxel
+// observation costs 1/8 of its float32 [4][V] form.
+__global__ void __launch_bounds__(256) rt_pack_kernel(Grid G, const EnvRec *rec, const uint2 *cells, int first, long long slot0,
+                                                      __nv_bfloat16 *out_dose, double *out_pose, int32_t *out_tid)
 {
     const int env = first + blockIdx.y;
     const long long slot = slot0 + blockIdx.y;
-    const float4 *vol4 = reinterpret_cast<const float4 *>(dose + (size_t)env * G.vstride);
-    const uint32_t *vbits = valid + (size_t)env * G.vwords;
+    const uint4 *vol = reinterpret_cast<const uint4 *>(cells + (size_t)env * G.vstride);       // two cells per load
+    const uint32_t gen = rec[env].gen;
     uint2 *o = reinterpret_cast<uint2 *>(out_dose + (size_t)slot * G.vstride);
     const int nquads = G.vstride / 4;
     for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nquads; q += gridDim.x * blockDim.x) {
-        const int sec = q >> 1;                                    // 4 voxels per quad, 8 per sector
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if ((vbits[sec >> 5] >> (sec & 31)) & 1u) v = vol4[q];
-        const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+        const uint4 c0 = __ldcs(vol + 2 * q), c1 = __ldcs(vol + 2 * q + 1);
+        const float v0 = c0.y == gen ? __uint_as_float(c0.x) : 0.0f, v1 = c0.w == gen ? __uint_as_float(c0.z) : 0.0f;
+        const float v2 = c1.y == gen ? __uint_as_float(c1.x) : 0.0f, v3 = c1.w == gen ? __uint_as_float(c1.z) : 0.0f;
+        const __nv_bfloat162 a = __floats2bfloat162_rn(v0, v1), b = __floats2bfloat162_rn(v2, v3);
         o[q] = make_uint2(*reinterpret_cast<const uint32_t *>(&a), *reinterpret_cast<const uint32_t *>(&b));
     }
     if (blockIdx.x == 0 && threadIdx.x < 6)
@@ -1193,24 +787,14 @@ struct rt_env {
     Tables T{};
     Schedule S{};
     EnvRec *rec = nullptr;
-    float *dose = nullptr;
-    uint32_t *valid = nullptr;
+    uint2 *cells = nullptr;   // sparse mode: {dose, generation} per voxel
+    float *dose = nullptr;    // dense mode: float32 volumes
     double *beams = nullptr;
     DenseWork *dense = nullptr;
     size_t dense_smem = 0;
     size_t step_smem = 0;
-    int step_kb = 0;          // envs per block of rt_step3_kernel (7, 14 or 28); 0 = the two-role kernel of rt_step_kernel;
-                              // -1 = thread-per-env kernel; -2 = pose + deposit kernels (rt_step_split.cuh)
-    int split_kw = 8;         // warps (= envs) per block of rt_split_deposit_kernel
-    BeamWork *work = nullptr; // split step: hand-over records and the slab walks
-    float2 *yzg = nullptr;
-    uint2 *brief = nullptr;
-    int split_blocks = 0, split_epb = 0;   // deposit kernel: blocks and envs per block
-    int yz_stride = 0;
-    size_t pose_smem = 0, deposit_smem = 0;
-    bool use_pdl = true;      // RT_PDL=0 in the environment switches programmatic dependent launch off
-    bool use_flag = false;    // RT_HOST_FLAG=1: rt_step_host polls a completion flag the kernel raises instead of waiting for the
-                              // stream (measured slower: 31.4 against 28.9 us per call - a system-scope fence per block)
+    int step_kb = 14;         // envs per block of rt_step_kernel: 7 while one block per SM covers the envs, else 14
+    bool use_pdl = true;      // programmatic dependent launch of consecutive steps (rt_set_pdl)
     uint32_t *d_lungs = nullptr;
     Tumour *d_tumours = nullptr;
     uint32_t *d_tbits = nullptr;
@@ -1223,12 +807,9 @@ struct rt_env {
     float *h_actions = nullptr, *h_obs = nullptr;
     double *h_reward = nullptr, *h_info = nullptr;
     uint8_t *h_term = nullptr, *h_trunc = nullptr, *h_mask = nullptr;
-    // completion flag of rt_step_host: polled by the host instead of cudaStreamSynchronize
-    unsigned int *done_counter = nullptr;            // device
-    volatile unsigned int *h_flag = nullptr;         // pinned host memory
-    volatile unsigned int *h_flag_dev = nullptr;     // ... as the device sees it
-    unsigned int signal_value = 0;
-    bool signal_next = false, signal_armed = false;
+    // Device-pointer entry points run on the caller's stream, the *_host entry points on hstream: a host call that
+    // follows device-side work waits for it first (the reverse order needs nothing: host calls return drained).
+    bool dev_pending = false;
 };
 
 namespace {
@@ -1239,8 +820,6 @@ Grid make_grid(const int32_t g[3])
     G.g0 = g[0]; G.g1 = g[1]; G.g2 = g[2];
     G.nvox = g[0] * g[1] * g[2];
     G.vstride = (G.nvox + 31) / 32 * 32;
-    const int sectors = G.vstride / 8;
-    G.vwords = ((sectors + 31) / 32 + 31) / 32 * 32;
     return G;
 }
 
@@ -1294,7 +873,6 @@ int rt_create(rt_env **out, int device, int n_envs, uint32_t flags, const rt_pha
     e->T.gnorm = sqrt((double)(G.g0 * G.g0 + G.g1 * G.g1 + G.g2 * G.g2));
     e->T.n_tumours = ph->n_tumours;
     e->T.stage_clock = nullptr;
-    e->T.debug = getenv("RT_STEP_DEBUG") ? atoi(getenv("RT_STEP_DEBUG")) : 0;
 
     // tumour table: bbox, bbox-local bitmask, packed voxel coordinates
     std::vector<Tumour> tum(ph->n_tumours);
@@ -1386,82 +964,37 @@ int rt_create(rt_env **out, int device, int n_envs, uint32_t flags, const rt_pha
 
     int rc = RT_OK;
     const size_t lung_words = (size_t)(G.nvox + 31) / 32;
-    e->T.lung_words16 = (int)((lung_words + 3) / 4 * 4);
+    // device copy of the lungs bitmask: kLungPadBits zero bits in front, at least two zero words behind (bit_pair)
+    const size_t lung_pad_words = kLungPadBits / 32;
+    e->T.lung_words16 = (int)((lung_pad_words + lung_words + 2 + 3) / 4 * 4);
+    const bool dense_mode = (flags & RT_FLAG_DENSE) != 0;
     if ((rc = dev_alloc(&e->d_lungs, (size_t)e->T.lung_words16, &e->bytes)) || (rc = dev_alloc(&e->d_tumours, tum.size(), &e->bytes)) ||
         (rc = dev_alloc(&e->d_tbits, tbits.size(), &e->bytes)) || (rc = dev_alloc(&e->d_ptbits, ptbits.size(), &e->bytes)) || (rc = dev_alloc(&e->d_vox, vox_dev.size(), &e->bytes)) ||
         (rc = dev_alloc(&e->rec, (size_t)n_envs, &e->bytes)) ||
-        (rc = dev_alloc(&e->dose, (size_t)n_envs * G.vstride, &e->bytes)) ||
-        (rc = dev_alloc(&e->valid, (size_t)n_envs * G.vwords, &e->bytes))) {
+        (rc = dense_mode ? dev_alloc(&e->dose, (size_t)n_envs * G.vstride, &e->bytes)
+                         : dev_alloc(&e->cells, (size_t)n_envs * G.vstride, &e->bytes))) {
         rt_destroy(e);
         return rc;
     }
     if (flags & RT_FLAG_RECORD_BEAMS)
         if ((rc = dev_alloc(&e->beams, (size_t)n_envs * RT_MAX_TIME_STEPS * 6, &e->bytes))) { rt_destroy(e); return rc; }
-    if (const char *v = getenv("RT_PDL")) e->use_pdl = atoi(v) != 0;
-    if (const char *v = getenv("RT_HOST_FLAG")) e->use_flag = atoi(v) != 0;
     {
-        // Envs per block of the step kernel: 7 while that covers the envs with one block per SM, else 14 (two
-        // blocks per SM; measured a little faster than one block of 28 both at 4096 envs and at 65536).
-        // RT_STEP_KB overrides: 7, 14, 28 (the stage-clock instrumentation exists for 28 only), 0 = the previous
-        // two-role kernel rt_step_kernel<false>.
+        // Envs per block of the step kernel: 7 while that covers the envs with one block per SM (four blocks fit an
+        // SM, lungs bitmask through L1), else 14 (two blocks per SM, lungs bitmask staged in shared memory).
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
         const int per_sm = (n_envs + sms - 1) / sms;
         e->step_kb = per_sm <= 7 ? 7 : 14;
-        if (const char *v = getenv("RT_STEP_KB")) {
-            const int kb = atoi(v);
-            if (kb == 0 || kb == 7 || kb == 14 || kb == 28 || kb == -1 || kb == -2) e->step_kb = kb;    // -1: thread-per-env kernel, -2: split
-        }
-        if (e->step_kb == -2) {
-            int gmax = G.g0 > G.g1 ? G.g0 : G.g1;
-            gmax = gmax > G.g2 ? gmax : G.g2;
-            e->yz_stride = (gmax + 1 + 3) & ~3;                               // a beam has at most max(G) + 1 slabs; 32-byte rows
-            e->split_kw = 28;
-            if (const char *v = getenv("RT_SPLIT_KW")) {
-                const int kw = atoi(v);
-                if (kw == 14 || kw == 28) e->split_kw = kw;
-            }
-            if (ph->n_tumours > 65535) { rt_destroy(e); return fail(RT_ERR_INVALID, "rt_create: the split step supports at most 65535 tumours"); }
-            if ((rc = dev_alloc(&e->work, (size_t)n_envs, &e->bytes)) || (rc = dev_alloc(&e->brief, (size_t)n_envs, &e->bytes)) ||
-                (rc = dev_alloc(&e->yzg, (size_t)n_envs * e->yz_stride, &e->bytes))) { rt_destroy(e); return rc; }
-            // persistent deposit kernel: one block of 32 warps per SM (or two of 14 / 16), consecutive envs per block
-            int blocks_max = sms * (kSplitWarpsPerSM / e->split_kw);
-            if (const char *v = getenv("RT_SPLIT_BLOCKS")) {                  // tests: many envs per warp at small env counts
-                const int bm = atoi(v);
-                if (bm >= 1 && bm < blocks_max) blocks_max = bm;
-            }
-            e->split_epb = (n_envs + blocks_max - 1) / blocks_max;
-            e->split_blocks = (n_envs + e->split_epb - 1) / e->split_epb;
-            e->pose_smem = (size_t)kPoseThreads * RT_OBS_SIZE * sizeof(float);
-            e->deposit_smem = (size_t)e->T.lung_words16 * sizeof(uint32_t) +
-                              (size_t)e->split_kw * (sizeof(DepositWarp) + G.vwords * sizeof(uint32_t) + 2 * e->yz_stride * sizeof(float2));
-            cudaError_t se = cudaFuncSetAttribute(rt_split_pose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->pose_smem);
-            if (se == cudaSuccess) {
-                switch (e->split_kw) {
-                case 14: se = cudaFuncSetAttribute(rt_split_deposit_kernel<14>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->deposit_smem); break;
-                default: se = cudaFuncSetAttribute(rt_split_deposit_kernel<28>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->deposit_smem); break;
-                }
-            }
-            if (se != cudaSuccess) { rt_destroy(e); return fail(RT_ERR_CUDA, std::string("rt_split kernels smem: ") + cudaGetErrorString(se)); }
-        }
-        const int kb = e->step_kb > 0 ? e->step_kb : kEnvsPerBlock;
-        e->step_smem = (size_t)kb * G.vwords * sizeof(uint32_t) + (e->step_kb >= 14 ? (size_t)e->T.lung_words16 * sizeof(uint32_t) : 0);
+        e->step_smem = (e->step_kb >= 14 && !dense_mode) ? (size_t)e->T.lung_words16 * sizeof(uint32_t) : 0;
         cudaError_t ae = cudaSuccess;
-        switch (e->step_kb) {
-        case -1: break;
-        case -2: break;
-        case 0: ae = cudaFuncSetAttribute(rt_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->step_smem); break;
-        case 7: ae = cudaFuncSetAttribute(rt_step3_kernel<7, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->step_smem); break;
-        case 14: ae = cudaFuncSetAttribute(rt_step3_kernel<14, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->step_smem); break;
-        default:
-            ae = cudaFuncSetAttribute(rt_step3_kernel<28, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->step_smem);
+        if (e->step_smem) {
+            ae = cudaFuncSetAttribute(rt_step_kernel<14, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->step_smem);
             if (ae == cudaSuccess)
-                ae = cudaFuncSetAttribute(rt_step3_kernel<28, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->step_smem);
-            break;
+                ae = cudaFuncSetAttribute(rt_step_kernel<14, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->step_smem);
         }
         if (ae != cudaSuccess) { rt_destroy(e); return fail(RT_ERR_CUDA, std::string("rt_step_kernel smem: ") + cudaGetErrorString(ae)); }
     }
-    if (flags & RT_FLAG_DENSE) {
+    if (dense_mode) {
         int gmax = G.g0 > G.g1 ? G.g0 : G.g1;
         gmax = gmax > G.g2 ? gmax : G.g2;
         if (4 * (gmax + 1) > RT_BEAM_CAP) { rt_destroy(e); return fail(RT_ERR_INVALID, "rt_create: dense mode needs 4*(max(grid)+1) <= RT_BEAM_CAP"); }
@@ -1473,14 +1006,15 @@ int rt_create(rt_env **out, int device, int n_envs, uint32_t flags, const rt_pha
     cudaError_t ce = cudaSuccess;
     auto chk = [&](cudaError_t x) { if (ce == cudaSuccess) ce = x; };
     chk(cudaMemset(e->d_lungs, 0, (size_t)e->T.lung_words16 * sizeof(uint32_t)));
-    chk(cudaMemcpy(e->d_lungs, ph->lungs_bits, lung_words * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    chk(cudaMemcpy(e->d_lungs + lung_pad_words, ph->lungs_bits, lung_words * sizeof(uint32_t), cudaMemcpyHostToDevice));
     chk(cudaMemcpy(e->d_tumours, tum.data(), tum.size() * sizeof(Tumour), cudaMemcpyHostToDevice));
     chk(cudaMemcpy(e->d_tbits, tbits.data(), tbits.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     chk(cudaMemcpy(e->d_ptbits, ptbits.data(), ptbits.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     chk(cudaMemcpy(e->d_vox, vox_dev.data(), vox_dev.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     chk(cudaMemset(e->rec, 0, (size_t)n_envs * sizeof(EnvRec)));
-    chk(cudaMemset(e->valid, 0, (size_t)n_envs * G.vwords * sizeof(uint32_t)));
-    // dose is deliberately left uninitialised: a sector is only read once its valid bit is set
+    // every cell starts in generation 0xffffffff, which no env ever reaches (EnvRec::gen counts resets from 0): the
+    // volumes read as zero without being written; dense-mode volumes are zeroed by the first rt_reset
+    if (e->cells) chk(cudaMemset(e->cells, 0xff, (size_t)n_envs * G.vstride * sizeof(uint2)));
     chk(cudaStreamCreateWithFlags(&e->hstream, cudaStreamNonBlocking));
     chk(cudaMallocHost(&e->h_actions, (size_t)n_envs * RT_ACTION_SIZE * sizeof(float)));
     chk(cudaMallocHost(&e->h_obs, (size_t)n_envs * RT_OBS_SIZE * sizeof(float)));
@@ -1489,20 +1023,12 @@ int rt_create(rt_env **out, int device, int n_envs, uint32_t flags, const rt_pha
     chk(cudaMallocHost(&e->h_term, (size_t)n_envs));
     chk(cudaMallocHost(&e->h_trunc, (size_t)n_envs));
     chk(cudaMallocHost(&e->h_mask, (size_t)n_envs));
-    {
-        void *f = nullptr, *fd = nullptr;
-        chk(cudaMallocHost(&f, 64));
-        if (f) { memset(f, 0, 64); chk(cudaHostGetDevicePointer(&fd, f, 0)); }
-        e->h_flag = reinterpret_cast<volatile unsigned int *>(f);
-        e->h_flag_dev = reinterpret_cast<volatile unsigned int *>(fd);
-        chk(cudaMalloc(reinterpret_cast<void **>(&e->done_counter), sizeof(unsigned int)));
-        if (e->done_counter) chk(cudaMemset(e->done_counter, 0, sizeof(unsigned int)));
-    }
     if (ce != cudaSuccess) {
         rt_destroy(e);
         return fail(RT_ERR_CUDA, std::string("rt_create: ") + cudaGetErrorString(ce));
     }
-    e->T.lungs_bits = e->d_lungs;
+    e->T.lungs_pad = e->d_lungs;
+    e->T.lungs_bits = e->d_lungs + lung_pad_words;
     e->T.tumours = e->d_tumours;
     e->T.tumour_bits = e->d_tbits;
     e->T.tumour_pbits = e->d_ptbits;
@@ -1518,14 +1044,14 @@ int rt_destroy(rt_env *e)
 {
     if (!e) return RT_OK;
     cudaSetDevice(e->device);
+    cudaDeviceSynchronize();
     cudaFree(e->d_lungs); cudaFree(e->d_tumours); cudaFree(e->d_tbits); cudaFree(e->d_ptbits); cudaFree(e->d_vox);
-    cudaFree(e->rec); cudaFree(e->dose); cudaFree(e->valid); cudaFree(e->beams); cudaFree(e->dense); cudaFree(e->d_sched);
-    cudaFree(e->work); cudaFree(e->yzg); cudaFree(e->brief); cudaFree(e->done_counter);
-    if (e->h_flag) cudaFreeHost(const_cast<unsigned int *>(e->h_flag));
+    cudaFree(e->rec); cudaFree(e->cells); cudaFree(e->dose); cudaFree(e->beams); cudaFree(e->dense); cudaFree(e->d_sched);
     // the *_host staging buffers are device-visible pinned allocations of the same sizes
     cudaFreeHost(e->h_actions); cudaFreeHost(e->h_obs); cudaFreeHost(e->h_reward); cudaFreeHost(e->h_info);
     cudaFreeHost(e->h_term); cudaFreeHost(e->h_trunc); cudaFreeHost(e->h_mask);
     if (e->hstream) cudaStreamDestroy(e->hstream);
+    g_alias_epoch.fetch_add(1, std::memory_order_relaxed);      // addresses of freed pinned buffers may be reused: drop cached aliases
     delete e;
     return RT_OK;
 }
@@ -1561,15 +1087,26 @@ int rt_set_tumour_schedule(rt_env *e, const int32_t *ids_host, int n_episodes)
     return RT_OK;
 }
 
+// A *_host call runs on the handle's own stream; if device-pointer calls were issued since the last one (on
+// whatever stream the caller used), wait for them first.
+static int sync_before_host_call(rt_env *e)
+{
+    if (e->dev_pending) {
+        RT_CUDA(cudaDeviceSynchronize());
+        e->dev_pending = false;
+    }
+    return RT_OK;
+}
+
 int rt_reset(rt_env *e, const uint8_t *mask_dev, float *obs_dev, void *stream)
 {
     if (!e) return fail(RT_ERR_INVALID, "rt_reset: NULL handle");
     RT_CUDA(cudaSetDevice(e->device));
-    rt_reset_kernel<<<warps_grid(e->n, 256), 256, 0, (cudaStream_t)stream>>>(e->T, e->S, e->rec, e->valid, e->n,
-                                                                            mask_dev, obs_dev, e->dense);
+    if ((cudaStream_t)stream != e->hstream) e->dev_pending = true;
+    rt_reset_kernel<<<warps_grid(e->n, 256), 256, 0, (cudaStream_t)stream>>>(e->T, e->S, e->rec, e->n, mask_dev, obs_dev, e->dense);
     RT_LAUNCH_CHECK("rt_reset_kernel");
     if (e->dense) {
-        StepOut none{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0u};
+        StepOut none{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
         rt_dense_kernel<<<e->n, kDenseThreads, e->dense_smem, (cudaStream_t)stream>>>(e->T, e->rec, e->dose, e->dense, none);
         RT_LAUNCH_CHECK("rt_dense_kernel");
     }
@@ -1581,85 +1118,36 @@ int rt_step(rt_env *e, const float *actions_dev, float *obs_dev, double *reward_
 {
     if (!e || !actions_dev || !obs_dev) return fail(RT_ERR_INVALID, "rt_step: NULL handle, actions or obs");
     RT_CUDA(cudaSetDevice(e->device));
-    StepOut o{obs_dev, reward_dev, reward_f32_dev, terminated_dev, truncated_dev, info_dev, nullptr, nullptr, 0u};
-    if (e->signal_next && !e->dense && e->step_kb > 0) {      // rt_step_host asked for the completion flag (fused step kernel only)
-        o.done_counter = e->done_counter;
-        o.done_flag = e->h_flag_dev;
-        o.done_value = e->signal_value;
-        e->signal_armed = true;
-    }
-    e->signal_next = false;
-    const int grid = (e->n + kEnvsPerBlock - 1) / kEnvsPerBlock;
+    if ((cudaStream_t)stream != e->hstream) e->dev_pending = true;
+    StepOut o{obs_dev, reward_dev, reward_f32_dev, terminated_dev, truncated_dev, info_dev};
+    const int kb = e->step_kb;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((e->n + kb - 1) / kb);
+    cfg.blockDim = dim3((kb + 1) * kWarp);
+    cfg.dynamicSmemBytes = e->step_smem;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = e->use_pdl && !e->dense ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
     if (e->dense) {
-        rt_step_kernel<true><<<grid, kStepThreads, 0, (cudaStream_t)stream>>>(e->T, e->S, e->rec, e->dose, e->valid,
-                                                                             e->beams, e->n, actions_dev, o, e->dense);
+        if (kb == 7)
+            RT_CUDA(cudaLaunchKernelEx(&cfg, rt_step_kernel<7, false, true>, e->T, e->S, e->rec, e->cells, e->beams, e->n, actions_dev, o, e->dense));
+        else
+            RT_CUDA(cudaLaunchKernelEx(&cfg, rt_step_kernel<14, false, true>, e->T, e->S, e->rec, e->cells, e->beams, e->n, actions_dev, o, e->dense));
         RT_LAUNCH_CHECK("rt_step_kernel<dense>");
         rt_dense_kernel<<<e->n, kDenseThreads, e->dense_smem, (cudaStream_t)stream>>>(e->T, e->rec, e->dose, e->dense, o);
         RT_LAUNCH_CHECK("rt_dense_kernel");
-    } else if (e->step_kb == -2) {
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[0].val.programmaticStreamSerializationAllowed = e->use_pdl ? 1 : 0;
-        cudaLaunchConfig_t cfg = {};
-        cfg.stream = (cudaStream_t)stream;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        cfg.gridDim = dim3((e->n + kPoseThreads - 1) / kPoseThreads);
-        cfg.blockDim = dim3(kPoseThreads);
-        cfg.dynamicSmemBytes = e->pose_smem;
-        const int want_info = info_dev ? 1 : 0;
-        RT_CUDA(cudaLaunchKernelEx(&cfg, rt_split_pose_kernel, e->T, e->S, e->rec, e->beams, e->n, actions_dev, e->work, e->brief,
-                                   e->yzg, e->yz_stride, obs_dev, want_info));
-        RT_LAUNCH_CHECK("rt_split_pose_kernel");
-        const int kw = e->split_kw;
-        cfg.gridDim = dim3(e->split_blocks);
-        cfg.blockDim = dim3(kw * kWarp);
-        cfg.dynamicSmemBytes = e->deposit_smem;
-        const BeamWork *wk = e->work;
-        const uint2 *br = e->brief;
-        const float2 *yz = e->yzg;
-        switch (kw) {
-        case 14: RT_CUDA(cudaLaunchKernelEx(&cfg, rt_split_deposit_kernel<14>, e->T, e->rec, e->dose, e->valid, e->n, e->split_epb, wk, br, yz, e->yz_stride, o)); break;
-        default: RT_CUDA(cudaLaunchKernelEx(&cfg, rt_split_deposit_kernel<28>, e->T, e->rec, e->dose, e->valid, e->n, e->split_epb, wk, br, yz, e->yz_stride, o)); break;
-        }
-        RT_LAUNCH_CHECK("rt_split_deposit_kernel");
-    } else if (e->step_kb == -1) {
-        rt_step_wide_kernel<<<(e->n + kWideThreads - 1) / kWideThreads, kWideThreads, 0, (cudaStream_t)stream>>>(
-            e->T, e->S, e->rec, e->dose, e->valid, e->beams, e->n, actions_dev, o);
-        RT_LAUNCH_CHECK("rt_step_wide_kernel");
-    } else {
-        const int kb = e->step_kb ? e->step_kb : kEnvsPerBlock;
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((e->n + kb - 1) / kb);
-        cfg.blockDim = dim3((kb + 1) * kWarp);
-        cfg.dynamicSmemBytes = e->step_smem;
-        cfg.stream = (cudaStream_t)stream;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[0].val.programmaticStreamSerializationAllowed = e->use_pdl ? 1 : 0;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        DenseWork *no_dense = nullptr;
-        switch (e->step_kb) {
-        case 0:
-            RT_CUDA(cudaLaunchKernelEx(&cfg, rt_step_kernel<false>, e->T, e->S, e->rec, e->dose, e->valid, e->beams, e->n,
-                                       actions_dev, o, no_dense));
-            break;
-        case 7:
-            RT_CUDA(cudaLaunchKernelEx(&cfg, rt_step3_kernel<7, false>, e->T, e->S, e->rec, e->dose, e->valid, e->beams, e->n, actions_dev, o));
-            break;
-        case 14:
-            RT_CUDA(cudaLaunchKernelEx(&cfg, rt_step3_kernel<14, false>, e->T, e->S, e->rec, e->dose, e->valid, e->beams, e->n, actions_dev, o));
-            break;
-        default:
-            if (e->T.stage_clock)
-                RT_CUDA(cudaLaunchKernelEx(&cfg, rt_step3_kernel<28, true>, e->T, e->S, e->rec, e->dose, e->valid, e->beams, e->n, actions_dev, o));
-            else
-                RT_CUDA(cudaLaunchKernelEx(&cfg, rt_step3_kernel<28, false>, e->T, e->S, e->rec, e->dose, e->valid, e->beams, e->n, actions_dev, o));
-            break;
-        }
-        RT_LAUNCH_CHECK("rt_step_kernel");
+        return RT_OK;
     }
+    if (kb == 7)
+        RT_CUDA(cudaLaunchKernelEx(&cfg, rt_step_kernel<7, false, false>, e->T, e->S, e->rec, e->cells, e->beams, e->n, actions_dev, o, e->dense));
+    else if (e->T.stage_clock)
+        RT_CUDA(cudaLaunchKernelEx(&cfg, rt_step_kernel<14, true, false>, e->T, e->S, e->rec, e->cells, e->beams, e->n, actions_dev, o, e->dense));
+    else
+        RT_CUDA(cudaLaunchKernelEx(&cfg, rt_step_kernel<14, false, false>, e->T, e->S, e->rec, e->cells, e->beams, e->n, actions_dev, o, e->dense));
+    RT_LAUNCH_CHECK("rt_step_kernel");
     return RT_OK;
 }
 
@@ -1667,6 +1155,7 @@ int rt_reset_host(rt_env *e, const uint8_t *mask_host, float *obs_host)
 {
     if (!e || !obs_host) return fail(RT_ERR_INVALID, "rt_reset_host: NULL argument");
     RT_CUDA(cudaSetDevice(e->device));
+    if (int rc = sync_before_host_call(e)) return rc;
     uint8_t *dmask = nullptr;
     uint8_t *d_mask_dev = nullptr;
     if (mask_host) {
@@ -1682,11 +1171,18 @@ int rt_reset_host(rt_env *e, const uint8_t *mask_host, float *obs_host)
     return RT_OK;
 }
 
+int rt_set_pdl(rt_env *e, int enabled)
+{
+    if (!e) return fail(RT_ERR_INVALID, "rt_set_pdl: NULL handle");
+    e->use_pdl = enabled != 0;
+    return RT_OK;
+}
+
 int rt_set_stage_clock(rt_env *e, long long *stamps_dev)
 {
     if (!e) return fail(RT_ERR_INVALID, "rt_set_stage_clock: NULL handle");
-    if (stamps_dev && e->step_kb != 28)
-        return fail(RT_ERR_STATE, "rt_set_stage_clock: the instrumented step kernel exists for 28 envs per block only (RT_STEP_KB=28)");
+    if (stamps_dev && (e->step_kb != 14 || e->dense))
+        return fail(RT_ERR_STATE, "rt_set_stage_clock: the instrumented step kernel exists for sparse-mode handles with 14 envs per block (more than 7 envs per SM)");
     e->T.stage_clock = stamps_dev;
     return RT_OK;
 }
@@ -1704,6 +1200,7 @@ int rt_set_pose(rt_env *e, const double *pose_dev, void *stream)
 {
     if (!e || !pose_dev) return fail(RT_ERR_INVALID, "rt_set_pose: NULL argument");
     RT_CUDA(cudaSetDevice(e->device));
+    e->dev_pending = true;
     rt_set_pose_kernel<<<(e->n * 6 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(e->rec, e->n, pose_dev);
     RT_LAUNCH_CHECK("rt_set_pose_kernel");
     return RT_OK;
@@ -1723,7 +1220,7 @@ int rt_get_dose(rt_env *e, int env_index, float *dose_dev, void *stream)
     if (!e || !dose_dev) return fail(RT_ERR_INVALID, "rt_get_dose: NULL argument");
     if (env_index < 0 || env_index >= e->n) return fail(RT_ERR_INVALID, "rt_get_dose: env index out of range");
     RT_CUDA(cudaSetDevice(e->device));
-    rt_get_dose_kernel<<<(e->T.G.nvox + 255) / 256, 256, 0, (cudaStream_t)stream>>>(e->T.G, e->dose, e->valid,
+    rt_get_dose_kernel<<<(e->T.G.nvox + 255) / 256, 256, 0, (cudaStream_t)stream>>>(e->T.G, e->rec, DoseSrc{e->cells, e->dose},
                                                                                   env_index, dose_dev);
     RT_LAUNCH_CHECK("rt_get_dose_kernel");
     return RT_OK;
@@ -1755,7 +1252,7 @@ int rt_assemble_volumes(rt_env *e, int first, int count, float *obs_dev, void *s
         RT_CUDA(cudaFuncSetAttribute(rt_volumes_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
-    rt_volumes_kernel<false><<<count, kVolThreads, smem, (cudaStream_t)stream>>>(e->T, e->rec, e->dose, e->valid, first,
+    rt_volumes_kernel<false><<<count, kVolThreads, smem, (cudaStream_t)stream>>>(e->T, e->rec, DoseSrc{e->cells, e->dose}, first,
                                                                                 obs_dev, PackedObs{});
     RT_LAUNCH_CHECK("rt_volumes_kernel");
     return RT_OK;
@@ -1772,7 +1269,7 @@ int rt_pack_observations(rt_env *e, int first, int count, int64_t slot0, void *d
         return fail(RT_ERR_INVALID, "rt_pack_observations: env range out of bounds");
     if (e->dense) return fail(RT_ERR_STATE, "rt_pack_observations: not available for dense-mode handles");
     RT_CUDA(cudaSetDevice(e->device));
-    rt_pack_kernel<<<dim3(8, count), 256, 0, (cudaStream_t)stream>>>(e->T.G, e->rec, e->dose, e->valid, first, (long long)slot0,
+    rt_pack_kernel<<<dim3(8, count), 256, 0, (cudaStream_t)stream>>>(e->T.G, e->rec, e->cells, first, (long long)slot0,
                                                                     reinterpret_cast<__nv_bfloat16 *>(dose_bf16_dev), pose_dev,
                                                                     tumour_id_dev);
     RT_LAUNCH_CHECK("rt_pack_kernel");
@@ -1795,19 +1292,25 @@ int rt_render_observations(rt_env *e, const void *dose_bf16_dev, const double *p
         attr_set = true;
     }
     PackedObs P{reinterpret_cast<const __nv_bfloat16 *>(dose_bf16_dev), pose_dev, tumour_id_dev, index_dev};
-    rt_volumes_kernel<true><<<count, kVolThreads, smem, (cudaStream_t)stream>>>(e->T, nullptr, nullptr, nullptr, 0, obs_dev, P);
+    rt_volumes_kernel<true><<<count, kVolThreads, smem, (cudaStream_t)stream>>>(e->T, nullptr, DoseSrc{nullptr, nullptr}, 0, obs_dev, P);
     RT_LAUNCH_CHECK("rt_volumes_kernel<packed>");
     return RT_OK;
 }
 
-// Device alias of a host pointer if (and only if) it is page-locked, else NULL.  The answer is cached
-// per address (the attribute query costs about a microsecond and a step passes six buffers).
+// Device alias of a host pointer if (and only if) it is page-locked, else NULL.  The answer is cached per address
+// and thread (the attribute query costs about a microsecond and a step passes six buffers); the cache is dropped
+// whenever a handle is destroyed, because its pinned staging buffers are freed and their addresses can come back as
+// pageable memory.  Callers that free their own pinned buffers while a handle lives must not reuse the addresses for
+// pageable arrays passed to the *_host calls (documented in rt_env.h).
 static void *pinned_alias(const void *host)
 {
     struct Entry { const void *host; void *dev; };
     static thread_local Entry cache[16];
     static thread_local int n_cached = 0;
+    static thread_local unsigned epoch = 0;
     if (!host) return nullptr;
+    const unsigned now = g_alias_epoch.load(std::memory_order_relaxed);
+    if (now != epoch) { n_cached = 0; epoch = now; }
     for (int i = 0; i < n_cached; i++)
         if (cache[i].host == host) return cache[i].dev;
     cudaPointerAttributes at;
@@ -1823,6 +1326,7 @@ int rt_step_host(rt_env *e, const float *actions_host, float *obs_host, double *
 {
     if (!e || !actions_host || !obs_host) return fail(RT_ERR_INVALID, "rt_step_host: NULL argument");
     RT_CUDA(cudaSetDevice(e->device));
+    if (int rc = sync_before_host_call(e)) return rc;
     // Host buffers are reached zero-copy: the step kernel reads the actions and writes its
     // results straight over PCIe into page-locked memory (one launch, no copy-engine round
     // trips).  Caller buffers that are already pinned (e.g. torch pin_memory) are used in
@@ -1843,25 +1347,8 @@ int rt_step_host(rt_env *e, const float *actions_host, float *obs_host, double *
     if (s_trunc) d_trunc = (uint8_t *)pinned_alias(e->h_trunc);
     if (s_info) d_info = (double *)pinned_alias(e->h_info);
     if (!d_act || !d_obs) return fail(RT_ERR_CUDA, "rt_step_host: pinned staging buffers are not device-mapped");
-    e->signal_value += 1u;
-    e->signal_next = e->h_flag_dev != nullptr && e->done_counter != nullptr && e->use_flag;
-    e->signal_armed = false;
     if (int rc = rt_step(e, d_act, d_obs, d_rew, nullptr, d_term, d_trunc, d_info, e->hstream)) return rc;
-    bool done = false;
-    if (e->signal_armed) {
-        // The last block of the step kernel stores signal_value to the pinned flag after every block's outputs have
-        // been made visible to the host (__threadfence_system before its count): polling it saves the stream's own
-        // completion round trip.  A kernel that faults never signals: fall back to the stream after 2 s.
-        const unsigned int want = e->signal_value;
-        const auto t0 = std::chrono::steady_clock::now();
-        for (unsigned long long spins = 0;; spins++) {
-            if (*e->h_flag == want) { done = true; break; }
-            if ((spins & 0xffffull) == 0xffffull &&
-                std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 2.0) break;
-        }
-        std::atomic_thread_fence(std::memory_order_acquire);
-    }
-    if (!done) RT_CUDA(cudaStreamSynchronize(e->hstream));
+    RT_CUDA(cudaStreamSynchronize(e->hstream));
     if (s_obs) memcpy(obs_host, e->h_obs, n * RT_OBS_SIZE * sizeof(float));
     if (s_rew) memcpy(reward_host, e->h_reward, n * sizeof(double));
     if (s_term) memcpy(terminated_host, e->h_term, n);

@@ -1,24 +1,25 @@
-// rt_step.cuh — the sparse environment step (RadiotherapyEnv.step, environment.py:193-243), included by
-// rt_env.cu after the record / table definitions.
+// rt_step.cuh — the environment step (RadiotherapyEnv.step, environment.py:193-243), included by rt_env.cu after
+// the record / table definitions.
+//
+// Dose state of a sparse-mode handle: one 8-byte CELL per voxel, {float32 dose, uint32 generation}, C order of the
+// reference's volume.  A cell whose generation differs from its env's current one (EnvRec::gen, bumped by every
+// reset) reads as zero: reset touches nothing, a beam needs no validity bitmap, no zero fill and no atomics, and
+// every voxel a beam hits is one 8-byte load and one 8-byte store by the one lane that owns it.
 //
 // A block advances kB envs with kB + 1 warps and two kinds of work:
 //
-//   scalar warp (warp 0), one THREAD per env: everything that is one value per env — record and action
-//      load, float64 translation and rotation (transforms.py:7-69), beam clip/set-up and the serial float32
-//      slab walk (draw_line.py:19-66, 98-99), rewards, termination, observation, episode statistics, the
-//      record update and the NEXT_STEP autoreset.  One warp instruction serves up to 28 envs.
-//   env warps (1..kB), one WARP per env: the only part that is wide — one slab per lane, its 2x2 splat
-//      targets, the sparse dose read-modify-write, tumour / lung deltas (environment.py:107-110,164-182) —
-//      plus the distance-to-tumour minimum (environment.py:150-162) while the scalar warp is busy.
+//   scalar warp (warp 0), one THREAD per env: everything that is one value per env — record and action load,
+//      float64 translation and rotation (transforms.py:7-69), beam clip/set-up and the serial float32 slab walk
+//      (draw_line.py:19-66, 98-99), rewards, termination, observation, episode statistics, the record update and
+//      the NEXT_STEP autoreset.  One warp instruction serves up to 16 envs.
+//   env warps (1..kB), one WARP per env: the only part that is wide — one slab per lane, its 2x2 splat targets,
+//      the sparse dose read-modify-write, tumour / lung deltas (environment.py:107-110,164-182) — plus the
+//      distance-to-tumour minimum (environment.py:150-162) while the scalar warp is busy.
 //
 // Timeline of a block:
-//      scalar: load, translate | rotate, beam set-up, walk        | obs, distance reward, pose | reward, outputs
-//      env:    TMA bitmap      | tumour entry, min distance       | dose deposition            |
-//                          barrier A                          barrier 1                    barrier 2
-//
-// The env's sector-valid bitmap (3.2 KB) is brought to shared memory by one cp.async.bulk per env, issued
-// before anything else and waited for on an mbarrier right before the deposition, so the first-touch test is
-// a shared-memory lookup and dose values are only loaded for sectors that hold data.
+//      scalar: load, translate | rotate, beam set-up, walk   | obs, distance reward, pose, next dn | reward, outputs
+//      env:    (lungs TMA)     | tumour entry, min distance  | dose deposition                     |
+//                          barrier A                     barrier 1                             barrier 2
 #pragma once
 
 namespace {
@@ -26,16 +27,16 @@ namespace {
 struct __align__(16) EnvShared {
     Beam beam;               // scalar warp -> env warp (barrier 1)
     int needs_reset;         // scalar warp -> env warp (barrier A)
+    int tid;
+    uint32_t gen;            // the env's current dose generation
+    int d_cnt;               // env warp -> scalar warp (barrier 2)
     double p[3];             // translated beam position (barrier A)
     double best;             // env warp -> scalar warp: min squared distance to the tumour (barrier 1)
     double d_tum, d_lung;    // env warp -> scalar warp: dose deltas of this beam (barrier 2)
-    int tid;
-    int d_cnt;
     double os_t[3];          // translation overshoot (info only), parked by the scalar warp for itself
 };
 
 constexpr int kYZStride = kMaxSlabs + 1;   // odd float2 stride: the scalar warp's lanes store to distinct banks
-constexpr int kMaxPass = (kMaxSlabs + kWarp - 1) / kWarp;   // 32-slab passes of one beam (3)
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -65,18 +66,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity)
                  "}" ::"r"(mbar), "r"(parity) : "memory");
 }
 
-__device__ __forceinline__ void red_or(uint32_t *p, uint32_t v)
-{
-    asm volatile("red.global.or.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
-// one 32-byte sector of zeros with a single store (256-bit stores: sm_100, PTX 8.8): one write transaction
-// instead of two
-__device__ __forceinline__ void zero_sector(float *p)
-{
-    asm volatile("st.global.v8.f32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1};" ::"l"(p), "f"(0.0f) : "memory");
-}
-
 #define RT_STAMP3(env_, slot)                                                                    \
     do {                                                                                         \
         if (kClock) T.stage_clock[(size_t)(env_) * 12 + (slot)] = clock64();                     \
@@ -90,7 +79,6 @@ struct SlabCoord {
     float fy, fz;
 };
 
-template <int DOM>
 __device__ __forceinline__ SlabCoord slab_coords(const Grid &G, const Beam &b, int k, float2 cur, int &base, uint32_t &inb,
                                                  int &c0, int &c1, int &c2)
 {
@@ -100,9 +88,10 @@ __device__ __forceinline__ SlabCoord slab_coords(const Grid &G, const Beam &b, i
     s.yf = (int)yfl; s.zf = (int)zfl;
     s.fy = __fsub_rn(cur.x, yfl); s.fz = __fsub_rn(cur.y, zfl);              // :77, :81
     const int x = b.x0 + k * b.step;
-    if (DOM == 0) { c0 = x; c1 = s.yf; c2 = s.zf; }                          // idx[dom]=x, idx[o0]=yf, idx[o1]=zf
-    else if (DOM == 1) { c0 = s.yf; c1 = x; c2 = s.zf; }
-    else { c0 = s.yf; c1 = s.zf; c2 = x; }
+    // idx[dom] = x, idx[o0] = yf, idx[o1] = zf (b.dom is warp-uniform)
+    c0 = b.dom == 0 ? x : s.yf;
+    c1 = b.dom == 0 ? s.yf : (b.dom == 1 ? x : s.zf);
+    c2 = b.dom == 2 ? x : s.zf;
     const bool a0 = have && (unsigned)c0 < (unsigned)G.g0;
     const bool a10 = a0 && (unsigned)c1 < (unsigned)G.g1, a11 = a0 && (unsigned)(c1 + 1) < (unsigned)G.g1;
     const bool a20 = (unsigned)c2 < (unsigned)G.g2, a21 = (unsigned)(c2 + 1) < (unsigned)G.g2;
@@ -155,43 +144,44 @@ __device__ __forceinline__ void slab_weights(const Beam &b, int k, const SlabCoo
     }
 }
 
-// One 32-slab pass of a beam, as held by a lane between the load and the store phase of the deposition:
-// the lane's slab writes up to four voxels  base + dy*g2 + dz.
-struct PassState {
-    int base;          // linear index of target (dy, dz) = (0, 0)
-    uint32_t flags;    // bit j: target j is written by this lane; 4+j: this lane zero-fills its (fresh) sector;
-                       // 8+j: voxel belongs to the tumour; 12+j: to the lungs
-    float w[4];        // summed splat weights
-    float old[4];      // dose before the beam (0 for fresh sectors)
-};
-
-template <int kB, bool kClock>
-__global__ void __launch_bounds__((kB + 1) * kWarp, 28 / kB)
-rt_step3_kernel(Tables T, Schedule S, EnvRec *rec, float *dose, uint32_t *valid, double *beams, int n_envs,
-                const float *__restrict__ actions, StepOut out)
+// Two neighbouring bits (l, l + 1) of a bitmask padded by kLungPadBits leading zero bits and a trailing zero word.
+__device__ __forceinline__ uint32_t bit_pair(const uint32_t *bits, int l)
 {
+    const int p = l + kLungPadBits;
+    return __funnelshift_r(bits[p >> 5], bits[(p >> 5) + 1], p & 31) & 3u;
+}
+__device__ __forceinline__ uint32_t bit_pair_ldg(const uint32_t *bits, int l)
+{
+    const int p = l + kLungPadBits;
+    return __funnelshift_r(__ldg(bits + (p >> 5)), __ldg(bits + (p >> 5) + 1), p & 31) & 3u;
+}
+
+template <int kB, bool kClock, bool kDense>
+__global__ void __launch_bounds__((kB + 1) * kWarp, 28 / kB)
+rt_step_kernel(Tables T, Schedule S, EnvRec *rec, uint2 *cells, double *beams, int n_envs,
+               const float *__restrict__ actions, StepOut out, DenseWork *dense)
+{
+    static_assert(kB <= 16, "the scalar warp serves at most 16 envs");
     __shared__ EnvShared sh[kB];
     __shared__ Tumour tum[kB];
     __shared__ uint32_t tbits[kB][kMaxPTumourWords];
     __shared__ float2 yz[kB][kYZStride];
-    __shared__ __align__(8) unsigned long long mbars[kB + 1];
+    __shared__ __align__(8) unsigned long long mbars[1];
     // outputs are staged here by the scalar warp's lanes and copied out row-contiguously (full-line stores:
     // the host-buffer entry points map these arrays over PCIe)
     __shared__ float s_obs[kB * RT_OBS_SIZE];
     __shared__ double s_rew[kB];
     __shared__ uint8_t s_term[kB];
     __shared__ double s_info[kB * RT_INFO_SIZE];
-    extern __shared__ __align__(128) uint32_t dyn_smem[];         // [lung_words16] lungs bitmask, [kB][vwords] sector-valid bitmaps
+    extern __shared__ __align__(128) uint32_t dyn_smem[];         // [lung_words16] padded lungs bitmask (kB >= 14)
     const Grid &G = T.G;
     const int warp = threadIdx.x / kWarp;
     const int lane = threadIdx.x & (kWarp - 1);
     const int env0 = blockIdx.x * kB;
     // blocks of 7 envs run four to an SM and read the lungs bitmask through L1 instead of staging it four times
-    constexpr bool kStageLungs = kB >= 14;
-    const uint32_t *slungs = kStageLungs ? dyn_smem : T.lungs_bits;
-    uint32_t *vsm_all = dyn_smem + (kStageLungs ? T.lung_words16 : 0);
+    constexpr bool kStageLungs = kB >= 14 && !kDense;
 
-    if (lane == 0) mbar_init(smem_u32(&mbars[warp]), 1);          // mbars[0]: lungs bitmask, mbars[1 + le]: env le's bitmap
+    if (kStageLungs && threadIdx.x == 0) mbar_init(smem_u32(&mbars[0]), 1);
     // Programmatic dependent launch: nothing the previous step wrote is read before this point; the trigger
     // lets the next launch's blocks be scheduled as soon as ours retire.
     cudaGridDependencySynchronize();
@@ -201,22 +191,26 @@ rt_step3_kernel(Tables T, Schedule S, EnvRec *rec, float *dose, uint32_t *valid,
     if (warp == 0) {
         const int e = env0 + lane;
         const bool mine = lane < kB && e < n_envs;
-        if (kStageLungs && lane == 0) bulk_load(smem_u32(dyn_smem), T.lungs_bits, (uint32_t)(T.lung_words16 * sizeof(uint32_t)), smem_u32(&mbars[0]));
+        if (kStageLungs && lane == 0)
+            bulk_load(smem_u32(dyn_smem), T.lungs_pad, (uint32_t)(T.lung_words16 * sizeof(uint32_t)), smem_u32(&mbars[0]));
         if (mine) RT_STAMP3(e, 0);
         EnvRec *my = rec + (mine ? e : 0);
         EnvShared &se = sh[lane < kB ? lane : 0];
         const double gs[3] = {(double)G.g0, (double)G.g1, (double)G.g2};
         bool stepping = false;
         Pose s;
+        double dn[3] = {0.0, 1.0, 0.0};                                    // direction / |direction| (transforms.py:23)
         float ar[3] = {0.f, 0.f, 0.f};                                     // rotation part of the action
         int tid = 0;
+        uint32_t gen = 0u;
         if (mine) {
             // every load is issued before the first use: one round trip to L2
             const int needs_reset = my->needs_reset;
             tid = my->tumour_id;
+            gen = my->gen;
             double p0[3];
 #pragma unroll
-            for (int i = 0; i < 3; i++) { p0[i] = my->pos[i]; s.d[i] = my->dir[i]; }
+            for (int i = 0; i < 3; i++) { p0[i] = my->pos[i]; dn[i] = my->dn[i]; }
             const float2 *ap = reinterpret_cast<const float2 *>(actions + (size_t)e * RT_ACTION_SIZE);
             const float2 a01 = __ldg(ap), a23 = __ldg(ap + 1), a45 = __ldg(ap + 2);
             const float at[3] = {a01.x, a01.y, a23.x};
@@ -224,6 +218,7 @@ rt_step3_kernel(Tables T, Schedule S, EnvRec *rec, float *dose, uint32_t *valid,
             stepping = needs_reset == 0;
             se.needs_reset = needs_reset;
             se.tid = tid;
+            se.gen = gen;
             se.beam.nslab = 0;
             if (stepping) {
 #pragma unroll
@@ -243,7 +238,7 @@ rt_step3_kernel(Tables T, Schedule S, EnvRec *rec, float *dose, uint32_t *valid,
 #pragma unroll
             for (int i = 0; i < 3; i++)                                    // environment.py:139-141
                 rv[i] = (double)__fmul_rn(__fmul_rn(clip1(ar[i]), 3.14159274101257324f), 0.5f);
-            zc = rotate_env(s.d, rv);                                      // transforms.py:7-55
+            zc = rotate_normalized(dn, rv, s.d);                           // transforms.py:25-55 (:23 was done by the previous step)
             if (kClock) T.stage_clock[(size_t)e * 12 + 9] = clock64() + (long long)(s.d[0] * 0.0);
             const Beam b = beam_setup(G, s.p, s.d);                        // draw_line.py:19-66
             if (kClock) T.stage_clock[(size_t)e * 12 + 10] = clock64() + (b.nslab < -5);
@@ -264,6 +259,9 @@ rt_step3_kernel(Tables T, Schedule S, EnvRec *rec, float *dose, uint32_t *valid,
             lung_count = my->lung_count;
             n_beams = my->n_beams;
             float *obs = s_obs + lane * RT_OBS_SIZE;                       // environment.py:259-268
+            double nd0 = s.d[0], nd1 = s.d[1], nd2 = s.d[2];
+            normalize3(nd0, nd1, nd2);                                     // the next step's transforms.py:23
+            my->dn[0] = nd0; my->dn[1] = nd1; my->dn[2] = nd2;
 #pragma unroll
             for (int i = 0; i < 3; i++) {
                 obs[i] = (float)__dsub_rn(__dmul_rn(__ddiv_rn(s.p[i], gs[i]), 2.0), 1.0);
@@ -275,15 +273,27 @@ rt_step3_kernel(Tables T, Schedule S, EnvRec *rec, float *dose, uint32_t *valid,
             r_dist = __dmul_rn(__ddiv_rn(sqrt(se.best), T.gnorm), -1.0);   // environment.py:158-162
             mask_sum = (double)tm.lung_mask_sum;
             rcp_mask = __drcp_rn(mask_sum);
-            if (out.info) os_r = overshoot_from_z(zc);                     // transforms.py:29-33, 57 (info only)
+            if (out.info || kDense) os_r = overshoot_from_z(zc);           // transforms.py:29-33, 57 (info only)
             if (beams && n_beams < RT_MAX_TIME_STEPS) {                    // environment.py:110
                 double *bp = beams + ((size_t)e * RT_MAX_TIME_STEPS + n_beams) * 6;
 #pragma unroll
                 for (int i = 0; i < 3; i++) { bp[i] = s.p[i]; bp[3 + i] = s.d[i]; }
             }
+            if (kDense) {
+                // dense mode: rt_dense_kernel streams the volume, recomputes the reductions and finishes the step
+                DenseWork &dw = dense[e];
+                dw.mode = 0;
+                dw.tid = tid; dw.t = t; dw.n_beams = n_beams;
+                dw.best = se.best;
+                dw.os_t[0] = se.os_t[0]; dw.os_t[1] = se.os_t[1]; dw.os_t[2] = se.os_t[2];
+                dw.os_r = os_r;
+                dw.ep_return = ep_return;
+                my->t = t;
+                my->n_beams = n_beams + 1;
+            }
         } else if (mine) {
             // gymnasium 1.0.0 NEXT_STEP: the call after a terminal step resets and reports reward 0
-            // (environment.py:77-105; the env warp clears the sector-valid bitmap).
+            // (environment.py:77-105).  A new generation empties the dose volume.
             const int episode = my->episode + 1;
             tid = pick_tumour(T, S, e, n_envs, episode);
             const Tumour *tg = T.tumours + tid;
@@ -293,12 +303,15 @@ rt_step3_kernel(Tables T, Schedule S, EnvRec *rec, float *dose, uint32_t *valid,
                 const double p = gs[i] / 2.0, d = i == 1 ? 1.0 : 0.0;
                 my->pos[i] = p;
                 my->dir[i] = d;
+                my->dn[i] = d;
                 obs[i] = (float)__dsub_rn(__dmul_rn(__ddiv_rn(p, gs[i]), 2.0), 1.0);
                 obs[3 + i] = (float)d;
                 obs[6 + i] = __ldg(&tg->obs_c[i]);
             }
             my->tumour_dose = 0.0; my->lung_dose = 0.0; my->ep_return = 0.0;
             my->t = 0; my->tumour_id = tid; my->lung_count = 0; my->episode = episode; my->needs_reset = 0; my->n_beams = 0;
+            my->gen = gen + 1u;
+            if (kDense) dense[e].mode = 1;                                 // rt_dense_kernel zeroes the volume
             s_rew[lane] = 0.0;
             s_term[lane] = 0;
             if (out.info) {
@@ -312,18 +325,38 @@ rt_step3_kernel(Tables T, Schedule S, EnvRec *rec, float *dose, uint32_t *valid,
         for (int i = lane; i < nb * RT_OBS_SIZE; i += kWarp) out.obs[(size_t)env0 * RT_OBS_SIZE + i] = s_obs[i];
         if (kStageLungs) mbar_wait(smem_u32(&mbars[0]), 0);                // the lungs copy must land before the block retires
         __syncthreads();                                                   // ---- barrier 2
+        if (kDense) {
+            // the dense kernel writes reward / terminated / info of the envs that stepped
+            if (mine && !stepping) {
+                if (out.reward) out.reward[e] = 0.0;
+                if (out.reward_f32) out.reward_f32[e] = 0.0f;
+                if (out.terminated) out.terminated[e] = 0;
+                if (out.truncated) out.truncated[e] = 0;
+                if (out.info)
+                    for (int i = 0; i < RT_INFO_SIZE; i++) out.info[(size_t)e * RT_INFO_SIZE + i] = s_info[lane * RT_INFO_SIZE + i];
+            }
+            return;
+        }
         if (stepping) {
             RT_STAMP3(e, 11);
-            tumour_dose += (double)se.d_tum;
-            lung_dose += (double)se.d_lung;
+            tumour_dose += se.d_tum;
+            lung_dose += se.d_lung;
             lung_count += se.d_cnt;
             // rewards, termination (environment.py:158-191, 214-220)
-            const float tsum_f32 = (float)tumour_dose;                      // np.sum(dose*tumours) float32
-            const float ratio = fdiv_rn_zero_num(tsum_f32, tm.tumour_sum);   // no dose on the tumour yet: the common case
+            float tsum_f32 = (float)tumour_dose;                           // np.sum(dose*tumours) float32
+            float ratio = fdiv_rn_zero_num(tsum_f32, tm.tumour_sum);       // no dose on the tumour yet: the common case
+            if (fabsf(ratio - kDoneRatio) < kDoneWindow) {
+                // Within 2e-5 of the termination threshold the summation ORDER of np.sum decides `done`
+                // (environment.py:186-190): redo the sum exactly as NumPy's pairwise float32 reduction does.
+                const uint2 *vol = cells + (size_t)e * G.vstride;
+                tsum_f32 = np_pairwise_sparse(G.nvox, T.vox_xyz + tm.vox_off, tm.n_vox, G,
+                                              [&](int lin) { const uint2 c = vol[lin]; return c.y == gen ? __uint_as_float(c.x) : 0.0f; });
+                ratio = __fdiv_rn(tsum_f32, tm.tumour_sum);
+            }
             const float r_tumour = __fmul_rn(ratio, 10.0f);
             const double r_lung = __dmul_rn(div_shared((double)lung_count, mask_sum, rcp_mask), -1.0);
             const double reward = __dadd_rn(__dadd_rn((double)r_tumour, r_lung), r_dist);
-            const bool done = (ratio >= 0.899999976158142090f) || (t >= RT_MAX_TIME_STEPS);
+            const bool done = (ratio >= kDoneRatio) || (t >= RT_MAX_TIME_STEPS);
             ep_return += reward;
             my->tumour_dose = tumour_dose; my->lung_dose = lung_dose; my->ep_return = ep_return;
             my->t = t; my->lung_count = lung_count; my->needs_reset = done ? 1 : 0; my->n_beams = n_beams + 1;
@@ -359,20 +392,6 @@ rt_step3_kernel(Tables T, Schedule S, EnvRec *rec, float *dose, uint32_t *valid,
         }
         if (out.info)
             for (int i = lane; i < nb * RT_INFO_SIZE; i += kWarp) out.info[(size_t)env0 * RT_INFO_SIZE + i] = s_info[i];
-        if (out.done_flag) {
-            // host-buffer path: this warp wrote all of the block's outputs; make them visible to the host, count the
-            // block, and let the last block of the grid raise the host's flag
-            __threadfence_system();
-            __syncwarp();
-            if (lane == 0) {
-                const unsigned int prev = atomicAdd(out.done_counter, 1u);
-                if (prev == gridDim.x - 1) {
-                    *out.done_counter = 0u;                                // next launch counts from zero
-                    __threadfence_system();
-                    *out.done_flag = out.done_value;
-                }
-            }
-        }
         return;
     }
 
@@ -381,10 +400,6 @@ rt_step3_kernel(Tables T, Schedule S, EnvRec *rec, float *dose, uint32_t *valid,
     const int le = warp - 1;
     const int env = env0 + le;
     const bool active = env < n_envs;
-    uint32_t *vsm = vsm_all + (size_t)le * G.vwords;
-    const uint32_t mbar = smem_u32(&mbars[warp]);
-    if (active && lane == 0)
-        bulk_load(smem_u32(vsm), valid + (size_t)env * G.vwords, (uint32_t)(G.vwords * sizeof(uint32_t)), mbar);
     __syncthreads();                                                       // ---- barrier A
     EnvShared &se = sh[le];
     Tumour &tm = tum[le];
@@ -394,8 +409,9 @@ rt_step3_kernel(Tables T, Schedule S, EnvRec *rec, float *dose, uint32_t *valid,
         const int tid = se.tid;
         if (lane < kTumourWords)
             reinterpret_cast<uint32_t *>(&tm)[lane] = __ldg(reinterpret_cast<const uint32_t *>(T.tumours + tid) + lane);
-        for (int i = lane; i < T.pbits_words; i += kWarp)                  // pbits_words <= kMaxPTumourWords (rt_create)
-            tb[i] = __ldg(T.tumour_pbits + (size_t)tid * T.pbits_words + i);
+        if (!kDense)
+            for (int i = lane; i < T.pbits_words; i += kWarp)              // pbits_words <= kMaxPTumourWords (rt_create)
+                tb[i] = __ldg(T.tumour_pbits + (size_t)tid * T.pbits_words + i);
         __syncwarp();
         // distance_to_tumour_reward (environment.py:150-162): min over the tumour's voxel list
         const double p0 = se.p[0], p1 = se.p[1], p2 = se.p[2];
@@ -415,66 +431,91 @@ rt_step3_kernel(Tables T, Schedule S, EnvRec *rec, float *dose, uint32_t *valid,
         const uint32_t mhi = __reduce_min_sync(kFull, hi);
         const uint32_t mlo = __reduce_min_sync(kFull, hi == mhi ? (uint32_t)__double2loint(best) : 0xffffffffu);
         if (lane == 0) se.best = __hiloint2double((int)mhi, (int)mlo);
-    } else if (active) {
-        // autoreset (environment.py:104-105): no sector of the new episode's dose volume is valid
-        uint4 *vw = reinterpret_cast<uint4 *>(valid + (size_t)env * G.vwords);
-        for (int i = lane; i < G.vwords / 4; i += kWarp) vw[i] = make_uint4(0u, 0u, 0u, 0u);
     }
     if (active && lane == 0) RT_STAMP3(env, 2);
     __syncthreads();                                                       // ---- barrier 1
-    if (active) mbar_wait(mbar, 0);                                        // the staged bitmap has landed
-    if (stepping) {
-        if (kStageLungs) mbar_wait(smem_u32(&mbars[0]), 0);                // and so has the lungs bitmask
-        if (lane == 0) RT_STAMP3(env, 3);
-        // ---- dose deposition (environment.py:107-110): dose' = clip(dose + beam*0.1, 0, 1) on the voxels hit.
-        // All (up to three) 32-slab passes of the beam go through each phase together, so the beam costs one
-        // round trip to HBM however long it is:  targets + loads | zero fill | stores + accumulation.
+    if (stepping && kDense) {
+        // Dense mode: publish the beam (distinct voxels + summed weights); rt_dense_kernel streams the whole volume.
         const Beam b = se.beam;
         const float2 *myz = yz[le];
-        float *vol = dose + (size_t)env * G.vstride;
-        uint32_t *vbits = valid + (size_t)env * G.vwords;
+        DenseWork &dw = dense[env];
+        int nhit = 0;
+        for (int kbase = 0; kbase < b.nslab; kbase += kWarp) {
+            const int k = kbase + lane;
+            const int kk = k < b.nslab ? k : 0;
+            int lin[4], c0, c1, c2;
+            float w[4];
+            slab_targets_yz(G, b, k, myz[kk], myz[kk > 0 ? kk - 1 : 0], myz[kk + 1 < b.nslab ? kk + 1 : kk], lin, w, c0, c1, c2);
+            int mine = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) mine += lin[j] >= 0;
+            int incl = mine;
+#pragma unroll
+            for (int o = 1; o < kWarp; o <<= 1) {
+                const int v = __shfl_up_sync(kFull, incl, o);
+                if (lane >= o) incl += v;
+            }
+            int at = nhit + incl - mine;
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (lin[j] >= 0 && at < RT_BEAM_CAP) {
+                    dw.lin[at] = lin[j];
+                    dw.w[at] = w[j];
+                    at++;
+                }
+            nhit += __shfl_sync(kFull, incl, kWarp - 1);
+        }
+        if (lane == 0) dw.n_hits = nhit < RT_BEAM_CAP ? nhit : RT_BEAM_CAP;
+    }
+    if (stepping && !kDense) {
+        const uint32_t *slungs = kStageLungs ? dyn_smem : T.lungs_pad;
+        if (kStageLungs) mbar_wait(smem_u32(&mbars[0]), 0);                // the lungs bitmask has landed
+        if (lane == 0) RT_STAMP3(env, 3);
+        // ---- dose deposition (environment.py:107-110): dose' = clip(dose + beam*0.1, 0, 1) on the voxels hit.
+        // A voxel has exactly one owner lane per beam (slab_weights merges the two slabs that can meet), so the
+        // 32-slab passes of a beam are independent: load cells | weights, masks | new dose, store, deltas.
+        const Beam b = se.beam;
+        const uint32_t gen = se.gen;
+        const float2 *myz = yz[le];
+        uint2 *vol = cells + (size_t)env * G.vstride;
         const int g2 = G.g2;
         const int li0 = tm.lo[0], li1 = tm.lo[1] - 1, li2 = tm.lo[2] - 1;  // origin of the padded bbox
         const int td0 = tm.dim[0], td1 = tm.dim[1], td2 = tm.dim[2];
         const int pd1 = td1 + 2, pd2 = td2 + 2;
         const int variant = b.dom == 0 ? 0 : (b.dom * 2 - 1 + (b.step > 0 ? 0 : 1));   // warp-uniform
-        PassState ps[kMaxPass];
-#pragma unroll
-        for (int c = 0; c < kMaxPass; c++) {
-            if (c * kWarp >= b.nslab) break;                               // warp-uniform
-            PassState &q = ps[c];
-            const int k = c * kWarp + lane;
+        // per-lane partial sums of at most 12 float32 deltas; the running totals are float64 (scalar warp)
+        float d_tum = 0.0f, d_lung = 0.0f;
+        int d_cnt = 0;
+#pragma unroll 1
+        for (int k0 = 0; k0 < b.nslab; k0 += kWarp) {
+            const int k = k0 + lane;
             const int kk = k < b.nslab ? k : 0;
             const float2 cur = myz[kk], prv = myz[kk > 0 ? kk - 1 : 0], nxt = myz[kk + 1 < b.nslab ? kk + 1 : kk];
-            int c0, c1, c2;
+            int base, c0, c1, c2;
             uint32_t inb;
-            const SlabCoord sc = b.dom == 0 ? slab_coords<0>(G, b, k, cur, q.base, inb, c0, c1, c2)
-                               : b.dom == 1 ? slab_coords<1>(G, b, k, cur, q.base, inb, c0, c1, c2)
-                                            : slab_coords<2>(G, b, k, cur, q.base, inb, c0, c1, c2);
-            // the dose loads go out first (a voxel the previous slab owns is loaded for nothing: harmless)
-            uint32_t freshm = 0u, lungm = 0u;
-            int sec[4];
+            const SlabCoord sc = slab_coords(G, b, k, cur, base, inb, c0, c1, c2);
+            // the cell loads go out first (a voxel the previous slab owns is loaded for nothing: harmless)
+            uint2 cell[4];
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                const bool inj = (inb >> j) & 1u;
-                const int l = inj ? q.base + (j >> 1) * g2 + (j & 1) : 0;
-                sec[j] = l >> 3;
-                lungm |= (((kStageLungs ? slungs[l >> 5] : __ldg(slungs + (l >> 5))) >> (l & 31)) & 1u) << j;
-                const bool fresh = inj && !((vsm[sec[j] >> 5] >> (sec[j] & 31)) & 1u);   // never written this episode: reads as zero
-                q.old[j] = 0.0f;
-                if (inj && !fresh && !(kClock && (T.debug & 4))) q.old[j] = vol[l];   // re-touched sector: read from HBM / L2
-                freshm |= fresh ? 1u << j : 0u;
+                cell[j] = make_uint2(0u, ~gen);
+                if ((inb >> j) & 1u) cell[j] = __ldcg(vol + base + (j >> 1) * g2 + (j & 1));
             }
+            if (k0 == 0 && lane == 0) RT_STAMP3(env, 4);
             uint32_t drop;
+            float w[4];
             switch (variant) {
-            case 0: slab_weights<0, 0>(b, k, sc, prv, nxt, drop, q.w); break;
-            case 1: slab_weights<1, 0>(b, k, sc, prv, nxt, drop, q.w); break;
-            case 2: slab_weights<1, 1>(b, k, sc, prv, nxt, drop, q.w); break;
-            case 3: slab_weights<2, 0>(b, k, sc, prv, nxt, drop, q.w); break;
-            default: slab_weights<2, 1>(b, k, sc, prv, nxt, drop, q.w); break;
+            case 0: slab_weights<0, 0>(b, k, sc, prv, nxt, drop, w); break;
+            case 1: slab_weights<1, 0>(b, k, sc, prv, nxt, drop, w); break;
+            case 2: slab_weights<1, 1>(b, k, sc, prv, nxt, drop, w); break;
+            case 3: slab_weights<2, 0>(b, k, sc, prv, nxt, drop, w); break;
+            default: slab_weights<2, 1>(b, k, sc, prv, nxt, drop, w); break;
             }
             const uint32_t ok = inb & ~drop;
-            freshm &= ok;
+            // lungs membership: the two targets of a row are neighbouring bits of the (padded) bitmask
+            uint32_t lmask = 0u;
+            if (inb & 3u) lmask = kStageLungs ? bit_pair(slungs, base) : bit_pair_ldg(slungs, base);
+            if (inb & 12u) lmask |= (kStageLungs ? bit_pair(slungs, base + g2) : bit_pair_ldg(slungs, base + g2)) << 2;
             // tumour membership of the 2x2 block: one range test against the bounding box grown by one voxel on
             // axes 1 and 2 (the padded bitmask has empty border cells, so the four bits are always addressable)
             uint32_t tmask = 0u;
@@ -485,79 +526,31 @@ rt_step3_kernel(Tables T, Schedule S, EnvRec *rec, float *dose, uint32_t *valid,
                 const uint32_t r1 = __funnelshift_r(tb[b1 >> 5], tb[(b1 >> 5) + 1], b1 & 31) & 3u;
                 tmask = r0 | (r1 << 2);
             }
-            // targets 2q and 2q+1 are neighbours in memory: the second one usually shares the first one's sector
-            uint32_t fill = freshm;
-            if ((freshm & 3u) == 3u && sec[0] == sec[1]) fill &= ~2u;
-            if ((freshm & 12u) == 12u && sec[2] == sec[3]) fill &= ~8u;
-            q.flags = ok | (fill << 4) | ((tmask & ok) << 8) | ((lungm & ok) << 12);
-        }
-        if (lane == 0) RT_STAMP3(env, 4);
-        // First write to a sector this episode: materialise it as zeros and mark it valid for the next step.
-        // Freshness of every pass was decided on the bitmap as it was before the beam, so no pass can wipe what
-        // another one stored: all fills come before all stores.
-#pragma unroll
-        for (int c = 0; c < kMaxPass; c++) {
-            if (c * kWarp >= b.nslab) break;
-            const PassState &q = ps[c];
-            // the lane's (at most four) fresh sectors usually fall into one or two words of the bitmap: one RED per word
-            int wrd[2] = {-1, -1};
-            uint32_t msk[2] = {0u, 0u};
-#pragma unroll
-            for (int j = 0; j < 4; j++)
-                if ((q.flags & (16u << j)) && !(kClock && (T.debug & 1))) {
-                    const int sec = (q.base + (j >> 1) * g2 + (j & 1)) >> 3;
-                    if (!(kClock && (T.debug & 32))) zero_sector(vol + (sec << 3));
-                    const int w = sec >> 5;
-                    const uint32_t bit = 1u << (sec & 31);
-                    if (wrd[0] < 0 || wrd[0] == w) { wrd[0] = w; msk[0] |= bit; }
-                    else if (wrd[1] < 0 || wrd[1] == w) { wrd[1] = w; msk[1] |= bit; }
-                    else red_or(vbits + w, bit);                           // a third word: rows far apart and straddling
-                }
-            if (!(kClock && (T.debug & 16))) {
-                if (wrd[0] >= 0) red_or(vbits + wrd[0], msk[0]);
-                if (wrd[1] >= 0) red_or(vbits + wrd[1], msk[1]);
-            }
-        }
-        __syncwarp();   // zero fill (any lane) is ordered before the voxel stores below
-        if (lane == 0) RT_STAMP3(env, 5);
-        // per-lane partial sums of at most 12 float32 deltas; the running totals are float64 (scalar warp)
-        float d_tum = 0.0f, d_lung = 0.0f;
-        int d_cnt = 0;
-#pragma unroll
-        for (int c = 0; c < kMaxPass; c++) {
-            if (c * kWarp >= b.nslab) break;
-            const PassState &q = ps[c];
+            tmask &= ok;
+            lmask &= ok;
+            const uint32_t cmask = lmask & ~tmask;                 // lungs_mask = lungs*(1-tumours) (environment.py:174)
             float nd[4];
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                const float o = q.old[j];
-                nd[j] = fminf(__fadd_rn(o, __fmul_rn(q.w[j], 0.100000001490116119f)), 1.0f);   // clip(dose + beam*0.1, 0, 1), dose >= 0
+                const float o = cell[j].y == gen ? __uint_as_float(cell[j].x) : 0.0f;     // another generation reads as zero
+                nd[j] = fminf(__fadd_rn(o, __fmul_rn(w[j], 0.100000001490116119f)), 1.0f);   // clip(dose + beam*0.1, 0, 1), dose >= 0
+                const float delta = (ok >> j) & 1u ? nd[j] - o : 0.0f;                    // 0 for targets this lane does not write
+                d_tum += (tmask >> j) & 1u ? delta : 0.0f;
+                d_lung += (lmask >> j) & 1u ? delta : 0.0f;
+                // dose is monotone, so the count only grows (environment.py:175-177)
+                d_cnt += (int)((cmask >> j) & 1u) & (int)(!(o > 0.200000002980232239f) && nd[j] > 0.200000002980232239f);
             }
-            // the two targets of a row are neighbours in memory: one 8-byte store when both are written and aligned
+            // the two targets of a row are neighbours in memory: one 16-byte store when both are written and aligned
 #pragma unroll
             for (int r = 0; r < 2; r++) {
-                const int l = q.base + r * g2;
-                const uint32_t both = (q.flags >> (2 * r)) & 3u;
-                if (!(kClock && (T.debug & 2))) {
-                    if (both == 3u && !(l & 1)) {
-                        *reinterpret_cast<float2 *>(vol + l) = make_float2(nd[2 * r], nd[2 * r + 1]);
-                    } else {
-                        if (both & 1u) vol[l] = nd[2 * r];
-                        if (both & 2u) vol[l + 1] = nd[2 * r + 1];
-                    }
-                }
-            }
-            if (!(kClock && (T.debug & 8))) {
-                const uint32_t tmask = (q.flags >> 8) & 15u, lmask = (q.flags >> 12) & 15u;
-                const uint32_t cmask = lmask & ~tmask;             // lungs_mask = lungs*(1-tumours) (environment.py:174)
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const float o = q.old[j];
-                    const float delta = (q.flags >> j) & 1u ? nd[j] - o : 0.0f;      // 0 for targets this lane does not write
-                    d_tum += (tmask >> j) & 1u ? delta : 0.0f;
-                    d_lung += (lmask >> j) & 1u ? delta : 0.0f;
-                    // dose is monotone, so the count only grows (environment.py:175-177)
-                    d_cnt += (int)((cmask >> j) & 1u) & (int)(!(o > 0.200000002980232239f) && nd[j] > 0.200000002980232239f);
+                const int l = base + r * g2;
+                const uint32_t both = (ok >> (2 * r)) & 3u;
+                if (both == 3u && !(l & 1)) {
+                    __stcg(reinterpret_cast<uint4 *>(vol + l),
+                           make_uint4(__float_as_uint(nd[2 * r]), gen, __float_as_uint(nd[2 * r + 1]), gen));
+                } else {
+                    if (both & 1u) __stcg(vol + l, make_uint2(__float_as_uint(nd[2 * r]), gen));
+                    if (both & 2u) __stcg(vol + l + 1, make_uint2(__float_as_uint(nd[2 * r + 1]), gen));
                 }
             }
         }

@@ -521,46 +521,15 @@ def test_rng_tumour_choice_is_seeded_and_spread():
 
 
 # ------------------------------------------------------------------------------------ edge cases
-@pytest.mark.parametrize("kb", ["7", "14", "28", "0", "-1", "-2"])
-def test_step_kernel_block_shapes_vs_oracle(kb, monkeypatch):
-    """The step kernel exists for 7, 14 and 28 envs per block (picked from the env count in rt_create; RT_STEP_KB
-    overrides) and as the older two-role kernel (0).  Every variant, with a ragged last block, a full episode, the
-    autoreset call and the start of the next episode, against the CPU oracle."""
-    monkeypatch.setenv("RT_STEP_KB", kb)
-    n, T = 61, 112
-    rng = np.random.default_rng(11)
+@pytest.mark.parametrize("n", [61, 1501])
+def test_step_kernel_block_shapes_vs_oracle(n):
+    """The step kernel runs 7 envs per block while one block per SM covers the envs and 14 per block above that
+    (picked from the env count in rt_create): both, with a ragged last block, an env that never moves, a full episode,
+    the autoreset call and the start of the next episode, against the CPU oracle; final dose volumes bit for bit."""
+    T = 106
+    rng = np.random.default_rng(11 + n)
     acts = rng.uniform(-1, 1, (T, n, 6)).astype(np.float32)
-    sched = np.stack([(np.arange(n) * 7919) % 1000, (np.arange(n) * 104729 + 17) % 1000]).astype(np.int32)
-    ref_out, ref_done = O.rollout(O.Phantom(), sched, acts, threads=8)
-    env = rt.RadiotherapyVectorEnv(n, device=DEV, tumour_ids=sched)
-    env.reset()
-    for t in range(T):
-        obs, reward, term, _, _ = env.step(_cuda(acts[t]))
-        info = env.engine.info.cpu().numpy()
-        stepped = info[:, nat.INFO_STEPPED] > 0
-        assert stepped.all() == (t != 100)
-        _compare_step(info, obs.cpu().numpy(), reward.cpu().numpy(), term.cpu().numpy(), ref_out[t], ref_done[t], stepped)
-    # bit-exact dose volume of the last env (last, partly filled block) in the second episode
-    o = O.OracleEnv(O.Phantom(), int(sched[1, n - 1]))
-    for t in range(101, T):
-        o.step(acts[t, n - 1])
-    assert np.array_equal(env.engine.dose(n - 1).cpu().numpy().view(np.uint32), o.dose.view(np.uint32))
-    env.close()
-
-
-@pytest.mark.parametrize("blocks,kw", [("2", "28"), ("3", "14")])
-def test_split_step_persistent_loop_vs_oracle(blocks, kw, monkeypatch):
-    """The two-kernel step (RT_STEP_KB=-2) with its deposit kernel squeezed into a few blocks, so that every warp
-    works through 20-30 envs: the staged hand-over (slots alternate, bitmap buffer reused), the 16-env tail flush,
-    multi-pass beams, a full episode, the autoreset call and the next episode, against the CPU oracle; final dose
-    volumes of three envs bit for bit."""
-    monkeypatch.setenv("RT_STEP_KB", "-2")
-    monkeypatch.setenv("RT_SPLIT_KW", kw)
-    monkeypatch.setenv("RT_SPLIT_BLOCKS", blocks)
-    n, T = 1501, 106
-    rng = np.random.default_rng(23)
-    acts = rng.uniform(-1, 1, (T, n, 6)).astype(np.float32)
-    acts[:, 7, :] = 0.0                                     # an env that never moves: same sectors every step
+    acts[:, 7, :] = 0.0                                     # an env that never moves: the same voxels every step
     sched = np.stack([(np.arange(n) * 7919) % 1000, (np.arange(n) * 104729 + 17) % 1000]).astype(np.int32)
     ref_out, ref_done = O.rollout(O.Phantom(), sched, acts, threads=8)
     env = rt.RadiotherapyVectorEnv(n, device=DEV, tumour_ids=sched)
@@ -574,6 +543,7 @@ def test_split_step_persistent_loop_vs_oracle(blocks, kw, monkeypatch):
         # pose tolerance is amplified a thousandfold by acos; 150,000 random steps do get that close
         _compare_step(info, obs.cpu().numpy(), reward.cpu().numpy(), term.cpu().numpy(), ref_out[t], ref_done[t], stepped,
                       overshoot_atol=1e-7)
+    # bit-exact dose volumes in the second episode (the first episode's cells belong to another generation)
     for e in (0, 7, n - 1):
         o = O.OracleEnv(O.Phantom(), int(sched[1, e]))
         for t in range(101, T):
@@ -730,11 +700,9 @@ def test_full_size_rollout_vs_oracle_4096_envs(kind):
     env.close()
 
 
-@pytest.mark.parametrize("flag", ["1", "0"])
-def test_host_buffer_step_matches_device_step(flag, monkeypatch):
-    """rt_step_host (pinned and pageable host buffers; completion flag polled by the host, or the stream waited for)
-    gives bit for bit what rt_step gives on device buffers: a full episode, the autoreset call and the next steps."""
-    monkeypatch.setenv("RT_HOST_FLAG", flag)
+def test_host_buffer_step_matches_device_step():
+    """rt_step_host (pinned and pageable host buffers) gives bit for bit what rt_step gives on device buffers: a full
+    episode, the autoreset call and the next steps."""
     n, T = 333, 106
     rng = np.random.default_rng(31)
     acts = rng.uniform(-1, 1, (T, n, 6)).astype(np.float32)
@@ -760,4 +728,40 @@ def test_host_buffer_step_matches_device_step(flag, monkeypatch):
         assert np.array_equal(got[1].view(np.uint64), rew.cpu().numpy().view(np.uint64))
         assert np.array_equal(got[2], term.cpu().numpy()) and np.array_equal(got[3], trunc.cpu().numpy())
     assert np.array_equal(a.dose(n - 1).cpu().numpy().view(np.uint32), b.dose(n - 1).cpu().numpy().view(np.uint32))
+    a.close(); b.close()
+
+
+def test_host_call_waits_for_device_side_work():
+    """the *_host entry points run on the handle's own stream; a host step issued right after a device-side
+    reset / step / set_pose (any stream, here behind a long-running kernel) must see their effect."""
+    n = 257
+    tids = (np.arange(n) * 7919 % 1000).astype(np.int32)[None, :]
+    a = rt.BatchedEpisodes(n, device=DEV); a.set_tumour_schedule(tids)
+    b = rt.BatchedEpisodes(n, device=DEV); b.set_tumour_schedule(tids)
+    rng = np.random.default_rng(2)
+    acts = rng.uniform(-1, 1, (6, n, 6)).astype(np.float32)
+    h_obs, h_rew = np.empty((n, 9), np.float32), np.empty(n, np.float64)
+    h_term, h_trunc = np.empty(n, np.uint8), np.empty(n, np.uint8)
+    big = torch.empty(1 << 28, dtype=torch.float32, device=DEV)
+    side = torch.cuda.Stream(DEV)
+    for t in range(6):
+        with torch.cuda.stream(side):
+            for _ in range(20):
+                big.add_(1.0)                                  # tens of milliseconds of work in front of the device call
+            if t == 0:
+                b.reset()
+            elif t == 3:
+                b.set_pose(a.pose())
+            if t % 2 == 0:
+                b.step(_cuda(acts[t]), want_info=False)
+        if t == 0:
+            a.reset()
+        if t % 2 == 0:
+            a.step(_cuda(acts[t]), want_info=False)
+        else:
+            a.step(_cuda(acts[t]), want_info=False)
+            b.step_host(acts[t], h_obs, h_rew, h_term, h_trunc)           # no explicit synchronisation in between
+            assert np.array_equal(h_obs.view(np.uint32), a.obs.cpu().numpy().view(np.uint32))
+            assert np.array_equal(h_rew.view(np.uint64), a.reward.cpu().numpy().view(np.uint64))
+    torch.cuda.synchronize()
     a.close(); b.close()

@@ -8,8 +8,8 @@ set -x
 B="python bench.py --steps 120 --warmup 20 --no-graph --no-cpu-baseline --no-other-kernels --e2e-steps 5"
 $B > $out/${tag}_plain.log 2>&1 || exit 1
 ncu --metrics gpu__time_duration.sum --clock-control none -s 30 -c 200 --csv --log-file $out/${tag}_launches.csv $B > $out/${tag}_launches.log 2>&1
-ncu --set full --clock-control none --import-source on --warp-sampling-interval 0 -k regex:rt_step3 -s 140 -c 1 -f -o $out/${tag}_step $B > $out/${tag}_step.log 2>&1
-RT_STEP_KB=28 python tools/stage_clock.py 4096 > $out/${tag}_stage_clock.txt 2>&1
+ncu --set full --clock-control none --import-source on --warp-sampling-interval 0 -k regex:rt_step_kernel -s 140 -c 1 -f -o $out/${tag}_step $B > $out/${tag}_step.log 2>&1
+python tools/stage_clock.py 4096 > $out/${tag}_stage_clock.txt 2>&1
 python tools/convbench.py 592 > $out/${tag}_conv_plain.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:rt_conv1_tc -s 3 -c 1 -f -o $out/${tag}_conv1 python tools/convbench.py 592 > $out/${tag}_conv1.log 2>&1
 python tools/densebench.py > /dev/null 2>&1 && ncu --set full --clock-control none -k regex:rt_dense_kernel -s 4 -c 1 -f -o $out/${tag}_dense python tools/densebench.py > $out/${tag}_dense.log 2>&1

@@ -1,7 +1,6 @@
 #!/usr/bin/env python
 """Per-stage clock64() profile of the step kernel (rt_set_stage_clock)."""
 import sys, os, ctypes as C
-os.environ["RT_STEP_KB"] = "28"          # the instrumented kernel is the 28-envs-per-block variant
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import ppo_radiotherapy_b200 as rt
@@ -21,14 +20,14 @@ for i in range(20, 40):
     s = stamps.cpu().numpy().astype(np.float64)
     res.append(s)
 s = np.stack(res)            # [iters, n, 12]
-ok = (s[:, :, :12] > 0).all(axis=2)          # envs that walked a beam this step (all stamps written)
+ok = (s[:, :, order] > 0).all(axis=2)          # envs that walked a beam this step (all stamps written)
 rel = s - s[:, :, 0:1]                        # clock64 is per SM: only differences within an env's block are meaningful
-order = [0, 8, 9, 10, 1, 2, 3, 4, 5, 6, 11, 7]
+order = [0, 8, 9, 10, 1, 2, 3, 4, 6, 11, 7]
 names = {0: "scalar warp start", 8: "scalar: state loaded, translated", 9: "scalar: pose updated", 10: "scalar: beam set up",
-         1: "scalar: walk done", 2: "env warp: tumour + distance done", 3: "env warp: past barrier 1, bitmap landed",
-         4: "env warp: splat + loads issued", 5: "env warp: zero fill done (pass 1)", 6: "env warp: all passes done",
+         1: "scalar: walk done", 2: "env warp: tumour + distance done", 3: "env warp: past barrier 1, lungs landed",
+         4: "env warp: first pass's cell loads issued", 6: "env warp: all passes stored",
          11: "scalar: past barrier 2", 7: "end"}
-print(f"n={n}: cycles since the block's producer start (mean / p50 / p99 over {int(ok.sum())} env-steps)")
+print(f"n={n}: cycles since the block's scalar-warp start (mean / p50 / p99 over {int(ok.sum())} env-steps)")
 for k in order:
     v = rel[:, :, k][ok]
     print(f"  {k:2d} {names[k]:30s} {v.mean():9.0f} {np.percentile(v,50):9.0f} {np.percentile(v,99):9.0f}")

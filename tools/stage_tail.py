@@ -2,7 +2,6 @@
 """What makes an env's deposition slow?  Per-env duration (stage clocks of the instrumented 28-env kernel) against the
 beam it deposited: voxels hit, slabs, warp index in the block."""
 import sys, os, ctypes as C
-os.environ["RT_STEP_KB"] = "28"
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import ppo_radiotherapy_b200 as rt
