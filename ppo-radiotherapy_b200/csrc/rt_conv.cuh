@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rt_conv1_tc_kernel(ConvShape S,
             const Tumour tm = E.T.tumours[tumour_id];
             const uint32_t *tb = E.T.tumour_pbits + (size_t)tumour_id * E.T.pbits_words;
             const int pd1 = tm.dim[1] + 2, pd2 = tm.dim[2] + 2;
-            const uint2 *vol = E.cells + (size_t)env * G.vstride;
+            const uint2 *vol = E.cells + (size_t)env * G.cstride;
             // Work item = 8 consecutive voxels of the volume (64 bytes of cells) of one plane of the pair: four 16-byte
             // cell loads (a cell of another generation reads as zero), one lungs word, one view-hit bit; the tumour and
             // view tests only run for the few groups that can contain such voxels.
@@ -298,7 +298,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) rt_conv1_tc_kernel(ConvShape S,
                         float d[8];
 #pragma unroll
                         for (int i = 0; i < 4; i++) {
-                            const uint4 c = __ldg(reinterpret_cast<const uint4 *>(vol + l0) + i);
+                            // voxels (l0 + 2i, l0 + 2i + 1) share a row (W is even) and a brick of the cell layout
+                            const int lp = min(l0 + 2 * i, G.nvox - 2);
+                            const uint4 c = __ldg(reinterpret_cast<const uint4 *>(vol + cell_index_lin(G, lp)));
                             d[2 * i] = c.y == gen ? __uint_as_float(c.x) : 0.0f;
                             d[2 * i + 1] = c.w == gen ? __uint_as_float(c.z) : 0.0f;
                         }

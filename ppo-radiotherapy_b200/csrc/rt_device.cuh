@@ -21,8 +21,30 @@ constexpr int kLungPadBits = 128;
 struct Grid {
     int g0, g1, g2;
     int nvox;        // g0*g1*g2
-    int vstride;     // per-env dose stride in voxels (nvox rounded up to 32: 256 B of cells, 128 B of dense float32)
+    int vstride;     // per-env stride of C-order volumes (dense-mode float32 dose, bfloat16 records): nvox rounded up to 32
+    int nb1, nb2;    // bricks along axes 1 and 2 (sparse-mode cells, see cell_index)
+    int cstride;     // per-env stride of the sparse-mode cell array in cells: bricks * 16
 };
+
+// Sparse-mode dose cells are stored in BRICKS of 2 x 2 x 4 voxels = 16 cells of 8 bytes = one 128-byte line, bricks in C
+// order, cells inside a brick in C order.  A beam is a thin tube: the lanes of a warp (consecutive slabs) then share lines
+// whatever the beam's dominant axis is — in plain C order every slab of a beam along axis 0 or 1 lands in a line of its
+// own, and the load/store pipeline pays per distinct line of a warp instruction (tools/measure_layouts.py: 36 lines per
+// beam bricked against 53).  The two voxels (k, k + 1) of a row are neighbours in memory when k is even.
+__host__ __device__ __forceinline__ int cell_row_term(const Grid &G, int i, int j)
+{
+    return (((i >> 1) * G.nb1 + (j >> 1)) * G.nb2) * 16 + (i & 1) * 8 + (j & 1) * 4;
+}
+__host__ __device__ __forceinline__ int cell_col_term(int k) { return (k >> 2) * 16 + (k & 3); }
+__host__ __device__ __forceinline__ int cell_index(const Grid &G, int i, int j, int k)
+{
+    return cell_row_term(G, i, j) + cell_col_term(k);
+}
+__host__ __device__ __forceinline__ int cell_index_lin(const Grid &G, int lin)      // C-order linear voxel index -> cell
+{
+    const int k = lin % G.g2, ij = lin / G.g2;
+    return cell_index(G, ij / G.g1, ij % G.g1, k);
+}
 
 // ---------------------------------------------------------------------------------
 // Pose update: environment.py:112-143 (map_translation / map_rotation) and

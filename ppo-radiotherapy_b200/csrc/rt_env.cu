@@ -2,8 +2,8 @@
 //
 // HBM layout per handle (N envs, V voxels):
 //   rec     [N]            128-byte env record: pose f64, accumulators, counters, dose generation
-//   cells   [N][vstride]   sparse mode: one 8-byte cell per voxel {float32 dose, uint32 generation}, vstride = V
-//                          rounded up to 32 cells.  A cell of another generation than its env's reads as zero, so
+//   cells   [N][cstride]   sparse mode: one 8-byte cell per voxel {float32 dose, uint32 generation} in bricks of
+//                          2x2x4 voxels = one 128-byte line (cell_index, rt_device.cuh).  A cell of another generation than its env's reads as zero, so
 //                          reset never touches the 1.6 MB volume (it bumps EnvRec::gen) and a beam needs no
 //                          validity bitmap: every voxel it hits is one 8-byte load and one 8-byte store.
 //   dose    [N][vstride]   dense mode (RT_FLAG_DENSE): plain float32 volumes, streamed whole every step
@@ -563,7 +563,7 @@ __global__ void rt_get_counters_kernel(const EnvRec *rec, int n, int32_t *out)
 
 // Source of an env's dose volume: sparse-mode cells {dose, generation} or a dense-mode float32 volume.
 struct DoseSrc {
-    const uint2 *cells;      // [N][vstride] or nullptr
+    const uint2 *cells;      // [N][cstride] (bricked) or nullptr
     const float *dense;      // [N][vstride] or nullptr
 };
 
@@ -573,7 +573,7 @@ __global__ void rt_get_dose_kernel(Grid G, const EnvRec *rec, DoseSrc D, int env
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= G.nvox) return;
     if (D.cells) {
-        const uint2 c = D.cells[(size_t)env * G.vstride + v];
+        const uint2 c = D.cells[(size_t)env * G.cstride + cell_index_lin(G, v)];
         out[v] = c.y == rec[env].gen ? __uint_as_float(c.x) : 0.0f;
     } else {
         out[v] = D.dense[(size_t)env * G.vstride + v];
@@ -659,7 +659,7 @@ __global__ void __launch_bounds__(kVolThreads) rt_volumes_kernel(Tables T, const
     }
     __syncthreads();
     const float2 *vol2 = kPacked || !D.dense ? nullptr : reinterpret_cast<const float2 *>(D.dense + (size_t)env * G.vstride);
-    const uint4 *cell2 = kPacked || !D.cells ? nullptr : reinterpret_cast<const uint4 *>(D.cells + (size_t)env * G.vstride);
+    const uint2 *cellv = kPacked || !D.cells ? nullptr : D.cells + (size_t)env * G.cstride;
     const uint32_t gen = kPacked ? 0u : r.gen;
     const __nv_bfloat162 *pk2 = kPacked ? reinterpret_cast<const __nv_bfloat162 *>(P.dose + (size_t)env * G.vstride) : nullptr;
     float *o = out + (size_t)blockIdx.x * 4 * G.nvox;
@@ -676,8 +676,9 @@ __global__ void __launch_bounds__(kVolThreads) rt_volumes_kernel(Tables T, const
             if (q < npairs) {
                 if (kPacked) {
                     d[u] = __bfloat1622float2(pk2[q]);
-                } else if (cell2) {
-                    const uint4 c = __ldcs(cell2 + q);           // two cells; another generation reads as zero
+                } else if (cellv) {
+                    // voxels (2q, 2q + 1) share a row (g2 is even here: nvox even and the pair does not straddle) and a brick
+                    const uint4 c = __ldcs(reinterpret_cast<const uint4 *>(cellv + cell_index_lin(G, 2 * q)));   // another generation reads as zero
                     d[u] = make_float2(c.y == gen ? __uint_as_float(c.x) : 0.0f, c.w == gen ? __uint_as_float(c.z) : 0.0f);
                 } else {
                     d[u] = __ldcs(vol2 + q);
@@ -715,16 +716,19 @@ __global__ void __launch_bounds__(256) rt_pack_kernel(Grid G, const EnvRec *rec,
 {
     const int env = first + blockIdx.y;
     const long long slot = slot0 + blockIdx.y;
-    const uint4 *vol = reinterpret_cast<const uint4 *>(cells + (size_t)env * G.vstride);       // two cells per load
+    const uint2 *vol = cells + (size_t)env * G.cstride;
     const uint32_t gen = rec[env].gen;
-    uint2 *o = reinterpret_cast<uint2 *>(out_dose + (size_t)slot * G.vstride);
-    const int nquads = G.vstride / 4;
-    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nquads; q += gridDim.x * blockDim.x) {
-        const uint4 c0 = __ldcs(vol + 2 * q), c1 = __ldcs(vol + 2 * q + 1);
-        const float v0 = c0.y == gen ? __uint_as_float(c0.x) : 0.0f, v1 = c0.w == gen ? __uint_as_float(c0.z) : 0.0f;
-        const float v2 = c1.y == gen ? __uint_as_float(c1.x) : 0.0f, v3 = c1.w == gen ? __uint_as_float(c1.z) : 0.0f;
-        const __nv_bfloat162 a = __floats2bfloat162_rn(v0, v1), b = __floats2bfloat162_rn(v2, v3);
-        o[q] = make_uint2(*reinterpret_cast<const uint32_t *>(&a), *reinterpret_cast<const uint32_t *>(&b));
+    uint32_t *o = reinterpret_cast<uint32_t *>(out_dose + (size_t)slot * G.vstride);
+    const int npairs = G.vstride / 2, vpairs = G.nvox / 2;               // g2 is even: a pair never straddles a row
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < npairs; q += gridDim.x * blockDim.x) {
+        float v0 = 0.0f, v1 = 0.0f;
+        if (q < vpairs) {
+            const uint4 c = __ldcs(reinterpret_cast<const uint4 *>(vol + cell_index_lin(G, 2 * q)));
+            v0 = c.y == gen ? __uint_as_float(c.x) : 0.0f;
+            v1 = c.w == gen ? __uint_as_float(c.z) : 0.0f;
+        }
+        const __nv_bfloat162 a = __floats2bfloat162_rn(v0, v1);
+        o[q] = *reinterpret_cast<const uint32_t *>(&a);
     }
     if (blockIdx.x == 0 && threadIdx.x < 6)
         out_pose[slot * 6 + threadIdx.x] = threadIdx.x < 3 ? rec[env].pos[threadIdx.x] : rec[env].dir[threadIdx.x - 3];
@@ -820,6 +824,9 @@ Grid make_grid(const int32_t g[3])
     G.g0 = g[0]; G.g1 = g[1]; G.g2 = g[2];
     G.nvox = g[0] * g[1] * g[2];
     G.vstride = (G.nvox + 31) / 32 * 32;
+    G.nb1 = (G.g1 + 1) / 2;
+    G.nb2 = (G.g2 + 3) / 4;
+    G.cstride = ((G.g0 + 1) / 2) * G.nb1 * G.nb2 * 16;
     return G;
 }
 
@@ -972,7 +979,7 @@ int rt_create(rt_env **out, int device, int n_envs, uint32_t flags, const rt_pha
         (rc = dev_alloc(&e->d_tbits, tbits.size(), &e->bytes)) || (rc = dev_alloc(&e->d_ptbits, ptbits.size(), &e->bytes)) || (rc = dev_alloc(&e->d_vox, vox_dev.size(), &e->bytes)) ||
         (rc = dev_alloc(&e->rec, (size_t)n_envs, &e->bytes)) ||
         (rc = dense_mode ? dev_alloc(&e->dose, (size_t)n_envs * G.vstride, &e->bytes)
-                         : dev_alloc(&e->cells, (size_t)n_envs * G.vstride, &e->bytes))) {
+                         : dev_alloc(&e->cells, (size_t)n_envs * G.cstride, &e->bytes))) {
         rt_destroy(e);
         return rc;
     }
@@ -1014,7 +1021,7 @@ int rt_create(rt_env **out, int device, int n_envs, uint32_t flags, const rt_pha
     chk(cudaMemset(e->rec, 0, (size_t)n_envs * sizeof(EnvRec)));
     // every cell starts in generation 0xffffffff, which no env ever reaches (EnvRec::gen counts resets from 0): the
     // volumes read as zero without being written; dense-mode volumes are zeroed by the first rt_reset
-    if (e->cells) chk(cudaMemset(e->cells, 0xff, (size_t)n_envs * G.vstride * sizeof(uint2)));
+    if (e->cells) chk(cudaMemset(e->cells, 0xff, (size_t)n_envs * G.cstride * sizeof(uint2)));
     chk(cudaStreamCreateWithFlags(&e->hstream, cudaStreamNonBlocking));
     chk(cudaMallocHost(&e->h_actions, (size_t)n_envs * RT_ACTION_SIZE * sizeof(float)));
     chk(cudaMallocHost(&e->h_obs, (size_t)n_envs * RT_OBS_SIZE * sizeof(float)));
@@ -1244,7 +1251,8 @@ int rt_assemble_volumes(rt_env *e, int first, int count, float *obs_dev, void *s
     if (first < 0 || count < 1 || first + count > e->n)
         return fail(RT_ERR_INVALID, "rt_assemble_volumes: env range out of bounds");
     RT_CUDA(cudaSetDevice(e->device));
-    if (e->T.G.nvox % 2) return fail(RT_ERR_INVALID, "rt_assemble_volumes: the voxel count must be even");
+    if (e->T.G.nvox % 2 || (e->cells && e->T.G.g2 % 2))
+        return fail(RT_ERR_INVALID, "rt_assemble_volumes: the voxel count (sparse mode: the last grid extent) must be even");
     const size_t smem = (size_t)(2 * (e->T.G.vstride / 32)) * sizeof(uint32_t) + (size_t)kHashSlots * (sizeof(int) + sizeof(float));
     static bool attr_set = false;
     if (!attr_set) {
@@ -1268,6 +1276,7 @@ int rt_pack_observations(rt_env *e, int first, int count, int64_t slot0, void *d
     if (first < 0 || count < 0 || first + count > e->n || slot0 < 0)
         return fail(RT_ERR_INVALID, "rt_pack_observations: env range out of bounds");
     if (e->dense) return fail(RT_ERR_STATE, "rt_pack_observations: not available for dense-mode handles");
+    if (e->T.G.g2 % 2) return fail(RT_ERR_INVALID, "rt_pack_observations: the last grid extent must be even");
     RT_CUDA(cudaSetDevice(e->device));
     rt_pack_kernel<<<dim3(8, count), 256, 0, (cudaStream_t)stream>>>(e->T.G, e->rec, e->cells, first, (long long)slot0,
                                                                     reinterpret_cast<__nv_bfloat16 *>(dose_bf16_dev), pose_dev,

@@ -348,9 +348,11 @@ rt_step_kernel(Tables T, Schedule S, EnvRec *rec, uint2 *cells, double *beams, i
             if (fabsf(ratio - kDoneRatio) < kDoneWindow) {
                 // Within 2e-5 of the termination threshold the summation ORDER of np.sum decides `done`
                 // (environment.py:186-190): redo the sum exactly as NumPy's pairwise float32 reduction does.
-                const uint2 *vol = cells + (size_t)e * G.vstride;
-                tsum_f32 = np_pairwise_sparse(G.nvox, T.vox_xyz + tm.vox_off, tm.n_vox, G,
-                                              [&](int lin) { const uint2 c = vol[lin]; return c.y == gen ? __uint_as_float(c.x) : 0.0f; });
+                const uint2 *vol = cells + (size_t)e * G.cstride;
+                tsum_f32 = np_pairwise_sparse(G.nvox, T.vox_xyz + tm.vox_off, tm.n_vox, G, [&](int lin) {
+                    const uint2 c = __ldcg(vol + cell_index_lin(G, lin));
+                    return c.y == gen ? __uint_as_float(c.x) : 0.0f;
+                });
                 ratio = __fdiv_rn(tsum_f32, tm.tumour_sum);
             }
             const float r_tumour = __fmul_rn(ratio, 10.0f);
@@ -477,7 +479,7 @@ rt_step_kernel(Tables T, Schedule S, EnvRec *rec, uint2 *cells, double *beams, i
         const Beam b = se.beam;
         const uint32_t gen = se.gen;
         const float2 *myz = yz[le];
-        uint2 *vol = cells + (size_t)env * G.vstride;
+        uint2 *vol = cells + (size_t)env * G.cstride;
         const int g2 = G.g2;
         const int li0 = tm.lo[0], li1 = tm.lo[1] - 1, li2 = tm.lo[2] - 1;  // origin of the padded bbox
         const int td0 = tm.dim[0], td1 = tm.dim[1], td2 = tm.dim[2];
@@ -494,12 +496,14 @@ rt_step_kernel(Tables T, Schedule S, EnvRec *rec, uint2 *cells, double *beams, i
             int base, c0, c1, c2;
             uint32_t inb;
             const SlabCoord sc = slab_coords(G, b, k, cur, base, inb, c0, c1, c2);
-            // the cell loads go out first (a voxel the previous slab owns is loaded for nothing: harmless)
+            // the cell loads go out first (a voxel the previous slab owns is loaded for nothing: harmless); bricked layout
+            const int ca[4] = {cell_row_term(G, c0, c1) + cell_col_term(c2), cell_row_term(G, c0, c1) + cell_col_term(c2 + 1),
+                               cell_row_term(G, c0, c1 + 1) + cell_col_term(c2), cell_row_term(G, c0, c1 + 1) + cell_col_term(c2 + 1)};
             uint2 cell[4];
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 cell[j] = make_uint2(0u, ~gen);
-                if ((inb >> j) & 1u) cell[j] = __ldcg(vol + base + (j >> 1) * g2 + (j & 1));
+                if ((inb >> j) & 1u) cell[j] = __ldcg(vol + ca[j]);
             }
             if (k0 == 0 && lane == 0) RT_STAMP3(env, 4);
             uint32_t drop;
@@ -543,14 +547,13 @@ rt_step_kernel(Tables T, Schedule S, EnvRec *rec, uint2 *cells, double *beams, i
             // the two targets of a row are neighbours in memory: one 16-byte store when both are written and aligned
 #pragma unroll
             for (int r = 0; r < 2; r++) {
-                const int l = base + r * g2;
                 const uint32_t both = (ok >> (2 * r)) & 3u;
-                if (both == 3u && !(l & 1)) {
-                    __stcg(reinterpret_cast<uint4 *>(vol + l),
+                if (both == 3u && !(c2 & 1)) {                      // (k, k + 1) with k even: neighbours inside a brick, 16-byte aligned
+                    __stcg(reinterpret_cast<uint4 *>(vol + ca[2 * r]),
                            make_uint4(__float_as_uint(nd[2 * r]), gen, __float_as_uint(nd[2 * r + 1]), gen));
                 } else {
-                    if (both & 1u) __stcg(vol + l, make_uint2(__float_as_uint(nd[2 * r]), gen));
-                    if (both & 2u) __stcg(vol + l + 1, make_uint2(__float_as_uint(nd[2 * r + 1]), gen));
+                    if (both & 1u) __stcg(vol + ca[2 * r], make_uint2(__float_as_uint(nd[2 * r]), gen));
+                    if (both & 2u) __stcg(vol + ca[2 * r + 1], make_uint2(__float_as_uint(nd[2 * r + 1]), gen));
                 }
             }
         }

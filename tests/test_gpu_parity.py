@@ -733,35 +733,46 @@ def test_host_buffer_step_matches_device_step():
 
 def test_host_call_waits_for_device_side_work():
     """the *_host entry points run on the handle's own stream; a host step issued right after a device-side
-    reset / step / set_pose (any stream, here behind a long-running kernel) must see their effect."""
+    reset / step / set_pose (on any stream, here behind tens of milliseconds of queued work) must see their effect."""
     n = 257
     tids = (np.arange(n) * 7919 % 1000).astype(np.int32)[None, :]
-    a = rt.BatchedEpisodes(n, device=DEV); a.set_tumour_schedule(tids)
-    b = rt.BatchedEpisodes(n, device=DEV); b.set_tumour_schedule(tids)
     rng = np.random.default_rng(2)
-    acts = rng.uniform(-1, 1, (6, n, 6)).astype(np.float32)
+    acts = rng.uniform(-1, 1, (8, n, 6)).astype(np.float32)
+    dacts = _cuda(acts)
+    a = rt.BatchedEpisodes(n, device=DEV); a.set_tumour_schedule(tids)       # reference: device calls on one stream
+    b = rt.BatchedEpisodes(n, device=DEV); b.set_tumour_schedule(tids)       # device calls on a busy side stream + host calls
     h_obs, h_rew = np.empty((n, 9), np.float32), np.empty(n, np.float64)
     h_term, h_trunc = np.empty(n, np.uint8), np.empty(n, np.uint8)
-    big = torch.empty(1 << 28, dtype=torch.float32, device=DEV)
+    big = torch.zeros(1 << 27, dtype=torch.float32, device=DEV)
     side = torch.cuda.Stream(DEV)
-    for t in range(6):
-        with torch.cuda.stream(side):
-            for _ in range(20):
-                big.add_(1.0)                                  # tens of milliseconds of work in front of the device call
-            if t == 0:
-                b.reset()
-            elif t == 3:
-                b.set_pose(a.pose())
-            if t % 2 == 0:
-                b.step(_cuda(acts[t]), want_info=False)
-        if t == 0:
-            a.reset()
-        if t % 2 == 0:
-            a.step(_cuda(acts[t]), want_info=False)
-        else:
-            a.step(_cuda(acts[t]), want_info=False)
-            b.step_host(acts[t], h_obs, h_rew, h_term, h_trunc)           # no explicit synchronisation in between
-            assert np.array_equal(h_obs.view(np.uint32), a.obs.cpu().numpy().view(np.uint32))
-            assert np.array_equal(h_rew.view(np.uint64), a.reward.cpu().numpy().view(np.uint64))
     torch.cuda.synchronize()
+
+    def busy():
+        for _ in range(20):
+            big.add_(1.0)
+
+    a.reset()
+    with torch.cuda.stream(side):
+        busy()
+        b.reset()                                               # queued behind the adds
+    for t in range(8):
+        a.step(dacts[t], want_info=False)
+        if t % 2 == 0:
+            with torch.cuda.stream(side):
+                busy()
+                b.step(dacts[t], want_info=False)               # device-side step, still pending when the next call comes
+        else:
+            b.step_host(acts[t], h_obs, h_rew, h_term, h_trunc)  # no explicit synchronisation in between
+            assert np.array_equal(h_obs.view(np.uint32), a.obs.cpu().numpy().view(np.uint32)), t
+            assert np.array_equal(h_rew.view(np.uint64), a.reward.cpu().numpy().view(np.uint64)), t
+        if t == 4:
+            pose = a.pose()
+            pose[:, :3] = torch.flip(pose[:, :3], dims=(0,))    # move the beams: a pose set on the device ...
+            torch.cuda.synchronize()
+            a.set_pose(pose)
+            with torch.cuda.stream(side):
+                busy()
+                b.set_pose(pose)                                # ... must be seen by the host step that follows
+    torch.cuda.synchronize()
+    assert torch.equal(a.pose(), b.pose())
     a.close(); b.close()

@@ -20,9 +20,9 @@ for i in range(20, 40):
     s = stamps.cpu().numpy().astype(np.float64)
     res.append(s)
 s = np.stack(res)            # [iters, n, 12]
+order = [0, 8, 9, 10, 1, 2, 3, 4, 6, 11, 7]
 ok = (s[:, :, order] > 0).all(axis=2)          # envs that walked a beam this step (all stamps written)
 rel = s - s[:, :, 0:1]                        # clock64 is per SM: only differences within an env's block are meaningful
-order = [0, 8, 9, 10, 1, 2, 3, 4, 6, 11, 7]
 names = {0: "scalar warp start", 8: "scalar: state loaded, translated", 9: "scalar: pose updated", 10: "scalar: beam set up",
          1: "scalar: walk done", 2: "env warp: tumour + distance done", 3: "env warp: past barrier 1, lungs landed",
          4: "env warp: first pass's cell loads issued", 6: "env warp: all passes stored",
