@@ -513,7 +513,7 @@ constexpr float kDoneWindow = 2e-5f;
 // ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) plus a sequential tail, halves split at a multiple of eight.  `get(lin)` returns
 // the value at linear voxel index lin.  Rare path (one thread, a few thousand instructions).
 template <typename Get>
-__device__ __noinline__ float np_pairwise_sparse(int n, const uint32_t *vox, int nv, const Grid &G, Get get)
+__device__ __noinline__ float np_pairwise_sparse(int n, const uint32_t *vox, int nv, int g1, int g2, Get get)
 {
     int lo[20], len[20], phase[20];
     float acc[20];
@@ -522,7 +522,7 @@ __device__ __noinline__ float np_pairwise_sparse(int n, const uint32_t *vox, int
     lo[0] = 0; len[0] = n; phase[0] = 0; acc[0] = 0.0f;
     auto lin_of = [&](int i) {
         const uint32_t pk = __ldg(vox + i);
-        return ((int)(pk & 255u) * G.g1 + (int)((pk >> 8) & 255u)) * G.g2 + (int)(pk >> 16);
+        return ((int)(pk & 255u) * g1 + (int)((pk >> 8) & 255u)) * g2 + (int)(pk >> 16);
     };
     int nl = nv > 0 ? lin_of(0) : 0x7fffffff;                       // linear index of the next unvisited voxel
     while (sp >= 0) {

@@ -347,7 +347,7 @@ __global__ void __launch_bounds__(kDenseThreads) rt_dense_kernel(Tables T, EnvRe
         __threadfence_block();
         const float *vol = dose + (size_t)env * G.vstride;
         if (lane == 0)
-            tsum_f32 = np_pairwise_sparse(G.nvox, T.vox_xyz + tm.vox_off, tm.n_vox, G, [&](int lin) { return __ldcg(vol + lin); });
+            tsum_f32 = np_pairwise_sparse(G.nvox, T.vox_xyz + tm.vox_off, tm.n_vox, G.g1, G.g2, [=](int lin) { return __ldcg(vol + lin); });
         tsum_f32 = __shfl_sync(kFull, tsum_f32, 0);
         ratio = __fdiv_rn(tsum_f32, tm.tumour_sum);
     }
@@ -992,12 +992,19 @@ int rt_create(rt_env **out, int device, int n_envs, uint32_t flags, const rt_pha
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
         const int per_sm = (n_envs + sms - 1) / sms;
         e->step_kb = per_sm <= 7 ? 7 : 14;
-        e->step_smem = (e->step_kb >= 14 && !dense_mode) ? (size_t)e->T.lung_words16 * sizeof(uint32_t) : 0;
+        // dynamic shared memory of a block: the item slots of its envs (kMaxPass x 32 slabs x 4 targets x 8 bytes each) and,
+        // for 14-env blocks, the padded lungs bitmask
+        e->step_smem = dense_mode ? 0 : (size_t)e->step_kb * kMaxPass * 4 * kWarp * sizeof(uint2) +
+                                        (e->step_kb >= 14 ? (size_t)e->T.lung_words16 * sizeof(uint32_t) : 0);
         cudaError_t ae = cudaSuccess;
         if (e->step_smem) {
-            ae = cudaFuncSetAttribute(rt_step_kernel<14, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->step_smem);
-            if (ae == cudaSuccess)
-                ae = cudaFuncSetAttribute(rt_step_kernel<14, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->step_smem);
+            if (e->step_kb == 7)
+                ae = cudaFuncSetAttribute(rt_step_kernel<7, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->step_smem);
+            else {
+                ae = cudaFuncSetAttribute(rt_step_kernel<14, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->step_smem);
+                if (ae == cudaSuccess)
+                    ae = cudaFuncSetAttribute(rt_step_kernel<14, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->step_smem);
+            }
         }
         if (ae != cudaSuccess) { rt_destroy(e); return fail(RT_ERR_CUDA, std::string("rt_step_kernel smem: ") + cudaGetErrorString(ae)); }
     }

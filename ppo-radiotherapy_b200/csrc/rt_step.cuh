@@ -37,6 +37,7 @@ struct __align__(16) EnvShared {
 };
 
 constexpr int kYZStride = kMaxSlabs + 1;   // odd float2 stride: the scalar warp's lanes store to distinct banks
+constexpr int kMaxPass = (kMaxSlabs + kWarp - 1) / kWarp;   // 32-slab passes of one beam (3)
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -64,6 +65,20 @@ __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity)
                  "bra RT_MBAR_WAIT;\n"
                  "RT_MBAR_DONE:\n"
                  "}" ::"r"(mbar), "r"(parity) : "memory");
+}
+
+// 8-byte asynchronous copy global -> shared (cp.async: the data never passes through registers)
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+// wait until at most `pending` (0..2, warp-uniform) of this thread's copy groups are still in flight
+__device__ __forceinline__ void cp_async_wait(int pending)
+{
+    if (pending >= 2) asm volatile("cp.async.wait_group 2;" ::: "memory");
+    else if (pending == 1) asm volatile("cp.async.wait_group 1;" ::: "memory");
+    else asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 #define RT_STAMP3(env_, slot)                                                                    \
@@ -173,7 +188,11 @@ rt_step_kernel(Tables T, Schedule S, EnvRec *rec, uint2 *cells, double *beams, i
     __shared__ double s_rew[kB];
     __shared__ uint8_t s_term[kB];
     __shared__ double s_info[kB * RT_INFO_SIZE];
-    extern __shared__ __align__(128) uint32_t dyn_smem[];         // [lung_words16] padded lungs bitmask (kB >= 14)
+    // dynamic: [kB][kMaxPass][32 slabs][4 targets] item slots of 8 bytes (cell index, then the prefetched cell, then the new
+    // dose + cell index), then [lung_words16] padded lungs bitmask (kB >= 14)
+    extern __shared__ __align__(128) uint32_t dyn_smem[];
+    uint2 *cellbuf_all = reinterpret_cast<uint2 *>(dyn_smem);
+    uint32_t *lungs_sm = dyn_smem + (kDense ? 0 : kB * kMaxPass * 4 * kWarp * 2);
     const Grid &G = T.G;
     const int warp = threadIdx.x / kWarp;
     const int lane = threadIdx.x & (kWarp - 1);
@@ -192,7 +211,7 @@ rt_step_kernel(Tables T, Schedule S, EnvRec *rec, uint2 *cells, double *beams, i
         const int e = env0 + lane;
         const bool mine = lane < kB && e < n_envs;
         if (kStageLungs && lane == 0)
-            bulk_load(smem_u32(dyn_smem), T.lungs_pad, (uint32_t)(T.lung_words16 * sizeof(uint32_t)), smem_u32(&mbars[0]));
+            bulk_load(smem_u32(lungs_sm), T.lungs_pad, (uint32_t)(T.lung_words16 * sizeof(uint32_t)), smem_u32(&mbars[0]));
         if (mine) RT_STAMP3(e, 0);
         EnvRec *my = rec + (mine ? e : 0);
         EnvShared &se = sh[lane < kB ? lane : 0];
@@ -349,8 +368,10 @@ rt_step_kernel(Tables T, Schedule S, EnvRec *rec, uint2 *cells, double *beams, i
                 // Within 2e-5 of the termination threshold the summation ORDER of np.sum decides `done`
                 // (environment.py:186-190): redo the sum exactly as NumPy's pairwise float32 reduction does.
                 const uint2 *vol = cells + (size_t)e * G.cstride;
-                tsum_f32 = np_pairwise_sparse(G.nvox, T.vox_xyz + tm.vox_off, tm.n_vox, G, [&](int lin) {
-                    const uint2 c = __ldcg(vol + cell_index_lin(G, lin));
+                const int g1 = G.g1, g2 = G.g2, nb1 = G.nb1, nb2 = G.nb2;       // by value: nothing of the kernel's parameters is addressed
+                tsum_f32 = np_pairwise_sparse(G.nvox, T.vox_xyz + tm.vox_off, tm.n_vox, g1, g2, [=](int lin) {
+                    const int k = lin % g2, ij = lin / g2, i = ij / g1, j = ij - i * g1;
+                    const uint2 c = __ldcg(vol + ((((i >> 1) * nb1 + (j >> 1)) * nb2) * 16 + (i & 1) * 8 + (j & 1) * 4 + (k >> 2) * 16 + (k & 3)));
                     return c.y == gen ? __uint_as_float(c.x) : 0.0f;
                 });
                 ratio = __fdiv_rn(tsum_f32, tm.tumour_sum);
@@ -470,17 +491,65 @@ rt_step_kernel(Tables T, Schedule S, EnvRec *rec, uint2 *cells, double *beams, i
         if (lane == 0) dw.n_hits = nhit < RT_BEAM_CAP ? nhit : RT_BEAM_CAP;
     }
     if (stepping && !kDense) {
-        const uint32_t *slungs = kStageLungs ? dyn_smem : T.lungs_pad;
-        if (kStageLungs) mbar_wait(smem_u32(&mbars[0]), 0);                // the lungs bitmask has landed
+        const uint32_t *slungs = kStageLungs ? lungs_sm : T.lungs_pad;
         if (lane == 0) RT_STAMP3(env, 3);
         // ---- dose deposition (environment.py:107-110): dose' = clip(dose + beam*0.1, 0, 1) on the voxels hit.
         // A voxel has exactly one owner lane per beam (slab_weights merges the two slabs that can meet), so the
-        // 32-slab passes of a beam are independent: load cells | weights, masks | new dose, store, deltas.
+        // 32-slab passes of a beam are independent.
+        //   Phase 1 issues the loads of every pass before it uses any (the beam pays one HBM round trip however long it
+        //   is); phase 2 takes the passes in order: weights, masks, new dose, deltas, stores.
+        //   The MEMORY instructions use another lane mapping than the arithmetic: a lane computes one slab and its
+        //   four targets, but load / store instruction i of a pass moves item 32 i + lane of the pass's item list
+        //   [slab][target] — the four targets of eight consecutive slabs.  The load/store pipeline pays per distinct
+        //   128-byte line of an instruction: with one target of 32 slabs per instruction that is ~15 lines, with all
+        //   targets of 8 slabs ~4 (the tube of a beam crosses a brick every 2 to 4 slabs).  Cell indices and cells
+        //   change lanes through one shared-memory slot per item (item-major, conflict-free both ways).
         const Beam b = se.beam;
         const uint32_t gen = se.gen;
         const float2 *myz = yz[le];
         uint2 *vol = cells + (size_t)env * G.cstride;
+        uint2 *cbuf = cellbuf_all + (size_t)le * (kMaxPass * 4 * kWarp);          // [pass][slab][target]: cell index -> cell -> {new dose, cell index}
         const int g2 = G.g2;
+        const int npass = (b.nslab + kWarp - 1) / kWarp;
+#pragma unroll
+        for (int c = 0; c < kMaxPass; c++) {
+            if (c < npass) {                                                       // warp-uniform
+                const int k = c * kWarp + lane;
+                const float2 cur = myz[k < b.nslab ? k : 0];
+                int base, c0, c1, c2;
+                uint32_t inb;
+                slab_coords(G, b, k, cur, base, inb, c0, c1, c2);
+                const int r0 = cell_row_term(G, c0, c1), r1 = cell_row_term(G, c0, c1 + 1);
+                const int q0 = cell_col_term(c2), q1 = cell_col_term(c2 + 1);
+                // the cell index of every target goes into its own slot (-1: outside the grid) ...
+                uint4 *mine4 = reinterpret_cast<uint4 *>(cbuf + c * 4 * kWarp) + 2 * lane;
+                mine4[0] = make_uint4((uint32_t)(inb & 1u ? r0 + q0 : -1), 0u, (uint32_t)(inb & 2u ? r0 + q1 : -1), 0u);
+                mine4[1] = make_uint4((uint32_t)(inb & 4u ? r1 + q0 : -1), 0u, (uint32_t)(inb & 8u ? r1 + q1 : -1), 0u);
+            }
+        }
+        __syncwarp();
+        // ... every load of the beam goes out (item-major lane mapping) before the first one is used, then the cells
+        // replace the indices
+        uint2 got[kMaxPass][4];
+#pragma unroll
+        for (int c = 0; c < kMaxPass; c++)
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                got[c][i] = make_uint2(0u, ~gen);                                  // outside the grid: reads as "another generation"
+                if (c < npass) {
+                    const int a = (int)cbuf[c * 4 * kWarp + i * kWarp + lane].x;
+                    if (a >= 0) got[c][i] = __ldcg(vol + a);
+                }
+            }
+#pragma unroll
+        for (int c = 0; c < kMaxPass; c++)
+            if (c < npass) {
+#pragma unroll
+                for (int i = 0; i < 4; i++) cbuf[c * 4 * kWarp + i * kWarp + lane] = got[c][i];
+            }
+        __syncwarp();
+        if (lane == 0) RT_STAMP3(env, 4);
+        if (kStageLungs) mbar_wait(smem_u32(&mbars[0]), 0);                // the lungs bitmask has landed
         const int li0 = tm.lo[0], li1 = tm.lo[1] - 1, li2 = tm.lo[2] - 1;  // origin of the padded bbox
         const int td0 = tm.dim[0], td1 = tm.dim[1], td2 = tm.dim[2];
         const int pd1 = td1 + 2, pd2 = td2 + 2;
@@ -489,23 +558,15 @@ rt_step_kernel(Tables T, Schedule S, EnvRec *rec, uint2 *cells, double *beams, i
         float d_tum = 0.0f, d_lung = 0.0f;
         int d_cnt = 0;
 #pragma unroll 1
-        for (int k0 = 0; k0 < b.nslab; k0 += kWarp) {
-            const int k = k0 + lane;
+        for (int c = 0; c < npass; c++) {
+            const int k = c * kWarp + lane;
             const int kk = k < b.nslab ? k : 0;
             const float2 cur = myz[kk], prv = myz[kk > 0 ? kk - 1 : 0], nxt = myz[kk + 1 < b.nslab ? kk + 1 : kk];
             int base, c0, c1, c2;
             uint32_t inb;
             const SlabCoord sc = slab_coords(G, b, k, cur, base, inb, c0, c1, c2);
-            // the cell loads go out first (a voxel the previous slab owns is loaded for nothing: harmless); bricked layout
-            const int ca[4] = {cell_row_term(G, c0, c1) + cell_col_term(c2), cell_row_term(G, c0, c1) + cell_col_term(c2 + 1),
-                               cell_row_term(G, c0, c1 + 1) + cell_col_term(c2), cell_row_term(G, c0, c1 + 1) + cell_col_term(c2 + 1)};
-            uint2 cell[4];
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                cell[j] = make_uint2(0u, ~gen);
-                if ((inb >> j) & 1u) cell[j] = __ldcg(vol + ca[j]);
-            }
-            if (k0 == 0 && lane == 0) RT_STAMP3(env, 4);
+            const int r0 = cell_row_term(G, c0, c1), r1 = cell_row_term(G, c0, c1 + 1);
+            const int q0 = cell_col_term(c2), q1 = cell_col_term(c2 + 1);
             uint32_t drop;
             float w[4];
             switch (variant) {
@@ -533,10 +594,13 @@ rt_step_kernel(Tables T, Schedule S, EnvRec *rec, uint2 *cells, double *beams, i
             tmask &= ok;
             lmask &= ok;
             const uint32_t cmask = lmask & ~tmask;                 // lungs_mask = lungs*(1-tumours) (environment.py:174)
+            uint4 *mine4 = reinterpret_cast<uint4 *>(cbuf + c * 4 * kWarp) + 2 * lane;
+            const uint4 ca = mine4[0], cb = mine4[1];
+            const uint32_t cv[4] = {ca.x, ca.z, cb.x, cb.z}, cg[4] = {ca.y, ca.w, cb.y, cb.w};
             float nd[4];
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                const float o = cell[j].y == gen ? __uint_as_float(cell[j].x) : 0.0f;     // another generation reads as zero
+                const float o = cg[j] == gen ? __uint_as_float(cv[j]) : 0.0f;             // another generation reads as zero
                 nd[j] = fminf(__fadd_rn(o, __fmul_rn(w[j], 0.100000001490116119f)), 1.0f);   // clip(dose + beam*0.1, 0, 1), dose >= 0
                 const float delta = (ok >> j) & 1u ? nd[j] - o : 0.0f;                    // 0 for targets this lane does not write
                 d_tum += (tmask >> j) & 1u ? delta : 0.0f;
@@ -544,17 +608,15 @@ rt_step_kernel(Tables T, Schedule S, EnvRec *rec, uint2 *cells, double *beams, i
                 // dose is monotone, so the count only grows (environment.py:175-177)
                 d_cnt += (int)((cmask >> j) & 1u) & (int)(!(o > 0.200000002980232239f) && nd[j] > 0.200000002980232239f);
             }
-            // the two targets of a row are neighbours in memory: one 16-byte store when both are written and aligned
+            // {new dose, cell index or -1 for targets this lane does not write} back into the item list, then store
+            // instruction i writes items 32 i + lane
+            mine4[0] = make_uint4(__float_as_uint(nd[0]), (uint32_t)(ok & 1u ? r0 + q0 : -1), __float_as_uint(nd[1]), (uint32_t)(ok & 2u ? r0 + q1 : -1));
+            mine4[1] = make_uint4(__float_as_uint(nd[2]), (uint32_t)(ok & 4u ? r1 + q0 : -1), __float_as_uint(nd[3]), (uint32_t)(ok & 8u ? r1 + q1 : -1));
+            __syncwarp();
 #pragma unroll
-            for (int r = 0; r < 2; r++) {
-                const uint32_t both = (ok >> (2 * r)) & 3u;
-                if (both == 3u && !(c2 & 1)) {                      // (k, k + 1) with k even: neighbours inside a brick, 16-byte aligned
-                    __stcg(reinterpret_cast<uint4 *>(vol + ca[2 * r]),
-                           make_uint4(__float_as_uint(nd[2 * r]), gen, __float_as_uint(nd[2 * r + 1]), gen));
-                } else {
-                    if (both & 1u) __stcg(vol + ca[2 * r], make_uint2(__float_as_uint(nd[2 * r]), gen));
-                    if (both & 2u) __stcg(vol + ca[2 * r + 1], make_uint2(__float_as_uint(nd[2 * r + 1]), gen));
-                }
+            for (int i = 0; i < 4; i++) {
+                const uint2 it = cbuf[c * 4 * kWarp + i * kWarp + lane];
+                if ((int)it.y >= 0) __stcg(vol + (int)it.y, make_uint2(it.x, gen));
             }
         }
         if (lane == 0) RT_STAMP3(env, 6);
