@@ -1137,7 +1137,7 @@ int rt_step(rt_env *e, const float *actions_dev, float *obs_dev, double *reward_
     const int kb = e->step_kb;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((e->n + kb - 1) / kb);
-    cfg.blockDim = dim3((kb + 1) * kWarp);
+    cfg.blockDim = dim3((kb + 1 + (kb >= 14 && !e->dense ? 1 : 0)) * kWarp);     // scalar warp, env warps, predictor warp
     cfg.dynamicSmemBytes = e->step_smem;
     cfg.stream = (cudaStream_t)stream;
     cudaLaunchAttribute attr[1];
