@@ -188,6 +188,53 @@ __device__ __forceinline__ uint32_t bit_pair_ldg(const uint32_t *bits, int l)
 // one HBM round trip later, a brick it fetches in vain 128 bytes of bandwidth.
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
+// draw_line.py:19-66 with fast divisions: the same clip and set-up as beam_setup (rt_device.cuh), good to a few ulp, which
+// is all a prefetch needs
+__device__ __forceinline__ Beam beam_setup_fast(const Grid &G, const float p[3], float v0, float v1, float v2)
+{
+    const float eps = 9.99999997475242708e-07f;
+    Beam b;
+    b.nslab = 0; b.dom = 0; b.o0 = 1; b.o1 = 2; b.step = 1; b.x0 = 0;
+    b.y0 = b.z0 = b.sgy = b.sgz = 0.0f;
+    const float v[3] = {v0, v1, v2};
+    const int gsz[3] = {G.g0, G.g1, G.g2};
+    float t_entry = -CUDART_INF_F, t_exit = CUDART_INF_F;
+    bool empty = false;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const float gm1 = (float)(gsz[i] - 1);
+        float te = -CUDART_INF_F, tx = CUDART_INF_F;
+        if (fabsf(v[i]) > eps) {
+            const float r = __frcp_rn(v[i]);
+            const float t1 = -p[i] * r, t2 = (gm1 - p[i]) * r;
+            te = fminf(t1, t2); tx = fmaxf(t1, t2);
+        } else if (p[i] < 0.0f || p[i] > gm1) empty = true;
+        t_entry = fmaxf(t_entry, te);
+        t_exit = fminf(t_exit, tx);
+    }
+    if (empty || t_entry > t_exit) return b;
+    const float a0 = fabsf(v[0]), a1 = fabsf(v[1]), a2 = fabsf(v[2]);
+    int dom = 0;
+    float best = a0;
+    if (a1 > best) { best = a1; dom = 1; }
+    if (a2 > best) { best = a2; dom = 2; }
+    const int o0 = dom == 0 ? 1 : 0, o1 = dom == 2 ? 1 : 2;
+    const float vd = dom == 0 ? v[0] : (dom == 1 ? v[1] : v[2]), pdm = dom == 0 ? p[0] : (dom == 1 ? p[1] : p[2]);
+    const float vo0 = o0 == 0 ? v[0] : v[1], po0 = o0 == 0 ? p[0] : p[1];
+    const float vo1 = o1 == 1 ? v[1] : v[2], po1 = o1 == 1 ? p[1] : p[2];
+    const int step = vd > 0.0f ? 1 : -1;
+    const int x0 = (int)floorf(pdm + t_entry * vd), x1 = (int)floorf(pdm + t_exit * vd);
+    const float rden = __frcp_rn(vd + eps);
+    b.y0 = po0 + t_entry * vo0;
+    b.z0 = po1 + t_entry * vo1;
+    b.sgy = step > 0 ? vo0 * rden : -(vo0 * rden);
+    b.sgz = step > 0 ? vo1 * rden : -(vo1 * rden);
+    b.dom = dom; b.o0 = o0; b.o1 = o1; b.step = step; b.x0 = x0;
+    const int n = (x1 - x0) * step + 1;
+    b.nslab = n < 0 ? 0 : n;
+    return b;
+}
+
 __device__ __forceinline__ Beam predict_beam(const Grid &G, const double pd[3], const double dn[3], const float ar[3])
 {
     const float rx = clip1(ar[0]) * 1.57079633f, ry = clip1(ar[1]) * 1.57079633f, rz = clip1(ar[2]) * 1.57079633f;
@@ -208,8 +255,9 @@ __device__ __forceinline__ Beam predict_beam(const Grid &G, const double pd[3], 
         const float px = pn < 1e-8f ? 1.0f : __fdividef(r1, pn), py = pn < 1e-8f ? 0.0f : __fdividef(r2, pn);
         r0 = copysignf(0.70710678f, r0); r1 = px * 0.70710678f; r2 = py * 0.70710678f;
     }
-    const double dd[3] = {(double)r0, (double)r1, (double)r2};
-    return beam_setup(G, pd, dd);                                           // draw_line.py:19-66 on the predicted direction
+    const float inv2 = rsqrtf(r0 * r0 + r1 * r1 + r2 * r2);
+    const float pf[3] = {(float)pd[0], (float)pd[1], (float)pd[2]};
+    return beam_setup_fast(G, pf, r0 * inv2, r1 * inv2, r2 * inv2);         // draw_line.py:19-66 on the predicted direction
 }
 
 __device__ __forceinline__ void prefetch_beam(const Grid &G, const Beam &b, const uint2 *vol, int lane)
@@ -540,30 +588,36 @@ rt_step_kernel(Tables T, Schedule S, EnvRec *rec, uint2 *cells, double *beams, i
             for (int i = lane; i < T.pbits_words; i += kWarp)              // pbits_words <= kMaxPTumourWords (rt_create)
                 tb[i] = __ldg(T.tumour_pbits + (size_t)tid * T.pbits_words + i);
         __syncwarp();
-        // distance_to_tumour_reward (environment.py:150-162): min over the tumour's voxel list
+        // distance_to_tumour_reward (environment.py:150-162): min over the tumour's voxel list.  The first four voxels
+        // of every lane are requested, then the predicted beam's bricks go to the L2 while those loads are in flight.
         const double p0 = se.p[0], p1 = se.p[1], p2 = se.p[2];
         double best = CUDART_INF;
         const int nv = tm.n_vox;
         const uint32_t *vx = T.vox_xyz + tm.vox_off;
-#pragma unroll 4
-        for (int k = lane; k < nv; k += kWarp) {
-            const uint32_t pk = __ldg(vx + k);
+        uint32_t pk4[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) pk4[i] = lane + i * kWarp < nv ? __ldg(vx + lane + i * kWarp) : 0xffffffffu;
+        if (kPredict) {
+            mbar_wait(smem_u32(&mbars[1]), 0);                             // the predictor warp has published its beams
+            prefetch_beam(G, pred[le], cells + (size_t)env * G.cstride, lane);
+        }
+        auto take = [&](uint32_t pk) {
             const double dx = (double)(pk & 255u) - p0;
             const double dy = (double)((pk >> 8) & 255u) - p1;
             const double dz = (double)(pk >> 16) - p2;
             const double d2 = __fma_rn(dz, dz, __fma_rn(dy, dy, dx * dx));
             best = d2 < best ? d2 : best;
-        }
+        };
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            if (lane + i * kWarp < nv) take(pk4[i]);
+#pragma unroll 4
+        for (int k = lane + 4 * kWarp; k < nv; k += kWarp) take(__ldg(vx + k));
         // min of non-negative doubles = min of their bit patterns: two integer warp reductions
         const uint32_t hi = (uint32_t)__double2hiint(best);
         const uint32_t mhi = __reduce_min_sync(kFull, hi);
         const uint32_t mlo = __reduce_min_sync(kFull, hi == mhi ? (uint32_t)__double2loint(best) : 0xffffffffu);
         if (lane == 0) se.best = __hiloint2double((int)mhi, (int)mlo);
-        if (kPredict) {
-            // the predicted beam has long been published: its bricks -> L2 while the scalar warp finishes the exact chain
-            mbar_wait(smem_u32(&mbars[1]), 0);
-            prefetch_beam(G, pred[le], cells + (size_t)env * G.cstride, lane);
-        }
     }
     if (active && lane == 0) RT_STAMP3(env, 2);
     work_barrier<(kB + 1) * kWarp>();                                      // ---- barrier 1
