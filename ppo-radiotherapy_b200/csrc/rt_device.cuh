@@ -24,6 +24,7 @@ struct Grid {
     int vstride;     // per-env stride of C-order volumes (dense-mode float32 dose, bfloat16 records): nvox rounded up to 32
     int nb1, nb2;    // bricks along axes 1 and 2 (sparse-mode cells, see cell_index)
     int cstride;     // per-env stride of the sparse-mode cell array in cells: bricks * 16
+    uint32_t mg1, mg2;   // ceil(2^32 / g1), ceil(2^32 / g2): n / g = umulhi(n, m) for the voxel indices of a grid (n * g < 2^32)
 };
 
 // Sparse-mode dose cells are stored in BRICKS of 2 x 2 x 4 voxels = 16 cells of 8 bytes = one 128-byte line, bricks in C
@@ -42,8 +43,12 @@ __host__ __device__ __forceinline__ int cell_index(const Grid &G, int i, int j, 
 }
 __host__ __device__ __forceinline__ int cell_index_lin(const Grid &G, int lin)      // C-order linear voxel index -> cell
 {
-    const int k = lin % G.g2, ij = lin / G.g2;
-    return cell_index(G, ij / G.g1, ij % G.g1, k);
+#ifdef __CUDA_ARCH__
+    const int ij = (int)__umulhi((uint32_t)lin, G.mg2), i = (int)__umulhi((uint32_t)ij, G.mg1);
+#else
+    const int ij = lin / G.g2, i = ij / G.g1;
+#endif
+    return cell_index(G, i, ij - i * G.g1, lin - ij * G.g2);
 }
 
 // ---------------------------------------------------------------------------------

@@ -678,7 +678,8 @@ __global__ void __launch_bounds__(kVolThreads) rt_volumes_kernel(Tables T, const
                     d[u] = __bfloat1622float2(pk2[q]);
                 } else if (cellv) {
                     // voxels (2q, 2q + 1) share a row (g2 is even here: nvox even and the pair does not straddle) and a brick
-                    const uint4 c = __ldcs(reinterpret_cast<const uint4 *>(cellv + cell_index_lin(G, 2 * q)));   // another generation reads as zero
+                    // (the other rows of the brick are read a moment later: keep the line in the caches)
+                    const uint4 c = __ldg(reinterpret_cast<const uint4 *>(cellv + cell_index_lin(G, 2 * q)));   // another generation reads as zero
                     d[u] = make_float2(c.y == gen ? __uint_as_float(c.x) : 0.0f, c.w == gen ? __uint_as_float(c.z) : 0.0f);
                 } else {
                     d[u] = __ldcs(vol2 + q);
@@ -723,7 +724,7 @@ __global__ void __launch_bounds__(256) rt_pack_kernel(Grid G, const EnvRec *rec,
     for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < npairs; q += gridDim.x * blockDim.x) {
         float v0 = 0.0f, v1 = 0.0f;
         if (q < vpairs) {
-            const uint4 c = __ldcs(reinterpret_cast<const uint4 *>(vol + cell_index_lin(G, 2 * q)));
+            const uint4 c = __ldg(reinterpret_cast<const uint4 *>(vol + cell_index_lin(G, 2 * q)));
             v0 = c.y == gen ? __uint_as_float(c.x) : 0.0f;
             v1 = c.w == gen ? __uint_as_float(c.z) : 0.0f;
         }
@@ -827,6 +828,8 @@ Grid make_grid(const int32_t g[3])
     G.nb1 = (G.g1 + 1) / 2;
     G.nb2 = (G.g2 + 3) / 4;
     G.cstride = ((G.g0 + 1) / 2) * G.nb1 * G.nb2 * 16;
+    G.mg1 = (uint32_t)(((1ull << 32) + (uint64_t)G.g1 - 1) / (uint64_t)G.g1);
+    G.mg2 = (uint32_t)(((1ull << 32) + (uint64_t)G.g2 - 1) / (uint64_t)G.g2);
     return G;
 }
 
