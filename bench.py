@@ -295,17 +295,6 @@ def other_kernels(rt, dev, peak):
                     "state_gb": se.device_bytes / 1e9})
         se.close()
     del acts
-    # dense-mode step (BASELINE configs[4]): read + write every dose volume, 1,613,360 B per env-step
-    n = 1024
-    de = rt.BatchedEpisodes(n, device=dev, dense=True, seed=3)
-    de.reset()
-    a = torch.rand((n, 6), device=dev, generator=g) * 2 - 1
-    s = timed(lambda: de.step(a, want_info=False), 10)
-    b = n * 2 * de.nvox * 4
-    out.append({"kernel": "rt_step_kernel<dense> + rt_dense_kernel", "workload": f"{n} envs, full-volume dose update",
-                "bytes": b, "us": s * 1e6, "achieved": b / s / 1e9, "unit": "GB/s", "frac": b / s / 1e9 / peak,
-                "env_steps_per_s": n / s})
-    de.close()
     # voxel observation (BASELINE configs[3]): 4 planes written + dose read, 4,033,400 B per env
     n = 256
     ve = rt.BatchedEpisodes(n, device=dev, seed=4)
@@ -316,9 +305,12 @@ def other_kernels(rt, dev, peak):
     vol = torch.empty((n, 4) + ve.grid, dtype=torch.float32, device=dev)
     s = timed(lambda: ve.volumes(0, n, out=vol), 10)
     b = n * 5 * ve.nvox * 4
+    moved = n * (4 * ve.nvox * 4 + 1723392)          # 4 planes written + the bricked 8-byte dose cells read
     out.append({"kernel": "rt_volumes_kernel", "workload": f"{n} envs, (4,67,43,70) float32 observations",
                 "bytes": b, "us": s * 1e6, "achieved": b / s / 1e9, "unit": "GB/s", "frac": b / s / 1e9 / peak,
-                "env_steps_per_s": n / s})
+                "env_steps_per_s": n / s, "bytes_moved": moved, "moved_gbs": moved / s / 1e9,
+                "note": "algorithmic bytes count the dose as 4 bytes per voxel (SURVEY 8d); the sparse-mode state keeps 8-byte cells "
+                        "{dose, generation}, so the kernel actually moves bytes_moved"})
     ve.close()
     del vol
     # GAE (train.py:164-181): T=128, N=65536 (BASELINE configs[2] size), 20 B per element, two rotating sets > L2
