@@ -394,7 +394,7 @@ def ppo_leg(rt, torch, dist, dev, world, rank, envs_per_gpu=8192, num_steps=128,
                     f"minibatches (BASELINE.json configs[2]); {steady} steady iterations of {iterations}",
         "value": steady * total * num_steps / (float(it[0]) * 1e-3), "unit": "env-steps/s",
         "iter_ms": float(it[0]) / steady, "rollout_ms": float(it[1]) / steady, "update_ms": float(it[2]) / steady,
-        "fused_rollout": bool(prof.get("fused_rollout")),
+        "fused_rollout": bool(prof.get("fused_rollout")), "rollout_one_launch": bool(prof.get("rollout_kernel")),
         "allreduce": None if world == 1 else {
             "calls_per_iteration": len(prof["allreduce_us"]) // max(1, iterations), "elements": int(flat.numel()),
             "bytes": int(flat.numel()) * 4, "us_median": ar[len(ar) // 2] if ar else None,

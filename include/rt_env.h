@@ -212,17 +212,33 @@ typedef struct rt_mlp_params {
  * obs_dev / next_done_dev; `agent.get_action_and_value(next_obs)` (networks.py:132-147, no_grad) is evaluated in float32;
  * action = mean + exp(logstd) * N(0,1) from Philox4x32-10 keyed by (seed, env, counters_dev[1]); values [T][n],
  * actions [T][n][n_act], logprobs [T][n] receive row t; action_out_dev [n][n_act] is the input of rt_step.  Any rollout
- * buffer may be NULL.  `p` is a HOST struct of device pointers. */
+ * buffer may be NULL.  `rows` is the row count T of the rollout buffers: when counters_dev[0] is outside [0, rows) the
+ * kernel still produces the actions but stores no row (a caller that steps past the end of its buffers does not write
+ * past them).  `p` is a HOST struct of device pointers. */
 RT_API int rt_ppo_act(const rt_mlp_params *p, const float *obs_dev, const float *next_done_dev, int n, uint64_t seed,
-                      const int64_t *counters_dev, float *obs_buf_dev, float *dones_buf_dev, float *values_buf_dev,
+                      const int64_t *counters_dev, int rows, float *obs_buf_dev, float *dones_buf_dev, float *values_buf_dev,
                       float *actions_buf_dev, float *logprobs_buf_dev, float *action_out_dev, void *stream);
 /* train.py:153-161 after rt_step: rewards [T][n] row t = counters_dev[0] <- reward_f32_dev, next_done_dev [n] <-
  * terminated | truncated, and for the envs that terminated the episode statistics train.py:42-66 logs
  * (episode_stats_dev float64 [7]: finished, sum of episode returns, lengths, last-step tumour / lung / distance / total
  * reward; accumulated, the caller zeroes it) from info_dev [n][RT_INFO_SIZE].  truncated, info, rewards, stats may be NULL. */
 RT_API int rt_ppo_record(const float *reward_f32_dev, const uint8_t *terminated_dev, const uint8_t *truncated_dev,
-                         const double *info_dev, int n, const int64_t *counters_dev, float *rewards_buf_dev,
+                         const double *info_dev, int n, const int64_t *counters_dev, int rows, float *rewards_buf_dev,
                          float *next_done_dev, double *episode_stats_dev, void *stream);
+
+/* The whole rollout of train.py:138-161 in ONE launch: n_steps times { obs / done -> row, policy forward + sample +
+ * log-prob -> value / action / log-prob rows, environment step, reward -> row, done -> next_done, episode statistics },
+ * every block keeping its envs for all steps (no grid-wide barrier between steps).  Rows row0 .. row0 + n_steps - 1 of
+ * the rollout buffers (obs [rows][n][9], dones / values / logprobs / rewards [rows][n], actions [rows][n][6]) are written;
+ * the call fails if they do not fit in `rows`.  next_obs_dev [n][9] / next_done_dev [n] hold the observation / done flag
+ * before the first step on entry (e.g. the obs_dev of rt_reset) and after the last step on return.  The random stream
+ * is the one of rt_ppo_act: step t uses Philox key (seed, env, rng_step0 + t), so the rows equal n_steps x (rt_ppo_act,
+ * rt_step, rt_ppo_record) bit for bit.  The agent must be the reference's MLP for this env (n_obs 9, hidden 64, n_act 6).
+ * Sparse-mode handles only. */
+RT_API int rt_rollout(rt_env *env, const rt_mlp_params *p, int n_steps, int64_t row0, int rows, uint64_t seed, int64_t rng_step0,
+                      float *obs_buf_dev, float *dones_buf_dev, float *values_buf_dev, float *actions_buf_dev,
+                      float *logprobs_buf_dev, float *rewards_buf_dev, float *next_obs_dev, float *next_done_dev,
+                      double *episode_stats_dev, void *stream);
 
 /* ---- FeaturesExtractor3D, first block (networks.py:15-24) ------------------------------------------ */
 /* Conv3d(4->16, k=3) + bias + ReLU + MaxPool3d(2, 2, padding=((D-2)%2, (H-2)%2, (W-2)%2)) fused in one tensor-core

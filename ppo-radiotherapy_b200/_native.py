@@ -130,8 +130,9 @@ _SIGNATURES = {
     "rt_conv1_from_env": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp]),
     "rt_conv2_relu_pool": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]),
     "rt_c3d_tail": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
-    "rt_ppo_act": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_uint64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "rt_ppo_record": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp]),
+    "rt_ppo_act": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_uint64, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "rt_ppo_record": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, _vp, C.c_int, _vp, _vp, _vp, _vp]),
+    "rt_rollout": (C.c_int, [_vp, _vp, C.c_int, C.c_int64, C.c_int, C.c_uint64, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "rt_launch_count": (C.c_int64, []),
     "rt_set_stage_clock": (C.c_int, [_vp, _vp]),
     "rt_set_pdl": (C.c_int, [_vp, C.c_int]),

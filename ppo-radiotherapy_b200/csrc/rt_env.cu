@@ -1477,3 +1477,4 @@ int rt_gae(const float *rewards_dev, const float *values_dev, const float *dones
 // FeaturesExtractor3D kernels (tcgen05 conv blocks, tail) and their C ABI
 #include "rt_conv.cuh"
 #include "rt_policy.cuh"
+#include "rt_rollout.cuh"

@@ -36,6 +36,7 @@ struct PolicyArgs {
     int n;
     unsigned long long seed;
     const long long *counters;                      // [0] rollout row t, [1] RNG step
+    int rows;                                       // rows of the rollout buffers: a row >= rows is not stored
     float *obs_buf, *dones_buf, *values_buf, *actions_buf, *logprobs_buf;   // rollout buffers, row t is written
     float *action_out;                              // [N][n_act]: this step's actions
 };
@@ -116,6 +117,9 @@ __global__ void __launch_bounds__(kPolThreads) rt_ppo_act_kernel(PolicyArgs A)
         sigma[kPolOut + t] = ls;
     }
     const long long row = A.counters[0], rng_step = A.counters[1];
+    if (row < 0 || row >= A.rows) {                               // past the end of the rollout buffers: act, but store no row
+        A.obs_buf = A.dones_buf = A.values_buf = A.actions_buf = A.logprobs_buf = nullptr;
+    }
     const int u = t & 63, e0 = (t >> 6) * 16;
 
     for (int tile = blockIdx.x; tile * kPolTile < A.n; tile += gridDim.x) {
@@ -190,6 +194,7 @@ struct RecordArgs {
     const double *info;                  // [N][RT_INFO_SIZE] or nullptr
     int n;
     const long long *counters;
+    int rows;                            // rows of the rewards buffer: a row >= rows is not stored
     float *rewards_buf;                  // [T][N]
     float *next_done;                    // [N]
     double *episode_stats;               // [7]: finished, sum return, sum length, sum last-step tumour / lung / distance / total reward
@@ -200,7 +205,7 @@ __global__ void __launch_bounds__(256) rt_ppo_record_kernel(RecordArgs A)
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= A.n) return;
     const long long row = A.counters[0];
-    if (A.rewards_buf) A.rewards_buf[(size_t)row * A.n + e] = A.reward_f32[e];             // train.py:154
+    if (A.rewards_buf && row >= 0 && row < A.rows) A.rewards_buf[(size_t)row * A.n + e] = A.reward_f32[e];   // train.py:154
     const bool term = A.terminated[e] != 0;
     const bool done = term || (A.truncated && A.truncated[e] != 0);                        // train.py:153
     A.next_done[e] = done ? 1.0f : 0.0f;                                                   // train.py:155-158
@@ -225,7 +230,7 @@ constexpr size_t kPolSmemFloats = 2 * kPolMaxObs * kPolWStride + 2 * kPolHidden 
 extern "C" {
 
 int rt_ppo_act(const rt_mlp_params *p, const float *obs_dev, const float *next_done_dev, int n, uint64_t seed,
-               const int64_t *counters_dev, float *obs_buf_dev, float *dones_buf_dev, float *values_buf_dev,
+               const int64_t *counters_dev, int rows, float *obs_buf_dev, float *dones_buf_dev, float *values_buf_dev,
                float *actions_buf_dev, float *logprobs_buf_dev, float *action_out_dev, void *stream)
 {
     if (!p || !obs_dev || !next_done_dev || !counters_dev || !action_out_dev) return fail(RT_ERR_INVALID, "rt_ppo_act: NULL argument");
@@ -254,6 +259,7 @@ int rt_ppo_act(const rt_mlp_params *p, const float *obs_dev, const float *next_d
     A.n_obs = p->n_obs; A.n_act = p->n_act;
     A.obs = obs_dev; A.next_done = next_done_dev; A.n = n; A.seed = seed;
     A.counters = reinterpret_cast<const long long *>(counters_dev);
+    A.rows = rows;
     A.obs_buf = obs_buf_dev; A.dones_buf = dones_buf_dev; A.values_buf = values_buf_dev;
     A.actions_buf = actions_buf_dev; A.logprobs_buf = logprobs_buf_dev; A.action_out = action_out_dev;
     const int tiles = (n + kPolTile - 1) / kPolTile;
@@ -269,14 +275,14 @@ int rt_ppo_act(const rt_mlp_params *p, const float *obs_dev, const float *next_d
 }
 
 int rt_ppo_record(const float *reward_f32_dev, const uint8_t *terminated_dev, const uint8_t *truncated_dev,
-                  const double *info_dev, int n, const int64_t *counters_dev, float *rewards_buf_dev, float *next_done_dev,
+                  const double *info_dev, int n, const int64_t *counters_dev, int rows, float *rewards_buf_dev, float *next_done_dev,
                   double *episode_stats_dev, void *stream)
 {
     if (!reward_f32_dev || !terminated_dev || !counters_dev || !next_done_dev) return fail(RT_ERR_INVALID, "rt_ppo_record: NULL argument");
     if (n < 0) return fail(RT_ERR_INVALID, "rt_ppo_record: n < 0");
     if (n == 0) return RT_OK;
     RecordArgs A{reward_f32_dev, terminated_dev, truncated_dev, info_dev, n, reinterpret_cast<const long long *>(counters_dev),
-                 rewards_buf_dev, next_done_dev, episode_stats_dev};
+                 rows, rewards_buf_dev, next_done_dev, episode_stats_dev};
     rt_ppo_record_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(A);
     RT_LAUNCH_CHECK("rt_ppo_record_kernel");
     return RT_OK;

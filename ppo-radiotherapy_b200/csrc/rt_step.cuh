@@ -281,29 +281,53 @@ __device__ __forceinline__ void prefetch_beam(const Grid &G, const Beam &b, cons
 
 // warps of a block: scalar warp, kB env warps and, for 14-env blocks of sparse-mode handles, the predictor warp
 template <int kB, bool kDense>
-constexpr int step_block_threads() { return (kB + 1 + (kB >= 14 && !kDense ? 1 : 0)) * kWarp; }
+__host__ __device__ constexpr int step_block_threads() { return (kB + 1 + (kB >= 14 && !kDense ? 1 : 0)) * kWarp; }
 
-template <int kB, bool kClock, bool kDense>
-__global__ void __launch_bounds__((step_block_threads<kB, kDense>()), 28 / kB)
-rt_step_kernel(Tables T, Schedule S, EnvRec *rec, uint2 *cells, double *beams, int n_envs,
-               const float *__restrict__ actions, StepOut out, DenseWork *dense)
-{
-    static_assert(kB <= 16, "the scalar warp serves at most 16 envs");
-    __shared__ EnvShared sh[kB];
-    __shared__ Tumour tum[kB];
-    __shared__ uint32_t tbits[kB][kMaxPTumourWords];
-    __shared__ float2 yz[kB][kYZStride];
-    __shared__ __align__(8) unsigned long long mbars[2];          // [0] lungs bitmask landed, [1] predicted beams published
-    __shared__ Beam pred[kB];
+// Shared memory of a block (static part).
+template <int kB>
+struct StepShared {
+    EnvShared sh[kB];
+    Tumour tum[kB];
+    uint32_t tbits[kB][kMaxPTumourWords];
+    float2 yz[kB][kYZStride];
+    __align__(8) unsigned long long mbars[2];          // [0] lungs bitmask landed, [1] predicted beams published
+    Beam pred[kB];
     // outputs are staged here by the scalar warp's lanes and copied out row-contiguously (full-line stores:
     // the host-buffer entry points map these arrays over PCIe)
-    __shared__ float s_obs[kB * RT_OBS_SIZE];
-    __shared__ double s_rew[kB];
-    __shared__ uint8_t s_term[kB];
-    __shared__ double s_info[kB * RT_INFO_SIZE];
+    float s_obs[kB * RT_OBS_SIZE];
+    double s_rew[kB];
+    uint8_t s_term[kB];
+    double s_info[kB * RT_INFO_SIZE];
+};
+
+// What the fused rollout kernel (rt_rollout.cuh) needs from a step besides the env state: row t of the rewards buffer
+// and the episode statistics of train.py:42-66.  Unused (all NULL) by rt_step_kernel.
+struct RollStep {
+    float *rewards_row;          // [N] row t of rewards [T][N] (train.py:154)
+    double *episode_stats;       // [7] finished, sum return, sum length, sum last-step tumour / lung / distance / total reward
+};
+
+// One environment step of the block's kB envs (see the top of the file).  `it` counts the steps this block has done
+// in this launch (0 for rt_step_kernel; the rollout kernel loops): the lungs bitmask is staged by step 0 only and
+// the predictor's mbarrier alternates its phase.  kRoll: `actions` is a shared-memory array [kB][6] indexed by the
+// env's position in the block, the observation stays in M.s_obs, reward / done go to `R` and M.s_term.
+template <int kB, bool kClock, bool kDense, bool kRoll>
+__device__ __forceinline__ void step_block(StepShared<kB> &M, uint32_t *dyn_smem, const Tables &T, const Schedule &S, EnvRec *rec,
+                                           uint2 *cells, double *beams, int n_envs, const float *actions, const StepOut &out,
+                                           DenseWork *dense, int env0, uint32_t it, const RollStep &R)
+{
+    EnvShared (&sh)[kB] = M.sh;
+    Tumour (&tum)[kB] = M.tum;
+    uint32_t (&tbits)[kB][kMaxPTumourWords] = M.tbits;
+    float2 (&yz)[kB][kYZStride] = M.yz;
+    unsigned long long (&mbars)[2] = M.mbars;
+    Beam (&pred)[kB] = M.pred;
+    float (&s_obs)[kB * RT_OBS_SIZE] = M.s_obs;
+    double (&s_rew)[kB] = M.s_rew;
+    uint8_t (&s_term)[kB] = M.s_term;
+    double (&s_info)[kB * RT_INFO_SIZE] = M.s_info;
     // dynamic: [kB][kMaxPass][32 slabs][4 targets] item slots of 8 bytes (cell index, then the prefetched cell, then the new
     // dose + cell index), then [lung_words16] padded lungs bitmask (kB >= 14)
-    extern __shared__ __align__(128) uint32_t dyn_smem[];
     uint2 *cellbuf_all = reinterpret_cast<uint2 *>(dyn_smem);
     uint32_t *lungs_sm = dyn_smem + (kDense ? 0 : kB * kMaxPass * 4 * kWarp * 2);
     const Grid &G = T.G;
@@ -314,26 +338,16 @@ rt_step_kernel(Tables T, Schedule S, EnvRec *rec, uint2 *cells, double *beams, i
     constexpr int kScalarWarp = kEnvWarp0 + kB;
     const int warp = threadIdx.x / kWarp;
     const int lane = threadIdx.x & (kWarp - 1);
-    const int env0 = blockIdx.x * kB;
     // blocks of 7 envs run four to an SM and read the lungs bitmask through L1 instead of staging it four times
     constexpr bool kStageLungs = kB >= 14 && !kDense;
     constexpr bool kPredict = kB >= 14 && !kDense;
-
-    if (kStageLungs && threadIdx.x == kScalarWarp * kWarp) {
-        mbar_init(smem_u32(&mbars[0]), 1);
-        mbar_init(smem_u32(&mbars[1]), 1);
-    }
-    if (kPredict) __syncthreads();                                // the env warps wait on mbars[1] before barrier A
-    // Programmatic dependent launch: nothing the previous step wrote is read before this point; the trigger
-    // lets the next launch's blocks be scheduled as soon as ours retire.
-    cudaGridDependencySynchronize();
-    cudaTriggerProgrammaticLaunchCompletion();
+    const uint32_t pred_parity = it & 1u;
 
     // =====================================================================================================
     if (warp == kScalarWarp) {
         const int e = env0 + lane;
         const bool mine = lane < kB && e < n_envs;
-        if (kStageLungs && lane == 0)
+        if (kStageLungs && lane == 0 && it == 0)
             bulk_load(smem_u32(lungs_sm), T.lungs_pad, (uint32_t)(T.lung_words16 * sizeof(uint32_t)), smem_u32(&mbars[0]));
         if (mine) RT_STAMP3(e, 0);
         EnvRec *my = rec + (mine ? e : 0);
@@ -353,8 +367,14 @@ rt_step_kernel(Tables T, Schedule S, EnvRec *rec, uint2 *cells, double *beams, i
             double p0[3];
 #pragma unroll
             for (int i = 0; i < 3; i++) { p0[i] = my->pos[i]; dn[i] = my->dn[i]; }
-            const float2 *ap = reinterpret_cast<const float2 *>(actions + (size_t)e * RT_ACTION_SIZE);
-            const float2 a01 = __ldg(ap), a23 = __ldg(ap + 1), a45 = __ldg(ap + 2);
+            float2 a01, a23, a45;
+            if (kRoll) {
+                const float2 *ap = reinterpret_cast<const float2 *>(actions + lane * RT_ACTION_SIZE);
+                a01 = ap[0]; a23 = ap[1]; a45 = ap[2];
+            } else {
+                const float2 *ap = reinterpret_cast<const float2 *>(actions + (size_t)e * RT_ACTION_SIZE);
+                a01 = __ldg(ap); a23 = __ldg(ap + 1); a45 = __ldg(ap + 2);
+            }
             const float at[3] = {a01.x, a01.y, a23.x};
             ar[0] = a23.y; ar[1] = a45.x; ar[2] = a45.y;
             stepping = needs_reset == 0;
@@ -464,7 +484,8 @@ rt_step_kernel(Tables T, Schedule S, EnvRec *rec, uint2 *cells, double *beams, i
         }
         const int nb = min(kB, n_envs - env0);                             // envs of this block
         __syncwarp();
-        for (int i = lane; i < nb * RT_OBS_SIZE; i += kWarp) out.obs[(size_t)env0 * RT_OBS_SIZE + i] = s_obs[i];
+        if (out.obs)
+            for (int i = lane; i < nb * RT_OBS_SIZE; i += kWarp) out.obs[(size_t)env0 * RT_OBS_SIZE + i] = s_obs[i];
         if (kStageLungs) mbar_wait(smem_u32(&mbars[0]), 0);                // the lungs copy must land before the block retires
         work_barrier<(kB + 1) * kWarp>();                                  // ---- barrier 2
         if (kDense) {
@@ -477,9 +498,8 @@ rt_step_kernel(Tables T, Schedule S, EnvRec *rec, uint2 *cells, double *beams, i
                 if (out.info)
                     for (int i = 0; i < RT_INFO_SIZE; i++) out.info[(size_t)e * RT_INFO_SIZE + i] = s_info[lane * RT_INFO_SIZE + i];
             }
-            return;
         }
-        if (stepping) {
+        if (!kDense && stepping) {
             RT_STAMP3(e, 11);
             tumour_dose += se.d_tum;
             lung_dose += se.d_lung;
@@ -508,6 +528,15 @@ rt_step_kernel(Tables T, Schedule S, EnvRec *rec, uint2 *cells, double *beams, i
             my->t = t; my->lung_count = lung_count; my->needs_reset = done ? 1 : 0; my->n_beams = n_beams + 1;
             s_rew[lane] = reward;
             s_term[lane] = done ? 1 : 0;
+            if (kRoll && done && R.episode_stats) {                        // train.py:42-66, 160-161
+                atomicAdd(R.episode_stats + 0, 1.0);
+                atomicAdd(R.episode_stats + 1, ep_return);
+                atomicAdd(R.episode_stats + 2, (double)t);
+                atomicAdd(R.episode_stats + 3, (double)r_tumour);
+                atomicAdd(R.episode_stats + 4, r_lung);
+                atomicAdd(R.episode_stats + 5, r_dist);
+                atomicAdd(R.episode_stats + 6, reward);
+            }
             if (out.info) {
                 double *ip = s_info + lane * RT_INFO_SIZE;
                 ip[RT_INFO_REWARD_TOTAL] = reward;
@@ -530,13 +559,14 @@ rt_step_kernel(Tables T, Schedule S, EnvRec *rec, uint2 *cells, double *beams, i
             RT_STAMP3(e, 7);
         }
         __syncwarp();
-        if (lane < nb) {
+        if (!kDense && lane < nb) {
             if (out.reward) out.reward[env0 + lane] = s_rew[lane];
             if (out.reward_f32) out.reward_f32[env0 + lane] = (float)s_rew[lane];
             if (out.terminated) out.terminated[env0 + lane] = s_term[lane];
             if (out.truncated) out.truncated[env0 + lane] = 0;
+            if (kRoll) R.rewards_row[env0 + lane] = (float)s_rew[lane];    // train.py:154
         }
-        if (out.info)
+        if (!kDense && out.info)
             for (int i = lane; i < nb * RT_INFO_SIZE; i += kWarp) out.info[(size_t)env0 * RT_INFO_SIZE + i] = s_info[i];
         return;
     }
@@ -553,8 +583,14 @@ rt_step_kernel(Tables T, Schedule S, EnvRec *rec, uint2 *cells, double *beams, i
             double p0[3], dn[3];
 #pragma unroll
             for (int i = 0; i < 3; i++) { p0[i] = my->pos[i]; dn[i] = my->dn[i]; }
-            const float2 *ap = reinterpret_cast<const float2 *>(actions + (size_t)e * RT_ACTION_SIZE);
-            const float2 a01 = __ldg(ap), a23 = __ldg(ap + 1), a45 = __ldg(ap + 2);
+            float2 a01, a23, a45;
+            if (kRoll) {
+                const float2 *ap = reinterpret_cast<const float2 *>(actions + lane * RT_ACTION_SIZE);
+                a01 = ap[0]; a23 = ap[1]; a45 = ap[2];
+            } else {
+                const float2 *ap = reinterpret_cast<const float2 *>(actions + (size_t)e * RT_ACTION_SIZE);
+                a01 = __ldg(ap); a23 = __ldg(ap + 1); a45 = __ldg(ap + 2);
+            }
             if (needs_reset == 0) {
                 const double gs[3] = {(double)G.g0, (double)G.g1, (double)G.g2};
                 const float at[3] = {a01.x, a01.y, a23.x}, ar[3] = {a23.y, a45.x, a45.y};
@@ -598,7 +634,7 @@ rt_step_kernel(Tables T, Schedule S, EnvRec *rec, uint2 *cells, double *beams, i
 #pragma unroll
         for (int i = 0; i < 4; i++) pk4[i] = lane + i * kWarp < nv ? __ldg(vx + lane + i * kWarp) : 0xffffffffu;
         if (kPredict) {
-            mbar_wait(smem_u32(&mbars[1]), 0);                             // the predictor warp has published its beams
+            mbar_wait(smem_u32(&mbars[1]), pred_parity);                   // the predictor warp has published its beams
             prefetch_beam(G, pred[le], cells + (size_t)env * G.cstride, lane);
         }
         auto take = [&](uint32_t pk) {
@@ -798,6 +834,36 @@ rt_step_kernel(Tables T, Schedule S, EnvRec *rec, uint2 *cells, double *beams, i
         }
     }
     work_barrier<(kB + 1) * kWarp>();                                      // ---- barrier 2
+}
+
+// Prologue shared by the kernels built on step_block: mbarriers, and the programmatic-dependent-launch hand-over.
+template <int kB, bool kDense>
+__device__ __forceinline__ void step_prologue(StepShared<kB> &M)
+{
+    constexpr int kEnvWarp0 = (kB >= 14 && !kDense) ? 1 : 0;
+    constexpr int kScalarWarp = kEnvWarp0 + kB;
+    constexpr bool kStageLungs = kB >= 14 && !kDense;
+    if (kStageLungs && threadIdx.x == kScalarWarp * kWarp) {
+        mbar_init(smem_u32(&M.mbars[0]), 1);
+        mbar_init(smem_u32(&M.mbars[1]), 1);
+    }
+    if (kStageLungs) __syncthreads();                             // the env warps wait on mbars[1] before any other barrier
+    // Programmatic dependent launch: nothing the previous launch wrote is read before this point; the trigger
+    // lets the next launch's blocks be scheduled as soon as ours retire.
+    cudaGridDependencySynchronize();
+    cudaTriggerProgrammaticLaunchCompletion();
+}
+
+template <int kB, bool kClock, bool kDense>
+__global__ void __launch_bounds__((step_block_threads<kB, kDense>()), 28 / kB)
+rt_step_kernel(Tables T, Schedule S, EnvRec *rec, uint2 *cells, double *beams, int n_envs,
+               const float *__restrict__ actions, StepOut out, DenseWork *dense)
+{
+    __shared__ StepShared<kB> M;
+    extern __shared__ __align__(128) uint32_t dyn_smem[];
+    step_prologue<kB, kDense>(M);
+    step_block<kB, kClock, kDense, false>(M, dyn_smem, T, S, rec, cells, beams, n_envs, actions, out, dense, blockIdx.x * kB, 0u,
+                                          RollStep{nullptr, nullptr});
 }
 
 }  // namespace

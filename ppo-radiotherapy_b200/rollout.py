@@ -6,7 +6,11 @@
     rollout.record(engine)             # rewards row, next_done, episode statistics  (rt_ppo_record, one kernel)
     rollout.advance()                  # device-side row / RNG counters
 
-replaces the ~45 small PyTorch launches of `agent.get_action_and_value` + buffer writes per step.  The parameters are
+replaces the ~45 small PyTorch launches of `agent.get_action_and_value` + buffer writes per step, and
+
+    rollout.rollout(engine, T)         # all T steps of an iteration in one launch                   (rt_rollout)
+
+runs the whole loop inside one kernel in which every block keeps its envs for all T steps (same rows, bit for bit).  The parameters are
 read in place from the agent's tensors (training keeps updating them through PyTorch); there is no CPU path.
 """
 import ctypes as C
@@ -42,6 +46,7 @@ class FusedRollout:
         self.seed = int(seed) & (2 ** 64 - 1)
         d = self.device
         self.counters = torch.zeros(2, dtype=torch.int64, device=d)           # [rollout row, RNG step]
+        self._row, self._rng = 0, 0                                           # host mirrors of the two counters
         self.action = torch.zeros((self.n, self.n_act), dtype=torch.float32, device=d)
         self.obs = torch.zeros((self.T, self.n, self.n_obs), dtype=torch.float32, device=d)
         self.actions = torch.zeros((self.T, self.n, self.n_act), dtype=torch.float32, device=d)
@@ -76,7 +81,7 @@ class FusedRollout:
         buf = (lambda t: C.c_void_p(t.data_ptr())) if store else (lambda t: z)
         with torch.cuda.device(self.device):
             nat.check(nat.lib().rt_ppo_act(C.byref(self._params), C.c_void_p(obs.data_ptr()), C.c_void_p(nd.data_ptr()), self.n,
-                                           C.c_uint64(self.seed), C.c_void_p(self.counters.data_ptr()), buf(self.obs),
+                                           C.c_uint64(self.seed), C.c_void_p(self.counters.data_ptr()), self.T, buf(self.obs),
                                            buf(self.dones), buf(self.values), buf(self.actions), buf(self.logprobs),
                                            C.c_void_p(self.action.data_ptr()), self._stream()), "rt_ppo_act")
         return self.action
@@ -87,14 +92,35 @@ class FusedRollout:
         with torch.cuda.device(self.device):
             nat.check(nat.lib().rt_ppo_record(C.c_void_p(engine.reward_f32.data_ptr()), C.c_void_p(engine.terminated.data_ptr()),
                                               C.c_void_p(engine.truncated.data_ptr()), C.c_void_p(engine.info.data_ptr()), self.n,
-                                              C.c_void_p(self.counters.data_ptr()),
+                                              C.c_void_p(self.counters.data_ptr()), self.T,
                                               C.c_void_p(self.rewards.data_ptr()) if store else z,
                                               C.c_void_p(self.next_done.data_ptr()), C.c_void_p(self.episode_stats.data_ptr()),
                                               self._stream()), "rt_ppo_record")
 
     def advance(self):
         self.counters.add_(1)
+        self._row += 1
+        self._rng += 1
 
     def begin_iteration(self):
         self.counters[:1].zero_()
+        self._row = 0
         self.episode_stats.zero_()
+
+    def rollout(self, engine, n_steps: Optional[int] = None) -> None:
+        """train.py:138-161 for `n_steps` steps (default: the rest of the iteration) in one launch: rows
+        [row, row + n_steps) of every rollout buffer, engine.obs / self.next_done carried across, episode statistics
+        accumulated.  Equal, bit for bit, to n_steps x (act, engine.step, record, advance)."""
+        n_steps = self.T - self._row if n_steps is None else int(n_steps)
+        if engine.num_envs != self.n or engine.device != self.device:
+            raise ValueError("FusedRollout.rollout: the engine must hold this rollout's envs on the agent's device")
+        with torch.cuda.device(self.device):
+            nat.check(nat.lib().rt_rollout(engine._h, C.byref(self._params), n_steps, self._row, self.T, C.c_uint64(self.seed),
+                                           self._rng, C.c_void_p(self.obs.data_ptr()), C.c_void_p(self.dones.data_ptr()),
+                                           C.c_void_p(self.values.data_ptr()), C.c_void_p(self.actions.data_ptr()),
+                                           C.c_void_p(self.logprobs.data_ptr()), C.c_void_p(self.rewards.data_ptr()),
+                                           C.c_void_p(engine.obs.data_ptr()), C.c_void_p(self.next_done.data_ptr()),
+                                           C.c_void_p(self.episode_stats.data_ptr()), self._stream()), "rt_rollout")
+        self.counters.add_(n_steps)
+        self._row += n_steps
+        self._rng += n_steps

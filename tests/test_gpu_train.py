@@ -224,3 +224,71 @@ def test_fused_rollout_other_shapes(n_obs, n_act, n):
     torch.testing.assert_close(fr.values[0], v.flatten(), rtol=1e-5, atol=2e-6)
     torch.testing.assert_close(fr.logprobs[0], lp, rtol=1e-5, atol=2e-4)
     assert torch.equal(fr.actions[0], a) and torch.equal(fr.obs[0], obs) and a.shape == (n, n_act)
+
+
+@pytest.mark.parametrize("n", [61, 1200])
+def test_rollout_kernel_equals_per_step_kernels(n):
+    """rt_rollout (all T steps in one launch, every block keeps its envs) against T x (rt_ppo_act, rt_step, rt_ppo_record)
+    on the same Philox stream: observation, done, value, action, log-prob and reward rows bit for bit, through the end of an
+    episode, the autoreset call and the start of the next one; same final env state; same episode statistics (atomics: to
+    rounding).  Both block shapes (7 and 14 envs per block), ragged last block, two chunks (rows 0..59, 60..T-1)."""
+    dev = torch.device(DEV)
+    T = 110
+    torch.manual_seed(5)
+    agent = rt.PPO((9,), (6,), 64).to(dev)
+    with torch.no_grad():
+        agent.actor_logstd.copy_(torch.linspace(-0.6, 0.3, 6).reshape(1, 6))
+    sched = np.stack([(np.arange(n) * 7919) % 1000, (np.arange(n) * 104729 + 17) % 1000]).astype(np.int32)
+    a = rt.BatchedEpisodes(n, device=dev); a.set_tumour_schedule(sched); a.reset()
+    b = rt.BatchedEpisodes(n, device=dev); b.set_tumour_schedule(sched); b.reset()
+    fa = rt.FusedRollout(agent, n, T, seed=77)
+    fb = rt.FusedRollout(agent, n, T, seed=77)
+    for t in range(T):                                   # per-step kernels (train.py:138-161 one step at a time)
+        fa.act(a.obs)
+        a.step(fa.action, want_info=True)
+        fa.record(a)
+        fa.advance()
+    fb.rollout(b, 60)                                    # one launch for rows 0..59, one for the rest
+    fb.rollout(b)
+    torch.cuda.synchronize()
+    for name in ("obs", "dones", "values", "actions", "logprobs", "rewards"):
+        x, y = getattr(fa, name), getattr(fb, name)
+        assert torch.equal(x.view(torch.int32), y.view(torch.int32)), name
+    assert torch.equal(fa.next_done, fb.next_done) and torch.equal(a.obs, b.obs)
+    assert torch.equal(a.pose(), b.pose()) and torch.equal(a.counters(), b.counters())
+    assert torch.equal(a.dose(n - 1), b.dose(n - 1))
+    assert fa.episode_stats[0] == n and fb.episode_stats[0] == n           # every env finished one episode (t = 100)
+    torch.testing.assert_close(fa.episode_stats, fb.episode_stats, rtol=1e-12, atol=1e-9)
+    assert fb._row == T and int(fb.counters[0]) == T and int(fb.counters[1]) == T
+    with pytest.raises(nat_err()):
+        fb.rollout(b, 1)                                 # past the end of the rollout buffers
+    a.close(); b.close()
+
+
+def nat_err():
+    from ppo_radiotherapy_b200 import _native as nat
+    return nat.RtError
+
+
+def test_act_and_record_past_the_last_row_store_nothing():
+    """rt_ppo_act / rt_ppo_record take the row count of the rollout buffers; a call whose device-side row
+    counter is past the end still produces actions but writes no row."""
+    dev = torch.device(DEV)
+    n, T = 70, 3
+    agent = rt.PPO((9,), (6,), 64).to(dev)
+    eng = rt.BatchedEpisodes(n, device=dev, seed=1); eng.reset()
+    fr = rt.FusedRollout(agent, n, T, seed=3)
+    guard = torch.full((4, n), 7.0, device=dev)
+    for t in range(T + 2):
+        before = [x.clone() for x in (fr.obs, fr.dones, fr.values, fr.actions, fr.logprobs, fr.rewards)]
+        fr.act(eng.obs)
+        eng.step(fr.action, want_info=True)
+        fr.record(eng)
+        fr.advance()
+        torch.cuda.synchronize()
+        if t >= T:
+            for x, y in zip(before, (fr.obs, fr.dones, fr.values, fr.actions, fr.logprobs, fr.rewards)):
+                assert torch.equal(x, y)
+            assert torch.isfinite(fr.action).all()
+    assert (guard == 7.0).all()
+    eng.close()
