@@ -279,6 +279,196 @@ __device__ __forceinline__ void prefetch_beam(const Grid &G, const Beam &b, cons
     }
 }
 
+// Env warp, before the beam is known: the env's tumour entry and padded bitmask into shared memory, and the
+// distance-to-tumour reward's minimum (environment.py:150-162) over the tumour's voxel list.  `meanwhile` runs between
+// the first voxel loads and their use (the per-call kernel prefetches the predicted beam there).
+template <bool kDense, typename Meanwhile>
+__device__ __forceinline__ void env_tumour_distance(const Tables &T, EnvShared &se, Tumour &tm, uint32_t *tb, int lane, Meanwhile meanwhile)
+{
+    const int tid = se.tid;
+    if (lane < kTumourWords)
+        reinterpret_cast<uint32_t *>(&tm)[lane] = __ldg(reinterpret_cast<const uint32_t *>(T.tumours + tid) + lane);
+    if (!kDense)
+        for (int i = lane; i < T.pbits_words; i += kWarp)              // pbits_words <= kMaxPTumourWords (rt_create)
+            tb[i] = __ldg(T.tumour_pbits + (size_t)tid * T.pbits_words + i);
+    __syncwarp();
+    // distance_to_tumour_reward (environment.py:150-162): min over the tumour's voxel list.  The first four voxels
+    // of every lane are requested, then the predicted beam's bricks go to the L2 while those loads are in flight.
+    const double p0 = se.p[0], p1 = se.p[1], p2 = se.p[2];
+    double best = CUDART_INF;
+    const int nv = tm.n_vox;
+    const uint32_t *vx = T.vox_xyz + tm.vox_off;
+    uint32_t pk4[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) pk4[i] = lane + i * kWarp < nv ? __ldg(vx + lane + i * kWarp) : 0xffffffffu;
+    meanwhile();
+    auto take = [&](uint32_t pk) {
+        const double dx = (double)(pk & 255u) - p0;
+        const double dy = (double)((pk >> 8) & 255u) - p1;
+        const double dz = (double)(pk >> 16) - p2;
+        const double d2 = __fma_rn(dz, dz, __fma_rn(dy, dy, dx * dx));
+        best = d2 < best ? d2 : best;
+    };
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+        if (lane + i * kWarp < nv) take(pk4[i]);
+#pragma unroll 4
+    for (int k = lane + 4 * kWarp; k < nv; k += kWarp) take(__ldg(vx + k));
+    // min of non-negative doubles = min of their bit patterns: two integer warp reductions
+    const uint32_t hi = (uint32_t)__double2hiint(best);
+    const uint32_t mhi = __reduce_min_sync(kFull, hi);
+    const uint32_t mlo = __reduce_min_sync(kFull, hi == mhi ? (uint32_t)__double2loint(best) : 0xffffffffu);
+    if (lane == 0) se.best = __hiloint2double((int)mhi, (int)mlo);
+}
+
+// Env warp, once the beam and its walk are published: the dose deposition of one env (environment.py:107-110) and the
+// tumour / lung deltas it causes (environment.py:164-182), left in se.d_tum / se.d_lung / se.d_cnt.  `vol` = the env's
+// cells, `cbuf` = this warp's [kMaxPass][32 slabs][4 targets] item slots, `slungs` = the padded lungs bitmask (shared
+// memory when kStageLungs, then `lungs_mbar` is the mbarrier its bulk copy completes on).
+template <bool kStageLungs, bool kClock>
+__device__ __forceinline__ void deposit_beam(const Tables &T, EnvShared &se, const Tumour &tm, const uint32_t *tb, const float2 *myz,
+                                             uint2 *vol, uint2 *cbuf, const uint32_t *slungs, uint32_t lungs_mbar, int env, int lane)
+{
+    if (lane == 0) RT_STAMP3(env, 3);
+    // ---- dose deposition (environment.py:107-110): dose' = clip(dose + beam*0.1, 0, 1) on the voxels hit.
+    // A voxel has exactly one owner lane per beam (slab_weights merges the two slabs that can meet), so the
+    // 32-slab passes of a beam are independent.
+    //   Phase 1 issues the loads of every pass before it uses any (the beam pays one HBM round trip however long it
+    //   is); phase 2 takes the passes in order: weights, masks, new dose, deltas, stores.
+    //   The MEMORY instructions use another lane mapping than the arithmetic: a lane computes one slab and its
+    //   four targets, but load / store instruction i of a pass moves item 32 i + lane of the pass's item list
+    //   [slab][target] — the four targets of eight consecutive slabs.  The load/store pipeline pays per distinct
+    //   128-byte line of an instruction: with one target of 32 slabs per instruction that is ~15 lines, with all
+    //   targets of 8 slabs ~4 (the tube of a beam crosses a brick every 2 to 4 slabs).  Cell indices and cells
+    //   change lanes through one shared-memory slot per item (item-major, conflict-free both ways).
+    const Grid &G = T.G;
+    const Beam b = se.beam;
+    const uint32_t gen = se.gen;
+    const int g2 = G.g2;
+    const int npass = (b.nslab + kWarp - 1) / kWarp;
+#pragma unroll
+    for (int c = 0; c < kMaxPass; c++) {
+        if (c < npass) {                                                       // warp-uniform
+            const int k = c * kWarp + lane;
+            const float2 cur = myz[k < b.nslab ? k : 0];
+            int base, c0, c1, c2;
+            uint32_t inb;
+            slab_coords(G, b, k, cur, base, inb, c0, c1, c2);
+            const int r0 = cell_row_term(G, c0, c1), r1 = cell_row_term(G, c0, c1 + 1);
+            const int q0 = cell_col_term(c2), q1 = cell_col_term(c2 + 1);
+            // the cell index of every target goes into its own slot (-1: outside the grid) ...
+            uint4 *mine4 = reinterpret_cast<uint4 *>(cbuf + c * 4 * kWarp) + 2 * lane;
+            mine4[0] = make_uint4((uint32_t)(inb & 1u ? r0 + q0 : -1), 0u, (uint32_t)(inb & 2u ? r0 + q1 : -1), 0u);
+            mine4[1] = make_uint4((uint32_t)(inb & 4u ? r1 + q0 : -1), 0u, (uint32_t)(inb & 8u ? r1 + q1 : -1), 0u);
+        }
+    }
+    __syncwarp();
+    // ... every load of the beam goes out (item-major lane mapping) before the first one is used, then the cells
+    // replace the indices
+    uint2 got[kMaxPass][4];
+#pragma unroll
+    for (int c = 0; c < kMaxPass; c++)
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            got[c][i] = make_uint2(0u, ~gen);                                  // outside the grid: reads as "another generation"
+            if (c < npass) {
+                const int a = (int)cbuf[c * 4 * kWarp + i * kWarp + lane].x;
+                if (a >= 0) got[c][i] = __ldcg(vol + a);
+            }
+        }
+#pragma unroll
+    for (int c = 0; c < kMaxPass; c++)
+        if (c < npass) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) cbuf[c * 4 * kWarp + i * kWarp + lane] = got[c][i];
+        }
+    __syncwarp();
+    if (lane == 0) RT_STAMP3(env, 4);
+    if (kStageLungs) mbar_wait(lungs_mbar, 0);                         // the lungs bitmask has landed
+    const int li0 = tm.lo[0], li1 = tm.lo[1] - 1, li2 = tm.lo[2] - 1;  // origin of the padded bbox
+    const int td0 = tm.dim[0], td1 = tm.dim[1], td2 = tm.dim[2];
+    const int pd1 = td1 + 2, pd2 = td2 + 2;
+    const int variant = b.dom == 0 ? 0 : (b.dom * 2 - 1 + (b.step > 0 ? 0 : 1));   // warp-uniform
+    // per-lane partial sums of at most 12 float32 deltas; the running totals are float64 (scalar warp)
+    float d_tum = 0.0f, d_lung = 0.0f;
+    int d_cnt = 0;
+#pragma unroll 1
+    for (int c = 0; c < npass; c++) {
+        const int k = c * kWarp + lane;
+        const int kk = k < b.nslab ? k : 0;
+        const float2 cur = myz[kk], prv = myz[kk > 0 ? kk - 1 : 0], nxt = myz[kk + 1 < b.nslab ? kk + 1 : kk];
+        int base, c0, c1, c2;
+        uint32_t inb;
+        const SlabCoord sc = slab_coords(G, b, k, cur, base, inb, c0, c1, c2);
+        const int r0 = cell_row_term(G, c0, c1), r1 = cell_row_term(G, c0, c1 + 1);
+        const int q0 = cell_col_term(c2), q1 = cell_col_term(c2 + 1);
+        uint32_t drop;
+        float w[4];
+        switch (variant) {
+        case 0: slab_weights<0, 0>(b, k, sc, prv, nxt, drop, w); break;
+        case 1: slab_weights<1, 0>(b, k, sc, prv, nxt, drop, w); break;
+        case 2: slab_weights<1, 1>(b, k, sc, prv, nxt, drop, w); break;
+        case 3: slab_weights<2, 0>(b, k, sc, prv, nxt, drop, w); break;
+        default: slab_weights<2, 1>(b, k, sc, prv, nxt, drop, w); break;
+        }
+        const uint32_t ok = inb & ~drop;
+        // lungs membership: the two targets of a row are neighbouring bits of the (padded) bitmask
+        uint32_t lmask = 0u;
+        if (inb & 3u) lmask = kStageLungs ? bit_pair(slungs, base) : bit_pair_ldg(slungs, base);
+        if (inb & 12u) lmask |= (kStageLungs ? bit_pair(slungs, base + g2) : bit_pair_ldg(slungs, base + g2)) << 2;
+        // tumour membership of the 2x2 block: one range test against the bounding box grown by one voxel on
+        // axes 1 and 2 (the padded bitmask has empty border cells, so the four bits are always addressable)
+        uint32_t tmask = 0u;
+        const int ti = c0 - li0, tj = c1 - li1, tk = c2 - li2;
+        if ((unsigned)ti < (unsigned)td0 && (unsigned)tj <= (unsigned)td1 && (unsigned)tk <= (unsigned)td2) {
+            const int b0 = (ti * pd1 + tj) * pd2 + tk, b1 = b0 + pd2;
+            const uint32_t r0 = __funnelshift_r(tb[b0 >> 5], tb[(b0 >> 5) + 1], b0 & 31) & 3u;
+            const uint32_t r1 = __funnelshift_r(tb[b1 >> 5], tb[(b1 >> 5) + 1], b1 & 31) & 3u;
+            tmask = r0 | (r1 << 2);
+        }
+        tmask &= ok;
+        lmask &= ok;
+        const uint32_t cmask = lmask & ~tmask;                 // lungs_mask = lungs*(1-tumours) (environment.py:174)
+        uint4 *mine4 = reinterpret_cast<uint4 *>(cbuf + c * 4 * kWarp) + 2 * lane;
+        const uint4 ca = mine4[0], cb = mine4[1];
+        const uint32_t cv[4] = {ca.x, ca.z, cb.x, cb.z}, cg[4] = {ca.y, ca.w, cb.y, cb.w};
+        float nd[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const float o = cg[j] == gen ? __uint_as_float(cv[j]) : 0.0f;             // another generation reads as zero
+            nd[j] = fminf(__fadd_rn(o, __fmul_rn(w[j], 0.100000001490116119f)), 1.0f);   // clip(dose + beam*0.1, 0, 1), dose >= 0
+            const float delta = (ok >> j) & 1u ? nd[j] - o : 0.0f;                    // 0 for targets this lane does not write
+            d_tum += (tmask >> j) & 1u ? delta : 0.0f;
+            d_lung += (lmask >> j) & 1u ? delta : 0.0f;
+            // dose is monotone, so the count only grows (environment.py:175-177)
+            d_cnt += (int)((cmask >> j) & 1u) & (int)(!(o > 0.200000002980232239f) && nd[j] > 0.200000002980232239f);
+        }
+        // {new dose, cell index or -1 for targets this lane does not write} back into the item list, then store
+        // instruction i writes items 32 i + lane
+        mine4[0] = make_uint4(__float_as_uint(nd[0]), (uint32_t)(ok & 1u ? r0 + q0 : -1), __float_as_uint(nd[1]), (uint32_t)(ok & 2u ? r0 + q1 : -1));
+        mine4[1] = make_uint4(__float_as_uint(nd[2]), (uint32_t)(ok & 4u ? r1 + q0 : -1), __float_as_uint(nd[3]), (uint32_t)(ok & 8u ? r1 + q1 : -1));
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const uint2 it = cbuf[c * 4 * kWarp + i * kWarp + lane];
+            if ((int)it.y >= 0) __stcg(vol + (int)it.y, make_uint2(it.x, gen));
+        }
+    }
+    if (lane == 0) RT_STAMP3(env, 6);
+    // both sums in one butterfly: after the first exchange the lower half-warp carries the tumour sum, the
+    // upper one the lung sum
+    {
+        const bool upper = lane >= 16;
+        const float keep = upper ? d_lung : d_tum, give = upper ? d_tum : d_lung;
+        double v = (double)keep + (double)__shfl_xor_sync(kFull, give, 16);
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+        d_cnt = __reduce_add_sync(kFull, d_cnt);
+        if (lane == 0) { se.d_tum = v; se.d_cnt = d_cnt; }
+        if (lane == 16) se.d_lung = v;
+    }
+}
+
 // warps of a block: scalar warp, kB env warps and, for 14-env blocks of sparse-mode handles, the predictor warp
 template <int kB, bool kDense>
 __host__ __device__ constexpr int step_block_threads() { return (kB + 1 + (kB >= 14 && !kDense ? 1 : 0)) * kWarp; }
@@ -617,43 +807,12 @@ __device__ __forceinline__ void step_block(StepShared<kB> &M, uint32_t *dyn_smem
     uint32_t *tb = tbits[le];
     const bool stepping = active && se.needs_reset == 0;
     if (stepping) {
-        const int tid = se.tid;
-        if (lane < kTumourWords)
-            reinterpret_cast<uint32_t *>(&tm)[lane] = __ldg(reinterpret_cast<const uint32_t *>(T.tumours + tid) + lane);
-        if (!kDense)
-            for (int i = lane; i < T.pbits_words; i += kWarp)              // pbits_words <= kMaxPTumourWords (rt_create)
-                tb[i] = __ldg(T.tumour_pbits + (size_t)tid * T.pbits_words + i);
-        __syncwarp();
-        // distance_to_tumour_reward (environment.py:150-162): min over the tumour's voxel list.  The first four voxels
-        // of every lane are requested, then the predicted beam's bricks go to the L2 while those loads are in flight.
-        const double p0 = se.p[0], p1 = se.p[1], p2 = se.p[2];
-        double best = CUDART_INF;
-        const int nv = tm.n_vox;
-        const uint32_t *vx = T.vox_xyz + tm.vox_off;
-        uint32_t pk4[4];
-#pragma unroll
-        for (int i = 0; i < 4; i++) pk4[i] = lane + i * kWarp < nv ? __ldg(vx + lane + i * kWarp) : 0xffffffffu;
-        if (kPredict) {
-            mbar_wait(smem_u32(&mbars[1]), pred_parity);                   // the predictor warp has published its beams
-            prefetch_beam(G, pred[le], cells + (size_t)env * G.cstride, lane);
-        }
-        auto take = [&](uint32_t pk) {
-            const double dx = (double)(pk & 255u) - p0;
-            const double dy = (double)((pk >> 8) & 255u) - p1;
-            const double dz = (double)(pk >> 16) - p2;
-            const double d2 = __fma_rn(dz, dz, __fma_rn(dy, dy, dx * dx));
-            best = d2 < best ? d2 : best;
-        };
-#pragma unroll
-        for (int i = 0; i < 4; i++)
-            if (lane + i * kWarp < nv) take(pk4[i]);
-#pragma unroll 4
-        for (int k = lane + 4 * kWarp; k < nv; k += kWarp) take(__ldg(vx + k));
-        // min of non-negative doubles = min of their bit patterns: two integer warp reductions
-        const uint32_t hi = (uint32_t)__double2hiint(best);
-        const uint32_t mhi = __reduce_min_sync(kFull, hi);
-        const uint32_t mlo = __reduce_min_sync(kFull, hi == mhi ? (uint32_t)__double2loint(best) : 0xffffffffu);
-        if (lane == 0) se.best = __hiloint2double((int)mhi, (int)mlo);
+        env_tumour_distance<kDense>(T, se, tm, tb, lane, [&]() {
+            if (kPredict) {
+                mbar_wait(smem_u32(&mbars[1]), pred_parity);               // the predictor warp has published its beams
+                prefetch_beam(G, pred[le], cells + (size_t)env * G.cstride, lane);
+            }
+        });
     }
     if (active && lane == 0) RT_STAMP3(env, 2);
     work_barrier<(kB + 1) * kWarp>();                                      // ---- barrier 1
@@ -690,149 +849,10 @@ __device__ __forceinline__ void step_block(StepShared<kB> &M, uint32_t *dyn_smem
         }
         if (lane == 0) dw.n_hits = nhit < RT_BEAM_CAP ? nhit : RT_BEAM_CAP;
     }
-    if (stepping && !kDense) {
-        const uint32_t *slungs = kStageLungs ? lungs_sm : T.lungs_pad;
-        if (lane == 0) RT_STAMP3(env, 3);
-        // ---- dose deposition (environment.py:107-110): dose' = clip(dose + beam*0.1, 0, 1) on the voxels hit.
-        // A voxel has exactly one owner lane per beam (slab_weights merges the two slabs that can meet), so the
-        // 32-slab passes of a beam are independent.
-        //   Phase 1 issues the loads of every pass before it uses any (the beam pays one HBM round trip however long it
-        //   is); phase 2 takes the passes in order: weights, masks, new dose, deltas, stores.
-        //   The MEMORY instructions use another lane mapping than the arithmetic: a lane computes one slab and its
-        //   four targets, but load / store instruction i of a pass moves item 32 i + lane of the pass's item list
-        //   [slab][target] — the four targets of eight consecutive slabs.  The load/store pipeline pays per distinct
-        //   128-byte line of an instruction: with one target of 32 slabs per instruction that is ~15 lines, with all
-        //   targets of 8 slabs ~4 (the tube of a beam crosses a brick every 2 to 4 slabs).  Cell indices and cells
-        //   change lanes through one shared-memory slot per item (item-major, conflict-free both ways).
-        const Beam b = se.beam;
-        const uint32_t gen = se.gen;
-        const float2 *myz = yz[le];
-        uint2 *vol = cells + (size_t)env * G.cstride;
-        uint2 *cbuf = cellbuf_all + (size_t)le * (kMaxPass * 4 * kWarp);          // [pass][slab][target]: cell index -> cell -> {new dose, cell index}
-        const int g2 = G.g2;
-        const int npass = (b.nslab + kWarp - 1) / kWarp;
-#pragma unroll
-        for (int c = 0; c < kMaxPass; c++) {
-            if (c < npass) {                                                       // warp-uniform
-                const int k = c * kWarp + lane;
-                const float2 cur = myz[k < b.nslab ? k : 0];
-                int base, c0, c1, c2;
-                uint32_t inb;
-                slab_coords(G, b, k, cur, base, inb, c0, c1, c2);
-                const int r0 = cell_row_term(G, c0, c1), r1 = cell_row_term(G, c0, c1 + 1);
-                const int q0 = cell_col_term(c2), q1 = cell_col_term(c2 + 1);
-                // the cell index of every target goes into its own slot (-1: outside the grid) ...
-                uint4 *mine4 = reinterpret_cast<uint4 *>(cbuf + c * 4 * kWarp) + 2 * lane;
-                mine4[0] = make_uint4((uint32_t)(inb & 1u ? r0 + q0 : -1), 0u, (uint32_t)(inb & 2u ? r0 + q1 : -1), 0u);
-                mine4[1] = make_uint4((uint32_t)(inb & 4u ? r1 + q0 : -1), 0u, (uint32_t)(inb & 8u ? r1 + q1 : -1), 0u);
-            }
-        }
-        __syncwarp();
-        // ... every load of the beam goes out (item-major lane mapping) before the first one is used, then the cells
-        // replace the indices
-        uint2 got[kMaxPass][4];
-#pragma unroll
-        for (int c = 0; c < kMaxPass; c++)
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                got[c][i] = make_uint2(0u, ~gen);                                  // outside the grid: reads as "another generation"
-                if (c < npass) {
-                    const int a = (int)cbuf[c * 4 * kWarp + i * kWarp + lane].x;
-                    if (a >= 0) got[c][i] = __ldcg(vol + a);
-                }
-            }
-#pragma unroll
-        for (int c = 0; c < kMaxPass; c++)
-            if (c < npass) {
-#pragma unroll
-                for (int i = 0; i < 4; i++) cbuf[c * 4 * kWarp + i * kWarp + lane] = got[c][i];
-            }
-        __syncwarp();
-        if (lane == 0) RT_STAMP3(env, 4);
-        if (kStageLungs) mbar_wait(smem_u32(&mbars[0]), 0);                // the lungs bitmask has landed
-        const int li0 = tm.lo[0], li1 = tm.lo[1] - 1, li2 = tm.lo[2] - 1;  // origin of the padded bbox
-        const int td0 = tm.dim[0], td1 = tm.dim[1], td2 = tm.dim[2];
-        const int pd1 = td1 + 2, pd2 = td2 + 2;
-        const int variant = b.dom == 0 ? 0 : (b.dom * 2 - 1 + (b.step > 0 ? 0 : 1));   // warp-uniform
-        // per-lane partial sums of at most 12 float32 deltas; the running totals are float64 (scalar warp)
-        float d_tum = 0.0f, d_lung = 0.0f;
-        int d_cnt = 0;
-#pragma unroll 1
-        for (int c = 0; c < npass; c++) {
-            const int k = c * kWarp + lane;
-            const int kk = k < b.nslab ? k : 0;
-            const float2 cur = myz[kk], prv = myz[kk > 0 ? kk - 1 : 0], nxt = myz[kk + 1 < b.nslab ? kk + 1 : kk];
-            int base, c0, c1, c2;
-            uint32_t inb;
-            const SlabCoord sc = slab_coords(G, b, k, cur, base, inb, c0, c1, c2);
-            const int r0 = cell_row_term(G, c0, c1), r1 = cell_row_term(G, c0, c1 + 1);
-            const int q0 = cell_col_term(c2), q1 = cell_col_term(c2 + 1);
-            uint32_t drop;
-            float w[4];
-            switch (variant) {
-            case 0: slab_weights<0, 0>(b, k, sc, prv, nxt, drop, w); break;
-            case 1: slab_weights<1, 0>(b, k, sc, prv, nxt, drop, w); break;
-            case 2: slab_weights<1, 1>(b, k, sc, prv, nxt, drop, w); break;
-            case 3: slab_weights<2, 0>(b, k, sc, prv, nxt, drop, w); break;
-            default: slab_weights<2, 1>(b, k, sc, prv, nxt, drop, w); break;
-            }
-            const uint32_t ok = inb & ~drop;
-            // lungs membership: the two targets of a row are neighbouring bits of the (padded) bitmask
-            uint32_t lmask = 0u;
-            if (inb & 3u) lmask = kStageLungs ? bit_pair(slungs, base) : bit_pair_ldg(slungs, base);
-            if (inb & 12u) lmask |= (kStageLungs ? bit_pair(slungs, base + g2) : bit_pair_ldg(slungs, base + g2)) << 2;
-            // tumour membership of the 2x2 block: one range test against the bounding box grown by one voxel on
-            // axes 1 and 2 (the padded bitmask has empty border cells, so the four bits are always addressable)
-            uint32_t tmask = 0u;
-            const int ti = c0 - li0, tj = c1 - li1, tk = c2 - li2;
-            if ((unsigned)ti < (unsigned)td0 && (unsigned)tj <= (unsigned)td1 && (unsigned)tk <= (unsigned)td2) {
-                const int b0 = (ti * pd1 + tj) * pd2 + tk, b1 = b0 + pd2;
-                const uint32_t r0 = __funnelshift_r(tb[b0 >> 5], tb[(b0 >> 5) + 1], b0 & 31) & 3u;
-                const uint32_t r1 = __funnelshift_r(tb[b1 >> 5], tb[(b1 >> 5) + 1], b1 & 31) & 3u;
-                tmask = r0 | (r1 << 2);
-            }
-            tmask &= ok;
-            lmask &= ok;
-            const uint32_t cmask = lmask & ~tmask;                 // lungs_mask = lungs*(1-tumours) (environment.py:174)
-            uint4 *mine4 = reinterpret_cast<uint4 *>(cbuf + c * 4 * kWarp) + 2 * lane;
-            const uint4 ca = mine4[0], cb = mine4[1];
-            const uint32_t cv[4] = {ca.x, ca.z, cb.x, cb.z}, cg[4] = {ca.y, ca.w, cb.y, cb.w};
-            float nd[4];
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const float o = cg[j] == gen ? __uint_as_float(cv[j]) : 0.0f;             // another generation reads as zero
-                nd[j] = fminf(__fadd_rn(o, __fmul_rn(w[j], 0.100000001490116119f)), 1.0f);   // clip(dose + beam*0.1, 0, 1), dose >= 0
-                const float delta = (ok >> j) & 1u ? nd[j] - o : 0.0f;                    // 0 for targets this lane does not write
-                d_tum += (tmask >> j) & 1u ? delta : 0.0f;
-                d_lung += (lmask >> j) & 1u ? delta : 0.0f;
-                // dose is monotone, so the count only grows (environment.py:175-177)
-                d_cnt += (int)((cmask >> j) & 1u) & (int)(!(o > 0.200000002980232239f) && nd[j] > 0.200000002980232239f);
-            }
-            // {new dose, cell index or -1 for targets this lane does not write} back into the item list, then store
-            // instruction i writes items 32 i + lane
-            mine4[0] = make_uint4(__float_as_uint(nd[0]), (uint32_t)(ok & 1u ? r0 + q0 : -1), __float_as_uint(nd[1]), (uint32_t)(ok & 2u ? r0 + q1 : -1));
-            mine4[1] = make_uint4(__float_as_uint(nd[2]), (uint32_t)(ok & 4u ? r1 + q0 : -1), __float_as_uint(nd[3]), (uint32_t)(ok & 8u ? r1 + q1 : -1));
-            __syncwarp();
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const uint2 it = cbuf[c * 4 * kWarp + i * kWarp + lane];
-                if ((int)it.y >= 0) __stcg(vol + (int)it.y, make_uint2(it.x, gen));
-            }
-        }
-        if (lane == 0) RT_STAMP3(env, 6);
-        // both sums in one butterfly: after the first exchange the lower half-warp carries the tumour sum, the
-        // upper one the lung sum
-        {
-            const bool upper = lane >= 16;
-            const float keep = upper ? d_lung : d_tum, give = upper ? d_tum : d_lung;
-            double v = (double)keep + (double)__shfl_xor_sync(kFull, give, 16);
-#pragma unroll
-            for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
-            d_cnt = __reduce_add_sync(kFull, d_cnt);
-            if (lane == 0) { se.d_tum = v; se.d_cnt = d_cnt; }
-            if (lane == 16) se.d_lung = v;
-        }
-    }
+    if (stepping && !kDense)
+        deposit_beam<kStageLungs, kClock>(T, se, tm, tb, yz[le], cells + (size_t)env * G.cstride,
+                                          cellbuf_all + (size_t)le * (kMaxPass * 4 * kWarp), kStageLungs ? lungs_sm : T.lungs_pad,
+                                          smem_u32(&mbars[0]), env, lane);
     work_barrier<(kB + 1) * kWarp>();                                      // ---- barrier 2
 }
 
