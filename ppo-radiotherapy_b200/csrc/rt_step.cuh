@@ -272,10 +272,12 @@ __device__ __forceinline__ void prefetch_beam(const Grid &G, const Beam &b, cons
         const int j0 = min(max(c1, 0), G.g1 - 1), j1 = min(max(c1 + 1, 0), G.g1 - 1);
         const int k0 = min(max(c2, 0), G.g2 - 1), k1 = min(max(c2 + 1, 0), G.g2 - 1);
         const bool dj = (j1 >> 1) != (j0 >> 1), dk = (k1 >> 2) != (k0 >> 2);
-        prefetch_l2(vol + cell_index(G, c0, j0, k0));
-        if (dk) prefetch_l2(vol + cell_index(G, c0, j0, k1));
-        if (dj) prefetch_l2(vol + cell_index(G, c0, j1, k0));
-        if (dj && dk) prefetch_l2(vol + cell_index(G, c0, j1, k1));
+        // a brick is one 128-byte line of 16 cells: its first cell's address will do
+        const int br0 = ((c0 >> 1) * G.nb1 + (j0 >> 1)) * G.nb2, br1 = ((c0 >> 1) * G.nb1 + (j1 >> 1)) * G.nb2;
+        prefetch_l2(vol + (br0 + (k0 >> 2)) * 16);
+        if (dk) prefetch_l2(vol + (br0 + (k1 >> 2)) * 16);
+        if (dj) prefetch_l2(vol + (br1 + (k0 >> 2)) * 16);
+        if (dj && dk) prefetch_l2(vol + (br1 + (k1 >> 2)) * 16);
     }
 }
 
@@ -358,13 +360,13 @@ __device__ __forceinline__ void deposit_beam(const Tables &T, EnvShared &se, con
             const int q0 = cell_col_term(c2), q1 = cell_col_term(c2 + 1);
             // the cell index of every target goes into its own slot (-1: outside the grid) ...
             uint4 *mine4 = reinterpret_cast<uint4 *>(cbuf + c * 4 * kWarp) + 2 * lane;
-            mine4[0] = make_uint4((uint32_t)(inb & 1u ? r0 + q0 : -1), 0u, (uint32_t)(inb & 2u ? r0 + q1 : -1), 0u);
-            mine4[1] = make_uint4((uint32_t)(inb & 4u ? r1 + q0 : -1), 0u, (uint32_t)(inb & 8u ? r1 + q1 : -1), 0u);
+            mine4[0] = make_uint4(0u, (uint32_t)(inb & 1u ? r0 + q0 : -1), 0u, (uint32_t)(inb & 2u ? r0 + q1 : -1));
+            mine4[1] = make_uint4(0u, (uint32_t)(inb & 4u ? r1 + q0 : -1), 0u, (uint32_t)(inb & 8u ? r1 + q1 : -1));
         }
     }
     __syncwarp();
-    // ... every load of the beam goes out (item-major lane mapping) before the first one is used, then the cells
-    // replace the indices
+    // ... every load of the beam goes out (item-major lane mapping) before the first one is used; then the dose as this
+    // generation sees it joins the index: slot = {dose, cell index}
     uint2 got[kMaxPass][4];
 #pragma unroll
     for (int c = 0; c < kMaxPass; c++)
@@ -372,7 +374,7 @@ __device__ __forceinline__ void deposit_beam(const Tables &T, EnvShared &se, con
         for (int i = 0; i < 4; i++) {
             got[c][i] = make_uint2(0u, ~gen);                                  // outside the grid: reads as "another generation"
             if (c < npass) {
-                const int a = (int)cbuf[c * 4 * kWarp + i * kWarp + lane].x;
+                const int a = (int)cbuf[c * 4 * kWarp + i * kWarp + lane].y;
                 if (a >= 0) got[c][i] = __ldcg(vol + a);
             }
         }
@@ -380,7 +382,8 @@ __device__ __forceinline__ void deposit_beam(const Tables &T, EnvShared &se, con
     for (int c = 0; c < kMaxPass; c++)
         if (c < npass) {
 #pragma unroll
-            for (int i = 0; i < 4; i++) cbuf[c * 4 * kWarp + i * kWarp + lane] = got[c][i];
+            for (int i = 0; i < 4; i++)                                        // another generation reads as zero
+                cbuf[c * 4 * kWarp + i * kWarp + lane].x = got[c][i].y == gen ? got[c][i].x : 0u;
         }
     __syncwarp();
     if (lane == 0) RT_STAMP3(env, 4);
@@ -400,8 +403,6 @@ __device__ __forceinline__ void deposit_beam(const Tables &T, EnvShared &se, con
         int base, c0, c1, c2;
         uint32_t inb;
         const SlabCoord sc = slab_coords(G, b, k, cur, base, inb, c0, c1, c2);
-        const int r0 = cell_row_term(G, c0, c1), r1 = cell_row_term(G, c0, c1 + 1);
-        const int q0 = cell_col_term(c2), q1 = cell_col_term(c2 + 1);
         uint32_t drop;
         float w[4];
         switch (variant) {
@@ -431,11 +432,11 @@ __device__ __forceinline__ void deposit_beam(const Tables &T, EnvShared &se, con
         const uint32_t cmask = lmask & ~tmask;                 // lungs_mask = lungs*(1-tumours) (environment.py:174)
         uint4 *mine4 = reinterpret_cast<uint4 *>(cbuf + c * 4 * kWarp) + 2 * lane;
         const uint4 ca = mine4[0], cb = mine4[1];
-        const uint32_t cv[4] = {ca.x, ca.z, cb.x, cb.z}, cg[4] = {ca.y, ca.w, cb.y, cb.w};
+        const uint32_t cv[4] = {ca.x, ca.z, cb.x, cb.z}, ci[4] = {ca.y, ca.w, cb.y, cb.w};
         float nd[4];
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            const float o = cg[j] == gen ? __uint_as_float(cv[j]) : 0.0f;             // another generation reads as zero
+            const float o = __uint_as_float(cv[j]);
             nd[j] = fminf(__fadd_rn(o, __fmul_rn(w[j], 0.100000001490116119f)), 1.0f);   // clip(dose + beam*0.1, 0, 1), dose >= 0
             const float delta = (ok >> j) & 1u ? nd[j] - o : 0.0f;                    // 0 for targets this lane does not write
             d_tum += (tmask >> j) & 1u ? delta : 0.0f;
@@ -445,8 +446,8 @@ __device__ __forceinline__ void deposit_beam(const Tables &T, EnvShared &se, con
         }
         // {new dose, cell index or -1 for targets this lane does not write} back into the item list, then store
         // instruction i writes items 32 i + lane
-        mine4[0] = make_uint4(__float_as_uint(nd[0]), (uint32_t)(ok & 1u ? r0 + q0 : -1), __float_as_uint(nd[1]), (uint32_t)(ok & 2u ? r0 + q1 : -1));
-        mine4[1] = make_uint4(__float_as_uint(nd[2]), (uint32_t)(ok & 4u ? r1 + q0 : -1), __float_as_uint(nd[3]), (uint32_t)(ok & 8u ? r1 + q1 : -1));
+        mine4[0] = make_uint4(__float_as_uint(nd[0]), ok & 1u ? ci[0] : 0xffffffffu, __float_as_uint(nd[1]), ok & 2u ? ci[1] : 0xffffffffu);
+        mine4[1] = make_uint4(__float_as_uint(nd[2]), ok & 4u ? ci[2] : 0xffffffffu, __float_as_uint(nd[3]), ok & 8u ? ci[3] : 0xffffffffu);
         __syncwarp();
 #pragma unroll
         for (int i = 0; i < 4; i++) {
