@@ -281,28 +281,34 @@ __device__ __forceinline__ void prefetch_beam(const Grid &G, const Beam &b, cons
     }
 }
 
-// Env warp, before the beam is known: the env's tumour entry and padded bitmask into shared memory, and the
-// distance-to-tumour reward's minimum (environment.py:150-162) over the tumour's voxel list.  `meanwhile` runs between
-// the first voxel loads and their use (the per-call kernel prefetches the predicted beam there).
-template <bool kDense, typename Meanwhile>
-__device__ __forceinline__ void env_tumour_distance(const Tables &T, EnvShared &se, Tumour &tm, uint32_t *tb, int lane, Meanwhile meanwhile)
+// Env warp, before the beam is known — part 1, needs only the env's tumour id: the tumour entry and its padded bitmask
+// into shared memory, then the first four voxels per lane of the tumour's voxel list requested (pk4).
+template <bool kDense>
+__device__ __forceinline__ void env_tumour_fetch(const Tables &T, int tid, Tumour &tm, uint32_t *tb, int lane, uint32_t (&pk4)[4])
 {
-    const int tid = se.tid;
     if (lane < kTumourWords)
         reinterpret_cast<uint32_t *>(&tm)[lane] = __ldg(reinterpret_cast<const uint32_t *>(T.tumours + tid) + lane);
     if (!kDense)
         for (int i = lane; i < T.pbits_words; i += kWarp)              // pbits_words <= kMaxPTumourWords (rt_create)
             tb[i] = __ldg(T.tumour_pbits + (size_t)tid * T.pbits_words + i);
     __syncwarp();
-    // distance_to_tumour_reward (environment.py:150-162): min over the tumour's voxel list.  The first four voxels
-    // of every lane are requested, then the predicted beam's bricks go to the L2 while those loads are in flight.
+    const int nv = tm.n_vox;
+    const uint32_t *vx = T.vox_xyz + tm.vox_off;
+#pragma unroll
+    for (int i = 0; i < 4; i++) pk4[i] = lane + i * kWarp < nv ? __ldg(vx + lane + i * kWarp) : 0xffffffffu;
+}
+
+// Part 2, needs the translated beam position se.p: the distance-to-tumour reward's minimum (environment.py:150-162) over
+// the tumour's voxel list -> se.best.  `meanwhile` runs before the first voxels are used (the per-call kernel prefetches
+// the predicted beam there).
+template <typename Meanwhile>
+__device__ __forceinline__ void env_distance(const Tables &T, EnvShared &se, const Tumour &tm, int lane, const uint32_t (&pk4)[4],
+                                             Meanwhile meanwhile)
+{
     const double p0 = se.p[0], p1 = se.p[1], p2 = se.p[2];
     double best = CUDART_INF;
     const int nv = tm.n_vox;
     const uint32_t *vx = T.vox_xyz + tm.vox_off;
-    uint32_t pk4[4];
-#pragma unroll
-    for (int i = 0; i < 4; i++) pk4[i] = lane + i * kWarp < nv ? __ldg(vx + lane + i * kWarp) : 0xffffffffu;
     meanwhile();
     auto take = [&](uint32_t pk) {
         const double dx = (double)(pk & 255u) - p0;
@@ -481,7 +487,7 @@ struct StepShared {
     Tumour tum[kB];
     uint32_t tbits[kB][kMaxPTumourWords];
     float2 yz[kB][kYZStride];
-    __align__(8) unsigned long long mbars[2];          // [0] lungs bitmask landed, [1] predicted beams published
+    __align__(8) unsigned long long mbars[3];          // [0] lungs bitmask landed, [1] predicted beams published, [2] beams and walks published
     Beam pred[kB];
     // outputs are staged here by the scalar warp's lanes and copied out row-contiguously (full-line stores:
     // the host-buffer entry points map these arrays over PCIe)
@@ -511,7 +517,7 @@ __device__ __forceinline__ void step_block(StepShared<kB> &M, uint32_t *dyn_smem
     Tumour (&tum)[kB] = M.tum;
     uint32_t (&tbits)[kB][kMaxPTumourWords] = M.tbits;
     float2 (&yz)[kB][kYZStride] = M.yz;
-    unsigned long long (&mbars)[2] = M.mbars;
+    unsigned long long (&mbars)[3] = M.mbars;
     Beam (&pred)[kB] = M.pred;
     float (&s_obs)[kB * RT_OBS_SIZE] = M.s_obs;
     double (&s_rew)[kB] = M.s_rew;
@@ -599,10 +605,17 @@ __device__ __forceinline__ void step_block(StepShared<kB> &M, uint32_t *dyn_smem
             se.beam = b;
             RT_STAMP3(e, 1);
         }
-        work_barrier<(kB + 1) * kWarp>();                                  // ---- barrier 1
+        if (kDense) {
+            work_barrier<(kB + 1) * kWarp>();                              // ---- barrier 1
+        } else {
+            // beams and walks published: every env warp goes on as soon as ITS tumour work is done, not the block's slowest
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&mbars[2])) : "memory");
+        }
 
         // While the env warps deposit the dose: everything that does not depend on it.
-        const Tumour &tm = tum[lane < kB ? lane : 0];
+        const Tumour &tm = tum[lane < kB ? lane : 0];                       // sparse mode: staged by the env warp, complete at barrier 2
+        const Tumour *tg = T.tumours + tid;
         int t = 0, n_beams = 0, lung_count = 0;
         double r_dist = 0.0, os_r = 0.0, rcp_mask = 0.0, mask_sum = 1.0;
         double tumour_dose = 0.0, lung_dose = 0.0, ep_return = 0.0;
@@ -619,12 +632,12 @@ __device__ __forceinline__ void step_block(StepShared<kB> &M, uint32_t *dyn_smem
             for (int i = 0; i < 3; i++) {
                 obs[i] = (float)__dsub_rn(__dmul_rn(__ddiv_rn(s.p[i], gs[i]), 2.0), 1.0);
                 obs[3 + i] = (float)s.d[i];
-                obs[6 + i] = tm.obs_c[i];
+                obs[6 + i] = __ldg(&tg->obs_c[i]);
                 my->pos[i] = s.p[i];
                 my->dir[i] = s.d[i];
             }
-            r_dist = __dmul_rn(__ddiv_rn(sqrt(se.best), T.gnorm), -1.0);   // environment.py:158-162
-            mask_sum = (double)tm.lung_mask_sum;
+            if (kDense) r_dist = __dmul_rn(__ddiv_rn(sqrt(se.best), T.gnorm), -1.0);   // environment.py:158-162
+            mask_sum = (double)__ldg(&tg->lung_mask_sum);
             rcp_mask = __drcp_rn(mask_sum);
             if (out.info || kDense) os_r = overshoot_from_z(zc);           // transforms.py:29-33, 57 (info only)
             if (beams && n_beams < RT_MAX_TIME_STEPS) {                    // environment.py:110
@@ -692,6 +705,7 @@ __device__ __forceinline__ void step_block(StepShared<kB> &M, uint32_t *dyn_smem
         }
         if (!kDense && stepping) {
             RT_STAMP3(e, 11);
+            r_dist = __dmul_rn(__ddiv_rn(sqrt(se.best), T.gnorm), -1.0);   // environment.py:158-162 (se.best: env warp, before its deposition)
             tumour_dose += se.d_tum;
             lung_dose += se.d_lung;
             lung_count += se.d_cnt;
@@ -802,13 +816,16 @@ __device__ __forceinline__ void step_block(StepShared<kB> &M, uint32_t *dyn_smem
     const int le = warp - kEnvWarp0;
     const int env = env0 + le;
     const bool active = env < n_envs;
-    work_barrier<(kB + 1) * kWarp>();                                      // ---- barrier A
     EnvShared &se = sh[le];
     Tumour &tm = tum[le];
     uint32_t *tb = tbits[le];
-    const bool stepping = active && se.needs_reset == 0;
+    // what the tumour work needs from the record, read here so that it starts before the scalar warp has published anything
+    const bool stepping = active && __ldcg(&rec[active ? env : 0].needs_reset) == 0;
+    uint32_t pk4[4];
+    if (stepping) env_tumour_fetch<kDense>(T, __ldcg(&rec[env].tumour_id), tm, tb, lane, pk4);
+    work_barrier<(kB + 1) * kWarp>();                                      // ---- barrier A
     if (stepping) {
-        env_tumour_distance<kDense>(T, se, tm, tb, lane, [&]() {
+        env_distance(T, se, tm, lane, pk4, [&]() {
             if (kPredict) {
                 mbar_wait(smem_u32(&mbars[1]), pred_parity);               // the predictor warp has published its beams
                 prefetch_beam(G, pred[le], cells + (size_t)env * G.cstride, lane);
@@ -816,7 +833,8 @@ __device__ __forceinline__ void step_block(StepShared<kB> &M, uint32_t *dyn_smem
         });
     }
     if (active && lane == 0) RT_STAMP3(env, 2);
-    work_barrier<(kB + 1) * kWarp>();                                      // ---- barrier 1
+    if (kDense) work_barrier<(kB + 1) * kWarp>();                          // ---- barrier 1
+    else mbar_wait(smem_u32(&mbars[2]), pred_parity);                      // beams and walks published
     if (stepping && kDense) {
         // Dense mode: publish the beam (distinct voxels + summed weights); rt_dense_kernel streams the whole volume.
         const Beam b = se.beam;
@@ -864,11 +882,12 @@ __device__ __forceinline__ void step_prologue(StepShared<kB> &M)
     constexpr int kEnvWarp0 = (kB >= 14 && !kDense) ? 1 : 0;
     constexpr int kScalarWarp = kEnvWarp0 + kB;
     constexpr bool kStageLungs = kB >= 14 && !kDense;
-    if (kStageLungs && threadIdx.x == kScalarWarp * kWarp) {
+    if (!kDense && threadIdx.x == kScalarWarp * kWarp) {
         mbar_init(smem_u32(&M.mbars[0]), 1);
         mbar_init(smem_u32(&M.mbars[1]), 1);
+        mbar_init(smem_u32(&M.mbars[2]), 1);
     }
-    if (kStageLungs) __syncthreads();                             // the env warps wait on mbars[1] before any other barrier
+    if (!kDense) __syncthreads();                                 // the env warps wait on the mbarriers before any other barrier
     // Programmatic dependent launch: nothing the previous launch wrote is read before this point; the trigger
     // lets the next launch's blocks be scheduled as soon as ours retire.
     cudaGridDependencySynchronize();
