@@ -270,31 +270,6 @@ def other_kernels(rt, dev, peak):
 
     out = []
     g = torch.Generator(device=dev).manual_seed(7)
-    # the step kernel again at 65,536 envs on this GPU (16 waves): its throughput once launch latency and the
-    # per-env dependent chain are amortised (SURVEY.md 8d: "roofline fraction per kernel at large N")
-    n = 65536
-    # one distinct action batch per call of an episode cycle: a short repeating pool would walk every beam into the
-    # bounds of the volume (a lighter workload than the uniform-random policy the algorithmic bytes were counted on)
-    n_pool = 104
-    acts = [torch.rand((n, 6), device=dev, generator=g) * 2 - 1 for _ in range(n_pool)]
-    b = n * ALGO_BYTES_SECTOR
-    for name in ("rt_step_kernel",):
-        se = rt.BatchedEpisodes(n, device=dev, seed=11)
-        se.reset()
-        for i in range(127):                       # into the second episode (timed() adds three more warm-up calls)
-            se.step(acts[i % n_pool], want_info=False)
-        k = [0]
-
-        def big_step():
-            se.step(acts[k[0] % n_pool], want_info=False)
-            k[0] += 1
-        s = timed(big_step, 101)                   # one full episode cycle incl. the autoreset call: steady-state mix of
-                                                   # first-touched and re-touched cells
-        out.append({"kernel": name, "workload": f"{n} envs (visionless sparse step)", "bytes": b, "us": s * 1e6,
-                    "achieved": b / s / 1e9, "unit": "GB/s", "frac": b / s / 1e9 / peak, "env_steps_per_s": n / s,
-                    "state_gb": se.device_bytes / 1e9})
-        se.close()
-    del acts
     # voxel observation (BASELINE configs[3]): 4 planes written + dose read, 4,033,400 B per env
     n = 256
     ve = rt.BatchedEpisodes(n, device=dev, seed=4)
@@ -360,6 +335,33 @@ def other_kernels(rt, dev, peak):
                     "flops": fl, "us": s * 1e6, "achieved": fl / s / 1e12, "unit": "TFLOP/s", "bound": "fp32",
                     "frac": fl / s / 1e12 / fpeak, "peak": fpeak, "peak_source": "SMs x 128 FFMA x 2 x 1.965 GHz"})
         del fr
+    # Last, because the 113 GB handle it allocates and frees leaves the next measurements of the process 20-100 % slower
+    # (volumes 581 us against 262 us, 4096-env step 15.2 us against 12.2 us, measured with tools/stepbench.py).
+    # the step kernel again at 65,536 envs on this GPU (16 waves): its throughput once launch latency and the
+    # per-env dependent chain are amortised (SURVEY.md 8d: "roofline fraction per kernel at large N")
+    n = 65536
+    # one distinct action batch per call of an episode cycle: a short repeating pool would walk every beam into the
+    # bounds of the volume (a lighter workload than the uniform-random policy the algorithmic bytes were counted on)
+    n_pool = 104
+    acts = [torch.rand((n, 6), device=dev, generator=g) * 2 - 1 for _ in range(n_pool)]
+    b = n * ALGO_BYTES_SECTOR
+    for name in ("rt_step_kernel",):
+        se = rt.BatchedEpisodes(n, device=dev, seed=11)
+        se.reset()
+        for i in range(127):                       # into the second episode (timed() adds three more warm-up calls)
+            se.step(acts[i % n_pool], want_info=False)
+        k = [0]
+
+        def big_step():
+            se.step(acts[k[0] % n_pool], want_info=False)
+            k[0] += 1
+        s = timed(big_step, 101)                   # one full episode cycle incl. the autoreset call: steady-state mix of
+                                                   # first-touched and re-touched cells
+        out.append({"kernel": name, "workload": f"{n} envs (visionless sparse step)", "bytes": b, "us": s * 1e6,
+                    "achieved": b / s / 1e9, "unit": "GB/s", "frac": b / s / 1e9 / peak, "env_steps_per_s": n / s,
+                    "state_gb": se.device_bytes / 1e9})
+        se.close()
+    del acts
     return out
 
 
