@@ -5,8 +5,10 @@
 //        evaluate the reference's MLP agent (critic and actor_mean: Linear(n_obs,64)-Tanh-Linear(64,64)-Tanh-Linear,
 //        float32, FFMA), sample the diagonal Gaussian (action = mean + exp(logstd) * N(0,1), Philox4x32-10 keyed by
 //        (seed, env, step)), log-probability, store values / actions / logprobs, hand the action to the env step.
-//        A block takes 64 envs: the 10,061 parameters sit transposed in shared memory, a thread owns one hidden unit
-//        for 16 envs (16 accumulators; per input one weight + four 128-bit broadcast loads for 16 FFMA).
+//        A block takes 64 envs: the 10,061 parameters sit transposed in shared memory, a thread owns four hidden units
+//        for four envs (16 accumulators; per input one 128-bit load of four weights + one 128-bit broadcast load of four
+//        activations for 16 FFMA; activation rows are XOR-swizzled in groups of four envs so that both the unit-major
+//        stores and the env-major loads are conflict-free).
 //   rt_ppo_record_kernel  train.py:154-161: reward and next_done into the rollout buffers, episode statistics of the
 //        envs that finished (infos["episode"], infos["reward_components"]) accumulated on the device.
 //
@@ -20,9 +22,9 @@ namespace {
 constexpr int kPolHidden = 64;       // feature_dim of the reference's configs (configs/default.yaml.template)
 constexpr int kPolTile = 64;         // envs per block
 constexpr int kPolThreads = 256;
-constexpr int kPolStride = kPolTile + 4;   // activation rows [unit][env]: 16-byte aligned, conflict-free 128-bit stores
+constexpr int kPolStride = kPolTile;       // activation rows [unit][env], the groups of four envs XOR-swizzled by the row (pol_col)
 constexpr int kPolMaxObs = 16;
-constexpr int kPolWStride = kPolHidden + 1;   // transposed weight rows [k][unit]: conflict-free both for the transposing store and the unit-wise read
+constexpr int kPolWStride = kPolHidden + 4;   // transposed weight rows [k][unit]: 16-byte aligned rows, four units per 128-bit load
 constexpr int kPolOut = 8;           // output columns: actor means 0..n_act-1 (n_act <= 6), critic value 6, unused 7
 
 struct PolicyNet {
@@ -41,32 +43,39 @@ struct PolicyArgs {
     float *action_out;                              // [N][n_act]: this step's actions
 };
 
-// one hidden layer for this thread's unit u and its 16 envs: out[u][e] = tanh(b[u] + sum_k wT[k][u] * in[k][e])
-template <bool kTanh>
-__device__ __forceinline__ void policy_layer(const float *wT, const float *bias, const float *in, int K, float *out, int u, int e0)
+// Column of env e in activation row r: rows are [64 envs] floats, the sixteen groups of four envs permuted by the row's
+// (r / 4) mod 8.  A thread stores a 128-bit group per row for rows 4 ug .. 4 ug + 3: the eight lanes of a quarter-warp
+// (ug = 0..7, same env group) then hit eight different bank quads; a layer loads row k for one env group per
+// half-warp: a broadcast.
+__device__ __forceinline__ int pol_col(int r, int e) { return ((((e >> 2) ^ ((r >> 2) & 7)) << 2) | (e & 3)); }
+
+// one hidden layer for this thread's units 4 ug .. 4 ug + 3 and envs 4 eg .. 4 eg + 3:
+// out[u][e] = tanh(b[u] + sum_k wT[k][u] * in[k][e]), every sum the fmaf chain k = 0 .. K-1 from the bias
+__device__ __forceinline__ void policy_layer(const float *wT, const float *bias, const float *in, int K, float *out, int ug, int eg)
 {
-    float acc[16];
-    const float b = bias[u];
+    float acc[4][4];
+    const float4 b = *reinterpret_cast<const float4 *>(bias + 4 * ug);
+    const float bb[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-    for (int j = 0; j < 16; j++) acc[j] = b;
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j] = bb[i];
 #pragma unroll 4
     for (int k = 0; k < K; k++) {
-        const float w = wT[k * kPolWStride + u];
-        const float4 *x = reinterpret_cast<const float4 *>(in + k * kPolStride + e0);
+        const float4 w = *reinterpret_cast<const float4 *>(wT + k * kPolWStride + 4 * ug);
+        const float4 x = *reinterpret_cast<const float4 *>(in + k * kPolStride + ((eg ^ ((k >> 2) & 7)) << 2));
+        const float ww[4] = {w.x, w.y, w.z, w.w}, xx[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const float4 v = x[j];
-            acc[4 * j] = fmaf(w, v.x, acc[4 * j]);
-            acc[4 * j + 1] = fmaf(w, v.y, acc[4 * j + 1]);
-            acc[4 * j + 2] = fmaf(w, v.z, acc[4 * j + 2]);
-            acc[4 * j + 3] = fmaf(w, v.w, acc[4 * j + 3]);
-        }
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) acc[i][j] = fmaf(ww[i], xx[j], acc[i][j]);
     }
-    float4 *o = reinterpret_cast<float4 *>(out + u * kPolStride + e0);
 #pragma unroll
-    for (int j = 0; j < 4; j++)
-        o[j] = kTanh ? make_float4(tanhf(acc[4 * j]), tanhf(acc[4 * j + 1]), tanhf(acc[4 * j + 2]), tanhf(acc[4 * j + 3]))
-                     : make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+    for (int i = 0; i < 4; i++) {
+        const int r = 4 * ug + i;
+        *reinterpret_cast<float4 *>(out + r * kPolStride + ((eg ^ (ug & 7)) << 2)) =
+            make_float4(tanhf(acc[i][0]), tanhf(acc[i][1]), tanhf(acc[i][2]), tanhf(acc[i][3]));
+    }
 }
 
 __global__ void __launch_bounds__(kPolThreads) rt_ppo_act_kernel(PolicyArgs A)
@@ -120,7 +129,7 @@ __global__ void __launch_bounds__(kPolThreads) rt_ppo_act_kernel(PolicyArgs A)
     if (row < 0 || row >= A.rows) {                               // past the end of the rollout buffers: act, but store no row
         A.obs_buf = A.dones_buf = A.values_buf = A.actions_buf = A.logprobs_buf = nullptr;
     }
-    const int u = t & 63, e0 = (t >> 6) * 16;
+    const int ug = t & 15, eg = t >> 4;                           // this thread's four units and four envs of a layer
 
     for (int tile = blockIdx.x; tile * kPolTile < A.n; tile += gridDim.x) {
         const int env0 = tile * kPolTile;
@@ -134,15 +143,15 @@ __global__ void __launch_bounds__(kPolThreads) rt_ppo_act_kernel(PolicyArgs A)
                 v = A.obs[(size_t)env0 * n_obs + i];
                 if (A.obs_buf) A.obs_buf[((size_t)row * A.n + env0) * n_obs + i] = v;
             }
-            xin[k * kPolStride + e] = v;
+            xin[k * kPolStride + pol_col(k, e)] = v;
         }
         if (t < nb && A.dones_buf) A.dones_buf[(size_t)row * A.n + env0 + t] = A.next_done[env0 + t];   // train.py:141
         __syncthreads();
         for (int net = 0; net < 2; net++) {
-            policy_layer<true>(w0T + net * kPolMaxObs * kPolWStride, b0 + net * kPolHidden, xin, n_obs, h1, u, e0);
+            policy_layer(w0T + net * kPolMaxObs * kPolWStride, b0 + net * kPolHidden, xin, n_obs, h1, ug, eg);
             __syncthreads();
-            policy_layer<true>(w1T + net * kPolHidden * kPolWStride, b1 + net * kPolHidden, h1, kPolHidden,
-                               h2 + net * kPolHidden * kPolStride, u, e0);
+            policy_layer(w1T + net * kPolHidden * kPolWStride, b1 + net * kPolHidden, h1, kPolHidden,
+                         h2 + net * kPolHidden * kPolStride, ug, eg);
             __syncthreads();
         }
         // output layer: thread = (env, pair of output columns); columns 0..5 read the actor's features, 6 the critic's
@@ -153,7 +162,7 @@ __global__ void __launch_bounds__(kPolThreads) rt_ppo_act_kernel(PolicyArgs A)
             float a = b2[oa], b = b2[ob];
 #pragma unroll 8
             for (int k = 0; k < kPolHidden; k++) {
-                const float h = hf[k * kPolStride + e];
+                const float h = hf[k * kPolStride + pol_col(k, e)];
                 a = fmaf(w2T[k * kPolOut + oa], h, a);
                 b = fmaf(w2T[k * kPolOut + ob], h, b);
             }
