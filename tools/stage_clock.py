@@ -24,8 +24,8 @@ order = [0, 8, 9, 10, 1, 2, 3, 4, 6, 11, 7]
 ok = (s[:, :, order] > 0).all(axis=2)          # envs that walked a beam this step (all stamps written)
 rel = s - s[:, :, 0:1]                        # clock64 is per SM: only differences within an env's block are meaningful
 names = {0: "scalar warp start", 8: "scalar: state loaded, translated", 9: "scalar: pose updated", 10: "scalar: beam set up",
-         1: "scalar: walk done", 2: "env warp: tumour + distance done", 3: "env warp: past barrier 1, lungs landed",
-         4: "env warp: first pass's cell loads issued", 6: "env warp: all passes stored",
+         1: "scalar: walk done", 2: "env warp: tumour + distance done", 3: "env warp: beams seen (mbarrier)",
+         4: "env warp: cells of all passes back", 6: "env warp: all passes stored",
          11: "scalar: past barrier 2", 7: "end"}
 print(f"n={n}: cycles since the block's scalar-warp start (mean / p50 / p99 over {int(ok.sum())} env-steps)")
 for k in order:
