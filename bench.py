@@ -157,7 +157,7 @@ def workload_config(E: int, world: int, dose_gb=None):
                     "uniform(-1,1) actions, tumour id (i*7919) mod 1000 then seeded RNG, NEXT_STEP autoreset calls "
                     "counted in autoreset_calls_in_timed_region",
         "envs_per_gpu": E, "total_envs": E * world, "parallelism": f"env-sharded x{world}, no data-path collective",
-        "l2": "no flush: the dose state (6.6 GB/GPU at 4096 envs) >> 126 MB L2 and every step touches cells not "
+        "l2": "no flush: the dose state (7.1 GB/GPU at 4096 envs) >> 126 MB L2 and every step touches cells not "
               "touched before in the episode; the 0.5 MB of env records are L2-resident by design",
     }
 
