@@ -1,5 +1,5 @@
 import os, sys
-sys.path.insert(0, '/root/repo')
+import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, ppo_radiotherapy_b200 as rt
 from ppo_radiotherapy_b200 import train as T
 from torch.profiler import profile, ProfilerActivity
