@@ -270,43 +270,6 @@ def other_kernels(rt, dev, peak):
 
     out = []
     g = torch.Generator(device=dev).manual_seed(7)
-    # the headline workload again with CHAINED steps (rt_set_pdl 2, an opt-in contract: nothing the next step depends on is
-    # enqueued between two steps — true for this replay of precomputed action batches, not for a policy in the loop, which
-    # is why the headline above stays on the default launch mode): block b of a launch waits only for block b of the
-    # previous launch, a step costs its average block instead of its slowest
-    n, pool, chunk = 4096, 100, 50
-    ce = rt.BatchedEpisodes(n, device=dev, seed=0)
-    ce.set_pdl(2)
-    ce.reset()
-    acts = torch.rand((pool, n, 6), device=dev, generator=g) * 2 - 1
-    st = torch.cuda.Stream()
-    with torch.cuda.stream(st):
-        for i in range(130):
-            ce.step(acts[i % pool], want_info=False)
-        st.synchronize()
-        graphs = []
-        for gi in range(pool // chunk):
-            gr = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(gr, stream=st):
-                for j in range(chunk):
-                    ce.step(acts[gi * chunk + j], want_info=False)
-            graphs.append(gr)
-        for gr in graphs:
-            gr.replay()
-        st.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = 20
-        e0.record(st)
-        for i in range(reps):
-            graphs[i % len(graphs)].replay()
-        e1.record(st)
-        st.synchronize()
-    s = e0.elapsed_time(e1) * 1e-3 / (reps * chunk)
-    b = n * ALGO_BYTES_SECTOR
-    out.append({"kernel": "rt_step_kernel, chained steps (rt_set_pdl 2)", "workload": f"{n} envs (the headline workload), CUDA graphs of {chunk} steps",
-                "bytes": b, "us": s * 1e6, "achieved": b / s / 1e9, "unit": "GB/s", "frac": b / s / 1e9 / peak, "env_steps_per_s": n / s})
-    ce.close()
-    del acts, graphs
     # voxel observation (BASELINE configs[3]): 4 planes written + dose read, 4,033,400 B per env
     n = 256
     ve = rt.BatchedEpisodes(n, device=dev, seed=4)

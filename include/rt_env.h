@@ -279,18 +279,9 @@ RT_API int64_t rt_launch_count(void);
  * barrier 1, 4 first pass's cell loads issued, 6 all passes stored).  Sparse-mode handles with more than
  * 7 envs per SM only.  NULL (the default) switches it off. */
 RT_API int rt_set_stage_clock(rt_env *env, long long *stamps_dev);
-/* How consecutive rt_step launches of a handle follow each other on a stream.
- *   mode 1 (default): programmatic dependent launch — the next launch's blocks are scheduled while the previous one
- *     drains, and wait for the whole previous grid before they read anything.
- *   mode 2: chained steps.  Episodes are independent and block b of every launch advances the same envs, so block b
- *     of a launch waits only for block b of the previous launch (per-block completion counters): steps overlap and cost
- *     their average block instead of their slowest.  CONTRACT: between two rt_step calls of this handle on a stream the
- *     caller enqueues nothing that the later step depends on — in particular the action batches are complete before the
- *     first chained call (replaying precomputed actions, open-loop evaluation, benchmarks).  rt_step itself falls back to
- *     mode 1 for the first step after any other call on the handle (reset, rollout, getters, ...) or on another stream.
- *     Results are identical in every mode.
- *   mode 0: plain stream-ordered launches (A/B timing). */
-RT_API int rt_set_pdl(rt_env *env, int mode);
+/* Measurement aid: consecutive rt_step launches overlap through programmatic dependent launch (the next
+ * launch's blocks are scheduled while the previous one drains).  enabled = 0 switches that off for A/B timing. */
+RT_API int rt_set_pdl(rt_env *env, int enabled);
 
 #ifdef __cplusplus
 }

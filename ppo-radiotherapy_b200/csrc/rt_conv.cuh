@@ -874,7 +874,6 @@ int rt_conv1_relu_pool_grouped(const float *x_dev, const float *weight_dev, cons
 int rt_conv1_from_env(rt_env *e, int first, int count, const float *weight_dev, const float *bias_dev, void *out_dev,
                       void *scratch_dev, void *stream)
 {
-    if (e) e->chain_ok = false;
     if (!e) return fail(RT_ERR_INVALID, "rt_conv1_from_env: NULL handle");
     if (first < 0 || count < 0 || first + count > e->n) return fail(RT_ERR_INVALID, "rt_conv1_from_env: env range out of bounds");
     if (e->dense) return fail(RT_ERR_STATE, "rt_conv1_from_env: not available for dense-mode handles");

@@ -799,13 +799,7 @@ struct rt_env {
     size_t dense_smem = 0;
     size_t step_smem = 0;
     int step_kb = 14;         // envs per block of rt_step_kernel: 7 while one block per SM covers the envs, else 14
-    int pdl_mode = 1;         // rt_set_pdl: 0 plain launches, 1 programmatic dependent launch (grid mode), 2 + chain mode
-    // chain mode (rt_step.cuh, StepSync): per-block launch / completion counters, and whether the last thing enqueued for
-    // this handle was an rt_step on `chain_stream` (any other entry point that touches the handle's state clears it)
-    unsigned int *blk_sync = nullptr;
-    int blk_sync_n = 0;
-    bool chain_ok = false;
-    void *chain_stream = nullptr;
+    bool use_pdl = true;      // programmatic dependent launch of consecutive steps (rt_set_pdl)
     uint32_t *d_lungs = nullptr;
     Tumour *d_tumours = nullptr;
     uint32_t *d_tbits = nullptr;
@@ -1001,14 +995,6 @@ int rt_create(rt_env **out, int device, int n_envs, uint32_t flags, const rt_pha
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
         const int per_sm = (n_envs + sms - 1) / sms;
         e->step_kb = per_sm <= 7 ? 7 : 14;
-        if (!dense_mode) {
-            e->blk_sync_n = (n_envs + e->step_kb - 1) / e->step_kb;
-            if ((rc = dev_alloc(&e->blk_sync, (size_t)e->blk_sync_n, &e->bytes))) { rt_destroy(e); return rc; }
-            if (cudaMemset(e->blk_sync, 0, (size_t)e->blk_sync_n * sizeof(unsigned int)) != cudaSuccess) {
-                rt_destroy(e);
-                return fail(RT_ERR_CUDA, "rt_create: cudaMemset(blk_sync)");
-            }
-        }
         // dynamic shared memory of a block: the item slots of its envs (kMaxPass x 32 slabs x 4 targets x 8 bytes each) and,
         // for 14-env blocks, the padded lungs bitmask
         e->step_smem = dense_mode ? 0 : (size_t)e->step_kb * kMaxPass * 4 * kWarp * sizeof(uint2) +
@@ -1076,7 +1062,6 @@ int rt_destroy(rt_env *e)
     if (!e) return RT_OK;
     cudaSetDevice(e->device);
     cudaDeviceSynchronize();
-    cudaFree(e->blk_sync);
     cudaFree(e->d_lungs); cudaFree(e->d_tumours); cudaFree(e->d_tbits); cudaFree(e->d_ptbits); cudaFree(e->d_vox);
     cudaFree(e->rec); cudaFree(e->cells); cudaFree(e->dose); cudaFree(e->beams); cudaFree(e->dense); cudaFree(e->d_sched);
     // the *_host staging buffers are device-visible pinned allocations of the same sizes
@@ -1093,7 +1078,6 @@ int64_t rt_device_bytes(const rt_env *e) { return e ? e->bytes : 0; }
 
 int rt_seed(rt_env *e, uint64_t seed)
 {
-    if (e) e->chain_ok = false;
     if (!e) return fail(RT_ERR_INVALID, "rt_seed: NULL handle");
     e->S.seed = seed;
     return RT_OK;
@@ -1101,7 +1085,6 @@ int rt_seed(rt_env *e, uint64_t seed)
 
 int rt_set_tumour_schedule(rt_env *e, const int32_t *ids_host, int n_episodes)
 {
-    if (e) e->chain_ok = false;
     if (!e) return fail(RT_ERR_INVALID, "rt_set_tumour_schedule: NULL handle");
     RT_CUDA(cudaSetDevice(e->device));
     RT_CUDA(cudaDeviceSynchronize());
@@ -1134,7 +1117,6 @@ static int sync_before_host_call(rt_env *e)
 
 int rt_reset(rt_env *e, const uint8_t *mask_dev, float *obs_dev, void *stream)
 {
-    if (e) e->chain_ok = false;
     if (!e) return fail(RT_ERR_INVALID, "rt_reset: NULL handle");
     RT_CUDA(cudaSetDevice(e->device));
     if ((cudaStream_t)stream != e->hstream) e->dev_pending = true;
@@ -1156,12 +1138,6 @@ int rt_step(rt_env *e, const float *actions_dev, float *obs_dev, double *reward_
     if ((cudaStream_t)stream != e->hstream) e->dev_pending = true;
     StepOut o{obs_dev, reward_dev, reward_f32_dev, terminated_dev, truncated_dev, info_dev};
     const int kb = e->step_kb;
-    // chain mode (rt_set_pdl 2): bookkeeping in every launch, the per-block wait only directly after another rt_step of
-    // this handle on the same stream
-    StepSync Y{e->pdl_mode == 2 ? e->blk_sync : nullptr,
-               e->pdl_mode == 2 && e->chain_ok && e->chain_stream == stream && e->blk_sync ? 1 : 0};
-    e->chain_ok = !e->dense;
-    e->chain_stream = stream;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((e->n + kb - 1) / kb);
     cfg.blockDim = dim3((kb + 1 + (kb >= 14 && !e->dense ? 1 : 0)) * kWarp);     // scalar warp, env warps, predictor warp
@@ -1169,25 +1145,25 @@ int rt_step(rt_env *e, const float *actions_dev, float *obs_dev, double *reward_
     cfg.stream = (cudaStream_t)stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = e->pdl_mode > 0 && !e->dense ? 1 : 0;
+    attr[0].val.programmaticStreamSerializationAllowed = e->use_pdl && !e->dense ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     if (e->dense) {
         if (kb == 7)
-            RT_CUDA(cudaLaunchKernelEx(&cfg, rt_step_kernel<7, false, true>, e->T, e->S, e->rec, e->cells, e->beams, e->n, actions_dev, o, e->dense, Y));
+            RT_CUDA(cudaLaunchKernelEx(&cfg, rt_step_kernel<7, false, true>, e->T, e->S, e->rec, e->cells, e->beams, e->n, actions_dev, o, e->dense));
         else
-            RT_CUDA(cudaLaunchKernelEx(&cfg, rt_step_kernel<14, false, true>, e->T, e->S, e->rec, e->cells, e->beams, e->n, actions_dev, o, e->dense, Y));
+            RT_CUDA(cudaLaunchKernelEx(&cfg, rt_step_kernel<14, false, true>, e->T, e->S, e->rec, e->cells, e->beams, e->n, actions_dev, o, e->dense));
         RT_LAUNCH_CHECK("rt_step_kernel<dense>");
         rt_dense_kernel<<<e->n, kDenseThreads, e->dense_smem, (cudaStream_t)stream>>>(e->T, e->rec, e->dose, e->dense, o);
         RT_LAUNCH_CHECK("rt_dense_kernel");
         return RT_OK;
     }
     if (kb == 7)
-        RT_CUDA(cudaLaunchKernelEx(&cfg, rt_step_kernel<7, false, false>, e->T, e->S, e->rec, e->cells, e->beams, e->n, actions_dev, o, e->dense, Y));
+        RT_CUDA(cudaLaunchKernelEx(&cfg, rt_step_kernel<7, false, false>, e->T, e->S, e->rec, e->cells, e->beams, e->n, actions_dev, o, e->dense));
     else if (e->T.stage_clock)
-        RT_CUDA(cudaLaunchKernelEx(&cfg, rt_step_kernel<14, true, false>, e->T, e->S, e->rec, e->cells, e->beams, e->n, actions_dev, o, e->dense, Y));
+        RT_CUDA(cudaLaunchKernelEx(&cfg, rt_step_kernel<14, true, false>, e->T, e->S, e->rec, e->cells, e->beams, e->n, actions_dev, o, e->dense));
     else
-        RT_CUDA(cudaLaunchKernelEx(&cfg, rt_step_kernel<14, false, false>, e->T, e->S, e->rec, e->cells, e->beams, e->n, actions_dev, o, e->dense, Y));
+        RT_CUDA(cudaLaunchKernelEx(&cfg, rt_step_kernel<14, false, false>, e->T, e->S, e->rec, e->cells, e->beams, e->n, actions_dev, o, e->dense));
     RT_LAUNCH_CHECK("rt_step_kernel");
     return RT_OK;
 }
@@ -1212,25 +1188,15 @@ int rt_reset_host(rt_env *e, const uint8_t *mask_host, float *obs_host)
     return RT_OK;
 }
 
-int rt_set_pdl(rt_env *e, int mode)
+int rt_set_pdl(rt_env *e, int enabled)
 {
     if (!e) return fail(RT_ERR_INVALID, "rt_set_pdl: NULL handle");
-    if (mode < 0 || mode > 2) return fail(RT_ERR_INVALID, "rt_set_pdl: mode must be 0, 1 or 2");
-    if (mode == 2) {
-        if (!e->blk_sync) return fail(RT_ERR_STATE, "rt_set_pdl: chained steps exist for sparse-mode handles");
-        // every block of the handle idle and its claim word clear before the first launch that keeps the books
-        RT_CUDA(cudaSetDevice(e->device));
-        RT_CUDA(cudaDeviceSynchronize());
-        RT_CUDA(cudaMemset(e->blk_sync, 0, (size_t)e->blk_sync_n * sizeof(unsigned int)));
-    }
-    e->pdl_mode = mode;
-    e->chain_ok = false;
+    e->use_pdl = enabled != 0;
     return RT_OK;
 }
 
 int rt_set_stage_clock(rt_env *e, long long *stamps_dev)
 {
-    if (e) e->chain_ok = false;
     if (!e) return fail(RT_ERR_INVALID, "rt_set_stage_clock: NULL handle");
     if (stamps_dev && (e->step_kb != 14 || e->dense))
         return fail(RT_ERR_STATE, "rt_set_stage_clock: the instrumented step kernel exists for sparse-mode handles with 14 envs per block (more than 7 envs per SM)");
@@ -1240,7 +1206,6 @@ int rt_set_stage_clock(rt_env *e, long long *stamps_dev)
 
 int rt_get_pose(rt_env *e, double *pose_dev, void *stream)
 {
-    if (e) e->chain_ok = false;
     if (!e || !pose_dev) return fail(RT_ERR_INVALID, "rt_get_pose: NULL argument");
     RT_CUDA(cudaSetDevice(e->device));
     rt_get_pose_kernel<<<(e->n * 6 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(e->rec, e->n, pose_dev);
@@ -1250,7 +1215,6 @@ int rt_get_pose(rt_env *e, double *pose_dev, void *stream)
 
 int rt_set_pose(rt_env *e, const double *pose_dev, void *stream)
 {
-    if (e) e->chain_ok = false;
     if (!e || !pose_dev) return fail(RT_ERR_INVALID, "rt_set_pose: NULL argument");
     RT_CUDA(cudaSetDevice(e->device));
     e->dev_pending = true;
@@ -1261,7 +1225,6 @@ int rt_set_pose(rt_env *e, const double *pose_dev, void *stream)
 
 int rt_get_counters(rt_env *e, int32_t *counters_dev, void *stream)
 {
-    if (e) e->chain_ok = false;
     if (!e || !counters_dev) return fail(RT_ERR_INVALID, "rt_get_counters: NULL argument");
     RT_CUDA(cudaSetDevice(e->device));
     rt_get_counters_kernel<<<(e->n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(e->rec, e->n, counters_dev);
@@ -1271,7 +1234,6 @@ int rt_get_counters(rt_env *e, int32_t *counters_dev, void *stream)
 
 int rt_get_dose(rt_env *e, int env_index, float *dose_dev, void *stream)
 {
-    if (e) e->chain_ok = false;
     if (!e || !dose_dev) return fail(RT_ERR_INVALID, "rt_get_dose: NULL argument");
     if (env_index < 0 || env_index >= e->n) return fail(RT_ERR_INVALID, "rt_get_dose: env index out of range");
     RT_CUDA(cudaSetDevice(e->device));
@@ -1283,7 +1245,6 @@ int rt_get_dose(rt_env *e, int env_index, float *dose_dev, void *stream)
 
 int rt_get_beams(rt_env *e, int env_index, double *beams_dev, int32_t *n_dev, void *stream)
 {
-    if (e) e->chain_ok = false;
     if (!e || !beams_dev) return fail(RT_ERR_INVALID, "rt_get_beams: NULL argument");
     if (!e->beams) return fail(RT_ERR_STATE, "rt_get_beams: handle was created without RT_FLAG_RECORD_BEAMS");
     if (env_index < 0 || env_index >= e->n) return fail(RT_ERR_INVALID, "rt_get_beams: env index out of range");
@@ -1296,7 +1257,6 @@ int rt_get_beams(rt_env *e, int env_index, double *beams_dev, int32_t *n_dev, vo
 
 int rt_assemble_volumes(rt_env *e, int first, int count, float *obs_dev, void *stream)
 {
-    if (e) e->chain_ok = false;
     if (!e || !obs_dev) return fail(RT_ERR_INVALID, "rt_assemble_volumes: NULL argument");
     if (first < 0 || count < 1 || first + count > e->n)
         return fail(RT_ERR_INVALID, "rt_assemble_volumes: env range out of bounds");
@@ -1321,7 +1281,6 @@ int rt_observation_record_stride(const rt_env *e) { return e ? e->T.G.vstride : 
 int rt_pack_observations(rt_env *e, int first, int count, int64_t slot0, void *dose_bf16_dev, double *pose_dev,
                          int32_t *tumour_id_dev, void *stream)
 {
-    if (e) e->chain_ok = false;
     if (!e || !dose_bf16_dev || !pose_dev || !tumour_id_dev) return fail(RT_ERR_INVALID, "rt_pack_observations: NULL argument");
     if (count == 0) return RT_OK;
     if (first < 0 || count < 0 || first + count > e->n || slot0 < 0)

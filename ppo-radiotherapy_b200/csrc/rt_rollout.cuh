@@ -62,7 +62,7 @@ rt_rollout_kernel(Tables T, Schedule S, EnvRec *rec, uint2 *cells, double *beams
     const int env0 = blockIdx.x * kB;
     const int nb = min(kB, n_envs - env0);
 
-    step_prologue<kB, false>(M, StepSync{nullptr, 0});
+    step_prologue<kB, false>(M);
     for (int i = tid; i < nb * RT_OBS_SIZE; i += nthreads) M.s_obs[i] = A.next_obs[(size_t)env0 * RT_OBS_SIZE + i];
     for (int i = nb * RT_OBS_SIZE + tid; i < kB * RT_OBS_SIZE; i += nthreads) M.s_obs[i] = 0.0f;
     if (tid < kB) s_done[tid] = tid < nb ? A.next_done[env0 + tid] : 0.0f;
@@ -231,7 +231,6 @@ int rt_rollout(rt_env *e, const rt_mlp_params *p, int n_steps, int64_t row0, int
     if (n_steps < 0 || row0 < 0 || rng_step0 < 0 || row0 + n_steps > rows)
         return fail(RT_ERR_INVALID, "rt_rollout: rows [row0, row0 + n_steps) must lie inside the rollout buffers");
     if (n_steps == 0) return RT_OK;
-    e->chain_ok = false;
     RT_CUDA(cudaSetDevice(e->device));
     if ((cudaStream_t)stream != e->hstream) e->dev_pending = true;
     RolloutArgs A;
@@ -260,7 +259,7 @@ int rt_rollout(rt_env *e, const rt_mlp_params *p, int n_steps, int64_t row0, int
     cfg.stream = (cudaStream_t)stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = e->pdl_mode > 0 ? 1 : 0;
+    attr[0].val.programmaticStreamSerializationAllowed = e->use_pdl ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     if (kb == 7)

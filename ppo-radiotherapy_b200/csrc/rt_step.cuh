@@ -562,13 +562,12 @@ __device__ __forceinline__ void step_block(StepShared<kB> &M, uint32_t *dyn_smem
         uint32_t gen = 0u;
         if (mine) {
             // every load is issued before the first use: one round trip to L2
-            // (the record is read past the L1: consecutive launches overlap and a block may land on another SM)
-            const int needs_reset = __ldcg(&my->needs_reset);
-            tid = __ldcg(&my->tumour_id);
-            gen = __ldcg(&my->gen);
+            const int needs_reset = my->needs_reset;
+            tid = my->tumour_id;
+            gen = my->gen;
             double p0[3];
 #pragma unroll
-            for (int i = 0; i < 3; i++) { p0[i] = __ldcg(&my->pos[i]); dn[i] = __ldcg(&my->dn[i]); }
+            for (int i = 0; i < 3; i++) { p0[i] = my->pos[i]; dn[i] = my->dn[i]; }
             float2 a01, a23, a45;
             if (kRoll) {
                 const float2 *ap = reinterpret_cast<const float2 *>(actions + lane * RT_ACTION_SIZE);
@@ -625,10 +624,10 @@ __device__ __forceinline__ void step_block(StepShared<kB> &M, uint32_t *dyn_smem
         double r_dist = 0.0, os_r = 0.0, rcp_mask = 0.0, mask_sum = 1.0;
         double tumour_dose = 0.0, lung_dose = 0.0, ep_return = 0.0;
         if (stepping) {
-            tumour_dose = __ldcg(&my->tumour_dose); lung_dose = __ldcg(&my->lung_dose); ep_return = __ldcg(&my->ep_return);   // consumed after barrier 2
-            t = __ldcg(&my->t) + 1;                                        // environment.py:194
-            lung_count = __ldcg(&my->lung_count);
-            n_beams = __ldcg(&my->n_beams);
+            tumour_dose = my->tumour_dose; lung_dose = my->lung_dose; ep_return = my->ep_return;   // consumed after barrier 2
+            t = my->t + 1;                                                 // environment.py:194
+            lung_count = my->lung_count;
+            n_beams = my->n_beams;
             float *obs = s_obs + lane * RT_OBS_SIZE;                       // environment.py:259-268
             double nd0 = s.d[0], nd1 = s.d[1], nd2 = s.d[2];
             normalize3(nd0, nd1, nd2);                                     // the next step's transforms.py:23
@@ -665,7 +664,7 @@ __device__ __forceinline__ void step_block(StepShared<kB> &M, uint32_t *dyn_smem
         } else if (mine) {
             // gymnasium 1.0.0 NEXT_STEP: the call after a terminal step resets and reports reward 0
             // (environment.py:77-105).  A new generation empties the dose volume.
-            const int episode = __ldcg(&my->episode) + 1;
+            const int episode = my->episode + 1;
             tid = pick_tumour(T, S, e, n_envs, episode);
             const Tumour *tg = T.tumours + tid;
             float *obs = s_obs + lane * RT_OBS_SIZE;
@@ -789,10 +788,10 @@ __device__ __forceinline__ void step_block(StepShared<kB> &M, uint32_t *dyn_smem
         pb.nslab = 0;
         if (lane < kB && e < n_envs) {
             const EnvRec *my = rec + e;
-            const int needs_reset = __ldcg(&my->needs_reset);
+            const int needs_reset = my->needs_reset;
             double p0[3], dn[3];
 #pragma unroll
-            for (int i = 0; i < 3; i++) { p0[i] = __ldcg(&my->pos[i]); dn[i] = __ldcg(&my->dn[i]); }
+            for (int i = 0; i < 3; i++) { p0[i] = my->pos[i]; dn[i] = my->dn[i]; }
             float2 a01, a23, a45;
             if (kRoll) {
                 const float2 *ap = reinterpret_cast<const float2 *>(actions + lane * RT_ACTION_SIZE);
@@ -880,78 +879,35 @@ __device__ __forceinline__ void step_block(StepShared<kB> &M, uint32_t *dyn_smem
     work_barrier<(kB + 1) * kWarp>();                                      // ---- barrier 2
 }
 
-// Launch-to-launch ordering of consecutive steps on one handle.  Envs are independent and block b of every launch
-// advances the same kB envs, so block b of launch t + 1 depends on block b of launch t and on nothing else of that grid.
-//   grid mode:  cudaGridDependencySynchronize() — every block waits until the whole previous grid has completed; a step
-//               then costs its SLOWEST block plus the bubble between grids (a three-pass beam anywhere on the GPU, a
-//               large tumour, a busy SM: 21.7 k cycles + ~2.5 k against 18.1 k for the average block at 4,096 envs);
-//   chain mode: busy[b] says whether a launch's block b is still working on its envs.  A block claims it at its start
-//               (compare-and-swap 0 -> 1, acquire) and releases it after its last store.  Launch t + 1's block b —
-//               scheduled early by programmatic dependent launch, as soon as a slot frees up — spins on the claim
-//               until launch t's block b has released it, and goes: blocks run back to back per env group and a step
-//               costs the AVERAGE block plus ~1.5 k cycles of hand-over.  (A block triggers the next launch only after
-//               its claim, so at most one successor of a block spins at a time.)  Chain mode is only correct when
-//               nothing but rt_step launches of this handle separate two steps on the stream (rt_set_pdl(env, 2)
-//               states that contract; rt_step falls back to grid mode after any other call on the handle).
-struct StepSync {
-    unsigned int *busy;               // [blocks]; NULL: grid mode without bookkeeping (rt_set_pdl 0 / 1, rollout kernel, dense mode)
-    int chain;
-};
-
-// Prologue shared by the kernels built on step_block: mbarriers, and the hand-over from the previous launch.
+// Prologue shared by the kernels built on step_block: mbarriers, and the programmatic-dependent-launch hand-over.
 template <int kB, bool kDense>
-__device__ __forceinline__ void step_prologue(StepShared<kB> &M, const StepSync &Y)
+__device__ __forceinline__ void step_prologue(StepShared<kB> &M)
 {
     constexpr int kEnvWarp0 = (kB >= 14 && !kDense) ? 1 : 0;
     constexpr int kScalarWarp = kEnvWarp0 + kB;
-    if (threadIdx.x == kScalarWarp * kWarp) {
-        if (!kDense) {
-            mbar_init(smem_u32(&M.mbars[0]), 1);
-            mbar_init(smem_u32(&M.mbars[1]), 1);
-            mbar_init(smem_u32(&M.mbars[2]), 1);
-        }
-        if (Y.busy) {
-            if (Y.chain) {
-                while (atomicCAS(Y.busy + blockIdx.x, 0u, 1u) != 0u) __nanosleep(32);
-                __threadfence();                                  // acquire: the predecessor's stores
-            } else {
-                atomicExch(Y.busy + blockIdx.x, 1u);              // the whole previous grid is waited for below
-            }
-        }
+    constexpr bool kStageLungs = kB >= 14 && !kDense;
+    if (!kDense && threadIdx.x == kScalarWarp * kWarp) {
+        mbar_init(smem_u32(&M.mbars[0]), 1);
+        mbar_init(smem_u32(&M.mbars[1]), 1);
+        mbar_init(smem_u32(&M.mbars[2]), 1);
     }
-    if (!kDense || Y.busy) __syncthreads();                    // the env warps wait on the mbarriers before any other barrier
+    if (!kDense) __syncthreads();                                 // the env warps wait on the mbarriers before any other barrier
     // Programmatic dependent launch: nothing the previous launch wrote is read before this point; the trigger
     // lets the next launch's blocks be scheduled as soon as ours retire.
-    if (!Y.chain) cudaGridDependencySynchronize();
+    cudaGridDependencySynchronize();
     cudaTriggerProgrammaticLaunchCompletion();
-}
-
-// Last thing a step block does (scalar warp, after its outputs): release its envs for chain mode.
-template <int kB, bool kDense>
-__device__ __forceinline__ void step_epilogue(const StepSync &Y)
-{
-    constexpr int kEnvWarp0 = (kB >= 14 && !kDense) ? 1 : 0;
-    constexpr int kScalarWarp = kEnvWarp0 + kB;
-    if (Y.busy && threadIdx.x / kWarp == kScalarWarp) {
-        __syncwarp();                                             // the other lanes' output stores
-        if ((threadIdx.x & (kWarp - 1)) == 0) {
-            __threadfence();                                      // ... and, through barrier 2, the env warps' cell stores
-            atomicExch(Y.busy + blockIdx.x, 0u);
-        }
-    }
 }
 
 template <int kB, bool kClock, bool kDense>
 __global__ void __launch_bounds__((step_block_threads<kB, kDense>()), 28 / kB)
 rt_step_kernel(Tables T, Schedule S, EnvRec *rec, uint2 *cells, double *beams, int n_envs,
-               const float *__restrict__ actions, StepOut out, DenseWork *dense, StepSync Y)
+               const float *__restrict__ actions, StepOut out, DenseWork *dense)
 {
     __shared__ StepShared<kB> M;
     extern __shared__ __align__(128) uint32_t dyn_smem[];
-    step_prologue<kB, kDense>(M, Y);
+    step_prologue<kB, kDense>(M);
     step_block<kB, kClock, kDense, false>(M, dyn_smem, T, S, rec, cells, beams, n_envs, actions, out, dense, blockIdx.x * kB, 0u,
                                           RollStep{nullptr, nullptr});
-    step_epilogue<kB, kDense>(Y);
 }
 
 }  // namespace

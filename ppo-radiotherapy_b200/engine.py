@@ -84,12 +84,6 @@ class BatchedEpisodes:
     def seed(self, seed: int):
         nat.check(self._lib.rt_seed(self._h, C.c_uint64(int(seed) & 0xFFFFFFFFFFFFFFFF)), "rt_seed")
 
-    def set_pdl(self, mode: int = 1):
-        """How consecutive steps follow each other on a stream (rt_set_pdl): 1 programmatic dependent launch (default),
-        2 chained steps — block b of a launch waits only for block b of the previous one; the caller promises that nothing
-        the later step depends on is enqueued between two steps (precomputed action batches) —, 0 plain launches."""
-        nat.check(self._lib.rt_set_pdl(self._h, int(mode)), "rt_set_pdl")
-
     def set_tumour_schedule(self, ids):
         """ids int [E][N]: episode e of env i uses tumour ids[min(e, E-1)][i]; None = device RNG."""
         if ids is None:

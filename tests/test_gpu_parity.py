@@ -552,54 +552,6 @@ def test_step_kernel_block_shapes_vs_oracle(n):
     env.close()
 
 
-@pytest.mark.parametrize("n", [4096, 9000, 300])
-def test_chained_steps_equal_grid_ordered_steps(n):
-    """rt_set_pdl(2): consecutive steps chained per block (a block waits only for its own predecessor, launches overlap)
-    against the default grid-ordered launches, 230 back-to-back steps from precomputed action batches — two full episodes,
-    two autoreset calls — eagerly and replayed from a CUDA graph: every piece of env state (pose, counters, episode
-    return through the info block, dose volumes) and the last outputs equal bit for bit.  A getter in the middle of the
-    sequence makes the next step fall back to a grid-ordered launch."""
-    T = 230
-    g = torch.Generator(device=DEV).manual_seed(n)
-    acts = torch.rand((T, n, 6), device=DEV, generator=g) * 2 - 1
-    torch.cuda.synchronize()
-    results = []
-    for mode, graph in ((1, False), (2, False), (2, True)):
-        eng = rt.BatchedEpisodes(n, device=DEV, seed=9)
-        eng.set_pdl(mode)
-        s = torch.cuda.Stream()
-        with torch.cuda.stream(s):
-            eng.reset()
-            if graph:
-                for t in range(10):
-                    eng.step(acts[t])
-                s.synchronize()
-                gr = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(gr, stream=s):
-                    for t in range(10, 120):
-                        eng.step(acts[t])
-                gr.replay()
-                mid = eng.pose().clone()                     # a getter: the next step must not chain past it
-                for t in range(120, T):
-                    eng.step(acts[t])
-            else:
-                for t in range(120):
-                    eng.step(acts[t])
-                mid = eng.pose().clone()
-                for t in range(120, T):
-                    eng.step(acts[t])
-            s.synchronize()
-        results.append((mid, eng.pose(), eng.counters(), eng.obs.clone(), eng.reward.clone(), eng.terminated.clone(),
-                        eng.info.clone(), [eng.dose(e).clone() for e in (0, 7, n // 2, n - 1)]))
-        eng.close()
-    ref = results[0]
-    for other in results[1:]:
-        for a, b in zip(ref[:-1], other[:-1]):
-            assert torch.equal(a, b)
-        for a, b in zip(ref[-1], other[-1]):
-            assert torch.equal(a, b)
-
-
 @pytest.mark.parametrize("n", [1, 6, 7, 8, 13, 33])
 def test_ragged_env_counts(n):
     """Env counts that do not fill the kernel's 7-env blocks (and N = 1) behave like the oracle."""

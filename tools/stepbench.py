@@ -1,8 +1,7 @@
 #!/usr/bin/env python
 """Device-time the sparse step for a list of env counts, the way bench.py does (steady state incl. autoreset calls,
 pool of action batches, CUDA graphs of 50 steps, CUDA events); `nopdl:` in front of a count switches programmatic
-dependent launch off (rt_set_pdl), `chain:` selects chained steps (rt_set_pdl 2: a block waits only for its own
-predecessor), `eager:` launches every step from Python instead of replaying graphs.
+dependent launch off (rt_set_pdl), `eager:` launches every step from Python instead of replaying graphs.
 
     python tools/stepbench.py 4096 nopdl:4096 eager:4096 8192 65536
 """
@@ -23,8 +22,6 @@ def run(mode, n, steps=600, warm=150, pool=104, chunk=50):
     eng = rt.BatchedEpisodes(n, device=dev)
     if "nopdl" in mode:
         nat.check(nat.lib().rt_set_pdl(eng._h, 0))
-    if "chain" in mode:
-        eng.set_pdl(2)
     eng.reset()
     g = torch.Generator(device=dev).manual_seed(0)
     acts = torch.rand((pool, n, 6), device=dev, generator=g) * 2 - 1
