@@ -60,16 +60,25 @@ __device__ __forceinline__ void policy_layer(const float *wT, const float *bias,
     for (int i = 0; i < 4; i++)
 #pragma unroll
         for (int j = 0; j < 4; j++) acc[i][j] = bb[i];
-#pragma unroll 4
-    for (int k = 0; k < K; k++) {
-        const float4 w = *reinterpret_cast<const float4 *>(wT + k * kPolWStride + 4 * ug);
-        const float4 x = *reinterpret_cast<const float4 *>(in + k * kPolStride + ((eg ^ ((k >> 2) & 7)) << 2));
+    // rows in groups of four: the swizzle of the activation row is the same for k = 4 kk .. 4 kk + 3, so one address per group
+    auto step = [&](const float *wrow, const float *xrow) {
+        const float4 w = *reinterpret_cast<const float4 *>(wrow);
+        const float4 x = *reinterpret_cast<const float4 *>(xrow);
         const float ww[4] = {w.x, w.y, w.z, w.w}, xx[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
         for (int i = 0; i < 4; i++)
 #pragma unroll
             for (int j = 0; j < 4; j++) acc[i][j] = fmaf(ww[i], xx[j], acc[i][j]);
+    };
+    const float *wp = wT + 4 * ug;
+    int k = 0;
+#pragma unroll 2
+    for (; k + 4 <= K; k += 4) {
+        const float *xp = in + k * kPolStride + ((eg ^ ((k >> 2) & 7)) << 2);
+#pragma unroll
+        for (int q = 0; q < 4; q++) step(wp + (k + q) * kPolWStride, xp + q * kPolStride);
     }
+    for (; k < K; k++) step(wp + k * kPolWStride, in + k * kPolStride + ((eg ^ ((k >> 2) & 7)) << 2));
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         const int r = 4 * ug + i;
@@ -160,11 +169,15 @@ __global__ void __launch_bounds__(kPolThreads) rt_ppo_act_kernel(PolicyArgs A)
             const float *hf = h2 + (q < 3 ? kPolHidden * kPolStride : 0);
             const int oa = q < 3 ? 2 * q : 6, ob = q < 3 ? 2 * q + 1 : 7;
             float a = b2[oa], b = b2[ob];
-#pragma unroll 8
-            for (int k = 0; k < kPolHidden; k++) {
-                const float h = hf[k * kPolStride + pol_col(k, e)];
-                a = fmaf(w2T[k * kPolOut + oa], h, a);
-                b = fmaf(w2T[k * kPolOut + ob], h, b);
+#pragma unroll 2
+            for (int k = 0; k < kPolHidden; k += 4) {
+                const float *hp = hf + k * kPolStride + pol_col(k, e);          // one swizzle per four rows
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const float h = hp[q * kPolStride];
+                    a = fmaf(w2T[(k + q) * kPolOut + oa], h, a);
+                    b = fmaf(w2T[(k + q) * kPolOut + ob], h, b);
+                }
             }
             // networks.py:141-147: action = mean + std * N(0,1); log_prob = -(a-mean)^2/(2 var) - log std - log sqrt(2 pi)
             float part = 0.0f;
