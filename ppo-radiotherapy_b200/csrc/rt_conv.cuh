@@ -1,4 +1,4 @@
-// rt_conv.cu — first block of FeaturesExtractor3D (networks.py:22-24) as ONE kernel on the tensor cores:
+// rt_conv.cuh — first block of FeaturesExtractor3D (networks.py:22-24) as ONE kernel on the tensor cores:
 //     Conv3d(4 -> 16, k = 3)  +  bias  +  ReLU  +  MaxPool3d(2, 2, padding = (pd, ph, 0))
 // for the voxel observation [n][4][D][H][W] float32 (environment.py:252-257) -> [n][16][Pd][Ph][Pw] bfloat16.
 //
@@ -174,7 +174,7 @@ __global__ void rt_conv_prepare_tc_kernel(const float *__restrict__ weight, __nv
 
 // Source of the first block's input when it is not a materialised observation tensor: the live env state.  The
 // loader warps then generate the four observation planes of environment.py:245-257 voxel by voxel — lungs bit,
-// tumour bit, dose (sector-valid bitmap applied), clip(current beam + horizontal beam, 0, 1) — exactly as
+// tumour bit, dose (cells of another generation read as zero), clip(current beam + horizontal beam, 0, 1) — exactly as
 // rt_volumes_kernel would have written them, and the 3.2 MB float32 observation never exists.
 struct EnvSource {
     Tables T;
